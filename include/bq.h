@@ -1,0 +1,154 @@
+/*
+ * bq.h — C ABI of libbq_b200.so: B200 (sm_100a) block-quantisation hot path.
+ *
+ * This is the drop-in boundary for llm-mixed-q's software-emulated quantisation
+ * path.  The reference (ChengZhang-98/llm-mixed-q @ 740bf48) has no FFI: its
+ * boundary is the Python operator API under src/llm_mixed_q/models/quantize/.
+ * Every entry point below names the reference function it replaces (file:line,
+ * relative to that directory).  The Python host mirror (llm_mixed_q_b200/) binds
+ * these with ctypes and keeps the reference's names / kwargs / exceptions.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless it says "host";
+ *   - the caller (PyTorch) owns every buffer, including workspaces — nothing here
+ *     allocates or frees device memory;
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed as
+ *     void*) and re-entrant; there is no hidden mutable global state;
+ *   - return value: 0 on success, otherwise a bq_status (see bq_strerror);
+ *   - there is NO CPU fallback: on a machine without a B200 the calls fail with
+ *     BQ_ERR_CUDA.
+ */
+#ifndef BQ_B200_H
+#define BQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BQ_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BQ_API __attribute__((visibility("default")))
+#else
+#define BQ_API
+#endif
+
+typedef enum bq_status {
+  BQ_OK = 0,
+  BQ_ERR_BAD_ARG = 1,      /* null pointer, negative size, misaligned pointer          -> ValueError          */
+  BQ_ERR_UNSUPPORTED = 2,  /* legal in the reference but not implemented here           -> NotImplementedError */
+  BQ_ERR_BAD_FORMAT = 3,   /* width / exponent width outside the representable range    -> ValueError          */
+  BQ_ERR_WORKSPACE = 4,    /* workspace too small (see the *_workspace_bytes functions) -> ValueError          */
+  BQ_ERR_CUDA = 5,         /* a CUDA runtime/driver call failed                         -> RuntimeError        */
+  BQ_ERR_NOT_BF16_EXACT = 6/* quantised operand does not fit bf16's 8 significant bits  -> NotImplementedError */
+} bq_status;
+
+/* Arithmetic ("name" key of the reference's quant config, quant_config_parser.py:32-155). */
+typedef enum bq_kind {
+  BQ_KIND_BLOCK_FP = 0,         /* quantizers/block_fp.py:21-96        */
+  BQ_KIND_BLOCK_MINIFLOAT = 1,  /* quantizers/block_minifloat.py:22-74 */
+  BQ_KIND_BLOCK_LOG = 2,        /* quantizers/block_log.py:23-69       */
+  BQ_KIND_MINIFLOAT_DENORM = 3, /* quantizers/minifloat.py:21-82       */
+  BQ_KIND_MINIFLOAT_IEEE = 4,   /* quantizers/minifloat.py:134-196 (scalar bias) */
+  BQ_KIND_INTEGER = 5,          /* quantizers/integer.py:25-58         */
+  BQ_KIND_NONE = 6              /* bypass: plain fp32 -> bf16 round-to-nearest (GEMM feeds only) */
+} bq_kind;
+
+/*
+ * One operand format = the `<prefix>_*` keys of a reference quant-config node
+ * (prefix = data_in | weight | bias).  The host resolves the reference's
+ * `exponent_bias in (None,"none","None") -> 2^(ew-1)-1` rule (block_fp.py:61-62)
+ * before filling this struct.
+ */
+typedef struct bq_format {
+  int32_t kind;                 /* bq_kind                                                        */
+  int32_t width;                /* *_width                                                        */
+  int32_t exponent_width;       /* *_exponent_width   (block_fp, block_minifloat, minifloat_*)     */
+  int32_t exponent_bias;        /* *_exponent_bias, resolved (block_fp, minifloat_*); integer: *_frac_width */
+  int32_t exponent_bias_width;  /* *_exponent_bias_width (block_minifloat, block_log)             */
+  int32_t block_rows;           /* inferred block extent on the second-to-last dim (utils.py:42-67) */
+  int32_t block_cols;           /* inferred block extent on the last dim                          */
+  int32_t fold_zero;            /* 1: the reference un-blocks this case with F.fold (2-D weight / 3-D
+                                   activation, utils.py:186-258), which turns -0.0 into +0.0      */
+} bq_format;
+
+/* Output element type of a quantizer launch. */
+typedef enum bq_dtype { BQ_F32 = 0, BQ_BF16 = 1 } bq_dtype;
+
+/*
+ * Logical operand of a quantizer call: a 3-D fp32 tensor [L, R, C] (the reference's
+ * 1-D bias / 2-D activation / 2-D weight / 3-D activation cases canonicalised, L is
+ * never blocked), addressed with element strides so that transposed views such as
+ * k^T in bmm_0 (models/opt_quantized/modeling_opt.py:246) need no copy.
+ */
+typedef struct bq_tensor3 {
+  int64_t L, R, C;
+  int64_t sL, sR, sC;           /* element strides of the INPUT                                    */
+} bq_tensor3;
+
+BQ_API const char* bq_strerror(int status);
+BQ_API int bq_abi_version(void);
+/* last CUDA error string seen by this thread inside the library ("" if none) */
+BQ_API const char* bq_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantizers.  Replaces block_fp_quantizer (block_fp.py:127-153), block_minifloat_quantizer
+ * (block_minifloat.py:110-141), block_log_quantizer (block_log.py:95-120),
+ * minifloat_denorm_quantizer (minifloat.py:104-131), minifloat_ieee_quantizer (minifloat.py:199-239)
+ * and integer_quantizer (integer.py:77-95) together with block()/unblock() (utils.py:261-321).
+ *
+ * y has the logical shape [L, R, C]; it is written contiguous row-major, or — when
+ * `transpose_out` != 0 — as [L, C, R] (used to hand V to the PV GEMM K-major).
+ * fp32 results are bit-identical to the reference's torch emulation; bf16 results are
+ * the same values rounded to nearest-even (exact whenever the format has <= 8
+ * significant bits, except |x| <= 1e-8 pass-through elements).
+ * `ws` must hold bq_quantize_workspace_bytes(...) bytes; contents need no initialisation.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API size_t bq_quantize_workspace_bytes(const bq_format* fmt, const bq_tensor3* x);
+BQ_API int bq_quantize(const bq_format* fmt, const bq_tensor3* x_desc, const float* x, void* y, int32_t y_dtype,
+                int32_t transpose_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense bf16 GEMM on the 5th-gen tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> fp32).
+ *   C[b][m][n] = sum_k A[b][m][k] * B[b][n][k]  (+ bias[n])          ("TN": both operands K-major)
+ * A: bf16 [batch][M][K] (row stride lda, batch stride sa), B: bf16 [batch][N][K] (ldb, sb; sb = 0
+ * broadcasts one weight matrix), C: fp32 [batch][M][N] (ldc, sc).  K-major operands must have
+ * lda, ldb multiples of 8 elements and 16-byte aligned bases.
+ * Replaces the fp32 F.linear / torch.matmul / torch.bmm calls of quantized_modules/linear.py:62,71,76
+ * and quantized_functions/matmul.py:25,196 for operands that are bf16-exact.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API int bq_gemm_bf16_tn(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M, int64_t N,
+                    int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantized Linear, PTQ steady state.  Replaces _LinearBase.forward (quantized_modules/linear.py:59-76):
+ *   y[M,N] = F.linear(Q_fx(x[M,K]), Wq, bias_q)
+ * Wq is the weight already quantised by bq_quantize to bf16 [N][K] (the in-place PTQ overwrite of
+ * linear.py:66-70, held as a bf16 cache), bias_q the quantised fp32 bias or NULL.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API size_t bq_linear_workspace_bytes(const bq_format* fx, int64_t M, int64_t K);
+BQ_API int bq_linear(const bq_format* fx, const float* x, int64_t M, int64_t K, int64_t ldx, const void* Wq_bf16, int64_t N,
+              const float* bias_q, float* y, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantized bmm / matmul.  Replaces generic_matmul_block_fp / _block_minifloat / _block_log /
+ * _minifloat_denorm (quantized_functions/matmul.py:146-297, :46-78):
+ *   out[b] = Q_fx(x[b]) @ Q_fy(y[b]),  x: [batch, M, K] fp32 contiguous (blocks along K),
+ *   y: logical [batch, K, N] fp32 (blocks along N) given with element strides (syK, syN) so that
+ *   k^T views (syK = 1) and plain [K,N] tensors (syN = 1) both work without a copy.
+ * fy == NULL or kind NONE leaves y unquantised (block_log quirk, matmul.py:293-296) — y is then
+ * rounded to bf16, which is NOT exact; the Python mirror routes that case elsewhere.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API size_t bq_bmm_workspace_bytes(const bq_format* fx, const bq_format* fy, int64_t batch, int64_t M, int64_t K, int64_t N);
+BQ_API int bq_bmm(const bq_format* fx, const bq_format* fy, const float* x, const float* y, int64_t batch, int64_t M,
+           int64_t K, int64_t N, int64_t sy_batch, int64_t syK, int64_t syN, float* out, void* ws, size_t ws_bytes,
+           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BQ_B200_H */

@@ -1,0 +1,135 @@
+"""
+ctypes binding of libbq_b200.so (C ABI: include/bq.h).  No logic lives here: tensors in,
+raw device pointers + the current CUDA stream out.  There is no CPU fallback — a missing
+library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbq_b200.so")
+
+# bq_kind (include/bq.h)
+KIND = {
+    "block_fp": 0,
+    "block_minifloat": 1,
+    "block_log": 2,
+    "minifloat_denorm": 3,
+    "minifloat_ieee": 4,
+    "integer": 5,
+    "none": 6,
+}
+BQ_F32, BQ_BF16 = 0, 1
+
+
+class BqFormat(Structure):
+    _fields_ = [
+        ("kind", c_int32),
+        ("width", c_int32),
+        ("exponent_width", c_int32),
+        ("exponent_bias", c_int32),
+        ("exponent_bias_width", c_int32),
+        ("block_rows", c_int32),
+        ("block_cols", c_int32),
+        ("fold_zero", c_int32),
+    ]
+
+
+class BqTensor3(Structure):
+    _fields_ = [("L", c_int64), ("R", c_int64), ("C", c_int64), ("sL", c_int64), ("sR", c_int64), ("sC", c_int64)]
+
+
+class BqError(RuntimeError):
+    pass
+
+
+_STATUS_EXC = {
+    1: ValueError,
+    2: NotImplementedError,
+    3: ValueError,
+    4: ValueError,
+    5: RuntimeError,
+    6: NotImplementedError,
+}
+
+_lib = None
+
+
+def load():
+    """Load libbq_b200.so (built by `__graft_entry__.build()` / csrc/build.sh). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BqError(
+            f"{LIB_PATH} not found: the sm_100a extension is not built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.bq_strerror.restype = c_char_p
+    lib.bq_strerror.argtypes = [ctypes.c_int]
+    lib.bq_last_cuda_error.restype = c_char_p
+    lib.bq_abi_version.restype = ctypes.c_int
+    lib.bq_quantize_workspace_bytes.restype = c_size_t
+    lib.bq_quantize_workspace_bytes.argtypes = [POINTER(BqFormat), POINTER(BqTensor3)]
+    lib.bq_quantize.restype = ctypes.c_int
+    lib.bq_quantize.argtypes = [POINTER(BqFormat), POINTER(BqTensor3), c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                c_size_t, c_void_p]
+    lib.bq_gemm_bf16_tn.restype = ctypes.c_int
+    lib.bq_gemm_bf16_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 10 + [c_void_p]
+    lib.bq_linear_workspace_bytes.restype = c_size_t
+    lib.bq_linear_workspace_bytes.argtypes = [POINTER(BqFormat), c_int64, c_int64]
+    lib.bq_linear.restype = ctypes.c_int
+    lib.bq_linear.argtypes = [POINTER(BqFormat), c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                              c_void_p, c_int64, c_void_p, c_size_t, c_void_p]
+    lib.bq_bmm_workspace_bytes.restype = c_size_t
+    lib.bq_bmm_workspace_bytes.argtypes = [POINTER(BqFormat), POINTER(BqFormat), c_int64, c_int64, c_int64, c_int64]
+    lib.bq_bmm.restype = ctypes.c_int
+    lib.bq_bmm.argtypes = [POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                           c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status == 0:
+        return
+    lib = load()
+    msg = lib.bq_strerror(status).decode()
+    if status == 5:
+        msg += ": " + lib.bq_last_cuda_error().decode()
+    raise _STATUS_EXC.get(status, BqError)(f"{what}: {msg}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda_f32(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: llm_mixed_q_b200 runs on CUDA (sm_100a) only — there is no CPU fallback"
+        )
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (the reference emulates in fp32), got {t.dtype}")
+
+
+# A small per-device cache of workspaces (owned by torch's caching allocator).
+_ws_cache: dict = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """uint8 scratch of at least nbytes, 256-byte aligned, reused across calls on the same stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf

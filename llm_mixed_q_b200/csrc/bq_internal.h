@@ -1,0 +1,30 @@
+// bq_internal.h — shared host-side declarations of libbq_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/bq.h"
+
+namespace bq {
+void set_last_cuda_error(const char* what, const char* file, int line);
+int num_sms();
+int quantize_impl(const bq_format* fmt, const bq_tensor3* t, const float* x, void* y, int y_dtype, int transpose_out,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+size_t quantize_ws_bytes(const bq_format* fmt, const bq_tensor3* t);
+int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M, int64_t N,
+                      int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc,
+                      cudaStream_t st);
+}  // namespace bq
+
+#define BQ_CUDA_CHECK(expr)                                                  \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) {                                                 \
+      bq::set_last_cuda_error(cudaGetErrorString(_e), __FILE__, __LINE__);   \
+      return BQ_ERR_CUDA;                                                    \
+    }                                                                        \
+  } while (0)

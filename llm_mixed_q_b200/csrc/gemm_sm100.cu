@@ -1,0 +1,283 @@
+// gemm_sm100.cu — persistent, warp-specialised bf16 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> smem ring -> tcgen05.mma (kind::f16, fp32 accumulate in
+//   TMEM, double-buffered) -> tcgen05.ld epilogue (+bias) -> fp32 global.
+//
+//   C[b][m][n] = sum_k A[b][m][k] * B[b][n][k] (+ bias[n])       both operands K-major ("TN")
+//
+// It is the multiply of the reference's quantized Linear / matmul / bmm
+// (quantized_modules/linear.py:71 F.linear, quantized_functions/matmul.py:196 torch.matmul/bmm, fp32 there):
+// block-quantised operands with <= 8 significant bits are exact in bf16 and their products are exact
+// in fp32, so only the accumulation order differs from the reference's fp32 GEMM.
+//
+// Warp roles (256 threads, 1 CTA per SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0   TMA producer (one elected lane)      warp 1   MMA issuer (one elected lane)
+//   warp 2   TMEM allocator                       warps 4-7 epilogue (TMEM lane quarter = warp % 4)
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty x2 accumulators (MMA <-> epilogue).
+#include "bq_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace bq {
+
+constexpr int kBM = 128;          // UMMA M (cta_group::1)
+constexpr int kBK = 64;           // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStageA = kBM * kBK * 2;
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;                     // two accumulators; power of two >= 32
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStage + kBarBytes + 1024;   // + alignment slack
+};
+
+struct GemmArgs {
+  float* C;
+  const float* bias;
+  int M, N, K, batch;
+  int64_t ldc, sc;
+  int tiles_m, tiles_n;
+  int b_broadcast;   // B has no batch dim (weights)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kStages * Cfg::kStage + 8 * (2 * Cfg::kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), 4);      // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_kb = (g.K + kBK - 1) / kBK;
+  const int tiles_per_batch = g.tiles_m * g.tiles_n;
+  const int total_tiles = tiles_per_batch * g.batch;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch;
+        const int t = tile - b * tiles_per_batch;
+        const int mb = t / g.tiles_n, nb = t - mb * g.tiles_n;   // n fastest: CTAs of a wave share A rows / stream B through L2
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+          ptx::mbar_expect_tx(full_bar(stage), Cfg::kStage);
+          const uint32_t sa = smem_base + stage * Cfg::kStage;
+          ptx::tma_load_3d(sa, &tmA, full_bar(stage), kb * kBK, mb * kBM, b);
+          ptx::tma_load_3d(sa + Cfg::kStageA, &tmB, full_bar(stage), kb * kBK, nb * BN, g.b_broadcast ? 0 : b);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStage;
+          const uint64_t adesc = ptx::smem_desc_sw128_kmajor(sa);
+          const uint64_t bdesc = ptx::smem_desc_sw128_kmajor(sa + Cfg::kStageA);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(tfull_bar(acc));          // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch;
+      const int t = tile - b * tiles_per_batch;
+      const int mb = t / g.tiles_n, nb = t - mb * g.tiles_n;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const int row = mb * kBM + q * 32 + lane;
+      float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
+      const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((g.sc & 3) == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        ptx::tmem_ld_wait();
+        const int col0 = nb * BN + c * 32;
+        if (row < g.M && col0 < g.N) {
+          if (vec_ok && col0 + 32 <= g.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (g.bias) {
+                const float4 bv = *reinterpret_cast<const float4*>(g.bias + col0 + j);
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              }
+              *reinterpret_cast<float4*>(crow + col0 + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < g.N) crow[col0 + j] = __uint_as_float(r[j]) + (g.bias ? g.bias[col0 + j] : 0.f);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode) return BQ_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  BQ_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) {
+    set_last_cuda_error("cuTensorMapEncodeTiled entry point not available", __FILE__, __LINE__);
+    return BQ_ERR_CUDA;
+  }
+  g_encode = (PFN_encodeTiled)fn;
+  return BQ_OK;
+}
+
+// bf16 [batch][rows][K] K-major tensor map, box {64, box_rows, 1}, 128B swizzle, zero OOB fill
+int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, int64_t K, int64_t rows, int64_t batch, int64_t ld,
+                          int64_t batch_stride, int box_rows) {
+  int rc = load_encode();
+  if (rc) return rc;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? batch_stride : rows * ld) * 2};
+  if (strides[1] == 0) strides[1] = (cuuint64_t)rows * ld * 2;
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    set_last_cuda_error(msg, __FILE__, __LINE__);
+    return BQ_ERR_CUDA;
+  }
+  return BQ_OK;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  g.tiles_m = (g.M + kBM - 1) / kBM;
+  g.tiles_n = (g.N + BN - 1) / BN;
+  int64_t total = (int64_t)g.tiles_m * g.tiles_n * g.batch;
+  if (total > 0x7fffffffll) return BQ_ERR_UNSUPPORTED;
+  int grid = (int)std::min<int64_t>(total, num_sms());
+  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, g);
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
+
+int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M, int64_t N,
+                      int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc,
+                      cudaStream_t st) {
+  if (batch < 0 || M < 0 || N < 0 || K < 0) return BQ_ERR_BAD_ARG;
+  if (batch == 0 || M == 0 || N == 0) return BQ_OK;
+  if (!A || !B || !C) return BQ_ERR_BAD_ARG;
+  if (K == 0) return BQ_ERR_UNSUPPORTED;
+  if ((lda % 8) || (ldb % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)C % 4)) return BQ_ERR_BAD_ARG;
+  if (batch > 1 && ((sa % 8) || (sb % 8))) return BQ_ERR_BAD_ARG;
+  if (lda < K || ldb < K || ldc < N) return BQ_ERR_BAD_ARG;
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff || batch > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, batch, lda, sa, kBM);
+  if (rc) return rc;
+  const bool bcast = (sb == 0) || batch == 1;
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, bcast ? 1 : batch, ldb, sb, BN);
+  if (rc) return rc;
+  GemmArgs g;
+  g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = (int)batch;
+  g.ldc = ldc; g.sc = sc; g.tiles_m = g.tiles_n = 0; g.b_broadcast = bcast ? 1 : 0;
+  switch (BN) {
+    case 64: return launch_gemm<64>(tmA, tmB, g, st);
+    case 128: return launch_gemm<128>(tmA, tmB, g, st);
+    default: return launch_gemm<256>(tmA, tmB, g, st);
+  }
+}
+
+}  // namespace bq
+
+extern "C" int bq_gemm_bf16_tn(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M,
+                               int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb,
+                               int64_t sc, void* stream) {
+  return bq::gemm_bf16_tn_impl(A, B, C, bias, batch, M, N, K, lda, ldb, ldc, sa, sb, sc, (cudaStream_t)stream);
+}

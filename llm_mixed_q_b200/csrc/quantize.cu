@@ -1,0 +1,526 @@
+// quantize.cu — standalone HBM-streaming quantizer kernels (sm_100a) + their C-ABI entry points.
+//
+// Replaces block()/unblock() (quantizers/utils.py:261-321) and the element math of
+// block_fp.py:21-96, block_minifloat.py:22-74, block_log.py:23-69, minifloat.py:21-82,134-196,
+// integer.py:25-58 — ~45 ATen launches and >=360 B/element of traffic in the reference — with one
+// pass at the algorithmic 8 B/element (fp32 in, fp32 out).
+//
+// Kernels
+//   quant_rows_kernel     hot path.  Blocks of b1 in {4..128} consecutive elements of the
+//                         unit-stride last dim (every shipped config: [1,16] / [16]).  One thread
+//                         owns 4 consecutive floats (one 16-byte load), a block is b1/4 adjacent
+//                         lanes, the shared exponent comes from a warp-shuffle max over those lanes.
+//                         Persistent grid (multiple of the SM count), 4 independent 16-byte loads
+//                         in flight per thread, streaming cache hints, no shared memory.
+//   blocklog_fixup_kernel block_log only: the reference replaces the max of all-zero blocks by the
+//                         tensor-wide smallest non-zero block max (block_log.py:50-53), which changes
+//                         what zeros quantise to.  The main pass records a per-warp zero-block mask and
+//                         the global min; this pass fills the flagged blocks.
+//   generic_*             any block shape (2-D blocks, whole-row blocks, odd sizes), any input strides
+//                         (k^T views), optional transposed output.  Two passes over a per-block max
+//                         workspace.  Correctness path, not a speed path.
+#include "bq_internal.h"
+#include "bq_numerics.cuh"
+
+#include <cuda_bf16.h>
+
+namespace bq {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream2(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t absbits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+
+template <typename OutT> __device__ __forceinline__ void store4(OutT* y, float4 o);
+template <> __device__ __forceinline__ void store4<float>(float* y, float4 o) { stg_stream4(y, o); }
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* y, float4 o) {
+  stg_stream2(y, pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+}
+template <typename OutT> __device__ __forceinline__ void store1(OutT* y, float o);
+template <> __device__ __forceinline__ void store1<float>(float* y, float o) { *y = o; }
+template <> __device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16* y, float o) { *y = __float2bfloat16_rn(o); }
+
+// Layout of a "rows" launch.  Index space: every row is padded to slots_per_row 4-float slots
+// (a multiple of lanes-per-block) so that a block never straddles a warp.
+struct RowsGeom {
+  uint64_t total_slots;     // n_rows * slots_per_row
+  uint32_t slots_per_row;
+  int32_t C;                // valid columns per row (multiple of 4)
+  int64_t ldx, ldy;         // row strides in elements
+  int32_t lpb;              // lanes per block = b1 / 4 (1 for the element-wise kinds)
+  int32_t flat;             // 1: rows are dense and C == padded C -> slot s is elements [4s, 4s+4)
+};
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ bool slot_addr(const RowsGeom& g, uint64_t slot, int64_t& xoff, int64_t& yoff) {
+  if (slot >= g.total_slots) return false;
+  if (g.flat) {
+    xoff = yoff = (int64_t)(slot * 4);
+    return true;
+  }
+  uint64_t row;
+  uint32_t srow;
+  if (g.total_slots <= 0xffffffffull) {
+    uint32_t s32 = (uint32_t)slot;
+    uint32_t r32 = s32 / g.slots_per_row;
+    srow = s32 - r32 * g.slots_per_row;
+    row = r32;
+  } else {
+    row = slot / g.slots_per_row;
+    srow = (uint32_t)(slot - row * g.slots_per_row);
+  }
+  int col = (int)(srow * 4);
+  if (col >= g.C) return false;
+  xoff = (int64_t)row * g.ldx + col;
+  yoff = (int64_t)row * g.ldy + col;
+  return true;
+}
+
+// gstate[0]: min over non-zero block maxima (uint bits, init 0xffffffff); gstate[1]: 0xffffffff until a zero block is seen
+template <int KIND, typename OutT>
+__global__ void __launch_bounds__(kThreads) quant_rows_kernel(const float* __restrict__ x, OutT* __restrict__ y, RowsGeom g,
+                                                               FmtParams p, uint32_t* __restrict__ gstate,
+                                                               uint32_t* __restrict__ zmask) {
+  constexpr bool kBlocked = IsBlocked<KIND>::value;
+  const uint64_t tile = (uint64_t)kThreads * kUnroll;
+  uint32_t run_min = 0xffffffffu;
+  bool saw_zero = false;
+  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < g.total_slots; base += (uint64_t)gridDim.x * tile) {
+    float4 v[kUnroll];
+    int64_t yoff[kUnroll];
+    bool act[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      uint64_t slot = base + (uint64_t)u * kThreads + threadIdx.x;
+      int64_t xo = 0;
+      yoff[u] = 0;
+      act[u] = slot_addr(g, slot, xo, yoff[u]);
+      v[u] = act[u] ? ldg_stream4(x + xo) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      BlockState st;
+      st.a = st.b = st.c = 0.f;
+      bool zero_block = false;
+      if (kBlocked) {
+        uint32_t m = max(max(absbits(v[u].x), absbits(v[u].y)), max(absbits(v[u].z), absbits(v[u].w)));
+        for (int o = 1; o < g.lpb; o <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        zero_block = (m == 0);
+        if (KIND == kBlockLog) {
+          // uniform branch per warp-slot: record which lanes sit in all-zero blocks
+          uint32_t zb = __ballot_sync(0xffffffffu, zero_block);
+          uint64_t slot0 = base + (uint64_t)u * kThreads + (threadIdx.x & ~31u);
+          if ((threadIdx.x & 31) == 0 && slot0 < g.total_slots) zmask[slot0 >> 5] = zb;
+          if (act[u]) {
+            if (zero_block) saw_zero = true; else run_min = min(run_min, m);
+          }
+        }
+        // block_fp / block_minifloat: an all-zero block only holds pass-through elements, whose result
+        // (+0) does not depend on the substituted max (block_fp.py:54-58) — use 1.
+        st = block_state<KIND>(zero_block ? 1.0f : __uint_as_float(m), p);
+      }
+      if (act[u] && !(KIND == kBlockLog && zero_block)) {
+        float4 o;
+        o.x = quant_elem<KIND>(v[u].x, st, p);
+        o.y = quant_elem<KIND>(v[u].y, st, p);
+        o.z = quant_elem<KIND>(v[u].z, st, p);
+        o.w = quant_elem<KIND>(v[u].w, st, p);
+        store4<OutT>(y + yoff[u], o);
+      }
+    }
+  }
+  if (KIND == kBlockLog) {
+    for (int o = 16; o > 0; o >>= 1) run_min = min(run_min, __shfl_xor_sync(0xffffffffu, run_min, o));
+    if ((threadIdx.x & 31) == 0 && run_min != 0xffffffffu) atomicMin(&gstate[0], run_min);
+    if (saw_zero) gstate[1] = 0u;
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads) blocklog_fixup_kernel(OutT* __restrict__ y, RowsGeom g, FmtParams p,
+                                                                   const uint32_t* __restrict__ gstate,
+                                                                   const uint32_t* __restrict__ zmask) {
+  if (gstate[1] != 0u) return;   // no all-zero block anywhere
+  uint32_t gm = gstate[0];
+  // all maxima zero -> ones (block_log.py:50-51); else zero maxima := global min non-zero max (:52-53)
+  BlockState st = block_state<kBlockLog>(gm == 0xffffffffu ? 1.0f : __uint_as_float(gm), p);
+  float fill = quant_elem<kBlockLog>(0.f, st, p);
+  float4 o = make_float4(fill, fill, fill, fill);
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t slot = (uint64_t)blockIdx.x * kThreads + threadIdx.x; slot < g.total_slots; slot += stride) {
+    uint32_t zb = zmask[slot >> 5];
+    if (!((zb >> (threadIdx.x & 31)) & 1u)) continue;
+    int64_t xo, yo;
+    if (slot_addr(g, slot, xo, yo)) store4<OutT>(y + yo, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic path
+// ------------------------------------------------------------------------------------------------
+struct GenGeom {
+  int64_t L, R, C, sL, sR, sC;
+  int64_t b0, b1, nb0, nb1;
+  int32_t transpose_out;
+};
+__device__ __forceinline__ void gen_index(const GenGeom& g, int64_t idx, int64_t& l, int64_t& r, int64_t& c) {
+  c = idx % g.C;
+  int64_t t = idx / g.C;
+  r = t % g.R;
+  l = t / g.R;
+}
+__global__ void generic_blockmax_kernel(const float* __restrict__ x, GenGeom g, uint32_t* __restrict__ blkmax) {
+  int64_t n = g.L * g.R * g.C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t l, r, c;
+    gen_index(g, idx, l, r, c);
+    uint32_t a = absbits(x[l * g.sL + r * g.sR + c * g.sC]);
+    if (a) atomicMax(&blkmax[(l * g.nb0 + r / g.b0) * g.nb1 + c / g.b1], a);
+  }
+}
+__global__ void generic_gmin_kernel(const uint32_t* __restrict__ blkmax, int64_t nblk, uint32_t* __restrict__ gstate) {
+  uint32_t m = 0xffffffffu;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nblk; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = blkmax[i];
+    if (v) m = min(m, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != 0xffffffffu) atomicMin(&gstate[0], m);
+}
+template <int KIND, typename OutT>
+__global__ void generic_quant_kernel(const float* __restrict__ x, OutT* __restrict__ y, GenGeom g, FmtParams p,
+                                     const uint32_t* __restrict__ blkmax, const uint32_t* __restrict__ gstate) {
+  constexpr bool kBlocked = IsBlocked<KIND>::value;
+  int64_t n = g.L * g.R * g.C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t l, r, c;
+    gen_index(g, idx, l, r, c);
+    float v = x[l * g.sL + r * g.sR + c * g.sC];
+    BlockState st;
+    st.a = st.b = st.c = 0.f;
+    if (kBlocked) {
+      uint32_t m = blkmax[(l * g.nb0 + r / g.b0) * g.nb1 + c / g.b1];
+      if (m == 0) {
+        uint32_t gm = gstate[0];
+        m = (gm == 0xffffffffu) ? __float_as_uint(1.0f) : gm;
+      }
+      st = block_state<KIND>(__uint_as_float(m), p);
+    }
+    float o = quant_elem<KIND>(v, st, p);
+    int64_t yo = g.transpose_out ? (l * g.C + c) * g.R + r : idx;
+    store1<OutT>(y + yo, o);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// tile path: blocks of b1 | 64 along the logical last dim C, input contiguous along C *or* along R
+// (k^T views: quantized_functions/matmul.py:187-193 receives key_states.transpose(1,2)), output either
+// [L,R,C] or transposed [L,C,R] (K-major hand-off of y to the GEMM).  A 64x64 tile is staged in shared
+// memory (pitch 65: conflict-free for both access directions), one thread quantises one block in place,
+// and the tile is written back along whichever output dim is contiguous.  block_fp / block_minifloat only
+// (all-zero blocks need no tensor-global information there).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTile = 64;
+template <int KIND, typename OutT>
+__global__ void __launch_bounds__(256) quant_tile_kernel(const float* __restrict__ x, OutT* __restrict__ y, GenGeom g,
+                                                         FmtParams p, int tiles_r, int tiles_c) {
+  __shared__ float tile[kTile][kTile + 1];
+  const int64_t tiles_per_l = (int64_t)tiles_r * tiles_c;
+  const int64_t total = tiles_per_l * g.L;
+  const bool in_r_contig = (g.sR == 1 && g.sC != 1);
+  const int b1 = (int)g.b1;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int64_t l = t / tiles_per_l;
+    const int64_t rem = t - l * tiles_per_l;
+    const int64_t r0 = (rem / tiles_c) * kTile, c0 = (rem % tiles_c) * kTile;
+    const float* xb = x + l * g.sL;
+    // ---- load (coalesced along the contiguous input dim)
+    for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
+      int a = i / kTile, b = i % kTile;            // b runs along the contiguous dim
+      int rr = in_r_contig ? b : a, cc = in_r_contig ? a : b;
+      int64_t r = r0 + rr, c = c0 + cc;
+      tile[rr][cc] = (r < g.R && c < g.C) ? xb[r * g.sR + c * g.sC] : 0.f;
+    }
+    __syncthreads();
+    // ---- quantise: one thread per block
+    const int blocks_per_row = kTile / b1;
+    for (int i = threadIdx.x; i < kTile * blocks_per_row; i += 256) {
+      int rr = i % kTile, cb = i / kTile;
+      float* bp = &tile[rr][cb * b1];
+      uint32_t m = 0;
+      for (int j = 0; j < b1; ++j) m = max(m, absbits(bp[j]));
+      BlockState st = block_state<KIND>(m == 0 ? 1.0f : __uint_as_float(m), p);
+      for (int j = 0; j < b1; ++j) bp[j] = quant_elem<KIND>(bp[j], st, p);
+    }
+    __syncthreads();
+    // ---- store (coalesced along the contiguous output dim)
+    for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
+      int a = i / kTile, b = i % kTile;
+      int rr = g.transpose_out ? b : a, cc = g.transpose_out ? a : b;
+      int64_t r = r0 + rr, c = c0 + cc;
+      if (r < g.R && c < g.C) {
+        int64_t yo = g.transpose_out ? (l * g.C + c) * g.R + r : (l * g.R + r) * g.C + c;
+        store1<OutT>(y + yo, tile[rr][cc]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline float p2(int e) { return ldexpf(1.0f, e); }
+
+int make_params(const bq_format* f, FmtParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->kind = f->kind;
+  p->fold_zero = f->fold_zero ? 1 : 0;
+  int mb = 0;
+  switch (f->kind) {
+    case kBlockFP:
+      mb = f->width - 1;
+      if (f->exponent_width < 1 || f->exponent_width > 30) return BQ_ERR_BAD_FORMAT;
+      p->emin = (float)(-(int64_t)f->exponent_bias);
+      p->emax = (float)(((int64_t)1 << f->exponent_width) - 1 - f->exponent_bias);
+      break;
+    case kBlockMinifloat:
+      mb = f->width - f->exponent_width - 1;
+      if (f->exponent_width < 1 || f->exponent_width > 30 || f->exponent_bias_width < 1 || f->exponent_bias_width > 30)
+        return BQ_ERR_BAD_FORMAT;
+      p->bias_hi = (float)(((int64_t)1 << f->exponent_bias_width) - 1);
+      p->eb_top = (float)(((int64_t)1 << f->exponent_width) - 1);
+      break;
+    case kBlockLog:
+      if (f->width < 2 || f->width > 31 || f->exponent_bias_width < 1 || f->exponent_bias_width > 30) return BQ_ERR_BAD_FORMAT;
+      p->bias_hi = (float)(((int64_t)1 << f->exponent_bias_width) - 1);
+      p->eb_top = (float)(((int64_t)1 << (f->width - 1)) - 1);
+      break;
+    case kMinifloatDenorm:
+    case kMinifloatIEEE:
+      mb = f->width - f->exponent_width - 1;
+      if (f->exponent_width < 1 || f->exponent_width > 30) return BQ_ERR_BAD_FORMAT;
+      p->emin = (float)(-(int64_t)f->exponent_bias);
+      p->emax = (float)(((int64_t)1 << f->exponent_width) - 1 - f->exponent_bias);
+      break;
+    case kInteger:
+      if (f->width < 1 || f->width > 31) return BQ_ERR_BAD_FORMAT;
+      mb = f->exponent_bias;   // frac_width
+      if (mb < -60 || mb > 60) return BQ_ERR_BAD_FORMAT;
+      p->emin = -(float)((int64_t)1 << (f->width - 1));
+      p->emax = (float)(((int64_t)1 << (f->width - 1)) - 1);
+      p->shift = p2(mb);
+      p->inv_shift = p2(-mb);
+      return BQ_OK;
+    case kNone:
+      return BQ_OK;
+    default:
+      return BQ_ERR_BAD_FORMAT;
+  }
+  if (f->kind != kBlockLog) {
+    if (mb < 0 || mb > 30) return BQ_ERR_BAD_FORMAT;
+    p->shift = p2(mb);
+    p->inv_shift = p2(-mb);
+    p->qmax = (float)(((int64_t)1 << mb) - 1);
+  }
+  return BQ_OK;
+}
+
+static bool is_blocked(int kind) { return kind == kBlockFP || kind == kBlockMinifloat || kind == kBlockLog; }
+
+// Normalised geometry shared by the workspace query and the launch.
+struct Plan {
+  bool fast;
+  bool tile;
+  RowsGeom rg;
+  GenGeom gg;
+  int64_t nblk;
+  size_t ws_bytes;
+};
+
+static int make_plan(const bq_format* f, const bq_tensor3* t, int transpose_out, const void* x, const void* y, int y_dtype,
+                     Plan* pl) {
+  if (t->L < 0 || t->R < 0 || t->C < 0) return BQ_ERR_BAD_ARG;
+  const bool blocked = is_blocked(f->kind);
+  int64_t b0 = 1, b1 = 1;
+  if (blocked) {
+    b0 = f->block_rows;
+    b1 = f->block_cols;
+    if (b0 < 1 || b1 < 1) return BQ_ERR_BAD_ARG;
+    if (b0 > t->R && t->R > 0) b0 = t->R;
+    if (b1 > t->C && t->C > 0) b1 = t->C;
+  }
+  GenGeom& gg = pl->gg;
+  gg.L = t->L; gg.R = t->R; gg.C = t->C; gg.sL = t->sL; gg.sR = t->sR; gg.sC = t->sC;
+  gg.b0 = b0; gg.b1 = b1;
+  gg.nb0 = (t->R + b0 - 1) / b0;
+  gg.nb1 = (t->C + b1 - 1) / b1;
+  gg.transpose_out = transpose_out ? 1 : 0;
+  pl->nblk = blocked ? t->L * gg.nb0 * gg.nb1 : 0;
+
+  // fast path eligibility
+  bool fast = !transpose_out && t->sC == 1 && (t->C % 4 == 0) && t->C > 0;
+  if (blocked) fast = fast && b0 == 1 && b1 >= 4 && b1 <= 128 && (b1 & (b1 - 1)) == 0;
+  // rows must collapse to a single row stride
+  int64_t n_rows = t->L * t->R;
+  int64_t ldx = t->sR;
+  if (t->R == 1) ldx = t->sL;
+  else if (t->L != 1 && t->sL != t->R * t->sR) fast = false;
+  if (n_rows <= 1) ldx = t->C;
+  fast = fast && (ldx % 4 == 0) && ldx >= t->C;
+  if (x) fast = fast && ((uintptr_t)x % 16 == 0);
+  if (y) fast = fast && ((uintptr_t)y % (y_dtype == BQ_F32 ? 16 : 8) == 0);
+  pl->fast = fast;
+  RowsGeom& rg = pl->rg;
+  memset(&rg, 0, sizeof(rg));
+  if (fast) {
+    int lpb = blocked ? (int)(b1 / 4) : 1;
+    int64_t padC = blocked ? gg.nb1 * b1 : t->C;
+    rg.slots_per_row = (uint32_t)(padC / 4);
+    rg.C = (int32_t)t->C;
+    rg.ldx = ldx;
+    rg.ldy = t->C;
+    rg.lpb = lpb;
+    rg.flat = (padC == t->C && ldx == t->C) ? 1 : 0;
+    rg.total_slots = (uint64_t)n_rows * rg.slots_per_row;
+    if (padC / 4 > 0x7fffffffll || t->C > 0x7fffffffll) pl->fast = false;
+  }
+  pl->tile = !pl->fast && (f->kind == kBlockFP || f->kind == kBlockMinifloat) && b0 == 1 && b1 <= kTile &&
+             (b1 & (b1 - 1)) == 0 && (t->sC == 1 || t->sR == 1) && t->C > 0 && t->R > 0;
+  size_t ws = 16;
+  if (pl->fast) {
+    if (f->kind == kBlockLog) ws += 4 * (size_t)((rg.total_slots + 31) / 32);
+  } else if (blocked) {
+    ws += 4 * (size_t)pl->nblk;
+  }
+  pl->ws_bytes = ws;
+  return BQ_OK;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    g_num_sms = n;
+  }
+  return g_num_sms;
+}
+
+template <int KIND, typename OutT>
+static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT* y, uint32_t* ws, cudaStream_t st) {
+  constexpr bool kBlocked = IsBlocked<KIND>::value;
+  uint32_t* gstate = ws;
+  uint32_t* aux = ws + 4;
+  const int sms = num_sms();
+  if (pl.fast) {
+    if (pl.rg.total_slots == 0) return BQ_OK;
+    if (KIND == kBlockLog) BQ_CUDA_CHECK(cudaMemsetAsync(gstate, 0xff, 8, st));
+    const uint64_t tile = (uint64_t)kThreads * kUnroll;
+    uint64_t tiles = (pl.rg.total_slots + tile - 1) / tile;
+    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)sms * 8);   // 8 resident CTAs of 256 threads per SM
+    quant_rows_kernel<KIND, OutT><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux);
+    if (KIND == kBlockLog) {
+      uint64_t blocks = (pl.rg.total_slots + kThreads - 1) / kThreads;
+      int g2 = (int)std::min<uint64_t>(blocks, (uint64_t)sms * 8);
+      blocklog_fixup_kernel<OutT><<<g2, kThreads, 0, st>>>(y, pl.rg, p, gstate, aux);
+    }
+  } else if (pl.tile && (KIND == kBlockFP || KIND == kBlockMinifloat)) {
+    int tiles_r = (int)((pl.gg.R + kTile - 1) / kTile), tiles_c = (int)((pl.gg.C + kTile - 1) / kTile);
+    int64_t total = (int64_t)tiles_r * tiles_c * pl.gg.L;
+    if (total == 0) return BQ_OK;
+    int grid = (int)std::min<int64_t>(total, (int64_t)sms * 8);
+    quant_tile_kernel<KIND, OutT><<<grid, 256, 0, st>>>(x, y, pl.gg, p, tiles_r, tiles_c);
+  } else {
+    int64_t n = pl.gg.L * pl.gg.R * pl.gg.C;
+    if (n == 0) return BQ_OK;
+    int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16);
+    if (kBlocked) {
+      BQ_CUDA_CHECK(cudaMemsetAsync(gstate, 0xff, 8, st));
+      BQ_CUDA_CHECK(cudaMemsetAsync(aux, 0, 4 * (size_t)pl.nblk, st));
+      generic_blockmax_kernel<<<grid, 256, 0, st>>>(x, pl.gg, aux);
+      int g2 = (int)std::min<int64_t>((pl.nblk + 255) / 256, (int64_t)sms * 4);
+      generic_gmin_kernel<<<g2, 256, 0, st>>>(aux, pl.nblk, gstate);
+    }
+    generic_quant_kernel<KIND, OutT><<<grid, 256, 0, st>>>(x, y, pl.gg, p, aux, gstate);
+  }
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
+
+template <typename OutT>
+static int launch_dtype(const Plan& pl, const FmtParams& p, const float* x, OutT* y, uint32_t* ws, cudaStream_t st) {
+  switch (p.kind) {
+    case kBlockFP: return launch_kind<kBlockFP, OutT>(pl, p, x, y, ws, st);
+    case kBlockMinifloat: return launch_kind<kBlockMinifloat, OutT>(pl, p, x, y, ws, st);
+    case kBlockLog: return launch_kind<kBlockLog, OutT>(pl, p, x, y, ws, st);
+    case kMinifloatDenorm: return launch_kind<kMinifloatDenorm, OutT>(pl, p, x, y, ws, st);
+    case kMinifloatIEEE: return launch_kind<kMinifloatIEEE, OutT>(pl, p, x, y, ws, st);
+    case kInteger: return launch_kind<kInteger, OutT>(pl, p, x, y, ws, st);
+    case kNone: return launch_kind<kNone, OutT>(pl, p, x, y, ws, st);
+  }
+  return BQ_ERR_BAD_FORMAT;
+}
+
+int quantize_impl(const bq_format* fmt, const bq_tensor3* t, const float* x, void* y, int y_dtype, int transpose_out,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!fmt || !t) return BQ_ERR_BAD_ARG;
+  FmtParams p;
+  int rc = make_params(fmt, &p);
+  if (rc) return rc;
+  if (y_dtype != BQ_F32 && y_dtype != BQ_BF16) return BQ_ERR_BAD_ARG;
+  int64_t n = t->L * t->R * t->C;
+  if (n == 0) return BQ_OK;
+  if (!x || !y) return BQ_ERR_BAD_ARG;
+  if (((uintptr_t)x % 4) || ((uintptr_t)y % (y_dtype == BQ_F32 ? 4 : 2))) return BQ_ERR_BAD_ARG;
+  Plan pl;
+  rc = make_plan(fmt, t, transpose_out, x, y, y_dtype, &pl);
+  if (rc) return rc;
+  if (pl.ws_bytes > 16 || is_blocked(fmt->kind)) {
+    if (!ws || ws_bytes < pl.ws_bytes) return BQ_ERR_WORKSPACE;
+    if ((uintptr_t)ws % 16) return BQ_ERR_BAD_ARG;
+  }
+  if (y_dtype == BQ_F32) return launch_dtype<float>(pl, p, x, (float*)y, (uint32_t*)ws, st);
+  return launch_dtype<__nv_bfloat16>(pl, p, x, (__nv_bfloat16*)y, (uint32_t*)ws, st);
+}
+
+size_t quantize_ws_bytes(const bq_format* fmt, const bq_tensor3* t) {
+  if (!fmt || !t) return 0;
+  // worst case over both paths (pointer alignment is unknown here)
+  Plan a;
+  if (make_plan(fmt, t, 0, nullptr, nullptr, BQ_F32, &a)) return 0;
+  size_t w = a.ws_bytes;
+  if (is_blocked(fmt->kind)) w = std::max(w, (size_t)16 + 4 * (size_t)a.nblk);
+  return (w + 255) & ~(size_t)255;
+}
+
+}  // namespace bq
+
+extern "C" {
+size_t bq_quantize_workspace_bytes(const bq_format* fmt, const bq_tensor3* x) { return bq::quantize_ws_bytes(fmt, x); }
+int bq_quantize(const bq_format* fmt, const bq_tensor3* x_desc, const float* x, void* y, int32_t y_dtype,
+                int32_t transpose_out, void* ws, size_t ws_bytes, void* stream) {
+  return bq::quantize_impl(fmt, x_desc, x, y, y_dtype, transpose_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+}
