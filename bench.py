@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the block-quantisation hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on): OPT-1.3B shape, random init,
+W6A6 block_fp (block 16, 8-bit shared exponent) on every Linear and on QK^T / PV, seq 2048, batch 8 per GPU,
+synthetic tokens.  One step = one full forward (embedding -> 24 layers -> fp32 lm_head -> shifted CE loss).
+Weak scaling: every rank runs its own replica on its own batch (seed = rank); no data-path collective.
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = device-resident tokens/s,
+e2e = same through the public module API with pinned-host inputs + loss read-back per step,
+roofline = dominant kernel (tcgen05 GEMM) achieved TFLOP/s from per-launch CUDA events inside the timed region,
+cpu_baseline = oracle port timed on this box's host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "W6A6-BFP fwd tokens/s (OPT-1.3B)"
+OPT13B = dict(hidden_size=2048, num_hidden_layers=24, ffn_dim=8192, num_attention_heads=32, vocab_size=50272,
+              max_position_embeddings=2048)
+SEQ, BATCH = 2048, 8
+WORKLOAD = "OPT-1.3B W6A6 block_fp(block16, 8b exp) full forward: quantized Linear + QK^T/PV bmm, seq 2048, batch 8 per GPU"
+
+
+def bfp_config(width=6):
+    d = {"bypass": False, "name": "block_fp", "is_ptq": True}
+    for p in ("data_in", "weight", "bias"):
+        d.update({f"{p}_width": width, f"{p}_exponent_width": 8, f"{p}_exponent_bias": 127,
+                  f"{p}_block_size": [16] if p == "bias" else [1, 16]})
+    return {"default": d}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference) — cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_layer_sample(steps, warmup):
+    """One OPT-1.3B decoder layer + lm_head share at batch 1, seq 2048 on the host cores with the oracle port of the
+    reference's torch emulation; tokens/s = 2048 / (24 * t_layer + t_head).  Returns (tokens_per_s, per-step ms list)."""
+    from llm_mixed_q_b200.models.opt_quantized import parse_opt_quantized_config
+    from oracle import opt_ref
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    H, F_, heads, L, V = 2048, 8192, 32, 24, 50272
+    g = torch.Generator().manual_seed(0)
+    p = "model.decoder.layers.0."
+    sd = {}
+    for name, shape in [("self_attn.q_proj", (H, H)), ("self_attn.k_proj", (H, H)), ("self_attn.v_proj", (H, H)),
+                        ("self_attn.out_proj", (H, H)), ("fc1", (F_, H)), ("fc2", (H, F_))]:
+        sd[p + name + ".weight"] = torch.randn(shape, generator=g) * 0.02
+        sd[p + name + ".bias"] = torch.zeros(shape[0])
+    for ln in ("self_attn_layer_norm", "final_layer_norm"):
+        sd[p + ln + ".weight"] = torch.ones(H)
+        sd[p + ln + ".bias"] = torch.zeros(H)
+    head_w = torch.randn(V, H, generator=g) * 0.02
+    qc = parse_opt_quantized_config(bfp_config(6), 1)
+    state = {}
+    with torch.no_grad():
+        opt_ref.opt_layer_forward(torch.randn(1, 16, H, generator=g), sd, 0, qc, heads, opt_ref.causal_mask(1, 16, torch.float32, "cpu"),
+                                  state)          # populates the one-off PTQ weight quantisation (excluded, like the reference's first call)
+        h = torch.randn(1, SEQ, H, generator=g)
+        mask = opt_ref.causal_mask(1, SEQ, torch.float32, "cpu")
+        t0 = time.perf_counter()
+        torch.nn.functional.linear(h, head_w)
+        t_head = time.perf_counter() - t0
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt_ref.opt_layer_forward(h, sd, 0, qc, heads, mask, state)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    t_layer = statistics.median(times)
+    return SEQ / (L * t_layer + t_head), [1e3 * (L * t + t_head) for t in times]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    tps, ms = cpu_layer_sample(steps, warmup)
+    cores = os.cpu_count() or 1
+    sample = (f"oracle port of the reference's torch CPU emulation: 1 of 24 OPT-1.3B decoder layers + fp32 lm_head at batch 1, "
+              f"seq 2048, {steps} timed step(s) after {warmup} warm-up (capped to bound the run); tokens/s = 2048/(24*t_layer+t_head)")
+    line = {"metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": statistics.median(ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "note": "CPU path does not scale with --gpus; one host process"},
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_model(device, width=6, layers=None):
+    from llm_mixed_q_b200.models.opt_quantized import OPTQuantizedConfig, OPTQuantizedForCausalLM
+
+    kw = dict(OPT13B)
+    if layers:
+        kw["num_hidden_layers"] = layers
+    cfg = OPTQuantizedConfig(quant_config=bfp_config(width), **kw)
+    torch.manual_seed(0)
+    with torch.device(device):
+        model = OPTQuantizedForCausalLM(cfg)
+    return model.eval()
+
+
+def sub_benchmarks(device, pk):
+    """config[1] sub-metrics: standalone quantizer GB/s and fused quantize+GEMM TFLOP/s at M=K=N=4096."""
+    from llm_mixed_q_b200.models.quantize import get_quantized_cls
+    from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer
+
+    out = {}
+    n_buf = 6                                           # 6 x 64 MiB inputs + outputs rotate: > 126 MB L2
+    xs = [torch.randn(4096, 4096, device=device) for _ in range(n_buf)]
+
+    def timed(fn, iters):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    for w in (6, 4):
+        ms = timed(lambda i: block_fp_quantizer(xs[i % n_buf], w, 8, 127, [1, 16], True), 30)
+        out[f"quantizer_bfp_w{w}_GBs"] = 8 * 4096 * 4096 / ms / 1e6
+        out[f"quantizer_bfp_w{w}_frac_of_hbm"] = out[f"quantizer_bfp_w{w}_GBs"] / pk["hbm"]
+        cfg = bfp_config(w)["default"]
+        lin = get_quantized_cls("linear", cfg)(4096, 4096, bias=True, config=cfg).to(device)
+        with torch.no_grad():
+            lin.weight.normal_(0, 0.02)
+            lin.bias.normal_(0, 0.02)
+            lin(xs[0])
+            ms = timed(lambda i: lin(xs[i % n_buf]), 30)
+        out[f"qlinear_w{w}a{w}_TFLOPs"] = 2 * 4096 ** 3 / ms / 1e9
+        out[f"qlinear_w{w}a{w}_frac_of_bf16_burst"] = out[f"qlinear_w{w}a{w}_TFLOPs"] / pk["tf_burst"]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=None, help="debug only: fewer decoder layers (result is then INVALID)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    from llm_mixed_q_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=device)
+    L.load()
+    pk = peaks()
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    model = build_model(device, layers=args.layers)
+    gen = torch.Generator(device="cpu").manual_seed(rank)
+    ids_host = torch.randint(0, OPT13B["vocab_size"], (BATCH, SEQ), generator=gen).pin_memory()
+    ids = ids_host.to(device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    with torch.no_grad():
+        for _ in range(W):
+            out = model(input_ids=ids, labels=ids)
+        torch.cuda.synchronize()
+        # ---- device-resident timed region --------------------------------------------------
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = L.launch_counts()
+        L.profile_enable(True)
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        ev[0].record()
+        for i in range(K):
+            out = model(input_ids=ids, labels=ids)
+            ev[i + 1].record()
+        barrier()
+        L.profile_enable(False)
+        clocks = sampler.stop() if rank == 0 else None
+        total_ms = max_over_ranks(ev[0].elapsed_time(ev[K]))
+        launches1 = L.launch_counts()
+        prof = L.profile_read()
+        loss_val = float(out.loss)
+        # ---- end-to-end: pinned host ids -> H2D, forward, loss D2H, every step ---------------
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            ids_dev = ids_host.to(device, non_blocking=True)
+            o = model(input_ids=ids_dev, labels=ids_dev)
+            _ = o.loss.item()
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    tokens_per_step = BATCH * SEQ * world
+    value = tokens_per_step * K / (total_ms / 1e3)
+    e2e_value = tokens_per_step * K / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM) ------------------------------------------
+    Lyr = args.layers or OPT13B["num_hidden_layers"]
+    H, F_, h, d = OPT13B["hidden_size"], OPT13B["ffn_dim"], OPT13B["num_attention_heads"], 64
+    T = BATCH * SEQ
+    flops_linear = 2 * T * (4 * H * H + 2 * H * F_) * Lyr
+    flops_bmm = 2 * 2 * BATCH * h * SEQ * SEQ * d * Lyr
+    gemm_ms, gemm_n = prof["gemm_bf16_tn_kernel"]
+    q_ms = sum(v[0] for k, v in prof.items() if k != "gemm_bf16_tn_kernel")
+    achieved = (flops_linear + flops_bmm) * K / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel", "achieved": achieved, "peak": pk["tf_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "peak_source": pk["source"] + ", sustained bf16",
+                "traffic": None, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                "share_of_step": gemm_ms / (ev[0].elapsed_time(ev[K])), "quantizer_kernels_share_of_step": q_ms / ev[0].elapsed_time(ev[K]),
+                "algorithmic_flops_per_step": flops_linear + flops_bmm}
+    gpu_launches = sum(launches1.values()) - sum(launches0.values())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    extra = {}
+    if not args.no_sub:
+        with torch.no_grad():
+            del model
+            torch.cuda.empty_cache()
+            extra = sub_benchmarks(device, pk)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        tps, _ = cpu_layer_sample(steps=1, warmup=0)
+        cpu_baseline = {"value": tps, "unit": "tokens/s", "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": "oracle port of the reference's torch CPU emulation: 1 of 24 OPT-1.3B decoder layers + fp32 lm_head, "
+                                  "batch 1, seq 2048, one timed pass (weights pre-quantised); tokens/s = 2048/(24*t_layer+t_head)"}
+    line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (independent replicas, no data-path collective)",
+                       "l2": "per-step working set (2.6 GB bf16 weights + >4 GB activations/layer) >> 126 MB L2; no flush needed",
+                       "arithmetic": "operands: exact block-quantised values carried in bf16; fp32 accumulation in TMEM",
+                       "loss": loss_val, "layers": Lyr},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * ids_host.element_size(),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K},
+            "gpu_launches": gpu_launches, "clocks": clocks, "launches_by_kernel": {k: launches1[k] - launches0[k] for k in launches1},
+            "sub_metrics": extra}
+    if args.layers:
+        line["INVALID"] = "reduced layer count (debug run)"
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

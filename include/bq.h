@@ -148,6 +148,18 @@ BQ_API int bq_bmm(const bq_format* fx, const bq_format* fy, const float* x, cons
            int64_t K, int64_t N, int64_t sy_batch, int64_t syK, int64_t syN, float* out, void* ws, size_t ws_bytes,
            void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Launch accounting (measurement support for bench.py; no reference counterpart).
+ * Every kernel this library launches is counted per kernel id.  With profiling enabled the library
+ * additionally brackets each launch with CUDA events on the launching stream; bq_profile_read
+ * synchronises those events and returns the summed device time.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API int bq_kernel_count(void);
+BQ_API const char* bq_kernel_name(int kernel_id);
+BQ_API int64_t bq_launch_count(int kernel_id);          /* launches since load (kernel_id < 0: all kernels) */
+BQ_API void bq_profile_enable(int on);                  /* turning it on clears earlier records */
+BQ_API int bq_profile_read(int kernel_id, double* total_ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

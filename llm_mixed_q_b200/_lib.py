@@ -92,6 +92,15 @@ def load():
     lib.bq_bmm.restype = ctypes.c_int
     lib.bq_bmm.argtypes = [POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                            c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.bq_kernel_count.restype = ctypes.c_int
+    lib.bq_kernel_name.restype = c_char_p
+    lib.bq_kernel_name.argtypes = [ctypes.c_int]
+    lib.bq_launch_count.restype = c_int64
+    lib.bq_launch_count.argtypes = [ctypes.c_int]
+    lib.bq_profile_enable.restype = None
+    lib.bq_profile_enable.argtypes = [ctypes.c_int]
+    lib.bq_profile_read.restype = ctypes.c_int
+    lib.bq_profile_read.argtypes = [ctypes.c_int, POINTER(ctypes.c_double), POINTER(c_int64)]
     _lib = lib
     return lib
 
@@ -133,3 +142,24 @@ def workspace(nbytes: int, device) -> torch.Tensor:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
+
+
+def launch_counts() -> dict:
+    """kernel name -> launches since the library was loaded."""
+    lib = load()
+    return {lib.bq_kernel_name(i).decode(): int(lib.bq_launch_count(i)) for i in range(lib.bq_kernel_count())}
+
+
+def profile_enable(on: bool):
+    load().bq_profile_enable(1 if on else 0)
+
+
+def profile_read() -> dict:
+    """kernel name -> (total device ms, launches) for launches recorded since profile_enable(True)."""
+    lib = load()
+    out = {}
+    for i in range(lib.bq_kernel_count()):
+        ms, n = ctypes.c_double(0), c_int64(0)
+        check(lib.bq_profile_read(i, ctypes.byref(ms), ctypes.byref(n)), "bq_profile_read")
+        out[lib.bq_kernel_name(i).decode()] = (ms.value, int(n.value))
+    return out

@@ -1,14 +1,78 @@
 // common.cu — status strings and error bookkeeping of the C ABI (include/bq.h).
 #include "bq_internal.h"
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 namespace bq {
 static thread_local char g_last_err[512] = "";
 void set_last_cuda_error(const char* what, const char* file, int line) {
   snprintf(g_last_err, sizeof(g_last_err), "%s (%s:%d)", what ? what : "?", file, line);
 }
+
+// ---------------------------------------------------------------------------------------------
+// launch accounting
+// ---------------------------------------------------------------------------------------------
+static const char* kKernelNames[kKernCount] = {"quant_rows_kernel", "blocklog_fixup_kernel", "quant_tile_kernel",
+                                               "generic_blockmax_kernel", "generic_gmin_kernel", "generic_quant_kernel",
+                                               "gemm_bf16_tn_kernel"};
+static std::atomic<int64_t> g_launches[kKernCount];
+static std::atomic<int> g_profiling{0};
+struct EventPair { int id; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<EventPair> g_events;
+
+LaunchScope::LaunchScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
+  g_launches[id].fetch_add(1, std::memory_order_relaxed);
+  if (g_profiling.load(std::memory_order_relaxed)) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) {
+      cudaEventRecord(a, st);
+      stop_ = b;
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_events.push_back({id, a, b});
+    }
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (stop_) cudaEventRecord(stop_, st_);
+}
 }  // namespace bq
 
 extern "C" {
+int bq_kernel_count(void) { return bq::kKernCount; }
+const char* bq_kernel_name(int id) { return (id >= 0 && id < bq::kKernCount) ? bq::kKernelNames[id] : ""; }
+int64_t bq_launch_count(int id) {
+  if (id >= 0 && id < bq::kKernCount) return bq::g_launches[id].load();
+  int64_t t = 0;
+  for (int i = 0; i < bq::kKernCount; ++i) t += bq::g_launches[i].load();
+  return t;
+}
+void bq_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(bq::g_prof_mu);
+  if (on) {
+    for (auto& e : bq::g_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    bq::g_events.clear();
+  }
+  bq::g_profiling.store(on ? 1 : 0);
+}
+int bq_profile_read(int id, double* total_ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lk(bq::g_prof_mu);
+  double tot = 0;
+  int64_t n = 0;
+  for (auto& e : bq::g_events) {
+    if (id >= 0 && e.id != id) continue;
+    if (cudaEventSynchronize(e.b) != cudaSuccess) return BQ_ERR_CUDA;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) return BQ_ERR_CUDA;
+    tot += ms;
+    ++n;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return BQ_OK;
+}
 const char* bq_strerror(int status) {
   switch (status) {
     case BQ_OK: return "ok";

@@ -144,7 +144,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::tc_fence_after();
       const int row = mb * kBM + q * 32 + lane;
       float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
-      const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((g.sc & 3) == 0);
+      const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((g.sc & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -241,7 +242,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs 
   int64_t total = (int64_t)g.tiles_m * g.tiles_n * g.batch;
   if (total > 0x7fffffffll) return BQ_ERR_UNSUPPORTED;
   int grid = (int)std::min<int64_t>(total, num_sms());
-  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, g);
+  {
+    LaunchScope ls(kKernGemm, st);
+    gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, g);
+  }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
 }

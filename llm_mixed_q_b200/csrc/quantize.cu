@@ -440,10 +440,11 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
     const uint64_t tile = (uint64_t)kThreads * kUnroll;
     uint64_t tiles = (pl.rg.total_slots + tile - 1) / tile;
     int grid = (int)std::min<uint64_t>(tiles, (uint64_t)sms * 8);   // 8 resident CTAs of 256 threads per SM
-    quant_rows_kernel<KIND, OutT><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux);
+    { LaunchScope ls(kKernQuantRows, st); quant_rows_kernel<KIND, OutT><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux); }
     if (KIND == kBlockLog) {
       uint64_t blocks = (pl.rg.total_slots + kThreads - 1) / kThreads;
       int g2 = (int)std::min<uint64_t>(blocks, (uint64_t)sms * 8);
+      LaunchScope ls(kKernBlockLogFixup, st);
       blocklog_fixup_kernel<OutT><<<g2, kThreads, 0, st>>>(y, pl.rg, p, gstate, aux);
     }
   } else if (pl.tile && (KIND == kBlockFP || KIND == kBlockMinifloat)) {
@@ -451,6 +452,7 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
     int64_t total = (int64_t)tiles_r * tiles_c * pl.gg.L;
     if (total == 0) return BQ_OK;
     int grid = (int)std::min<int64_t>(total, (int64_t)sms * 8);
+    LaunchScope ls(kKernQuantTile, st);
     quant_tile_kernel<KIND, OutT><<<grid, 256, 0, st>>>(x, y, pl.gg, p, tiles_r, tiles_c);
   } else {
     int64_t n = pl.gg.L * pl.gg.R * pl.gg.C;
@@ -459,11 +461,11 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
     if (kBlocked) {
       BQ_CUDA_CHECK(cudaMemsetAsync(gstate, 0xff, 8, st));
       BQ_CUDA_CHECK(cudaMemsetAsync(aux, 0, 4 * (size_t)pl.nblk, st));
-      generic_blockmax_kernel<<<grid, 256, 0, st>>>(x, pl.gg, aux);
+      { LaunchScope ls(kKernGenericMax, st); generic_blockmax_kernel<<<grid, 256, 0, st>>>(x, pl.gg, aux); }
       int g2 = (int)std::min<int64_t>((pl.nblk + 255) / 256, (int64_t)sms * 4);
-      generic_gmin_kernel<<<g2, 256, 0, st>>>(aux, pl.nblk, gstate);
+      { LaunchScope ls(kKernGenericMin, st); generic_gmin_kernel<<<g2, 256, 0, st>>>(aux, pl.nblk, gstate); }
     }
-    generic_quant_kernel<KIND, OutT><<<grid, 256, 0, st>>>(x, y, pl.gg, p, aux, gstate);
+    { LaunchScope ls(kKernGenericQuant, st); generic_quant_kernel<KIND, OutT><<<grid, 256, 0, st>>>(x, y, pl.gg, p, aux, gstate); }
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;

@@ -1,0 +1,248 @@
+"""
+Quantized Llama — HF-compatible parameter names (`model.layers.<i>.self_attn.q_proj.weight`, …).
+
+Quantisation wiring of reference llama_quantized/modeling_llama.py: seven quantized Linears without bias
+(:208-210, :237-240), RoPE with quantised cos/sin tables (:289-299), two quantized 4-D matmuls
+(:309-314, :341-344; scores divided by sqrt(d) AFTER matmul_0), fp32 RMSNorm / softmax / SiLU / lm_head (:772).
+Forward-only perplexity path; no KV cache.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch.nn import CrossEntropyLoss
+from transformers.activations import ACT2FN
+from transformers.modeling_outputs import CausalLMOutputWithPast
+from transformers.modeling_utils import PreTrainedModel
+
+from ..quantize import get_quantized_cls, get_quantized_func
+from .configuration_llama import LlamaQuantizedConfig
+
+
+class LlamaRMSNorm(nn.Module):
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, hidden_states):
+        dtype = hidden_states.dtype
+        variance = hidden_states.to(torch.float32).pow(2).mean(-1, keepdim=True)
+        hidden_states = hidden_states * torch.rsqrt(variance + self.variance_epsilon)
+        return (self.weight * hidden_states).to(dtype)
+
+
+class LlamaRotaryEmbedding(nn.Module):
+    """cos/sin tables [1, 1, seq, dim] (reference modeling_llama.py:119-165)."""
+
+    def __init__(self, dim, max_position_embeddings=2048, base=10000, device=None):
+        super().__init__()
+        self.dim, self.base = dim, base
+        inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2).float().to(device) / dim))
+        self.register_buffer("inv_freq", inv_freq, persistent=False)
+        self._build(max_position_embeddings, device=inv_freq.device)
+
+    def _build(self, seq_len, device):
+        self.max_seq_len_cached = seq_len
+        t = torch.arange(seq_len, device=device, dtype=self.inv_freq.dtype)
+        freqs = torch.einsum("i,j->ij", t, self.inv_freq.to(device))
+        emb = torch.cat((freqs, freqs), dim=-1)
+        self.register_buffer("cos_cached", emb.cos()[None, None, :, :], persistent=False)
+        self.register_buffer("sin_cached", emb.sin()[None, None, :, :], persistent=False)
+
+    def forward(self, x, seq_len=None):
+        if seq_len > self.max_seq_len_cached or self.cos_cached.device != x.device:
+            self._build(max(seq_len, self.max_seq_len_cached), device=x.device)
+        return self.cos_cached[:, :, :seq_len, ...].to(dtype=x.dtype), self.sin_cached[:, :, :seq_len, ...].to(dtype=x.dtype)
+
+
+class LlamaQuantizedMLP(nn.Module):
+    def __init__(self, hidden_size: int, intermediate_size: int, hidden_act: str, quant_config: dict):
+        super().__init__()
+        qc = quant_config
+        self.gate_proj = get_quantized_cls("linear", qc["gate_proj"])(hidden_size, intermediate_size, bias=False, config=qc["gate_proj"])
+        self.down_proj = get_quantized_cls("linear", qc["down_proj"])(intermediate_size, hidden_size, bias=False, config=qc["down_proj"])
+        self.up_proj = get_quantized_cls("linear", qc["up_proj"])(hidden_size, intermediate_size, bias=False, config=qc["up_proj"])
+        self.act_fn = ACT2FN[hidden_act]
+        self.quant_config = qc
+
+    def forward(self, x):
+        return self.down_proj(self.act_fn(self.gate_proj(x)) * self.up_proj(x))
+
+
+class LlamaQuantizedAttention(nn.Module):
+    def __init__(self, config: LlamaQuantizedConfig, layer_id: int = 0):
+        super().__init__()
+        self.config = config
+        self.hidden_size = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.head_dim = self.hidden_size // self.num_heads
+        self.max_position_embeddings = config.max_position_embeddings
+        if self.head_dim * self.num_heads != self.hidden_size:
+            raise ValueError(f"hidden_size must be divisible by num_heads (got `hidden_size`: {self.hidden_size} and `num_heads`: {self.num_heads}).")
+        qc = config.quant_config[f"model_layer_{layer_id}"]["self_attn"]
+        H = self.num_heads * self.head_dim
+        self.q_proj = get_quantized_cls("linear", qc["q_proj"])(self.hidden_size, H, bias=False, config=qc["q_proj"])
+        self.k_proj = get_quantized_cls("linear", qc["k_proj"])(self.hidden_size, H, bias=False, config=qc["k_proj"])
+        self.v_proj = get_quantized_cls("linear", qc["v_proj"])(self.hidden_size, H, bias=False, config=qc["v_proj"])
+        self.o_proj = get_quantized_cls("linear", qc["o_proj"])(H, self.hidden_size, bias=False, config=qc["o_proj"])
+        self.rotary_emb = LlamaRotaryEmbedding(self.head_dim, max_position_embeddings=self.max_position_embeddings)
+        self.quant_config = qc
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, output_attentions=False):
+        bsz, q_len, _ = hidden_states.size()
+        shp = (bsz, q_len, self.num_heads, self.head_dim)
+        query_states = self.q_proj(hidden_states).view(*shp).transpose(1, 2)
+        key_states = self.k_proj(hidden_states).view(*shp).transpose(1, 2)
+        value_states = self.v_proj(hidden_states).view(*shp).transpose(1, 2)
+
+        cos, sin = self.rotary_emb(value_states, seq_len=q_len)
+        rope_cfg = self.quant_config["rotary_positional_encoding"]
+        query_states, key_states = get_quantized_func("rotary_positional_encoding", rope_cfg)(
+            query_states, key_states, cos, sin, position_ids, rope_cfg)
+
+        mm0 = get_quantized_func("matmul", self.quant_config["matmul_0"])
+        attn_weights = mm0(query_states, key_states.transpose(2, 3), config=self.quant_config["matmul_0"]) / math.sqrt(self.head_dim)
+        if attention_mask is not None:
+            attn_weights = attn_weights + attention_mask
+            attn_weights = torch.max(attn_weights, torch.tensor(torch.finfo(attn_weights.dtype).min, device=attn_weights.device))
+        attn_weights = nn.functional.softmax(attn_weights, dim=-1, dtype=torch.float32).to(query_states.dtype)
+
+        mm1 = get_quantized_func("matmul", self.quant_config["matmul_1"])
+        attn_output = mm1(attn_weights, value_states, config=self.quant_config["matmul_1"])
+        attn_output = attn_output.transpose(1, 2).reshape(bsz, q_len, self.hidden_size)
+        attn_output = self.o_proj(attn_output)
+        return attn_output, (attn_weights if output_attentions else None)
+
+
+class LlamaQuantizedDecoderLayer(nn.Module):
+    def __init__(self, config: LlamaQuantizedConfig, layer_id: int = 0):
+        super().__init__()
+        self.hidden_size = config.hidden_size
+        self.self_attn = LlamaQuantizedAttention(config=config, layer_id=layer_id)
+        self.mlp = LlamaQuantizedMLP(self.hidden_size, config.intermediate_size, config.hidden_act,
+                                     config.quant_config[f"model_layer_{layer_id}"]["mlp"])
+        self.input_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, output_attentions=False):
+        residual = hidden_states
+        hidden_states = self.input_layernorm(hidden_states)
+        hidden_states, attn = self.self_attn(hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                                             output_attentions=output_attentions)
+        hidden_states = residual + hidden_states
+        residual = hidden_states
+        hidden_states = self.post_attention_layernorm(hidden_states)
+        hidden_states = self.mlp(hidden_states)
+        return residual + hidden_states, attn
+
+
+class LlamaQuantizedPreTrainedModel(PreTrainedModel):
+    config_class = LlamaQuantizedConfig
+    config: LlamaQuantizedConfig
+    base_model_prefix = "model"
+    supports_gradient_checkpointing = False
+    _no_split_modules = ["LlamaQuantizedDecoderLayer"]
+
+    @torch.no_grad()
+    def _init_weights(self, module):
+        std = self.config.initializer_range
+        if isinstance(module, nn.Linear):
+            module.weight.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.normal_(mean=0.0, std=std)
+            if module.padding_idx is not None:
+                module.weight[module.padding_idx].zero_()
+        elif isinstance(module, LlamaRMSNorm):
+            module.weight.fill_(1.0)
+
+
+def _causal_mask(attention_mask, bsz, q_len, dtype, device):
+    neg = torch.finfo(dtype).min
+    mask = torch.triu(torch.full((q_len, q_len), neg, device=device, dtype=dtype), diagonal=1)[None, None].expand(bsz, 1, q_len, q_len)
+    if attention_mask is not None and not bool(attention_mask.all()):
+        inv = 1.0 - attention_mask[:, None, None, :].to(dtype)
+        mask = mask + inv.masked_fill(inv.to(torch.bool), neg)
+    return mask
+
+
+class LlamaQuantizedModel(LlamaQuantizedPreTrainedModel):
+    def __init__(self, config: LlamaQuantizedConfig):
+        super().__init__(config)
+        self.padding_idx = config.pad_token_id
+        self.vocab_size = config.vocab_size
+        self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size, self.padding_idx)
+        self.layers = nn.ModuleList([LlamaQuantizedDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.embed_tokens = value
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, inputs_embeds=None, output_attentions=False,
+                output_hidden_states=False):
+        if inputs_embeds is None:
+            inputs_embeds = self.embed_tokens(input_ids)
+        bsz, q_len = inputs_embeds.shape[:2]
+        if position_ids is None:
+            position_ids = torch.arange(q_len, dtype=torch.long, device=inputs_embeds.device).unsqueeze(0).view(-1, q_len)
+        mask = _causal_mask(attention_mask, bsz, q_len, inputs_embeds.dtype, inputs_embeds.device)
+        hidden_states = inputs_embeds
+        all_h, all_a = (), ()
+        for layer in self.layers:
+            if output_hidden_states:
+                all_h += (hidden_states,)
+            hidden_states, attn = layer(hidden_states, attention_mask=mask, position_ids=position_ids,
+                                        output_attentions=output_attentions)
+            if output_attentions:
+                all_a += (attn,)
+        hidden_states = self.norm(hidden_states)
+        if output_hidden_states:
+            all_h += (hidden_states,)
+        return hidden_states, (all_h if output_hidden_states else None), (all_a if output_attentions else None)
+
+
+class LlamaQuantizedForCausalLM(LlamaQuantizedPreTrainedModel):
+    _tied_weights_keys = {"lm_head.weight": "model.embed_tokens.weight"}
+
+    def __init__(self, config: LlamaQuantizedConfig):
+        super().__init__(config)
+        self.model = LlamaQuantizedModel(config)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)   # unquantised (reference :772)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.model.embed_tokens = value
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def set_output_embeddings(self, new_embeddings):
+        self.lm_head = new_embeddings
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, inputs_embeds=None, labels=None,
+                output_attentions=False, output_hidden_states=False, return_dict=True, **unused):
+        hidden, all_h, all_a = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                                          inputs_embeds=inputs_embeds, output_attentions=output_attentions,
+                                          output_hidden_states=output_hidden_states)
+        logits = self.lm_head(hidden)
+        loss = None
+        if labels is not None:
+            shift_logits = logits[..., :-1, :].contiguous()
+            shift_labels = labels[..., 1:].contiguous().to(logits.device)
+            loss = CrossEntropyLoss()(shift_logits.view(-1, self.config.vocab_size), shift_labels.view(-1))
+        if not return_dict:
+            out = (logits, None, all_h, all_a)
+            return ((loss,) + out) if loss is not None else out
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=all_h, attentions=all_a)

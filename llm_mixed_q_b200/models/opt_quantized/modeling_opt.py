@@ -1,0 +1,280 @@
+"""
+Quantized OPT — module classes with HF-compatible parameter names
+(`model.decoder.layers.<i>.self_attn.q_proj.weight`, …) so OPT checkpoints load unchanged.
+
+Mirrors the quantisation wiring of reference opt_quantized/modeling_opt.py: six quantized Linears and two
+quantized bmm per decoder layer (:174-177, :246, :312, :353-354), everything else (embeddings, LayerNorm,
+softmax, ReLU, residuals, lm_head, loss) unquantised fp32 (:831-832, :942-944, :1086-1098).  The
+forward-only tier supports the perplexity path (`input_ids`, `attention_mask`, `labels`); KV-cache decoding
+is not wired.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch.nn import CrossEntropyLoss
+from transformers.activations import ACT2FN
+from transformers.modeling_outputs import CausalLMOutputWithPast
+from transformers.modeling_utils import PreTrainedModel
+
+from ..quantize import get_quantized_cls, get_quantized_func
+from .configuration_opt import OPTQuantizedConfig
+
+
+class OPTLearnedPositionalEmbedding(nn.Embedding):
+    """positions offset by 2 (HF OPT convention; reference modeling_opt.py:112-140)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int):
+        self.offset = 2
+        super().__init__(num_embeddings + self.offset, embedding_dim)
+
+    def forward(self, attention_mask: torch.LongTensor, past_key_values_length: int = 0):
+        attention_mask = attention_mask.long()
+        positions = (torch.cumsum(attention_mask, dim=1).type_as(attention_mask) * attention_mask).long() - 1
+        positions = positions[:, past_key_values_length:]
+        return super().forward(positions + self.offset)
+
+
+def _causal_additive_mask(attention_mask, bsz, tgt_len, dtype, device):
+    """[bsz, 1, tgt, src] additive mask: finfo.min above the diagonal and on padded keys (reference :520-548)."""
+    neg = torch.finfo(dtype).min
+    mask = torch.full((tgt_len, tgt_len), neg, device=device, dtype=dtype)
+    mask = torch.triu(mask, diagonal=1)[None, None].expand(bsz, 1, tgt_len, tgt_len)
+    if attention_mask is not None and not bool(attention_mask.all()):
+        pad = (1.0 - attention_mask[:, None, None, :].to(dtype)).masked_fill(attention_mask[:, None, None, :] == 0, 1.0)
+        pad = pad.masked_fill(pad.bool(), neg)
+        mask = mask + pad
+        mask = mask.clamp(min=neg)
+    return mask
+
+
+class OPTQauntizedAttention(nn.Module):      # (sic) class name kept from the reference, modeling_opt.py:143
+    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0, is_decoder: bool = False, bias: bool = True,
+                 quant_config: dict = None):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.head_dim = embed_dim // num_heads
+        if self.head_dim * num_heads != embed_dim:
+            raise ValueError(f"embed_dim must be divisible by num_heads (got `embed_dim`: {embed_dim} and `num_heads`: {num_heads}).")
+        self.scaling = self.head_dim**-0.5
+        self.is_decoder = is_decoder
+        qc = quant_config
+        self.k_proj = get_quantized_cls("linear", qc["k_proj"])(embed_dim, embed_dim, bias=bias, config=qc["k_proj"])
+        self.q_proj = get_quantized_cls("linear", qc["q_proj"])(embed_dim, embed_dim, bias=bias, config=qc["q_proj"])
+        self.v_proj = get_quantized_cls("linear", qc["v_proj"])(embed_dim, embed_dim, bias=bias, config=qc["v_proj"])
+        self.out_proj = get_quantized_cls("linear", qc["out_proj"])(embed_dim, embed_dim, bias=bias, config=qc["out_proj"])
+        self.quant_config = qc
+
+    def _shape(self, tensor: torch.Tensor, seq_len: int, bsz: int):
+        return tensor.view(bsz, seq_len, self.num_heads, self.head_dim).transpose(1, 2).contiguous()
+
+    def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                output_attentions: bool = False):
+        bsz, tgt_len, _ = hidden_states.size()
+        query_states = self.q_proj(hidden_states) * self.scaling
+        key_states = self._shape(self.k_proj(hidden_states), -1, bsz)
+        value_states = self._shape(self.v_proj(hidden_states), -1, bsz)
+
+        proj_shape = (bsz * self.num_heads, -1, self.head_dim)
+        query_states = self._shape(query_states, tgt_len, bsz).view(*proj_shape)
+        key_states = key_states.view(*proj_shape)
+        value_states = value_states.view(*proj_shape)
+        src_len = key_states.size(1)
+
+        bmm_0 = get_quantized_func("bmm", self.quant_config["bmm_0"])
+        attn_weights = bmm_0(query_states, key_states.transpose(1, 2), config=self.quant_config["bmm_0"])
+
+        if attention_mask is not None:
+            attn_weights = attn_weights.view(bsz, self.num_heads, tgt_len, src_len) + attention_mask
+            attn_weights = torch.max(attn_weights, torch.tensor(torch.finfo(attn_weights.dtype).min, device=attn_weights.device))
+            attn_weights = attn_weights.view(bsz * self.num_heads, tgt_len, src_len)
+        attn_weights = nn.functional.softmax(attn_weights, dim=-1)
+        attn_probs = nn.functional.dropout(attn_weights, p=self.dropout, training=self.training)
+
+        bmm_1 = get_quantized_func("bmm", self.quant_config["bmm_1"])
+        attn_output = bmm_1(attn_probs, value_states, config=self.quant_config["bmm_1"])
+
+        attn_output = attn_output.view(bsz, self.num_heads, tgt_len, self.head_dim).transpose(1, 2)
+        attn_output = attn_output.reshape(bsz, tgt_len, self.embed_dim)
+        attn_output = self.out_proj(attn_output)
+        return attn_output, (attn_weights.view(bsz, self.num_heads, tgt_len, src_len) if output_attentions else None)
+
+
+class OPTQuantizedDecoderLayer(nn.Module):
+    def __init__(self, config: OPTQuantizedConfig, layer_id: int):
+        super().__init__()
+        self.embed_dim = config.hidden_size
+        qc = config.quant_config[f"model_layer_{layer_id}"]
+        self.self_attn = OPTQauntizedAttention(embed_dim=self.embed_dim, num_heads=config.num_attention_heads,
+                                               dropout=config.attention_dropout, is_decoder=True, bias=config.enable_bias,
+                                               quant_config=qc["self_attn"])
+        self.do_layer_norm_before = config.do_layer_norm_before
+        self.dropout = config.dropout
+        self.activation_fn = ACT2FN[config.activation_function]
+        self.self_attn_layer_norm = nn.LayerNorm(self.embed_dim, elementwise_affine=config.layer_norm_elementwise_affine)
+        self.fc1 = get_quantized_cls("linear", qc["fc1"])(self.embed_dim, config.ffn_dim, bias=config.enable_bias, config=qc["fc1"])
+        self.fc2 = get_quantized_cls("linear", qc["fc2"])(config.ffn_dim, self.embed_dim, bias=config.enable_bias, config=qc["fc2"])
+        self.final_layer_norm = nn.LayerNorm(self.embed_dim, elementwise_affine=config.layer_norm_elementwise_affine)
+
+    def forward(self, hidden_states, attention_mask=None, output_attentions=False):
+        residual = hidden_states
+        if self.do_layer_norm_before:
+            hidden_states = self.self_attn_layer_norm(hidden_states)
+        hidden_states, attn = self.self_attn(hidden_states, attention_mask=attention_mask, output_attentions=output_attentions)
+        hidden_states = nn.functional.dropout(hidden_states, p=self.dropout, training=self.training)
+        hidden_states = residual + hidden_states
+        if not self.do_layer_norm_before:
+            hidden_states = self.self_attn_layer_norm(hidden_states)
+
+        shape = hidden_states.shape
+        hidden_states = hidden_states.reshape(-1, hidden_states.size(-1))      # fc1/fc2 see a 2-D input (reference :412)
+        residual = hidden_states
+        if self.do_layer_norm_before:
+            hidden_states = self.final_layer_norm(hidden_states)
+        hidden_states = self.fc2(self.activation_fn(self.fc1(hidden_states)))
+        hidden_states = nn.functional.dropout(hidden_states, p=self.dropout, training=self.training)
+        hidden_states = (residual + hidden_states).view(shape)
+        if not self.do_layer_norm_before:
+            hidden_states = self.final_layer_norm(hidden_states)
+        return hidden_states, attn
+
+
+class OPTQuantizedPreTrainedModel(PreTrainedModel):
+    config_class = OPTQuantizedConfig
+    config: OPTQuantizedConfig
+    base_model_prefix = "model"
+    supports_gradient_checkpointing = False
+    _no_split_modules = ["OPTQuantizedDecoderLayer"]
+
+    @torch.no_grad()
+    def _init_weights(self, module):
+        std = self.config.init_std                  # reference modeling_opt.py:472-481
+        if isinstance(module, nn.Linear):
+            module.weight.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.normal_(mean=0.0, std=std)
+            if module.padding_idx is not None:
+                module.weight[module.padding_idx].zero_()
+        elif isinstance(module, nn.LayerNorm):
+            if module.weight is not None:
+                module.weight.fill_(1.0)
+                module.bias.zero_()
+
+
+class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
+    def __init__(self, config: OPTQuantizedConfig):
+        super().__init__(config)
+        self.dropout = config.dropout
+        self.padding_idx = config.pad_token_id
+        self.max_target_positions = config.max_position_embeddings
+        self.vocab_size = config.vocab_size
+        self.embed_tokens = nn.Embedding(config.vocab_size, config.word_embed_proj_dim, self.padding_idx)
+        self.embed_positions = OPTLearnedPositionalEmbedding(config.max_position_embeddings, config.hidden_size)
+        if config.word_embed_proj_dim != config.hidden_size:
+            self.project_out = nn.Linear(config.hidden_size, config.word_embed_proj_dim, bias=False)
+            self.project_in = nn.Linear(config.word_embed_proj_dim, config.hidden_size, bias=False)
+        else:
+            self.project_out = None
+            self.project_in = None
+        if config.do_layer_norm_before and not config._remove_final_layer_norm:
+            self.final_layer_norm = nn.LayerNorm(config.hidden_size, elementwise_affine=config.layer_norm_elementwise_affine)
+        else:
+            self.final_layer_norm = None
+        self.layers = nn.ModuleList([OPTQuantizedDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.embed_tokens = value
+
+    def forward(self, input_ids=None, attention_mask=None, inputs_embeds=None, output_attentions=False,
+                output_hidden_states=False):
+        if inputs_embeds is None:
+            inputs_embeds = self.embed_tokens(input_ids)
+        bsz, seq_len = inputs_embeds.shape[:2]
+        if attention_mask is None:
+            attention_mask = torch.ones(bsz, seq_len, dtype=torch.bool, device=inputs_embeds.device)
+        causal = _causal_additive_mask(attention_mask, bsz, seq_len, inputs_embeds.dtype, inputs_embeds.device)
+        pos_embeds = self.embed_positions(attention_mask, 0)
+        if self.project_in is not None:
+            inputs_embeds = self.project_in(inputs_embeds)
+        hidden_states = inputs_embeds + pos_embeds
+        hidden_states = nn.functional.dropout(hidden_states, p=self.dropout, training=self.training)
+        all_h, all_a = ((), ())
+        for layer in self.layers:
+            if output_hidden_states:
+                all_h += (hidden_states,)
+            hidden_states, attn = layer(hidden_states, attention_mask=causal, output_attentions=output_attentions)
+            if output_attentions:
+                all_a += (attn,)
+        if self.final_layer_norm is not None:
+            hidden_states = self.final_layer_norm(hidden_states)
+        if self.project_out is not None:
+            hidden_states = self.project_out(hidden_states)
+        if output_hidden_states:
+            all_h += (hidden_states,)
+        return hidden_states, (all_h if output_hidden_states else None), (all_a if output_attentions else None)
+
+
+class OPTQuantizedModel(OPTQuantizedPreTrainedModel):
+    def __init__(self, config: OPTQuantizedConfig):
+        super().__init__(config)
+        self.decoder = OPTQuantizedDecoder(config)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.decoder.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.decoder.embed_tokens = value
+
+    def forward(self, *args, **kwargs):
+        return self.decoder(*args, **kwargs)
+
+
+class OPTQuantizedForCausalLM(OPTQuantizedPreTrainedModel):
+    _tied_weights_keys = {"lm_head.weight": "model.decoder.embed_tokens.weight"}
+
+    def __init__(self, config: OPTQuantizedConfig):
+        super().__init__(config)
+        self.model = OPTQuantizedModel(config)
+        # unquantised fp32 head, tied to the token embedding (reference modeling_opt.py:942-944)
+        self.lm_head = nn.Linear(config.word_embed_proj_dim, config.vocab_size, bias=False)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.model.decoder.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.model.decoder.embed_tokens = value
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def set_output_embeddings(self, new_embeddings):
+        self.lm_head = new_embeddings
+
+    def forward(self, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None, output_attentions=False,
+                output_hidden_states=False, return_dict=True, **unused):
+        hidden, all_h, all_a = self.model.decoder(input_ids=input_ids, attention_mask=attention_mask,
+                                                  inputs_embeds=inputs_embeds, output_attentions=output_attentions,
+                                                  output_hidden_states=output_hidden_states)
+        logits = self.lm_head(hidden).contiguous()
+        loss = None
+        if labels is not None:
+            labels = labels.to(logits.device)
+            shift_logits = logits[..., :-1, :].contiguous()
+            shift_labels = labels[..., 1:].contiguous()
+            loss = CrossEntropyLoss()(shift_logits.view(-1, self.config.vocab_size), shift_labels.view(-1))
+        if not return_dict:
+            out = (logits, None, all_h, all_a)
+            return ((loss,) + out) if loss is not None else out
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=all_h, attentions=all_a)

@@ -1,0 +1,240 @@
+"""
+Quantized Linear modules — host mirror of reference quantized_modules/linear.py:31-307.
+
+Same class names, constructor (`cls(in_features, out_features, bias=True, device=None, dtype=None, config=cfg)`),
+attributes (`config, bypass, is_ptq, weight_requires_quantisation, x_quantizer, w_quantizer, b_quantizer`),
+`forward` semantics and `from_float` as the reference, so HF model code written against the reference's
+`get_quantized_cls("linear", cfg)` runs unchanged.
+
+What changes underneath (PTQ steady state, the path every shipped TOML selects):
+  reference : x -> ~45 ATen kernels -> fp32 x_q -> cuBLAS SGEMM with the (in-place quantised) fp32 weight
+  here      : x -> one streaming quantize kernel emitting bf16 -> tcgen05 GEMM against a bf16 cache of the
+              quantised weight (exact: <= 8 significant bits), fp32 accumulation, fp32 bias add in the epilogue.
+The in-place PTQ overwrite of `weight` / `bias` on the first forward (linear.py:66-70) is kept — the fp32
+parameters hold bit-identical quantised values afterwards; the bf16 cache is derived state.
+"""
+from __future__ import annotations
+
+import ctypes
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .... import _lib as L
+from ..quantizers import (block_fp_quantizer, block_log_quantizer, block_minifloat_quantizer, integer_quantizer,
+                          minifloat_denorm_quantizer, minifloat_ieee_quantizer)
+from ..quantizers.utils import canonicalise, default_bias, launch_quantize, make_format
+
+
+def operand_format(config: dict, prefix: str):
+    """(kind, fmt kwargs, block_size) of one operand from the `<prefix>_*` keys of a config node."""
+    name = config["name"]
+    if name == "block_fp":
+        return "block_fp", dict(width=config[f"{prefix}_width"], exponent_width=config[f"{prefix}_exponent_width"],
+                                exponent_bias=default_bias(config[f"{prefix}_exponent_bias"],
+                                                           config[f"{prefix}_exponent_width"])), config[f"{prefix}_block_size"]
+    if name == "block_minifloat":
+        return "block_minifloat", dict(width=config[f"{prefix}_width"], exponent_width=config[f"{prefix}_exponent_width"],
+                                       exponent_bias_width=config[f"{prefix}_exponent_bias_width"]), config[f"{prefix}_block_size"]
+    if name in ("block_log", "log"):
+        return "block_log", dict(width=config[f"{prefix}_width"],
+                                 exponent_bias_width=config[f"{prefix}_exponent_bias_width"]), config[f"{prefix}_block_size"]
+    if name in ("minifloat_denorm", "minifloat_ieee"):
+        return name, dict(width=config[f"{prefix}_width"], exponent_width=config[f"{prefix}_exponent_width"],
+                          exponent_bias=default_bias(config[f"{prefix}_exponent_bias"],
+                                                     config[f"{prefix}_exponent_width"])), None
+    if name == "integer":
+        return "integer", dict(width=config[f"{prefix}_width"], exponent_bias=config[f"{prefix}_frac_width"]), None
+    raise KeyError(name)
+
+
+def significant_bits(kind: str, kw: dict) -> int:
+    """Significant bits of a quantised value; <= 8 means the value is exact in bf16."""
+    if kind == "block_fp":
+        return kw["width"] - 1
+    if kind in ("block_minifloat", "minifloat_ieee"):
+        return kw["width"] - kw["exponent_width"]          # implicit one + mantissa
+    if kind == "minifloat_denorm":
+        return kw["width"] - kw["exponent_width"] - 1
+    if kind == "block_log":
+        return 1
+    if kind == "integer":
+        return kw["width"] - 1
+    return 24
+
+
+def quantize_operand_bf16(x: torch.Tensor, kind, kw, block_size, skip_first_dim, transpose_out=False):
+    """Quantise to a bf16 GEMM operand (K-major); used for weights (once) and odd-shaped activations."""
+    blocked = block_size is not None
+    xd = x.detach()
+    if not blocked and not xd.is_contiguous():
+        xd = xd.contiguous()
+    canon = canonicalise(xd, block_size, skip_first_dim, blocked=blocked)
+    fmt = make_format(kind, b0=canon.b0, b1=canon.b1, fold=False, **kw)
+    return launch_quantize(xd, fmt, canon, out_dtype=torch.bfloat16, transpose_out=transpose_out)
+
+
+class _LinearBase(nn.Linear):
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None,
+                 config: dict = None) -> None:
+        super().__init__(in_features, out_features, bias, device, dtype)
+        self.config = config
+        self.bypass = config.get("bypass", False)
+        self.is_ptq = config.get("is_ptq", False)
+        self.weight_requires_quantisation = True if self.is_ptq else False
+        self.x_quantizer = None
+        self.w_quantizer = None
+        self.b_quantizer = None
+        self._wq_bf16 = None          # derived bf16 cache of the quantised weight [N, K]
+        self._wq_key = None
+        if not self.bypass:
+            self._setup_quantizers(config)
+
+    # subclasses bind the three quantizers from config keys (reference linear.py:113-281)
+    def _setup_quantizers(self, config: dict):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ fused PTQ path
+    def _fusable(self, x):
+        if not x.is_cuda or x.dtype != torch.float32 or self.weight.dtype != torch.float32:
+            return False
+        if self.in_features % 8 != 0 or x.ndim not in (2, 3):
+            return False
+        try:
+            kind, kw, _ = operand_format(self.config, "data_in")
+            wkind, wkw, _ = operand_format(self.config, "weight")
+        except KeyError:
+            return False
+        return significant_bits(kind, kw) <= 8 and significant_bits(wkind, wkw) <= 8
+
+    def _weight_cache(self):
+        w = self.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if self._wq_bf16 is None or self._wq_key != key:
+            # weight already holds quantised values (PTQ overwrite below); bf16 is an exact container for them
+            canon = canonicalise(w.detach(), None, False, blocked=False)
+            self._wq_bf16 = launch_quantize(w.detach(), make_format("none"), canon, out_dtype=torch.bfloat16)
+            self._wq_key = key
+        return self._wq_bf16
+
+    def _fused_forward(self, x):
+        lib = L.load()
+        kind, kw, block_size = operand_format(self.config, "data_in")
+        K, N = self.in_features, self.out_features
+        x2 = x.reshape(-1, K)
+        if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 4 != 0):
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        wq = self._weight_cache()
+        bias = self.bias.detach() if self.bias is not None else None
+        blocked = block_size is not None
+        b0, b1 = 1, 1
+        if blocked:
+            cn = canonicalise(x.detach(), block_size, True, blocked=True)
+            b0, b1 = cn.b0, cn.b1
+        if M > 0 and N > 0:
+            if b0 == 1:
+                fmt = make_format(kind, b0=1, b1=b1, fold=False, **kw)
+                nbytes = lib.bq_linear_workspace_bytes(ctypes.byref(fmt), M, K)
+                ws = L.workspace(nbytes, x.device)
+                rc = lib.bq_linear(ctypes.byref(fmt), x2.data_ptr(), M, K, x2.stride(0) if M > 1 else K, wq.data_ptr(), N,
+                                   bias.data_ptr() if bias is not None else None, y.data_ptr(), N, ws.data_ptr(),
+                                   ws.numel(), L.stream_ptr(x.device))
+                L.check(rc, "bq_linear")
+            else:
+                # blocks spanning rows (e.g. data_in_block_size=[16] on a 3-D input): quantise with the general
+                # kernel, then the same tensor-core GEMM
+                xq = quantize_operand_bf16(x, kind, kw, block_size, True).reshape(M, K)
+                rc = lib.bq_gemm_bf16_tn(xq.data_ptr(), wq.data_ptr(), y.data_ptr(),
+                                         bias.data_ptr() if bias is not None else None, 1, M, N, K, K, K, N, 0, 0, 0,
+                                         L.stream_ptr(x.device))
+                L.check(rc, "bq_gemm_bf16_tn")
+        return y.reshape(*x.shape[:-1], N)
+
+    def forward(self, x):
+        if self.bypass:
+            return F.linear(x, self.weight, self.bias)
+        elif self.is_ptq:
+            with torch.no_grad():
+                if self.weight_requires_quantisation:
+                    self.weight.copy_(self.w_quantizer(self.weight.data))
+                    if self.bias is not None:
+                        self.bias.copy_(self.b_quantizer(self.bias.data))
+                    self.weight_requires_quantisation = False
+                    self._wq_bf16 = None
+                if self._fusable(x):
+                    return self._fused_forward(x)
+                x = self.x_quantizer(x)
+            return F.linear(x, self.weight, self.bias)
+        else:
+            x = self.x_quantizer(x)
+            w = self.w_quantizer(self.weight)
+            bias = self.b_quantizer(self.bias) if self.bias is not None else None
+            return F.linear(x, w, bias)
+
+    @classmethod
+    def from_float(cls, linear_fp32: nn.Linear, config: dict):
+        linear = cls(linear_fp32.in_features, linear_fp32.out_features, bias=linear_fp32.bias is not None, config=config)
+        with torch.no_grad():
+            linear.weight.copy_(linear_fp32.weight)
+            if linear.bias is not None:
+                linear.bias.copy_(linear_fp32.bias)
+        return linear.to(linear_fp32.weight.device)
+
+    def __repr__(self):
+        return "{}(in_features={}, out_features={}, bias={}, bypass={}, is_ptq={}, x/w/b-width={}/{}/{})".format(
+            self.__class__.__name__, self.in_features, self.out_features, self.bias is not None, self.bypass, self.is_ptq,
+            self.config.get("data_in_width", "NA"), self.config.get("weight_width", "NA"), self.config.get("bias_width", "NA"))
+
+
+def _bind(self, quantizer, keys, config, with_blocks):
+    """Bind x / w / b quantizers from `<prefix>_<key>` entries (x: skip_first_dim=True, w/b: False)."""
+    def one(prefix, skip):
+        kw = {k: config[f"{prefix}_{k}"] for k in keys}
+        if with_blocks:
+            kw["block_size"] = config[f"{prefix}_block_size"]
+            kw["skip_first_dim"] = skip
+        return partial(quantizer, **kw)
+
+    self.x_quantizer = one("data_in", True)
+    self.w_quantizer = one("weight", False)
+    self.b_quantizer = one("bias", False) if self.bias is not None else None
+
+
+class LinearBlockFP(_LinearBase):
+    def _setup_quantizers(self, config: dict):
+        _bind(self, block_fp_quantizer, ("width", "exponent_width", "exponent_bias"), config, True)
+
+
+class LinearBlockMinifloat(_LinearBase):
+    def _setup_quantizers(self, config: dict):
+        _bind(self, block_minifloat_quantizer, ("width", "exponent_width", "exponent_bias_width"), config, True)
+
+
+class LinearBlockLog(_LinearBase):
+    def _setup_quantizers(self, config: dict):
+        _bind(self, block_log_quantizer, ("width", "exponent_bias_width"), config, True)
+
+
+class LinearMinifloatDenorm(_LinearBase):
+    def _setup_quantizers(self, config: dict):
+        _bind(self, minifloat_denorm_quantizer, ("width", "exponent_width", "exponent_bias"), config, False)
+
+
+class LinearMinifloatIEEE(_LinearBase):
+    def _setup_quantizers(self, config: dict):
+        _bind(self, minifloat_ieee_quantizer, ("width", "exponent_width", "exponent_bias"), config, False)
+
+
+class LinearInteger(_LinearBase):
+    def _setup_quantizers(self, config: dict):
+        def one(prefix):
+            return partial(integer_quantizer, width=config[f"{prefix}_width"], frac_width=config[f"{prefix}_frac_width"],
+                           is_signed=True)
+
+        self.x_quantizer = one("data_in")
+        self.w_quantizer = one("weight")
+        self.b_quantizer = one("bias") if self.bias is not None else None

@@ -325,6 +325,46 @@ def main():
         json.dump(out, f, indent=0, sort_keys=True)
     print("configs done")
 
+    # ---- tiny-model forward goldens (reference modeling code, CPU fp32) -----------------------
+    def sd_arrays(model):
+        return {"sd::" + k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+
+    for tag, tomlname in [("opt_tiny_bfp6", "bfp_6bit.toml"), ("opt_tiny_bfp4", "bfp_4bit.toml"),
+                          ("opt_tiny_mixed", None)]:
+        torch.manual_seed(0)
+        qc = deepcopy(cfgs[tomlname]) if tomlname else deepcopy(mixed)
+        cfg = models.opt_cfg.OPTQuantizedConfig(hidden_size=64, num_hidden_layers=2, ffn_dim=128, num_attention_heads=4,
+                                                vocab_size=512, max_position_embeddings=64, quant_config=qc)
+        model = models.opt.OPTQuantizedForCausalLM(cfg).eval()
+        arrs = sd_arrays(model)                      # weights BEFORE the in-place PTQ overwrite
+        ids = torch.from_numpy(rs(5).randint(0, 512, size=(2, 64)).astype(np.int64))
+        with torch.no_grad():
+            o = model(input_ids=ids, labels=ids)
+        arrs["input_ids"] = ids.numpy()
+        arrs["logits"] = o.logits.numpy().copy()
+        arrs["loss"] = np.array(float(o.loss))
+        np.savez_compressed(os.path.join(GOLD, tag + ".npz"), **arrs)
+        print(tag, "loss", float(o.loss))
+
+    # Llama: block_minifloat needs a scaled init (N(0,0.02) weights all quantise to 0)
+    for tag, tomlname, init in [("llama_tiny_bmf8", "block_minifloat.toml", 1.5), ("llama_tiny_bl8", "block_log.toml", 0.02),
+                                ("llama_tiny_bfp6", "bfp_6bit.toml", 0.02)]:
+        torch.manual_seed(0)
+        cfg = models.llama_cfg.LlamaQuantizedConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                                                    num_attention_heads=4, vocab_size=512, max_position_embeddings=64,
+                                                    initializer_range=init, quant_config=deepcopy(cfgs[tomlname]))
+        model = models.llama.LlamaQuantizedForCausalLM(cfg).eval()
+        arrs = {k: v for k, v in sd_arrays(model).items() if "rotary_emb" not in k}
+        ids = torch.from_numpy(rs(6).randint(0, 512, size=(2, 64)).astype(np.int64))
+        with torch.no_grad():
+            o = model(input_ids=ids, labels=ids)
+        arrs["input_ids"] = ids.numpy()
+        arrs["logits"] = o.logits.numpy().copy()
+        arrs["loss"] = np.array(float(o.loss))
+        arrs["init"] = np.array(init)
+        np.savez_compressed(os.path.join(GOLD, tag + ".npz"), **arrs)
+        print(tag, "loss", float(o.loss))
+
 
 if __name__ == "__main__":
     main()

@@ -1,0 +1,76 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden_quantizers():
+    arrays = np.load(os.path.join(GOLD, "quantizers.npz"))
+    with open(os.path.join(GOLD, "manifest.json")) as f:
+        manifest = json.load(f)
+    return arrays, manifest["cases"]
+
+
+@pytest.fixture(scope="session")
+def golden_consumers():
+    arrays = np.load(os.path.join(GOLD, "consumers.npz"))
+    with open(os.path.join(GOLD, "consumers.json")) as f:
+        return arrays, json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_configs():
+    with open(os.path.join(GOLD, "configs.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_hashed():
+    with open(os.path.join(GOLD, "hashed.json")) as f:
+        return json.load(f)
+
+
+def f32(bits: np.ndarray) -> torch.Tensor:
+    """int32 bit patterns -> fp32 tensor (keeps NaN payloads and -0.0)."""
+    return torch.from_numpy(np.ascontiguousarray(bits)).view(torch.float32)
+
+
+def case_input(arrays, case) -> torch.Tensor:
+    x = f32(arrays[case["x"]])
+    if case.get("transpose"):
+        x = x.transpose(*case["transpose"])
+    return x
+
+
+def case_kwargs(case):
+    return {k: (None if v == "NA->None" else v) for k, v in case["kwargs"].items()}
+
+
+def bits_equal(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return a.shape == b.shape and torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+
+
+def n_bits_diff(a: torch.Tensor, b: torch.Tensor) -> int:
+    return int((a.contiguous().view(torch.int32) != b.contiguous().view(torch.int32)).sum())

@@ -1,0 +1,161 @@
+"""GPU parity of the quantizer consumers: tcgen05 GEMM, quantized Linear modules, quantized matmul/bmm.
+
+Tolerance (stated): operands are bit-identical quantised values; products of two <=8-bit-significand values are
+exact in fp32, so the only difference to the reference's fp32 GEMM is accumulation order.  For a length-K
+dot product with fp32 accumulation  |err| <= gamma * sum_k |a_k b_k|,  gamma ~ sqrt(K) * 2^-24 typically and
+K * 2^-24 worst case.  We assert  |out - exact| <= 4 * sqrt(K) * 2^-24 * (|A| @ |B|) + 1e-30  against an fp64
+evaluation of the same quantised operands, and the same bound (x2, both sides round) against the golden
+fp32 outputs of the reference."""
+import copy
+
+import pytest
+import torch
+
+from conftest import bits_equal, f32
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS = 2.0 ** -24
+
+
+def assert_gemm_close(out, exact64, absprod64, K, factor=4.0):
+    bound = factor * (K ** 0.5) * EPS * absprod64 + 1e-30
+    err = (out.double() - exact64).abs()
+    worst = float((err / bound).max())
+    assert worst <= 1.0, f"GEMM error {worst:.2f}x the stated fp32-accumulation-order bound"
+
+
+def test_gemm_kernel_vs_fp64():
+    import ctypes
+
+    from llm_mixed_q_b200 import _lib as L
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (b, M, N, K) in [(1, 128, 256, 64), (1, 4096, 4096, 4096), (1, 1000, 520, 328), (3, 200, 136, 64), (4, 512, 64, 512),
+                         (2, 300, 100, 1000), (1, 1, 8, 8), (1, 129, 257, 72), (5, 2048, 2048, 64), (2, 2048, 64, 2048)]:
+        A = torch.randn(b, M, K, device="cuda", generator=g).to(torch.bfloat16)
+        B = torch.randn(b, N, K, device="cuda", generator=g).to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda", generator=g)
+        C = torch.full((b, M, N), float("nan"), device="cuda")
+        rc = lib.bq_gemm_bf16_tn(A.data_ptr(), B.data_ptr(), C.data_ptr(), bias.data_ptr(), b, M, N, K, K, K, N, M * K, N * K,
+                                 M * N, L.stream_ptr())
+        L.check(rc, "gemm")
+        exact = A.double() @ B.double().transpose(1, 2) + bias.double()
+        absprod = A.double().abs() @ B.double().abs().transpose(1, 2) + bias.double().abs()
+        assert_gemm_close(C, exact, absprod, K)
+
+
+def _module_for(cfg, in_f, out_f):
+    from llm_mixed_q_b200.models.quantize import get_quantized_cls
+
+    name = cfg["name"] if not cfg.get("bypass") else "block_fp"
+    return get_quantized_cls("linear", {"name": name})(in_f, out_f, bias=True, config=copy.deepcopy(cfg)).cuda()
+
+
+def test_linear_modules_vs_reference_goldens(golden_consumers):
+    arrays, cases = golden_consumers
+    for c in [c for c in cases if c["op"] == "linear"]:
+        k = c["key"]
+        x, w, b = f32(arrays[k + "_x"]).cuda(), f32(arrays[k + "_w"]), f32(arrays[k + "_b"])
+        lin = _module_for(c["config"], w.shape[1], w.shape[0])
+        with torch.no_grad():
+            lin.weight.copy_(w)
+            lin.bias.copy_(b)
+        y = lin(x)
+        ref = f32(arrays[k + "_y"]).reshape(y.shape)
+        # the PTQ in-place overwrite leaves bit-identical parameters (reference linear.py:66-70)
+        assert bits_equal(lin.weight.detach().cpu(), f32(arrays[k + "_wq"])), (k, c["config_name"])
+        assert bits_equal(lin.bias.detach().cpu(), f32(arrays[k + "_bq"])), (k, c["config_name"])
+        if not c["config"].get("bypass"):
+            assert lin.weight_requires_quantisation is False
+        xq = O.operand_quantizer(c["config"], "data_in", True)(x.cpu()).double() if not c["config"].get("bypass") else x.cpu().double()
+        wq, bq = lin.weight.detach().cpu().double(), lin.bias.detach().cpu().double()
+        absprod = xq.abs() @ wq.abs().T + bq.abs()
+        assert_gemm_close(y.cpu(), ref.double(), absprod, w.shape[1], factor=8.0)
+        y2 = lin(x)                                    # steady state: same result again
+        assert torch.equal(y, y2)
+
+
+def test_matmul_functions_vs_reference_goldens(golden_consumers):
+    from llm_mixed_q_b200.models.quantize import get_quantized_func
+
+    arrays, cases = golden_consumers
+    for c in [c for c in cases if c["op"] in ("bmm", "matmul")]:
+        k = c["key"]
+        x, yb = f32(arrays[k + "_x"]).cuda(), f32(arrays[k + "_y"]).cuda()
+        yv = yb.transpose(-1, -2) if c["y_transposed"] else yb
+        fn = get_quantized_func(c["op"], c["config"])
+        out = fn(x, yv, config=copy.deepcopy(c["config"]))
+        ref = f32(arrays[k + "_o"]).reshape(out.shape)
+        K = x.shape[-1]
+        scale = float(ref.abs().max())
+        assert float((out.cpu() - ref).abs().max()) <= 8 * (K ** 0.5) * EPS * max(scale, 1.0) * 16, (k, c["config_name"])
+
+
+CFG_BFP6 = {"name": "block_fp", "bypass": False, "is_ptq": True}
+for _p in ("data_in", "weight", "bias"):
+    CFG_BFP6.update({f"{_p}_width": 6, f"{_p}_exponent_width": 8, f"{_p}_exponent_bias": 127,
+                     f"{_p}_block_size": [16] if _p == "bias" else [1, 16]})
+
+
+@pytest.mark.parametrize("width", [6, 4])
+def test_linear_config2_vs_device_oracle(width):
+    """BASELINE config 2: M=K=N=4096, block_fp W6A6 / W4A4."""
+    from llm_mixed_q_b200.models.quantize import get_quantized_cls
+
+    cfg = copy.deepcopy(CFG_BFP6)
+    for p in ("data_in", "weight", "bias"):
+        cfg[f"{p}_width"] = width
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(4096, 4096, device="cuda", generator=g)
+    w = torch.randn(4096, 4096, device="cuda", generator=g) * 0.02
+    b = torch.randn(4096, device="cuda", generator=g) * 0.02
+    lin = get_quantized_cls("linear", cfg)(4096, 4096, bias=True, config=cfg).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(w)
+        lin.bias.copy_(b)
+    y = lin(x)
+    yo, wq, bq = O.linear_forward(x, w, b, cfg)          # oracle on the same device
+    assert bits_equal(lin.weight.detach(), wq) and bits_equal(lin.bias.detach(), bq)
+    xq = O.operand_quantizer(cfg, "data_in", True)(x).double()
+    exact = xq @ wq.double().T + bq.double()
+    absprod = xq.abs() @ wq.double().abs().T + bq.double().abs()
+    assert_gemm_close(y, exact, absprod, 4096)
+    assert_gemm_close(yo, exact, absprod, 4096)           # the reference's own fp32 GEMM obeys the same bound
+
+
+def test_attention_bmms_vs_device_oracle():
+    """bmm_0 (q @ k^T view, y blocked along key positions) and bmm_1 (P @ v) at OPT-1.3B head geometry."""
+    from llm_mixed_q_b200.models.quantize import get_quantized_func
+
+    g = torch.Generator(device="cuda").manual_seed(2)
+    BH, S, d = 16, 2048, 64
+    q = torch.randn(BH, S, d, device="cuda", generator=g)
+    k = torch.randn(BH, S, d, device="cuda", generator=g)
+    v = torch.randn(BH, S, d, device="cuda", generator=g)
+    fn = get_quantized_func("bmm", CFG_BFP6)
+    s = fn(q, k.transpose(1, 2), config=CFG_BFP6)
+    xq = O.operand_quantizer(CFG_BFP6, "data_in", True)(q).double()
+    yq = O.operand_quantizer(CFG_BFP6, "weight", True)(k.transpose(1, 2)).double()
+    assert_gemm_close(s, xq @ yq, xq.abs() @ yq.abs(), d)
+    mask = torch.triu(torch.ones(S, S, dtype=torch.bool, device="cuda"), diagonal=1)
+    p = torch.softmax(s.masked_fill(mask, torch.finfo(torch.float32).min), dim=-1)
+    o = fn(p, v, config=CFG_BFP6)
+    pq = O.operand_quantizer(CFG_BFP6, "data_in", True)(p).double()
+    vq = O.operand_quantizer(CFG_BFP6, "weight", True)(v).double()
+    assert_gemm_close(o, pq @ vq, pq.abs() @ vq.abs(), S)
+
+
+def test_block_log_matmul_leaves_y_unquantised():
+    from llm_mixed_q_b200.models.quantize import get_quantized_func
+
+    cfg = {"name": "block_log", "bypass": False, "data_in_width": 8, "data_in_exponent_bias_width": 8,
+           "data_in_block_size": [1, 16], "weight_width": 8, "weight_exponent_bias_width": 8, "weight_block_size": [1, 16]}
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(3, 64, 48, device="cuda", generator=g)
+    y = torch.randn(3, 48, 32, device="cuda", generator=g)
+    out = get_quantized_func("bmm", cfg)(x, y, config=cfg)
+    ref = torch.bmm(O.block_log_quantize(x, 8, 8, [1, 16], True), y)     # reference matmul.py:293-296
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    assert get_quantized_func("bmm", {"name": "log"}) is get_quantized_func("bmm", cfg)
