@@ -68,9 +68,14 @@ def case_kwargs(case):
     return {k: (None if v == "NA->None" else v) for k, v in case["kwargs"].items()}
 
 
-def bits_equal(a: torch.Tensor, b: torch.Tensor) -> bool:
-    return a.shape == b.shape and torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
-
-
 def n_bits_diff(a: torch.Tensor, b: torch.Tensor) -> int:
-    return int((a.contiguous().view(torch.int32) != b.contiguous().view(torch.int32)).sum())
+    """number of elements whose BIT PATTERNS differ (so -0.0 != +0.0).  NaN payloads are not compared: x86 produces
+    the negative "real indefinite" quiet NaN (0xffc00000) for inf*0, the GPU its canonical 0x7fffffff."""
+    a, b = a.contiguous(), b.contiguous()
+    diff = a.view(torch.int32) != b.view(torch.int32)
+    both_nan = torch.isnan(a) & torch.isnan(b)
+    return int((diff & ~both_nan).sum())
+
+
+def bits_equal(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return a.shape == b.shape and n_bits_diff(a, b) == 0

@@ -3,9 +3,12 @@
 Tolerance (stated): operands are bit-identical quantised values; products of two <=8-bit-significand values are
 exact in fp32, so the only difference to the reference's fp32 GEMM is accumulation order.  For a length-K
 dot product with fp32 accumulation  |err| <= gamma * sum_k |a_k b_k|,  gamma ~ sqrt(K) * 2^-24 typically and
-K * 2^-24 worst case.  We assert  |out - exact| <= 4 * sqrt(K) * 2^-24 * (|A| @ |B|) + 1e-30  against an fp64
-evaluation of the same quantised operands, and the same bound (x2, both sides round) against the golden
-fp32 outputs of the reference."""
+K * 2^-24 worst case.  We assert  |out - exact| <= 4 * sqrt(K) * 2^-24 * (|A| @ |B|) + pass_through_term  against an
+fp64 evaluation of the same quantised operands, and the same bound (x2, both sides round) against the golden
+fp32 outputs of the reference.
+pass_through_term: elements with |x| <= 1e-8 are returned UNQUANTISED by the reference (block_fp.py:93-94); they are
+arbitrary fp32 values and the bf16 operand carrier rounds them (relative 2^-9): each contributes at most
+2^-9 * 1e-8 * |b| — an absolute 2e-11 per term, stated here and in DESIGN.md."""
 import copy
 
 import pytest
@@ -18,8 +21,10 @@ pytestmark = pytest.mark.gpu
 EPS = 2.0 ** -24
 
 
-def assert_gemm_close(out, exact64, absprod64, K, factor=4.0):
+def assert_gemm_close(out, exact64, absprod64, K, factor=4.0, b_abs_colsum=None):
     bound = factor * (K ** 0.5) * EPS * absprod64 + 1e-30
+    if b_abs_colsum is not None:
+        bound = bound + (2.0 ** -9) * 1e-8 * b_abs_colsum
     err = (out.double() - exact64).abs()
     worst = float((err / bound).max())
     assert worst <= 1.0, f"GEMM error {worst:.2f}x the stated fp32-accumulation-order bound"
@@ -144,7 +149,7 @@ def test_attention_bmms_vs_device_oracle():
     o = fn(p, v, config=CFG_BFP6)
     pq = O.operand_quantizer(CFG_BFP6, "data_in", True)(p).double()
     vq = O.operand_quantizer(CFG_BFP6, "weight", True)(v).double()
-    assert_gemm_close(o, pq @ vq, pq.abs() @ vq.abs(), S)
+    assert_gemm_close(o, pq @ vq, pq.abs() @ vq.abs(), S, b_abs_colsum=vq.abs().sum(dim=1, keepdim=True))
 
 
 def test_block_log_matmul_leaves_y_unquantised():
