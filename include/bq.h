@@ -111,6 +111,11 @@ BQ_API size_t bq_quantize_workspace_bytes(const bq_format* fmt, const bq_tensor3
 BQ_API int bq_quantize(const bq_format* fmt, const bq_tensor3* x_desc, const float* x, void* y, int32_t y_dtype,
                 int32_t transpose_out, void* ws, size_t ws_bytes, void* stream);
 
+/* Exhaustive device self-test: compares the exponent-field shortcuts the quantizers use for
+ * ceil/floor/rint(log2f(x)) with libdevice's log2f on every positive finite fp32 bit pattern.
+ * Writes three mismatch counters (ceil, floor, rint) to mismatches_dev3 (device memory, 3 x uint64). */
+BQ_API int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense bf16 GEMM on the 5th-gen tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> fp32).
  *   C[b][m][n] = sum_k A[b][m][k] * B[b][n][k]  (+ bias[n])          ("TN": both operands K-major)

@@ -31,6 +31,8 @@ struct FmtParams {
   float qmax;        // 2^mantissa_bits - 1
   float bias_hi;     // block_minifloat / block_log: 2^exponent_bias_width - 1 (upper clamp of the shared bias)
   float eb_top;      // block_minifloat: 2^exponent_width - 1 ; block_log: 2^(width-1) - 1
+  int mbits;         // mantissa bits (log2 of shift)
+  int fast_fmt;      // host: the format's static ranges allow the fast path (see fast_state)
 };
 
 __device__ __forceinline__ float clamp_t(float x, float lo, float hi) {   // torch.clamp: NaN in -> NaN out
@@ -142,6 +144,119 @@ __device__ __forceinline__ float quant_elem(float x, const BlockState& s, const 
     out = blend_t(v <= 1e-8f, y, x);
   } else if (KIND == kInteger) {                           // integer.py:52
     out = __fmul_rn(clamp_t(rintf(__fmul_rn(x, p.shift)), p.emin, p.emax), p.inv_shift);
+  } else {
+    out = x;
+  }
+  if (p.fold_zero) out = __fadd_rn(out, 0.f);
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path.  Same results bit for bit, fewer instructions:
+//   * ceil/floor/rint(log2f(x)) come from the exponent field unless the mantissa sits in a narrow zone
+//     around the rounding cliff (2^-11 of all values), where the libdevice log2f is evaluated as before.
+//     tests/test_gpu_numerics.py checks the three helpers against libdevice on EVERY positive fp32 pattern.
+//   * powers of two are built from integer exponents; x / 2^e is a multiplication by 2^-e; the
+//     bool*float blends collapse to selects.  All of this is valid only while every intermediate is a
+//     finite normal number — FastState::ok says so per block, otherwise the literal path above runs.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kZone = 0x1000u;          // +-2^12 ulps around a cliff
+constexpr uint32_t kSqrt2Mant = 0x3504f3u;   // mantissa field of sqrt(2)
+
+__device__ __forceinline__ int ceil_log2_i(float x) {        // == (int)ceilf(log2f(x)) for x > 0 finite
+  const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
+  if (ex - 1u >= 254u || ((f + kZone) & 0x7fffffu) < 2 * kZone) return (int)ceilf(log2f(x));
+  return (int)ex - 126;
+}
+__device__ __forceinline__ int floor_log2_i(float x) {       // == (int)floorf(log2f(x))
+  const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
+  if (ex - 1u >= 254u || ((f + kZone) & 0x7fffffu) < 2 * kZone) return (int)floorf(log2f(x));
+  return (int)ex - 127;
+}
+__device__ __forceinline__ int rint_log2_i(float x) {        // == (int)rintf(log2f(x))
+  const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
+  if (ex - 1u >= 254u || (f - kSqrt2Mant + kZone) < 2 * kZone) return (int)rintf(log2f(x));
+  return (int)ex - 127 + (f > kSqrt2Mant ? 1 : 0);
+}
+__device__ __forceinline__ float pow2_i(int e) { return __int_as_float((e + 127) << 23); }   // e in [-126, 127]
+
+struct FastState {
+  bool ok;
+  float f0, f1;   // block_fp: scale 2^(m-E), step 2^(E-m)            block_log: delta, 2^emin
+  int i0, i1;     // block_minifloat / block_log: emin, emax (integers)
+};
+
+// host-known part of the validity check lives in FmtParams::fast_fmt (mantissa width / scalar exponent range)
+template <int KIND>
+__device__ __forceinline__ FastState fast_state(uint32_t mbits, const FmtParams& p) {
+  FastState s;
+  s.ok = false;
+  s.f0 = s.f1 = 0.f;
+  s.i0 = s.i1 = 0;
+  if (!p.fast_fmt || mbits >= 0x7f800000u) return s;           // inf / NaN block max -> literal path
+  const float mx = __uint_as_float(mbits);
+  if (KIND == kBlockFP) {
+    int E = ceil_log2_i(mx);
+    E = min(max(E, (int)p.emin), (int)p.emax);
+    if (E < -100 || E > 100) return s;
+    s.f0 = pow2_i(p.mbits - E);
+    s.f1 = pow2_i(E - p.mbits);
+    s.ok = true;
+  } else if (KIND == kBlockMinifloat) {
+    int b = floor_log2_i(mx);
+    b = min(max(b, 0), (int)p.bias_hi);
+    s.i0 = -b;
+    s.i1 = (int)p.eb_top - b;
+    s.ok = (s.i0 >= -126 && s.i1 <= 126 && s.i1 >= s.i0);
+  } else if (KIND == kBlockLog) {
+    int b = (int)p.eb_top - ceil_log2_i(mx);
+    b = min(max(b, 0), (int)p.bias_hi);
+    s.i0 = -b;
+    s.i1 = (int)p.eb_top - b;
+    s.ok = (s.i0 >= -126 && s.i1 <= 127 && s.i1 >= s.i0);
+    s.f1 = pow2_i(s.i0 < -126 ? -126 : s.i0);
+    s.f0 = __fmul_rn(s.f1, 0.1f);
+  } else {
+    s.ok = true;                                                 // element-wise kinds: format-level check only
+  }
+  return s;
+}
+
+template <int KIND>
+__device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, const FmtParams& p) {
+  const float ax = fabsf(x);
+  float out;
+  if (KIND == kBlockFP) {
+    const float v = __fadd_rn(ax, 1e-9f);
+    const float q = fminf(rintf(__fmul_rn(v, s.f0)), p.qmax);
+    float y = copysignf(__fmul_rn(q, s.f1), x);
+    if (p.fold_zero) y = __fadd_rn(y, 0.f);
+    return (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
+  } else if (KIND == kBlockMinifloat || KIND == kMinifloatIEEE) {
+    const int emin = (KIND == kBlockMinifloat) ? s.i0 : (int)p.emin;
+    const int emax = (KIND == kBlockMinifloat) ? s.i1 : (int)p.emax;
+    int e = floor_log2_i(__fadd_rn(ax, 1e-9f));
+    e = min(max(e, emin), emax);
+    const float ts = __fmul_rn(__fmul_rn(ax, pow2_i(-e)), p.shift);
+    const bool normal = (e != emin);
+    // one rounding unit for both branches: normal -> rint(ts - 2^M), subnormal -> rint(ts / 2), clamped to [0, 2^M - 1]
+    const float r = normal ? __fsub_rn(ts, p.shift) : __fmul_rn(ts, 0.5f);
+    const float frac = __fmul_rn(fminf(fmaxf(rintf(r), 0.f), p.qmax), p.inv_shift);
+    const float mant = normal ? __fadd_rn(1.0f, frac) : __fmul_rn(frac, 2.f);
+    const float y = copysignf(__fmul_rn(pow2_i(e), mant), x);
+    out = (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
+  } else if (KIND == kBlockLog) {
+    const float w = __fadd_rn(x, s.f0);
+    const float v = __fadd_rn(ax, s.f0);
+    // v < 2^emin (zeros: v = delta, possibly denormal) clamps to emin whatever log2f returns
+    int e = (v < s.f1) ? s.i0 : min(max(rint_log2_i(v), s.i0), s.i1);
+    out = (w == 0.f) ? 0.f : copysignf(pow2_i(e), w);
+  } else if (KIND == kMinifloatDenorm) {
+    int e = ceil_log2_i(__fadd_rn(ax, 1e-9f));
+    e = min(max(e, (int)p.emin), (int)p.emax);
+    const float q = fminf(rintf(__fmul_rn(__fmul_rn(ax, pow2_i(-e)), p.shift)), p.qmax);
+    const float y = copysignf(__fmul_rn(pow2_i(e), __fmul_rn(q, p.inv_shift)), x);
+    out = (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
   } else {
     out = x;
   }

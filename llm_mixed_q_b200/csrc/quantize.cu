@@ -58,10 +58,11 @@ template <> __device__ __forceinline__ void store1<float>(float* y, float o) { *
 template <> __device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16* y, float o) { *y = __float2bfloat16_rn(o); }
 
 // Layout of a "rows" launch.  Index space: every row is padded to slots_per_row 4-float slots
-// (a multiple of lanes-per-block) so that a block never straddles a warp.
+// (a multiple of lanes-per-block) so that a block never straddles a warp.  total_slots < 2^32.
 struct RowsGeom {
   uint64_t total_slots;     // n_rows * slots_per_row
   uint32_t slots_per_row;
+  uint32_t div_mul, div_shr;  // slot / slots_per_row: t = umulhi(slot, mul); (t + ((slot - t) >> 1)) >> (shr - 1)
   int32_t C;                // valid columns per row (multiple of 4)
   int64_t ldx, ldy;         // row strides in elements
   int32_t lpb;              // lanes per block = b1 / 4 (1 for the element-wise kinds)
@@ -71,64 +72,87 @@ struct RowsGeom {
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 
-__device__ __forceinline__ bool slot_addr(const RowsGeom& g, uint64_t slot, int64_t& xoff, int64_t& yoff) {
-  if (slot >= g.total_slots) return false;
-  if (g.flat) {
-    xoff = yoff = (int64_t)(slot * 4);
+template <bool FLAT>
+__device__ __forceinline__ bool slot_addr(const RowsGeom& g, uint32_t slot, uint32_t total, int64_t& xoff, int64_t& yoff) {
+  if (slot >= total) return false;
+  if (FLAT) {
+    xoff = yoff = (int64_t)slot * 4;
     return true;
   }
-  uint64_t row;
-  uint32_t srow;
-  if (g.total_slots <= 0xffffffffull) {
-    uint32_t s32 = (uint32_t)slot;
-    uint32_t r32 = s32 / g.slots_per_row;
-    srow = s32 - r32 * g.slots_per_row;
-    row = r32;
-  } else {
-    row = slot / g.slots_per_row;
-    srow = (uint32_t)(slot - row * g.slots_per_row);
-  }
-  int col = (int)(srow * 4);
+  const uint32_t t = __umulhi(slot, g.div_mul);
+  const uint32_t row = (t + ((slot - t) >> 1)) >> (g.div_shr - 1);
+  const int col = (int)((slot - row * g.slots_per_row) * 4);
   if (col >= g.C) return false;
   xoff = (int64_t)row * g.ldx + col;
   yoff = (int64_t)row * g.ldy + col;
   return true;
 }
 
+// Quantise the 4 elements a thread owns, given the block max (as bits).  The literal path is kept out of line:
+// it only runs for blocks whose exponents leave the normal range or that contain inf/NaN.
+template <int KIND>
+__device__ __noinline__ float4 quant4_literal(float4 v, uint32_t mbits, const FmtParams& p) {
+  BlockState st;
+  st.a = st.b = st.c = 0.f;
+  if (IsBlocked<KIND>::value) st = block_state<KIND>(__uint_as_float(mbits), p);
+  return make_float4(quant_elem<KIND>(v.x, st, p), quant_elem<KIND>(v.y, st, p), quant_elem<KIND>(v.z, st, p),
+                     quant_elem<KIND>(v.w, st, p));
+}
+template <int KIND>
+__device__ __forceinline__ float4 quant4(float4 v, uint32_t mbits, const FmtParams& p) {
+  if (KIND == kInteger || KIND == kNone) {
+    BlockState st;
+    st.a = st.b = st.c = 0.f;
+    return make_float4(quant_elem<KIND>(v.x, st, p), quant_elem<KIND>(v.y, st, p), quant_elem<KIND>(v.z, st, p),
+                       quant_elem<KIND>(v.w, st, p));
+  }
+  const FastState fs = fast_state<KIND>(mbits, p);
+  bool ok = fs.ok;
+  if (!IsBlocked<KIND>::value) {
+    // element-wise kinds: every element must be finite for the fast path
+    const uint32_t worst = max(max(absbits(v.x), absbits(v.y)), max(absbits(v.z), absbits(v.w)));
+    ok = ok && worst < 0x7f800000u;
+  }
+  if (!ok) return quant4_literal<KIND>(v, mbits, p);
+  return make_float4(quant_elem_fast<KIND>(v.x, fs, p), quant_elem_fast<KIND>(v.y, fs, p), quant_elem_fast<KIND>(v.z, fs, p),
+                     quant_elem_fast<KIND>(v.w, fs, p));
+}
+
 // gstate[0]: min over non-zero block maxima (uint bits, init 0xffffffff); gstate[1]: 0xffffffff until a zero block is seen
-template <int KIND, typename OutT>
+template <int KIND, typename OutT, bool FLAT>
 __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const float* __restrict__ x, OutT* __restrict__ y, RowsGeom g,
                                                                FmtParams p, uint32_t* __restrict__ gstate,
                                                                uint32_t* __restrict__ zmask) {
   constexpr bool kBlocked = IsBlocked<KIND>::value;
-  const uint64_t tile = (uint64_t)kThreads * kUnroll;
+  constexpr uint32_t tile = kThreads * kUnroll;
+  const uint32_t total = (uint32_t)g.total_slots;
   uint32_t run_min = 0xffffffffu;
   bool saw_zero = false;
-  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < g.total_slots; base += (uint64_t)gridDim.x * tile) {
+  for (uint64_t base64 = (uint64_t)blockIdx.x * tile; base64 < g.total_slots; base64 += (uint64_t)gridDim.x * tile) {
+    const uint32_t base = (uint32_t)base64;
     float4 v[kUnroll];
     int64_t yoff[kUnroll];
     bool act[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      uint64_t slot = base + (uint64_t)u * kThreads + threadIdx.x;
+      const uint32_t slot = base + u * kThreads + threadIdx.x;
       int64_t xo = 0;
       yoff[u] = 0;
-      act[u] = slot_addr(g, slot, xo, yoff[u]);
+      act[u] = (base64 + u * kThreads + threadIdx.x < g.total_slots) && slot_addr<FLAT>(g, slot, total, xo, yoff[u]);
       v[u] = act[u] ? ldg_stream4(x + xo) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      BlockState st;
-      st.a = st.b = st.c = 0.f;
       bool zero_block = false;
+      uint32_t m = 0x3f800000u;
       if (kBlocked) {
-        uint32_t m = max(max(absbits(v[u].x), absbits(v[u].y)), max(absbits(v[u].z), absbits(v[u].w)));
+        m = max(max(absbits(v[u].x), absbits(v[u].y)), max(absbits(v[u].z), absbits(v[u].w)));
         for (int o = 1; o < g.lpb; o <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
         zero_block = (m == 0);
         if (KIND == kBlockLog) {
           // uniform branch per warp-slot: record which lanes sit in all-zero blocks
           uint32_t zb = __ballot_sync(0xffffffffu, zero_block);
-          uint64_t slot0 = base + (uint64_t)u * kThreads + (threadIdx.x & ~31u);
+          const uint64_t slot0 = base64 + (uint64_t)u * kThreads + (threadIdx.x & ~31u);
           if ((threadIdx.x & 31) == 0 && slot0 < g.total_slots) zmask[slot0 >> 5] = zb;
           if (act[u]) {
             if (zero_block) saw_zero = true; else run_min = min(run_min, m);
@@ -136,15 +160,10 @@ __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const float* __res
         }
         // block_fp / block_minifloat: an all-zero block only holds pass-through elements, whose result
         // (+0) does not depend on the substituted max (block_fp.py:54-58) — use 1.
-        st = block_state<KIND>(zero_block ? 1.0f : __uint_as_float(m), p);
+        if (zero_block) m = 0x3f800000u;
       }
       if (act[u] && !(KIND == kBlockLog && zero_block)) {
-        float4 o;
-        o.x = quant_elem<KIND>(v[u].x, st, p);
-        o.y = quant_elem<KIND>(v[u].y, st, p);
-        o.z = quant_elem<KIND>(v[u].z, st, p);
-        o.w = quant_elem<KIND>(v[u].w, st, p);
-        store4<OutT>(y + yoff[u], o);
+        store4<OutT>(y + yoff[u], quant4<KIND>(v[u], m, p));
       }
     }
   }
@@ -166,11 +185,12 @@ __global__ void __launch_bounds__(kThreads) blocklog_fixup_kernel(OutT* __restri
   float fill = quant_elem<kBlockLog>(0.f, st, p);
   float4 o = make_float4(fill, fill, fill, fill);
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  const uint32_t total = (uint32_t)g.total_slots;
   for (uint64_t slot = (uint64_t)blockIdx.x * kThreads + threadIdx.x; slot < g.total_slots; slot += stride) {
     uint32_t zb = zmask[slot >> 5];
     if (!((zb >> (threadIdx.x & 31)) & 1u)) continue;
     int64_t xo, yo;
-    if (slot_addr(g, slot, xo, yo)) store4<OutT>(y + yo, o);
+    if (slot_addr<false>(g, (uint32_t)slot, total, xo, yo)) store4<OutT>(y + yo, o);
   }
 }
 
@@ -342,6 +362,17 @@ int make_params(const bq_format* f, FmtParams* p) {
     p->shift = p2(mb);
     p->inv_shift = p2(-mb);
     p->qmax = (float)(((int64_t)1 << mb) - 1);
+    p->mbits = mb;
+  }
+  // static part of the fast-path validity (per-block part: fast_state()).  Everything must stay a finite
+  // normal number: mantissa <= 22 bits, scalar exponent ranges inside [-100, 100].
+  switch (f->kind) {
+    case kBlockFP: p->fast_fmt = (mb <= 22 && p->emin >= -1e6f && p->emax <= 1e6f); break;
+    case kBlockMinifloat: p->fast_fmt = (mb <= 22 && p->eb_top <= 1e6f && p->bias_hi <= 1e6f); break;
+    case kBlockLog: p->fast_fmt = (p->eb_top <= 1e6f && p->bias_hi <= 1e6f); break;
+    case kMinifloatDenorm:
+    case kMinifloatIEEE: p->fast_fmt = (mb <= 22 && p->emin >= -100.f && p->emax <= 100.f && p->emax >= p->emin); break;
+    default: p->fast_fmt = 0;
   }
   return BQ_OK;
 }
@@ -403,7 +434,22 @@ static int make_plan(const bq_format* f, const bq_tensor3* t, int transpose_out,
     rg.lpb = lpb;
     rg.flat = (padC == t->C && ldx == t->C) ? 1 : 0;
     rg.total_slots = (uint64_t)n_rows * rg.slots_per_row;
-    if (padC / 4 > 0x7fffffffll || t->C > 0x7fffffffll) pl->fast = false;
+    if (padC / 4 > 0x7fffffffll || t->C > 0x7fffffffll || rg.total_slots >= 0xffffffffull) pl->fast = false;
+    // exact 32-bit division by the invariant d = slots_per_row (libdivide-style, 33-bit magic):
+    //   t = umulhi(n, mul);  q = (t + ((n - t) >> 1)) >> (shr - 1)      for every 32-bit n, d >= 2
+    // (powers of two: mul = 0 gives q = n >> log2 d).  Verified against n / d in tools/ (see DESIGN.md).
+    {
+      const uint64_t d = rg.slots_per_row;
+      if (d < 2) {
+        if (!rg.flat) pl->fast = false;
+        rg.div_mul = 0; rg.div_shr = 1;
+      } else {
+        uint32_t L = 0;
+        while ((2ull << L) <= d) ++L;                 // floor(log2 d)
+        if ((d & (d - 1)) == 0) { rg.div_mul = 0; rg.div_shr = L; }
+        else { rg.div_mul = (uint32_t)(((1ull << (33 + L)) / d + 1) - (1ull << 32)); rg.div_shr = L + 1; }
+      }
+    }
   }
   pl->tile = !pl->fast && (f->kind == kBlockFP || f->kind == kBlockMinifloat) && b0 == 1 && b1 <= kTile &&
              (b1 & (b1 - 1)) == 0 && (t->sC == 1 || t->sR == 1) && t->C > 0 && t->R > 0;
@@ -439,8 +485,22 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
     if (KIND == kBlockLog) BQ_CUDA_CHECK(cudaMemsetAsync(gstate, 0xff, 8, st));
     const uint64_t tile = (uint64_t)kThreads * kUnroll;
     uint64_t tiles = (pl.rg.total_slots + tile - 1) / tile;
-    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)sms * 8);   // 8 resident CTAs of 256 threads per SM
-    { LaunchScope ls(kKernQuantRows, st); quant_rows_kernel<KIND, OutT><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux); }
+    // persistent grid: exactly the number of CTAs that are co-resident (one wave), so the grid-stride loop balances
+    static int occ_flat = 0, occ_rows = 0;
+    int& occ = pl.rg.flat ? occ_flat : occ_rows;
+    if (occ == 0) {
+      int o = 0;
+      cudaError_t e = pl.rg.flat
+          ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, quant_rows_kernel<KIND, OutT, true>, kThreads, 0)
+          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, quant_rows_kernel<KIND, OutT, false>, kThreads, 0);
+      occ = (e == cudaSuccess && o > 0) ? o : 4;
+    }
+    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)sms * occ);
+    {
+      LaunchScope ls(kKernQuantRows, st);
+      if (pl.rg.flat) quant_rows_kernel<KIND, OutT, true><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux);
+      else quant_rows_kernel<KIND, OutT, false><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux);
+    }
     if (KIND == kBlockLog) {
       uint64_t blocks = (pl.rg.total_slots + kThreads - 1) / kThreads;
       int g2 = (int)std::min<uint64_t>(blocks, (uint64_t)sms * 8);
@@ -517,9 +577,35 @@ size_t quantize_ws_bytes(const bq_format* fmt, const bq_tensor3* t) {
   return (w + 255) & ~(size_t)255;
 }
 
+// ------------------------------------------------------------------------------------------------
+// exhaustive self-test of the exponent-field shortcuts against libdevice log2f
+// ------------------------------------------------------------------------------------------------
+__global__ void selftest_log2_kernel(unsigned long long* mism) {
+  unsigned long long bad0 = 0, bad1 = 0, bad2 = 0;
+  const uint64_t n = 0x7f800000ull;      // every positive finite pattern incl. denormals (0 excluded below)
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((uint32_t)i);
+    const float l = log2f(x);
+    bad0 += (ceil_log2_i(x) != (int)ceilf(l));
+    bad1 += (floor_log2_i(x) != (int)floorf(l));
+    bad2 += (rint_log2_i(x) != (int)rintf(l));
+  }
+  if (bad0) atomicAdd(&mism[0], bad0);
+  if (bad1) atomicAdd(&mism[1], bad1);
+  if (bad2) atomicAdd(&mism[2], bad2);
+}
+
 }  // namespace bq
 
 extern "C" {
+int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream) {
+  if (!mismatches_dev3) return BQ_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  BQ_CUDA_CHECK(cudaMemsetAsync(mismatches_dev3, 0, 3 * sizeof(unsigned long long), st));
+  bq::selftest_log2_kernel<<<bq::num_sms() * 8, 256, 0, st>>>(mismatches_dev3);
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
 size_t bq_quantize_workspace_bytes(const bq_format* fmt, const bq_tensor3* x) { return bq::quantize_ws_bytes(fmt, x); }
 int bq_quantize(const bq_format* fmt, const bq_tensor3* x_desc, const float* x, void* y, int32_t y_dtype,
                 int32_t transpose_out, void* ws, size_t ws_bytes, void* stream) {
