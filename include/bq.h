@@ -154,6 +154,20 @@ BQ_API int bq_bmm(const bq_format* fx, const bq_format* fy, const float* x, cons
            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused causal quantized attention.  Replaces bmm_0 -> (+causal mask, max finfo.min) -> softmax -> bmm_1 of
+ * models/opt_quantized/modeling_opt.py:246-312 (and matmul_0 / sqrt(d) -> ... -> matmul_1 of
+ * models/llama_quantized/modeling_llama.py:309-344) when the mask is purely causal:
+ *   out[b,s,h,:] = Q_fp( softmax_row( (Qq[b,:,h,:] Kq[b,:,h,:]^T) / score_div , causal ) ) @ Vq[b,:,h,:]
+ * Qq / Kq / Vq: bf16 [B,S,H,d] operands ALREADY quantised by bq_quantize (q: data_in of bmm_0, blocks along d;
+ * k: weight of bmm_0, blocks along S; v: weight of bmm_1, blocks along d), token strides ldq/ldk/ldv (elements).
+ * fp: format of the probabilities (data_in of bmm_1), block [1,16], block_fp or block_minifloat.
+ * out: fp32 [B,S,H,d] with token stride ldo.  d must be 64.  Scores and probabilities never touch HBM.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API int bq_attention_causal(const bq_format* fp, const void* Qq, const void* Kq, const void* Vq, float* out, int64_t B,
+                               int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                               float score_div, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Launch accounting (measurement support for bench.py; no reference counterpart).
  * Every kernel this library launches is counted per kernel id.  With profiling enabled the library
  * additionally brackets each launch with CUDA events on the launching stream; bq_profile_read

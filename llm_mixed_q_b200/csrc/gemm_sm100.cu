@@ -229,6 +229,28 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, int64_t K, int64_t 
   return BQ_OK;
 }
 
+// bf16 [B][S][H][d] (token stride ld_tok elements) as a 4-D map ordered {d, H, S, B} (strides ascending),
+// box {64, 1, box_rows, 1}: one head's [box_rows tokens x 64] tile lands as 128-byte rows, 128B-swizzled.
+int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, int64_t H, int64_t B, int64_t ld_tok,
+                      int box_rows) {
+  int rc = load_encode();
+  if (rc) return rc;
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)ld_tok * 2, (cuuint64_t)S * ld_tok * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
+    set_last_cuda_error(msg, __FILE__, __LINE__);
+    return BQ_ERR_CUDA;
+  }
+  return BQ_OK;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;

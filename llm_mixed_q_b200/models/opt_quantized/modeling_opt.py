@@ -20,6 +20,7 @@ from transformers.modeling_outputs import CausalLMOutputWithPast
 from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
+from ..quantize.quantized_functions.attention import fusable as _attn_fusable, fused_causal_attention
 from .configuration_opt import OPTQuantizedConfig
 
 
@@ -73,8 +74,18 @@ class OPTQauntizedAttention(nn.Module):      # (sic) class name kept from the re
         return tensor.view(bsz, seq_len, self.num_heads, self.head_dim).transpose(1, 2).contiguous()
 
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-                output_attentions: bool = False):
+                output_attentions: bool = False, causal_only: bool = False):
         bsz, tgt_len, _ = hidden_states.size()
+        if (causal_only and not output_attentions and hidden_states.is_cuda and not torch.is_grad_enabled()
+                and not (self.training and self.dropout > 0)
+                and _attn_fusable(self.quant_config["bmm_0"], self.quant_config["bmm_1"], self.head_dim, tgt_len)):
+            # one kernel for bmm_0 -> causal mask -> softmax -> bmm_1; scores / probabilities stay on chip
+            q = self.q_proj(hidden_states) * self.scaling
+            k = self.k_proj(hidden_states)
+            v = self.v_proj(hidden_states)
+            attn_output = fused_causal_attention(q, k, v, self.quant_config["bmm_0"], self.quant_config["bmm_1"],
+                                                 self.num_heads, score_div=1.0)
+            return self.out_proj(attn_output), None
         query_states = self.q_proj(hidden_states) * self.scaling
         key_states = self._shape(self.k_proj(hidden_states), -1, bsz)
         value_states = self._shape(self.v_proj(hidden_states), -1, bsz)
@@ -120,11 +131,12 @@ class OPTQuantizedDecoderLayer(nn.Module):
         self.fc2 = get_quantized_cls("linear", qc["fc2"])(config.ffn_dim, self.embed_dim, bias=config.enable_bias, config=qc["fc2"])
         self.final_layer_norm = nn.LayerNorm(self.embed_dim, elementwise_affine=config.layer_norm_elementwise_affine)
 
-    def forward(self, hidden_states, attention_mask=None, output_attentions=False):
+    def forward(self, hidden_states, attention_mask=None, output_attentions=False, causal_only=False):
         residual = hidden_states
         if self.do_layer_norm_before:
             hidden_states = self.self_attn_layer_norm(hidden_states)
-        hidden_states, attn = self.self_attn(hidden_states, attention_mask=attention_mask, output_attentions=output_attentions)
+        hidden_states, attn = self.self_attn(hidden_states, attention_mask=attention_mask, output_attentions=output_attentions,
+                                             causal_only=causal_only)
         hidden_states = nn.functional.dropout(hidden_states, p=self.dropout, training=self.training)
         hidden_states = residual + hidden_states
         if not self.do_layer_norm_before:
@@ -187,6 +199,7 @@ class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
         else:
             self.final_layer_norm = None
         self.layers = nn.ModuleList([OPTQuantizedDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.fused_attention = True      # set False to force the op-by-op attention path (QUANTIZED_FUNC_MAP bmm functions)
         self.post_init()
 
     def get_input_embeddings(self):
@@ -200,8 +213,10 @@ class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
         if inputs_embeds is None:
             inputs_embeds = self.embed_tokens(input_ids)
         bsz, seq_len = inputs_embeds.shape[:2]
+        causal_only = attention_mask is None or bool(attention_mask.all())
         if attention_mask is None:
             attention_mask = torch.ones(bsz, seq_len, dtype=torch.bool, device=inputs_embeds.device)
+        causal_only = causal_only and self.fused_attention
         causal = _causal_additive_mask(attention_mask, bsz, seq_len, inputs_embeds.dtype, inputs_embeds.device)
         pos_embeds = self.embed_positions(attention_mask, 0)
         if self.project_in is not None:
@@ -212,7 +227,8 @@ class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
         for layer in self.layers:
             if output_hidden_states:
                 all_h += (hidden_states,)
-            hidden_states, attn = layer(hidden_states, attention_mask=causal, output_attentions=output_attentions)
+            hidden_states, attn = layer(hidden_states, attention_mask=causal, output_attentions=output_attentions,
+                                        causal_only=causal_only)
             if output_attentions:
                 all_a += (attn,)
         if self.final_layer_norm is not None:

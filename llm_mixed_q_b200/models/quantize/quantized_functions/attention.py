@@ -1,0 +1,75 @@
+"""
+Fused causal quantized attention (host side of bq_attention_causal, include/bq.h).
+
+No single reference function corresponds to this: it is the composition the reference's attention modules
+spell out op by op — bmm_0 / matmul_0, causal mask + max(finfo.min), softmax, bmm_1 / matmul_1
+(models/opt_quantized/modeling_opt.py:246-312, models/llama_quantized/modeling_llama.py:309-344) — executed
+by one kernel that keeps scores and probabilities on chip.  The quantized model classes call it when the
+mask is purely causal and the layer's two matmul configs are block formats the kernel supports; otherwise
+they fall back to the op-by-op path through QUANTIZED_FUNC_MAP.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .... import _lib as L
+from ..quantized_modules.linear import operand_format, quantize_operand_bf16, significant_bits
+from ..quantizers.utils import make_format, resolve_block_shape
+
+_SUPPORTED_P = ("block_fp", "block_minifloat")
+
+
+def fusable(cfg0: dict, cfg1: dict, head_dim: int, seq_len: int) -> bool:
+    """Can (bmm_0 cfg, bmm_1 cfg) run on the fused kernel?"""
+    try:
+        if cfg0.get("bypass", False) or cfg1.get("bypass", False):
+            return False
+        if head_dim != 64:
+            return False
+        (qk, qkw, qbs), (kk, kkw, kbs) = operand_format(cfg0, "data_in"), operand_format(cfg0, "weight")
+        (pk, pkw, pbs), (vk, vkw, vbs) = operand_format(cfg1, "data_in"), operand_format(cfg1, "weight")
+    except KeyError:
+        return False
+    if pk not in _SUPPORTED_P or kk not in ("block_fp", "block_minifloat") or any(b is None for b in (qbs, kbs, pbs, vbs)):
+        return False
+    if max(significant_bits(qk, qkw), significant_bits(kk, kkw), significant_bits(pk, pkw), significant_bits(vk, vkw)) > 8:
+        return False
+    if qk == "block_log" or vk == "block_log":
+        return False                       # tensor-global zero-block rule: keep the op-by-op path
+    # blocks the reference would infer on the flattened [B*h, rows, cols] operands
+    qb = resolve_block_shape([1, seq_len, head_dim], qbs)
+    kb = resolve_block_shape([1, head_dim, seq_len], kbs)
+    pb = resolve_block_shape([1, seq_len, seq_len], pbs)
+    vb = resolve_block_shape([1, seq_len, head_dim], vbs)
+    ok_last = lambda b, n: b[1] == 1 and b[2] in (4, 8, 16, 32, 64) and n % b[2] == 0
+    return ok_last(qb, head_dim) and ok_last(vb, head_dim) and kb[1] == 1 and kb[2] in (1, 2, 4, 8, 16, 32, 64) and \
+        pb[1] == 1 and pb[2] == 16
+
+
+def fused_causal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cfg0: dict, cfg1: dict, num_heads: int,
+                           score_div: float = 1.0) -> torch.Tensor:
+    """
+    q, k, v: fp32 [B, S, H] projections (q already scaled where the model scales before bmm_0, as OPT does).
+    Returns fp32 [B, S, H] = concat over heads of  Q(softmax(Q(q) Q(k)^T / score_div, causal)) @ Q(v).
+    """
+    lib = L.load()
+    B, S, H = q.shape
+    d = H // num_heads
+    (qk, qkw, qbs), (kk, kkw, kbs) = operand_format(cfg0, "data_in"), operand_format(cfg0, "weight")
+    (pk, pkw, pbs), (vk, vkw, vbs) = operand_format(cfg1, "data_in"), operand_format(cfg1, "weight")
+    # q / v: blocks along d — identical to blocking the [B*S, H] matrix along H because b1 divides d
+    qb = resolve_block_shape([1, S, d], qbs)[2]
+    vb = resolve_block_shape([1, S, d], vbs)[2]
+    Qq = quantize_operand_bf16(q.reshape(B * S, H), qk, qkw, [1, qb], True)
+    Vq = quantize_operand_bf16(v.reshape(B * S, H), vk, vkw, [1, vb], True)
+    # k: the reference quantises k^T, i.e. blocks of consecutive KEY POSITIONS at fixed feature
+    kb = resolve_block_shape([1, d, S], kbs)[2]
+    Kq = quantize_operand_bf16(k.transpose(1, 2), kk, kkw, [1, kb], True, transpose_out=True)     # -> [B, S, H]
+    fp = make_format(pk, b0=1, b1=16, **pkw)
+    out = torch.empty((B, S, H), dtype=torch.float32, device=q.device)
+    rc = lib.bq_attention_causal(ctypes.byref(fp), Qq.data_ptr(), Kq.data_ptr(), Vq.data_ptr(), out.data_ptr(), B, num_heads,
+                                 S, d, H, H, H, H, float(score_div), L.stream_ptr(q.device))
+    L.check(rc, "bq_attention_causal")
+    return out

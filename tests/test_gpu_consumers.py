@@ -164,3 +164,48 @@ def test_block_log_matmul_leaves_y_unquantised():
     ref = torch.bmm(O.block_log_quantize(x, 8, 8, [1, 16], True), y)     # reference matmul.py:293-296
     torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
     assert get_quantized_func("bmm", {"name": "log"}) is get_quantized_func("bmm", cfg)
+
+
+def _oracle_attention(q, k, v, cfg, heads, score_div=1.0):
+    """op-by-op reference composition (modeling_opt.py:237-323) with the oracle's quantizers, on the same device."""
+    B, S, H = q.shape
+    d = H // heads
+
+    def shape(t):
+        return t.view(B, S, heads, d).transpose(1, 2).contiguous().view(B * heads, S, d)
+
+    q3, k3, v3 = shape(q), shape(k), shape(v)
+    s = O.matmul_forward(q3, k3.transpose(1, 2), cfg, style="bmm") / score_div
+    mask = torch.triu(torch.full((S, S), torch.finfo(torch.float32).min, device=q.device), diagonal=1)
+    s = torch.max(s + mask, torch.tensor(torch.finfo(torch.float32).min, device=q.device))
+    p = torch.softmax(s, dim=-1)
+    o = O.matmul_forward(p, v3, cfg, style="bmm")
+    return o.view(B, heads, S, d).transpose(1, 2).reshape(B, S, H), p
+
+
+@pytest.mark.parametrize("S", [128, 200, 1024, 2048])
+def test_fused_causal_attention_vs_op_by_op_oracle(S):
+    """The fused kernel computes the same function as bmm_0 -> mask -> softmax -> bmm_1.  Scores agree to fp32
+    accumulation order; the softmax is evaluated with a different summation order, so a probability can differ by an
+    ulp BEFORE quantisation and, when it sits on a rounding boundary, by one quantisation step after it
+    (SURVEY.md hard part 6).  Stated tolerance: every output within 2 quantisation steps of one probability times
+    max|v| (2 * 2^-5 * 2^-5 relative to the block scale) and mean error 100x smaller."""
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import fusable, fused_causal_attention
+
+    g = torch.Generator(device="cuda").manual_seed(100 + S)
+    B, heads, d = 2, 4, 64
+    H = heads * d
+    q = torch.randn(B, S, H, device="cuda", generator=g) * 0.5
+    k = torch.randn(B, S, H, device="cuda", generator=g)
+    v = torch.randn(B, S, H, device="cuda", generator=g)
+    assert fusable(CFG_BFP6, CFG_BFP6, d, S)
+    out = fused_causal_attention(q, k, v, CFG_BFP6, CFG_BFP6, heads)
+    ref, p = _oracle_attention(q, k, v, CFG_BFP6, heads)
+    err = (out - ref).abs()
+    vmax = float(v.abs().max())
+    assert float(err.max()) <= 2 * (2.0 ** -5) * vmax * 0.25, float(err.max())
+    assert float(err.mean()) <= 2e-4, float(err.mean())
+    # row 0 attends to a single key: p = 1 -> Q(1) = 31/32 exactly, out = 31/32 * Q(v[0])
+    vq = O.operand_quantizer(CFG_BFP6, "weight", True)(v.view(B, S, heads, d).transpose(1, 2).reshape(B * heads, S, d))
+    exp0 = (vq[:, 0, :] * (31.0 / 32.0)).view(B, heads, d).reshape(B, H)
+    assert torch.equal(out[:, 0, :], exp0)
