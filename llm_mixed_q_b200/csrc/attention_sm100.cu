@@ -7,8 +7,8 @@
 //     out    = bmm(Qx(probs), Qy(v))          probs quantised in 1x16 blocks along the key dim
 // with ONE kernel in which scores and probabilities never leave the SM:
 //     S = Q K^T on tcgen05 (bf16 operands = exact block-quantised q / k, fp32 accumulate in TMEM),
-//     row max, row sum of exp(s - max), p = exp(s - max) / sum   (three sweeps over the key tiles; S is
-//     recomputed each sweep — the tensor pipe is far from being the bottleneck),
+//     sweep 1: running row max / row sum of exp(s - max) (online rescaling), sweep 2: p = exp(s - max) * (1/sum)
+//     (S is recomputed in the second sweep — the tensor pipe is far from being the bottleneck),
 //     P quantised in registers (one thread owns a query row, so a 1x16 block is 16 consecutive registers),
 //     written as a swizzled bf16 K-major smem tile and multiplied with V (MN-major operand) into a TMEM
 //     accumulator.
@@ -19,10 +19,15 @@
 // Operands are produced by bq_quantize: Qq, Kq, Vq are bf16 [B, S, h, d] (token stride given), Kq blocked
 // along S (k^T's last dim), Vq along d.  d == 64.  Output: fp32 [B, S, h, d].
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over (b, h, 128-row query tile) work items, heaviest first):
+// Numerics vs the reference's torch softmax: same exp(x - max) with libdevice expf; the row sum is accumulated
+// in a different order and p uses one multiplication by the correctly rounded reciprocal instead of a division
+// (<= 1 ulp each).  An ulp-level difference only matters when a probability sits on a rounding boundary of the
+// block format (one quantisation step there); tests/test_gpu_consumers.py states the tolerance.
+//
+// Warp roles (640 threads, 1 CTA/SM, persistent over (b, h, 128-row query tile) work items, heaviest first):
 //   warp 0      TMA producer            warp 1   MMA issuer           warp 2   TMEM allocator
-//   warps 4-7   softmax/quantise, key columns [0,64) of each 128-key tile   (TMEM lane quarter = warp % 4)
-//   warps 8-11  softmax/quantise, key columns [64,128)
+//   warps 4-19  softmax/quantise: warp w owns TMEM lane quarter (w % 4) = 32 query rows and key columns
+//               [32*cq, 32*cq+32) of every 128-key tile, cq = (w - 4) / 4   (ALU-bound part: 16 warps)
 #include "bq_internal.h"
 #include "bq_numerics.cuh"
 #include "sm100_ptx.cuh"
@@ -35,15 +40,16 @@ namespace bq {
 constexpr int kAtBM = 128;      // query rows per work item (UMMA M)
 constexpr int kAtBN = 128;      // keys per tile
 constexpr int kAtD = 64;        // head dim
-constexpr int kAtThreads = 384;
+constexpr int kAtThreads = 640;
+constexpr int kSoftmaxWarps = 16;
 constexpr int kKStages = 3, kVStages = 2;
 constexpr int kTileBytes = 128 * 64 * 2;           // every smem tile here is 128 rows x 128 bytes = 16 KB
 constexpr int kSmemQ = 0;
 constexpr int kSmemK = kSmemQ + kTileBytes;
 constexpr int kSmemV = kSmemK + kKStages * kTileBytes;
 constexpr int kSmemP = kSmemV + kVStages * kTileBytes;          // 2 buffers x 2 sub-tiles (64 keys each)
-constexpr int kSmemX = kSmemP + 4 * kTileBytes;                 // row-stat exchange: 2 x 128 floats
-constexpr int kSmemBar = kSmemX + 2 * 128 * 4;
+constexpr int kSmemX = kSmemP + 4 * kTileBytes;                 // row-stat exchange: (m, l) x 4 column quarters x 128 rows
+constexpr int kSmemBar = kSmemX + 2 * 4 * 128 * 4;
 constexpr int kNumBars = 2 + 2 * kKStages + 2 * kVStages + 4 + 4 + 2;
 constexpr int kAtSmemBytes = kSmemBar + kNumBars * 8 + 16 + 1024;
 constexpr uint32_t kAtTmemCols = 512;                            // S: 2 x 128, O: 64  -> next power of two
@@ -140,12 +146,12 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int s = 0; s < kVStages; ++s) { ptx::mbar_init(v_full(s), 1); ptx::mbar_init(v_empty(s), 1); }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(s_full(s), 1);
-      ptx::mbar_init(s_empty(s), 8);
-      ptx::mbar_init(p_full(s), 8);
+      ptx::mbar_init(s_empty(s), kSoftmaxWarps);
+      ptx::mbar_init(p_full(s), kSoftmaxWarps);
       ptx::mbar_init(p_empty(s), 1);
     }
     ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(o_empty, 8);
+    ptx::mbar_init(o_empty, kSoftmaxWarps);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<kAtTmemCols>(tmem_slot);
@@ -176,13 +182,13 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         ptx::mbar_expect_tx(q_full, kTileBytes);
         tma_load_4d(sb + kSmemQ, &tmQ, q_full, 0, h, qt * kAtBM, b);
         qphase ^= 1;
-        for (int sweep = 0; sweep < 3; ++sweep) {
+        for (int sweep = 0; sweep < 2; ++sweep) {
           for (int j = 0; j < n; ++j) {
             ptx::mbar_wait(k_empty(kr.idx), kr.phase ^ 1);
             ptx::mbar_expect_tx(k_full(kr.idx), kTileBytes);
             tma_load_4d(sb + kSmemK + kr.idx * kTileBytes, &tmK, k_full(kr.idx), 0, h, j * kAtBN, b);
             kr.advance(kKStages);
-            if (sweep == 2) {
+            if (sweep == 1) {
               ptx::mbar_wait(v_empty(vr.idx), vr.phase ^ 1);
               ptx::mbar_expect_tx(v_full(vr.idx), kTileBytes);
               tma_load_4d(sb + kSmemV + vr.idx * kTileBytes, &tmV, v_full(vr.idx), 0, h, j * kAtBN, b);
@@ -219,9 +225,8 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int n = qt + 1;
         ptx::mbar_wait(q_full, qphase);
         qphase ^= 1;
-        for (int sweep = 0; sweep < 2; ++sweep)
-          for (int j = 0; j < n; ++j) issue_S();
-        issue_S();                                            // S(0) of the third sweep
+        for (int j = 0; j < n; ++j) issue_S();                // statistics sweep
+        issue_S();                                            // S(0) of the final sweep
         for (int j = 0; j < n; ++j) {
           if (j + 1 < n) issue_S();                           // keep the softmax warps one tile ahead
           ptx::mbar_wait(v_full(vr.idx), vr.phase);
@@ -249,103 +254,108 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax / quantise / epilogue
     const int quarter = warp & 3;                 // TMEM lane quarter
-    const int half = (warp - 4) >> 2;             // which 64 key columns of every tile
+    const int cq = (warp - 4) >> 2;               // which 32 key columns of every tile
     const int r_in = quarter * 32 + lane;         // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     Ring sr, pr;
     uint32_t ophase = 0;
     const bool scale = (g.score_div != 1.0f);
+    float* xm = xch;                              // [4][128] partial maxima
+    float* xl = xch + 4 * 128;                    // [4][128] partial sums
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       int b, h, qt;
       decode(w, b, h, qt);
       const int n = qt + 1;
       const int row = qt * kAtBM + r_in;
-      float m = -INFINITY, l = 0.f;
-      for (int sweep = 0; sweep < 3; ++sweep) {
+      float m = -INFINITY, l = 0.f, inv_l = 0.f;
+      for (int sweep = 0; sweep < 2; ++sweep) {
         for (int j = 0; j < n; ++j) {
           ptx::mbar_wait(s_full(sr.idx), sr.phase);
           ptx::tc_fence_after();
-          if (sweep == 2) ptx::mbar_wait(p_empty(pr.idx), pr.phase ^ 1);
-          const int col0 = j * kAtBN + half * 64;
-          const bool diag = (j == n - 1);
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(tmem + lane_addr + (uint32_t)(sr.idx * kAtBN + half * 64 + c * 32), r);
-            ptx::tmem_ld_wait();
-            const int cb = col0 + c * 32;
-            if (sweep == 0) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem + lane_addr + (uint32_t)(sr.idx * kAtBN + cq * 32), r);
+          ptx::tmem_ld_wait();
+          const int cb = j * kAtBN + cq * 32;                 // first key column of this thread's slice
+          const int nvalid = (j == n - 1) ? min(max(row - cb + 1, 0), 32) : 32;   // causal: keys <= row
+          if (scale) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float s = __uint_as_float(r[i]);
-                if (scale) s = __fdiv_rn(s, g.score_div);
-                if (!diag || cb + i <= row) m = fmaxf(m, s);
-              }
-            } else if (sweep == 1) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float s = __uint_as_float(r[i]);
-                if (scale) s = __fdiv_rn(s, g.score_div);
-                if (!diag || cb + i <= row) l = __fadd_rn(l, expf(__fsub_rn(s, m)));
-              }
-            } else {
-              // probabilities of 32 keys = two reference blocks; quantise and store as bf16 into the P tile
-              uint8_t* prow = smem + kSmemP + (pr.idx * 2 + half) * kTileBytes + r_in * 128;
-#pragma unroll
-              for (int blk = 0; blk < 2; ++blk) {
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  float s = __uint_as_float(r[blk * 16 + i]);
-                  if (scale) s = __fdiv_rn(s, g.score_div);
-                  const bool keep = !diag || (cb + blk * 16 + i <= row);
-                  v[i] = keep ? __fdiv_rn(expf(__fsub_rn(s, m)), l) : 0.f;
-                }
-                quantize_block16<KIND>(v, g.p);
-                uint32_t w32[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                  w32[i] = *reinterpret_cast<uint32_t*>(&t2);
-                }
-                // 16-byte chunk index inside the 128-byte row, XOR-swizzled by (row & 7)  (SWIZZLE_128B)
-                const int chunk = c * 4 + blk * 2;
-                *reinterpret_cast<uint4*>(prow + (((chunk) ^ (r_in & 7)) << 4)) = make_uint4(w32[0], w32[1], w32[2], w32[3]);
-                *reinterpret_cast<uint4*>(prow + (((chunk + 1) ^ (r_in & 7)) << 4)) = make_uint4(w32[4], w32[5], w32[6], w32[7]);
-              }
-            }
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__fdiv_rn(__uint_as_float(r[i]), g.score_div));
           }
-          if (sweep == 2) ptx::fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the MMA (async proxy)
+          if (sweep == 0) {
+            float tmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tmax = (i < nvalid) ? fmaxf(tmax, __uint_as_float(r[i])) : tmax;
+            if (tmax > m) {                                   // online rescale of the running sum
+              l = __fmul_rn(l, expf(__fsub_rn(m, tmax)));
+              m = tmax;
+            }
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc = (i < nvalid) ? __fadd_rn(acc, expf(__fsub_rn(__uint_as_float(r[i]), m))) : acc;
+            l = __fadd_rn(l, acc);
+          } else {
+            ptx::mbar_wait(p_empty(pr.idx), pr.phase ^ 1);
+            // probabilities of 32 keys = two reference blocks; quantise and store as bf16 into the P tile
+            uint8_t* prow = smem + kSmemP + (pr.idx * 2 + (cq >> 1)) * kTileBytes + r_in * 128;
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float e = expf(__fsub_rn(__uint_as_float(r[blk * 16 + i]), m));
+                v[i] = (blk * 16 + i < nvalid) ? __fmul_rn(e, inv_l) : 0.f;
+              }
+              quantize_block16<KIND>(v, g.p);
+              uint32_t w32[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w32[i] = *reinterpret_cast<uint32_t*>(&t2);
+              }
+              // 16-byte chunk index inside the 128-byte row, XOR-swizzled by (row & 7)  (SWIZZLE_128B)
+              const int chunk = (cq & 1) * 4 + blk * 2;
+              *reinterpret_cast<uint4*>(prow + ((chunk ^ (r_in & 7)) << 4)) = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+              *reinterpret_cast<uint4*>(prow + (((chunk + 1) ^ (r_in & 7)) << 4)) = make_uint4(w32[4], w32[5], w32[6], w32[7]);
+            }
+            ptx::fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the MMA (async proxy)
+          }
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (sweep == 2) ptx::mbar_arrive(p_full(pr.idx));
+            if (sweep == 1) ptx::mbar_arrive(p_full(pr.idx));
             ptx::mbar_arrive(s_empty(sr.idx));
           }
-          if (sweep == 2) pr.advance(2);
+          if (sweep == 1) pr.advance(2);
           sr.advance(2);
         }
-        if (sweep < 2) {
-          // combine the two column halves of every row: max (sweep 0) / sum (sweep 1)
-          xch[half * 128 + r_in] = (sweep == 0) ? m : l;
-          named_bar_sync(1, 256);
-          const float other = xch[(half ^ 1) * 128 + r_in];
-          if (sweep == 0) m = fmaxf(m, other);
-          else l = (half == 0) ? __fadd_rn(l, other) : __fadd_rn(other, l);
-          named_bar_sync(1, 256);
+        if (sweep == 0) {
+          // merge the four column quarters of every row:  m = max m_c,  l = sum_c l_c * exp(m_c - m)
+          xm[cq * 128 + r_in] = m;
+          xl[cq * 128 + r_in] = l;
+          named_bar_sync(1, kSoftmaxWarps * 32);
+          float mm = xm[r_in];
+#pragma unroll
+          for (int c = 1; c < 4; ++c) mm = fmaxf(mm, xm[c * 128 + r_in]);
+          float ll = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ll = __fadd_rn(ll, __fmul_rn(xl[c * 128 + r_in], expf(__fsub_rn(xm[c * 128 + r_in], mm))));
+          m = mm;
+          l = ll;
+          inv_l = __frcp_rn(l);
+          named_bar_sync(1, kSoftmaxWarps * 32);
         }
       }
-      // ---- epilogue: O (128 x 64 fp32 in TMEM) -> global; this warp group owns 32 of the 64 columns
+      // ---- epilogue: O (128 x 64 fp32 in TMEM) -> global; this warp owns 16 of the 64 columns of its 32 rows
       ptx::mbar_wait(o_full, ophase);
       ophase ^= 1;
       ptx::tc_fence_after();
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem + lane_addr + kTmemO + (uint32_t)(half * 32), r);
+      uint32_t r[16];
+      ptx::tmem_ld_32x16(tmem + lane_addr + kTmemO + (uint32_t)(cq * 16), r);
       ptx::tmem_ld_wait();
       if (row < g.S) {
-        float* o = g.out + ((int64_t)b * g.S + row) * g.ldo + (int64_t)h * kAtD + half * 32;
+        float* o = g.out + ((int64_t)b * g.S + row) * g.ldo + (int64_t)h * kAtD + cq * 16;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
+        for (int i = 0; i < 16; i += 4)
           *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
                                                           __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
       }
