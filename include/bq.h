@@ -130,6 +130,20 @@ BQ_API int bq_gemm_bf16_tn(const void* A, const void* B, float* C, const float* 
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * fp32-equivalent GEMM on the bf16 tensor cores, for the matmuls the reference leaves UNQUANTISED in fp32
+ * (lm_head: models/opt_quantized/modeling_opt.py:942-944, models/llama_quantized/modeling_llama.py:772; bypass
+ * layers: quantized_modules/linear.py:60-62; the y operand of block_log matmuls: quantized_functions/matmul.py:293-296).
+ *   bq_split3_bf16: x (fp32, n elements, n % 4 == 0) -> three bf16 planes [3][n] with x = p0 + p1 + p2 (+- 2^-25 |x|).
+ *   bq_gemm_split_tn: C[m][n] = sum_t  A_plane[term_a[t]][m][:] . B_plane[term_b[t]][n][:]   (+ bias[n]),
+ *   all terms accumulated in one fp32 TMEM accumulator.  Planes are dense [planes][rows][K]; an exactly
+ *   bf16-representable operand is passed as a single plane.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API int bq_split3_bf16(const float* x, void* planes_bf16, int64_t n, void* stream);
+BQ_API int bq_gemm_split_tn(const void* A_planes, const void* B_planes, float* C, const float* bias, int64_t M, int64_t N,
+                            int64_t K, int32_t planes_a, int32_t planes_b, int32_t n_terms, const int32_t* term_a,
+                            const int32_t* term_b, int64_t ldc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Quantized Linear, PTQ steady state.  Replaces _LinearBase.forward (quantized_modules/linear.py:59-76):
  *   y[M,N] = F.linear(Q_fx(x[M,K]), Wq, bias_q)
  * Wq is the weight already quantised by bq_quantize to bf16 [N][K] (the in-place PTQ overwrite of

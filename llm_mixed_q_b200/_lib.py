@@ -94,6 +94,11 @@ def load():
                            c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.bq_attention_causal.restype = ctypes.c_int
     lib.bq_attention_causal.argtypes = [POINTER(BqFormat), c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 8 + [ctypes.c_float, c_void_p]
+    lib.bq_split3_bf16.restype = ctypes.c_int
+    lib.bq_split3_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.bq_gemm_split_tn.restype = ctypes.c_int
+    lib.bq_gemm_split_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                     POINTER(c_int32), POINTER(c_int32), c_int64, c_void_p]
     lib.bq_selftest_log2.restype = ctypes.c_int
     lib.bq_selftest_log2.argtypes = [c_void_p, c_void_p]
     lib.bq_kernel_count.restype = ctypes.c_int

@@ -40,6 +40,10 @@ struct GemmArgs {
   int64_t ldc, sc;
   int tiles_m, tiles_n;
   int b_broadcast;   // B has no batch dim (weights)
+  // split-precision mode (n_terms > 0, batch == 1): A and B are stacks of bf16 planes [planes][rows][K]; the K loop runs
+  // over the (plane_a, plane_b) pairs below and accumulates every product into the same TMEM accumulator
+  int n_terms;
+  int8_t term_a[8], term_b[8];
 };
 
 template <int BN>
@@ -81,7 +85,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_kb = (g.K + kBK - 1) / kBK;
+  const int kb_per_term = (g.K + kBK - 1) / kBK;
+  const int num_kb = kb_per_term * (g.n_terms > 0 ? g.n_terms : 1);
   const int tiles_per_batch = g.tiles_m * g.tiles_n;
   const int total_tiles = tiles_per_batch * g.batch;
 
@@ -97,8 +102,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ptx::mbar_wait(empty_bar(stage), phase ^ 1);
           ptx::mbar_expect_tx(full_bar(stage), Cfg::kStage);
           const uint32_t sa = smem_base + stage * Cfg::kStage;
-          ptx::tma_load_3d(sa, &tmA, full_bar(stage), kb * kBK, mb * kBM, b);
-          ptx::tma_load_3d(sa + Cfg::kStageA, &tmB, full_bar(stage), kb * kBK, nb * BN, g.b_broadcast ? 0 : b);
+          int ca = b, cb = g.b_broadcast ? 0 : b, kk = kb;
+          if (g.n_terms > 0) {
+            const int t = kb / kb_per_term;
+            kk = kb - t * kb_per_term;
+            ca = g.term_a[t];
+            cb = g.term_b[t];
+          }
+          ptx::tma_load_3d(sa, &tmA, full_bar(stage), kk * kBK, mb * kBM, ca);
+          ptx::tma_load_3d(sa + Cfg::kStageA, &tmB, full_bar(stage), kk * kBK, nb * BN, cb);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -293,6 +305,39 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
   GemmArgs g;
   g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = (int)batch;
   g.ldc = ldc; g.sc = sc; g.tiles_m = g.tiles_n = 0; g.b_broadcast = bcast ? 1 : 0;
+  g.n_terms = 0;
+  switch (BN) {
+    case 64: return launch_gemm<64>(tmA, tmB, g, st);
+    case 128: return launch_gemm<128>(tmA, tmB, g, st);
+    default: return launch_gemm<256>(tmA, tmB, g, st);
+  }
+}
+
+// Split-precision GEMM: C = sum over terms (A_plane[ta] @ B_plane[tb]^T) (+ bias).  With x = x0 + x1 + x2 (three bf16
+// planes, see split3 in quantize.cu) and the six terms {(2,0),(0,2),(1,1),(1,0),(0,1),(0,0)} (smallest first) the
+// result carries ~2^-24 relative error per product, i.e. it stands in for an fp32 GEMM on the tensor cores.
+int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t M, int64_t N, int64_t K,
+                       int planes_a, int planes_b, int n_terms, const int* ta, const int* tb, int64_t ldc, cudaStream_t st) {
+  if (M < 0 || N < 0 || K <= 0 || n_terms < 1 || n_terms > 8 || !ta || !tb) return BQ_ERR_BAD_ARG;
+  if (M == 0 || N == 0) return BQ_OK;
+  if (!A || !B || !C) return BQ_ERR_BAD_ARG;
+  if ((K % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)C % 4) || ldc < N) return BQ_ERR_BAD_ARG;
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, planes_a, K, M * K, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, planes_b, K, N * K, BN);
+  if (rc) return rc;
+  GemmArgs g;
+  g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = 1;
+  g.ldc = ldc; g.sc = 0; g.tiles_m = g.tiles_n = 0; g.b_broadcast = 1;
+  g.n_terms = n_terms;
+  for (int i = 0; i < n_terms; ++i) {
+    if (ta[i] < 0 || ta[i] >= planes_a || tb[i] < 0 || tb[i] >= planes_b) return BQ_ERR_BAD_ARG;
+    g.term_a[i] = (int8_t)ta[i];
+    g.term_b[i] = (int8_t)tb[i];
+  }
   switch (BN) {
     case 64: return launch_gemm<64>(tmA, tmB, g, st);
     case 128: return launch_gemm<128>(tmA, tmB, g, st);
@@ -301,6 +346,13 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
 }
 
 }  // namespace bq
+
+extern "C" int bq_gemm_split_tn(const void* A_planes, const void* B_planes, float* C, const float* bias, int64_t M, int64_t N,
+                                int64_t K, int32_t planes_a, int32_t planes_b, int32_t n_terms, const int32_t* term_a,
+                                const int32_t* term_b, int64_t ldc, void* stream) {
+  return bq::gemm_split_tn_impl(A_planes, B_planes, C, bias, M, N, K, planes_a, planes_b, n_terms, term_a, term_b, ldc,
+                                (cudaStream_t)stream);
+}
 
 extern "C" int bq_gemm_bf16_tn(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M,
                                int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb,

@@ -578,6 +578,34 @@ size_t quantize_ws_bytes(const bq_format* fmt, const bq_tensor3* t) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 -> three bf16 planes with x == p0 + p1 + p2 up to 2^-25 |x| (error-free splitting by repeated rounding):
+// the operand format of the split-precision GEMM that stands in for the reference's UNQUANTISED fp32 matmuls
+// (lm_head, modeling_opt.py:942-944; the y operand of block_log matmuls, matmul.py:293-296).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n4,
+                                                      int64_t plane) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream4(x + 4 * i);
+    float a[4] = {v.x, v.y, v.z, v.w};
+    uint32_t p0[2], p1[2], p2[2];
+    float h0[4], h1[4], h2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h0[j] = __bfloat162float(__float2bfloat16_rn(a[j]));
+      const float r1 = __fsub_rn(a[j], h0[j]);
+      h1[j] = __bfloat162float(__float2bfloat16_rn(r1));
+      h2[j] = __bfloat162float(__float2bfloat16_rn(__fsub_rn(r1, h1[j])));
+    }
+    p0[0] = pack_bf16x2(h0[0], h0[1]); p0[1] = pack_bf16x2(h0[2], h0[3]);
+    p1[0] = pack_bf16x2(h1[0], h1[1]); p1[1] = pack_bf16x2(h1[2], h1[3]);
+    p2[0] = pack_bf16x2(h2[0], h2[1]); p2[1] = pack_bf16x2(h2[2], h2[3]);
+    stg_stream2(out + 4 * i, p0[0], p0[1]);
+    stg_stream2(out + plane + 4 * i, p1[0], p1[1]);
+    stg_stream2(out + 2 * plane + 4 * i, p2[0], p2[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // exhaustive self-test of the exponent-field shortcuts against libdevice log2f
 // ------------------------------------------------------------------------------------------------
 __global__ void selftest_log2_kernel(unsigned long long* mism) {
@@ -598,6 +626,20 @@ __global__ void selftest_log2_kernel(unsigned long long* mism) {
 }  // namespace bq
 
 extern "C" {
+int bq_split3_bf16(const float* x, void* planes_bf16, int64_t n, void* stream) {
+  if (n < 0) return BQ_ERR_BAD_ARG;
+  if (n == 0) return BQ_OK;
+  if (!x || !planes_bf16 || (n % 4) || ((uintptr_t)x % 16) || ((uintptr_t)planes_bf16 % 8)) return BQ_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n4 = n / 4;
+  int grid = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)bq::num_sms() * 8);
+  {
+    bq::LaunchScope ls(bq::kKernSplit3, st);
+    bq::split3_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes_bf16, n4, n);
+  }
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
 int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream) {
   if (!mismatches_dev3) return BQ_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;

@@ -19,6 +19,7 @@ from transformers.modeling_outputs import CausalLMOutputWithPast
 from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
+from ..quantize.quantized_functions.fp32_linear import fp32_linear
 from .configuration_llama import LlamaQuantizedConfig
 
 
@@ -236,7 +237,8 @@ class LlamaQuantizedForCausalLM(LlamaQuantizedPreTrainedModel):
         hidden, all_h, all_a = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
                                           inputs_embeds=inputs_embeds, output_attentions=output_attentions,
                                           output_hidden_states=output_hidden_states)
-        logits = self.lm_head(hidden)
+        # unquantised fp32 head (reference keeps nn.Linear): fp32-equivalent split-bf16 GEMM on the tensor cores
+        logits = fp32_linear(hidden, self.lm_head.weight, self.lm_head.bias)
         loss = None
         if labels is not None:
             shift_logits = logits[..., :-1, :].contiguous()

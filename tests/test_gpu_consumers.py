@@ -209,3 +209,22 @@ def test_fused_causal_attention_vs_op_by_op_oracle(S):
     vq = O.operand_quantizer(CFG_BFP6, "weight", True)(v.view(B, S, heads, d).transpose(1, 2).reshape(B * heads, S, d))
     exp0 = (vq[:, 0, :] * (31.0 / 32.0)).view(B, heads, d).reshape(B, H)
     assert torch.equal(out[:, 0, :], exp0)
+
+
+def test_fp32_equivalent_linear_for_unquantised_layers():
+    """lm_head-style fp32 Linear through the split-bf16 tensor-core GEMM: error must stay inside the same
+    fp32-accumulation-order bound an fp32 GEMM obeys (the reference's F.linear is checked against it too)."""
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fp32_linear import fp32_linear, split3
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(1024, 2048, device="cuda", generator=g)
+    w = torch.randn(5000, 2048, device="cuda", generator=g) * 0.02
+    planes = split3(x).float()
+    assert float((planes.sum(0).double() - x.double()).abs().max()) <= 2.0 ** -24 * float(x.abs().max())
+    y = fp32_linear(x, w)
+    exact = x.double() @ w.double().T
+    absprod = x.double().abs() @ w.double().abs().T
+    assert_gemm_close(y, exact, absprod, 2048)
+    assert_gemm_close(torch.nn.functional.linear(x, w), exact, absprod, 2048)
+    rel = float(((y.double() - exact).abs() / absprod).max())
+    assert rel < 1e-6, rel
