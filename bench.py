@@ -313,14 +313,21 @@ def main():
     T = BATCH * SEQ
     flops_linear = 2 * T * (4 * H * H + 2 * H * F_) * Lyr
     flops_bmm = 2 * 2 * BATCH * h * SEQ * SEQ * d * Lyr
-    gemm_ms, gemm_n = prof["gemm_bf16_tn_kernel"]
+    # quantized-Linear GEMMs: plain + fused-epilogue instances of the tcgen05 kernel (the 6-term split instance that stands
+    # in for the fp32 lm_head is accounted separately: its algorithmic FLOPs are 2*T*H*V, its tensor work 6x that)
+    gemm_ms = prof["gemm_bf16_tn_kernel"][0] + prof["gemm_bf16_tn_kernel<epilogue>"][0]
+    gemm_n = prof["gemm_bf16_tn_kernel"][1] + prof["gemm_bf16_tn_kernel<epilogue>"][1]
+    head_ms, head_n = prof["gemm_bf16_tn_kernel<split>"]
     attn_ms, attn_n = prof.get("attention_causal_kernel", (0.0, 0))
+    ln_ms, ln_n = prof["layernorm_quant_kernel"]
     q_ms = sum(v[0] for k, v in prof.items() if k.startswith("quant") or k.startswith("generic") or k.startswith("blocklog"))
     step_ms_local = ev[0].elapsed_time(ev[K])
     # the tcgen05 GEMM runs the six Linears of every layer; QK^T / PV run inside the fused attention kernel when it is active
     gemm_flops = flops_linear + (0 if attn_n else flops_bmm)
+    flops_head = 2 * T * H * OPT13B["vocab_size"]
     achieved = gemm_flops * K / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel", "achieved": achieved, "peak": pk["tf_sustained"],
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (plain + fused-epilogue instances; the six quantized Linears per layer)",
+                "achieved": achieved, "peak": pk["tf_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "peak_source": pk["source"] + ", sustained bf16",
                 "traffic": None, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "share_of_step": gemm_ms / step_ms_local, "algorithmic_flops_per_step": gemm_flops,
@@ -328,7 +335,13 @@ def main():
                     "attention_causal_kernel": {"share_of_step": attn_ms / step_ms_local, "launches": attn_n,
                                                 "avg_launch_ms": attn_ms / max(attn_n, 1),
                                                 "reference_flops_TFLOPs": (flops_bmm * K / (attn_ms / 1e3) / 1e12) if attn_ms else None,
-                                                "note": "reference-algorithmic 2*2*B*h*S^2*d FLOP per layer; masked key tiles are skipped and S is computed twice"},
+                                                "note": "reference-algorithmic 2*2*B*h*S^2*d FLOP per layer; masked key tiles are skipped and S is computed twice; ALU-issue bound (exp + quantize per score)"},
+                    "lm_head_split_gemm": {"share_of_step": head_ms / step_ms_local, "launches": head_n,
+                                           "fp32_equivalent_TFLOPs": (flops_head * K / (head_ms / 1e3) / 1e12) if head_ms else None,
+                                           "tensor_TFLOPs": (6 * flops_head * K / (head_ms / 1e3) / 1e12) if head_ms else None,
+                                           "note": "unquantised fp32 lm_head as 6 bf16 plane products (fp32-equivalent)"},
+                    "layernorm_quant_kernel": {"share_of_step": ln_ms / step_ms_local, "launches": ln_n,
+                                               "GBs": (T * H * 6 * ln_n / (ln_ms / 1e3) / 1e9) if ln_ms else None},
                     "quantizer_kernels": {"share_of_step": q_ms / step_ms_local}}}
     gpu_launches = sum(launches1.values()) - sum(launches0.values())
 

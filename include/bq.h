@@ -111,6 +111,17 @@ BQ_API size_t bq_quantize_workspace_bytes(const bq_format* fmt, const bq_tensor3
 BQ_API int bq_quantize(const bq_format* fmt, const bq_tensor3* x_desc, const float* x, void* y, int32_t y_dtype,
                 int32_t transpose_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm / RMSNorm + quantize.  y_k = Q_fmts[k]( norm(x) ), k < n_out <= 3, each written as bf16 [rows][H].
+ * Replaces nn.LayerNorm (models/opt_quantized/modeling_opt.py:386,:414) / LlamaRMSNorm
+ * (models/llama_quantized/modeling_llama.py:79-92) followed by the x-quantizers (quantized_modules/linear.py:63-71) of
+ * the Linears that consume the normalised tensor: q/k/v_proj read ONE tensor (modeling_opt.py:206,224-225), so it is
+ * normalised once and emitted once per DISTINCT data_in format.  beta == NULL selects RMSNorm (y = gamma * x * rstd).
+ * fmts: block_fp / block_minifloat with block [1,16]; H % 16 == 0, H <= 8192; x rows at stride ldx.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API int bq_norm_quantize(const float* x, int64_t rows, int64_t H, int64_t ldx, const float* gamma, const float* beta, float eps,
+                            int32_t n_out, const bq_format* fmts, void* const* outs_bf16, void* stream);
+
 /* Exhaustive device self-test: compares the exponent-field shortcuts the quantizers use for
  * ceil/floor/rint(log2f(x)) with libdevice's log2f on every positive finite fp32 bit pattern.
  * Writes three mismatch counters (ceil, floor, rint) to mismatches_dev3 (device memory, 3 x uint64). */
@@ -128,6 +139,31 @@ BQ_API int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream);
 BQ_API int bq_gemm_bf16_tn(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M, int64_t N,
                     int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Same GEMM (batch 1) with a fused epilogue, for the glue BETWEEN two quantized ops of a decoder layer:
+ *   v = acc + bias[n];  v *= scale;  v = act(v);  v = residual[m][n] + v;  v = Q_qfmt(v);  C[m][n] = v (fp32 or bf16)
+ * in exactly this order — the order of the reference's separate torch ops:
+ *   F.linear bias add (quantized_modules/linear.py:71), `q_proj(x) * self.scaling` (models/opt_quantized/modeling_opt.py:206),
+ *   ReLU between fc1 and fc2 (:416-418), `residual + hidden_states` (:395, :424), and the x-quantizer of the op that
+ *   consumes the result (linear.py:63-71; bmm_0 / bmm_1 operands, quantized_functions/matmul.py:165-193).
+ * qfmt (optional): block_fp or block_minifloat with blocks of 16 — qdir 0: along N (16 consecutive output features:
+ * data_in of a following Linear, q and v of the attention bmms), qdir 1: along M (16 consecutive tokens at one feature:
+ * the k^T operand of bmm_0, modeling_opt.py:246; needs M % 16 == 0).  With qfmt the natural out_dtype is BQ_BF16 (exact
+ * carrier); fp32 output of quantised values is also allowed.  N % 32 == 0; bias / residual / C 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bq_gemm_epilogue {
+  const float* bias;       /* [N] or NULL                                   */
+  const float* residual;   /* fp32 [M][ldr] or NULL                         */
+  int64_t ldr;
+  float scale;             /* 1.0f = none                                   */
+  int32_t act;             /* 0 none, 1 ReLU                                */
+  int32_t out_dtype;       /* bq_dtype of C                                 */
+  const bq_format* qfmt;   /* NULL = no quantisation                        */
+  int32_t qdir;            /* 0: blocks along N, 1: blocks along M          */
+} bq_gemm_epilogue;
+BQ_API int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_gemm_epilogue* ep, int64_t M, int64_t N, int64_t K,
+                              int64_t lda, int64_t ldb, int64_t ldc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fp32-equivalent GEMM on the bf16 tensor cores, for the matmuls the reference leaves UNQUANTISED in fp32
@@ -172,14 +208,22 @@ BQ_API int bq_bmm(const bq_format* fx, const bq_format* fy, const float* x, cons
  * models/opt_quantized/modeling_opt.py:246-312 (and matmul_0 / sqrt(d) -> ... -> matmul_1 of
  * models/llama_quantized/modeling_llama.py:309-344) when the mask is purely causal:
  *   out[b,s,h,:] = Q_fp( softmax_row( (Qq[b,:,h,:] Kq[b,:,h,:]^T) / score_div , causal ) ) @ Vq[b,:,h,:]
- * Qq / Kq / Vq: bf16 [B,S,H,d] operands ALREADY quantised by bq_quantize (q: data_in of bmm_0, blocks along d;
- * k: weight of bmm_0, blocks along S; v: weight of bmm_1, blocks along d), token strides ldq/ldk/ldv (elements).
- * fp: format of the probabilities (data_in of bmm_1), block [1,16], block_fp or block_minifloat.
- * out: fp32 [B,S,H,d] with token stride ldo.  d must be 64.  Scores and probabilities never touch HBM.
+ * Qq / Kq / Vq: bf16 [B,S,H,d] operands ALREADY quantised (bq_quantize or a quantising GEMM epilogue; q: data_in of
+ * bmm_0, blocks along d; k: weight of bmm_0, blocks along S; v: weight of bmm_1, blocks along d), token strides
+ * ldq/ldk/ldv (elements).  fp: format of the probabilities (data_in of bmm_1), block [1,16], block_fp or block_minifloat.
+ * out: fp32 [B,S,H,d] with token stride ldo.  d must be 64 or 128.  Scores and probabilities never touch HBM.
+ * score_div: scores are MULTIPLIED by 1.0f/score_div — what torch-CUDA evaluates for `tensor / python_float`.
+ *
+ * bq_attention_causal_q additionally applies the x-quantizer of the Linear that consumes the attention output
+ * (out_proj / o_proj, quantized_modules/linear.py:63-71; format fo, blocks [1,16] along the hidden dim) in the
+ * epilogue and writes the exact quantised values as bf16 [B,S,H,d] — the A operand of bq_gemm_bf16_tn.
  * ---------------------------------------------------------------------------------------------- */
 BQ_API int bq_attention_causal(const bq_format* fp, const void* Qq, const void* Kq, const void* Vq, float* out, int64_t B,
                                int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
                                float score_div, void* stream);
+BQ_API int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq,
+                                 void* out_bf16, int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk,
+                                 int64_t ldv, int64_t ldo, float score_div, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Launch accounting (measurement support for bench.py; no reference counterpart).

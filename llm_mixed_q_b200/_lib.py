@@ -44,6 +44,11 @@ class BqTensor3(Structure):
     _fields_ = [("L", c_int64), ("R", c_int64), ("C", c_int64), ("sL", c_int64), ("sR", c_int64), ("sC", c_int64)]
 
 
+class BqGemmEpilogue(Structure):
+    _fields_ = [("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64), ("scale", ctypes.c_float), ("act", c_int32),
+                ("out_dtype", c_int32), ("qfmt", POINTER(BqFormat)), ("qdir", c_int32)]
+
+
 class BqError(RuntimeError):
     pass
 
@@ -82,6 +87,11 @@ def load():
                                 c_size_t, c_void_p]
     lib.bq_gemm_bf16_tn.restype = ctypes.c_int
     lib.bq_gemm_bf16_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 10 + [c_void_p]
+    lib.bq_gemm_bf16_tn_ex.restype = ctypes.c_int
+    lib.bq_gemm_bf16_tn_ex.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(BqGemmEpilogue)] + [c_int64] * 6 + [c_void_p]
+    lib.bq_norm_quantize.restype = ctypes.c_int
+    lib.bq_norm_quantize.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, ctypes.c_float, c_int32,
+                                     POINTER(BqFormat), POINTER(c_void_p), c_void_p]
     lib.bq_linear_workspace_bytes.restype = c_size_t
     lib.bq_linear_workspace_bytes.argtypes = [POINTER(BqFormat), c_int64, c_int64]
     lib.bq_linear.restype = ctypes.c_int
@@ -94,6 +104,8 @@ def load():
                            c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.bq_attention_causal.restype = ctypes.c_int
     lib.bq_attention_causal.argtypes = [POINTER(BqFormat), c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 8 + [ctypes.c_float, c_void_p]
+    lib.bq_attention_causal_q.restype = ctypes.c_int
+    lib.bq_attention_causal_q.argtypes = [POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 8 + [ctypes.c_float, c_void_p]
     lib.bq_split3_bf16.restype = ctypes.c_int
     lib.bq_split3_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.bq_gemm_split_tn.restype = ctypes.c_int

@@ -5,31 +5,41 @@
 //     scores = bmm(Qx(q), Qy(k^T))            fp32 [B*h, S, S]  written to HBM
 //     scores = max(scores + causal_mask, finfo.min) ; probs = softmax(scores)       3 more HBM round trips
 //     out    = bmm(Qx(probs), Qy(v))          probs quantised in 1x16 blocks along the key dim
+// (and, optionally, the x-quantizer of the following out_proj / o_proj Linear, quantized_modules/linear.py:63-71)
 // with ONE kernel in which scores and probabilities never leave the SM:
 //     S = Q K^T on tcgen05 (bf16 operands = exact block-quantised q / k, fp32 accumulate in TMEM),
-//     sweep 1: running row max / row sum of exp(s - max) (online rescaling), sweep 2: p = exp(s - max) * (1/sum)
+//     sweep 0: running row max / row sum of exp(s - max) (online rescaling), sweep 1: p = exp(s - max) * (1/sum)
 //     (S is recomputed in the second sweep — the tensor pipe is far from being the bottleneck),
 //     P quantised in registers (one thread owns a query row, so a 1x16 block is 16 consecutive registers),
 //     written as a swizzled bf16 K-major smem tile and multiplied with V (MN-major operand) into a TMEM
-//     accumulator.
-// Blocks of P need FINAL probabilities, which is why this is a multi-sweep rather than an online-softmax
+//     accumulator; the epilogue optionally block-quantises O for the next Linear and emits bf16.
+// Blocks of P need FINAL probabilities, which is why this is a two-sweep rather than an online-softmax
 // (flash) schedule.  Key tiles above the diagonal are skipped: their probabilities are exactly 0 in the
 // reference (exp(finfo.min - max) == 0) and quantise to 0.
 //
-// Operands are produced by bq_quantize: Qq, Kq, Vq are bf16 [B, S, h, d] (token stride given), Kq blocked
-// along S (k^T's last dim), Vq along d.  d == 64.  Output: fp32 [B, S, h, d].
+// The kernel is ALU-issue bound (two exponentials and one block quantisation per score), so the inner loops are
+// written for instruction count: the statistics sweep uses ex2.approx on (s - max) * log2(e) (only the row SUM
+// depends on it), the final sweep uses libdevice expf like torch's softmax, rounding to the mantissa grid is the
+// exact magic-constant add/sub (== rintf for 0 <= t < 2^22), bf16 packing is a byte permute (quantised values have
+// <= 8 significant bits), and the causal predicate only exists in the code path of the diagonal tile.
 //
-// Numerics vs the reference's torch softmax: same exp(x - max) with libdevice expf; the row sum is accumulated
-// in a different order and p uses one multiplication by the correctly rounded reciprocal instead of a division
-// (<= 1 ulp each).  An ulp-level difference only matters when a probability sits on a rounding boundary of the
-// block format (one quantisation step there); tests/test_gpu_consumers.py states the tolerance.
+// Operands are produced by bq_quantize or by the quantising GEMM epilogues: Qq, Kq, Vq are bf16 [B, S, h, d]
+// (token stride given), Kq blocked along S (k^T's last dim), Vq along d.  d in {64, 128}.
 //
-// Warp roles (640 threads, 1 CTA/SM, persistent over (b, h, 128-row query tile) work items, heaviest first):
+// Numerics vs the reference's torch softmax: same exp(x - max) with libdevice expf for the numerators; the row sum
+// is accumulated in a different order from 2-ulp exponentials and p uses one multiplication by the correctly rounded
+// reciprocal instead of a division.  An ulp-level difference only matters when a probability sits on a
+// rounding boundary of the block format (one quantisation step there); tests/test_gpu_consumers.py states the
+// tolerance.  Pass-through probabilities (p <= 1e-8, returned unquantised by the reference) are truncated to bf16.
+//
+// Warp roles (640 threads, 1 CTA/SM, persistent):
 //   warp 0      TMA producer            warp 1   MMA issuer           warp 2   TMEM allocator
 //   warps 4-19  softmax/quantise: warp w owns TMEM lane quarter (w % 4) = 32 query rows and key columns
-//               [32*cq, 32*cq+32) of every 128-key tile, cq = (w - 4) / 4   (ALU-bound part: 16 warps)
+//               [32*cq, 32*cq+32) of every 128-key tile, cq = (w - 4) / 4
+// Work item = (b, h, pair p): query tile T-1-p followed by query tile p (equal cost for every item; the items of
+// one head are adjacent in the round-robin order, so ~8 neighbouring CTAs share that head's K / V through L2).
 #include "bq_internal.h"
-#include "bq_numerics.cuh"
+#include "bq_blockops.cuh"
 #include "sm100_ptx.cuh"
 
 #include <cuda_bf16.h>
@@ -39,35 +49,47 @@ namespace bq {
 
 constexpr int kAtBM = 128;      // query rows per work item (UMMA M)
 constexpr int kAtBN = 128;      // keys per tile
-constexpr int kAtD = 64;        // head dim
 constexpr int kAtThreads = 640;
 constexpr int kSoftmaxWarps = 16;
-constexpr int kKStages = 3, kVStages = 2;
-constexpr int kTileBytes = 128 * 64 * 2;           // every smem tile here is 128 rows x 128 bytes = 16 KB
-constexpr int kSmemQ = 0;
-constexpr int kSmemK = kSmemQ + kTileBytes;
-constexpr int kSmemV = kSmemK + kKStages * kTileBytes;
-constexpr int kSmemP = kSmemV + kVStages * kTileBytes;          // 2 buffers x 2 sub-tiles (64 keys each)
-constexpr int kSmemX = kSmemP + 4 * kTileBytes;                 // row-stat exchange: (m, l) x 4 column quarters x 128 rows
-constexpr int kSmemBar = kSmemX + 2 * 4 * 128 * 4;
-constexpr int kNumBars = 2 + 2 * kKStages + 2 * kVStages + 4 + 4 + 2;
-constexpr int kAtSmemBytes = kSmemBar + kNumBars * 8 + 16 + 1024;
-constexpr uint32_t kAtTmemCols = 512;                            // S: 2 x 128, O: 64  -> next power of two
+constexpr int kSubTile = 128 * 64 * 2;             // one 128-row x 128-byte swizzle-128B sub-tile = 16 KB
+constexpr uint32_t kAtTmemCols = 512;              // S: 2 x 128, O: up to 128  -> next power of two
 constexpr uint32_t kTmemO = 256;
+constexpr float kL2E = 1.4426950408889634f;
+constexpr float kMagic = 12582912.0f;              // 1.5 * 2^23: (t + kMagic) - kMagic == rintf(t) for 0 <= t < 2^22
+
+template <int D> struct AtCfg {
+  static constexpr int kQBufs = (D == 64) ? 2 : 1;
+  static constexpr int kKStages = (D == 64) ? 3 : 2;
+  static constexpr int kVStages = (D == 64) ? 2 : 1;
+  static constexpr int kTile = (D / 64) * kSubTile;               // Q / K / V tile bytes
+  static constexpr int kSmemQ = 0;
+  static constexpr int kSmemK = kSmemQ + kQBufs * kTile;
+  static constexpr int kSmemV = kSmemK + kKStages * kTile;
+  static constexpr int kSmemP = kSmemV + kVStages * kTile;        // 2 buffers x 2 sub-tiles (64 keys each)
+  static constexpr int kSmemX = kSmemP + 4 * kSubTile;            // row-stat exchange: 2 x (m, l) x 4 column quarters x 128 rows
+  static constexpr int kSmemBar = kSmemX + 2 * 2 * 4 * 128 * 4;            // double-buffered
+  static constexpr int kNumBars = 2 * kQBufs + 2 * kKStages + 2 * kVStages + 4 + 4 + 2;
+  static constexpr int kSmemBytes = kSmemBar + kNumBars * 8 + 16 + 1024;
+};
 
 struct AttnArgs {
-  float* out;
+  void* out;            // fp32 [B,S,H,d] (out_mode 0) or bf16 (out_mode 1)
   int B, H, S;
   int64_t ldo;          // token stride of out (elements)
   int q_tiles;          // ceil(S / 128)
-  float score_div;      // scores are divided by this before the softmax (Llama: sqrt(d); OPT: 1)
+  int scale_mode;       // 0: none; 1: multiply by score_mul = 1.0f / score_div — what torch-CUDA does for `tensor / python_float`
+                        // (BinaryDivTrueKernel: a * (1/b) for a CPU-scalar divisor); identical to a division for powers of two
+  float score_mul;
+  int out_mode;         // 0: fp32 unquantised; 1: bf16, block-quantised with `po` (blocks of 16 along d)
   FmtParams p;          // format of P (data_in of bmm_1 / matmul_1)
+  FmtParams po;         // format of the output (data_in of the following Linear), out_mode 1
 };
 
 // MN-major SWIZZLE_128B operand: rows of 128 bytes run along MN (64 bf16), 8 such rows (8 K indices) per
-// 1024-byte atom.  SBO = distance between 8-K groups; LBO = distance between 64-element MN chunks (unused: N = 64).
-__device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// 1024-byte atom.  SBO = distance between 8-K groups; LBO = distance between 64-element MN chunks.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __host__ __device__ constexpr uint32_t idesc_bf16_f32_bmn(int M, int N) {   // B operand MN-major (bit 16)
   return ptx::idesc_bf16_f32(M, N) | (1u << 16);
@@ -82,22 +104,113 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-
-// Quantise 16 consecutive probabilities (one reference block) in place.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Quantise 16 consecutive NON-NEGATIVE values (one reference block of probabilities) and pack them as bf16.
 template <int KIND>
-__device__ __forceinline__ void quantize_block16(float (&v)[16], const FmtParams& p) {
-  uint32_t m = 0;
+__device__ __forceinline__ void quantize_probs16(float (&v)[16], const FmtParams& p, uint32_t (&w)[8]) {
+  float mx = v[0];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) m = max(m, __float_as_uint(v[i]) & 0x7fffffffu);
-  if (m == 0) return;                                  // all-zero block -> zeros (pass-through)
-  const FastState fs = fast_state<KIND>(m, p);
+  for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[i]);
+  if (mx == 0.f) {                                      // all-zero block -> zeros (pass-through)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 0u;
+    return;
+  }
+  const uint32_t mbits = f2u(mx);
+  const FastState fs = fast_state<KIND>(mbits, p);
   if (fs.ok) {
+    if (KIND == kBlockFP) {
+      const float c0 = __fmul_rn(1e-9f, fs.f0);         // exact: f0 is a power of two
+      const float hi = __fadd_rn(kMagic, p.qmax);       // clamp bound in the magic-shifted domain (exact integer)
+      const float c1 = -__fmul_rn(kMagic, fs.f1);       // exact: f1 is a power of two
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = quant_elem_fast<KIND>(v[i], fs, p);
+      for (int i = 0; i < 16; ++i) {
+        const float t = __fmaf_rn(v[i], fs.f0, c0);     // == (v + 1e-9f) * 2^(m-E): scaling by 2^k commutes with rounding
+        const float tm = fminf(__fadd_rn(t, kMagic), hi);   // kMagic + min(rint(t), qmax)
+        const float y = __fmaf_rn(tm, fs.f1, c1);       // (tm - kMagic) * 2^(E-m): every term exact, so is the fma
+        v[i] = (v[i] <= 1e-8f) ? v[i] : y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = quant_elem_fast<KIND>(v[i], fs, p);
+    }
   } else {
-    const BlockState st = block_state<KIND>(__uint_as_float(m), p);
-#pragma unroll 1
-    for (int i = 0; i < 16; ++i) v[i] = quant_elem<KIND>(v[i], st, p);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = quant_literal_1<KIND>(v[i], mbits, p);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = pack_bf16_trunc(v[2 * i], v[2 * i + 1]);
+}
+
+// statistics of 32 scores: running max m (with mL = rn(m * log2 e)) and running sum l of 2^(s * log2 e - mL).
+// l is kept in "mL units": the exact exp(s - m) differs from the accumulated term by the factor 2^-(m * log2 e - mL),
+// which is constant per row and applied once in the merge (stat_fixup) — the per-element work is FFMA + EX2 + FADD.
+constexpr float kL2ELo = 1.925963033500011e-08f;     // log2(e) - (float)log2(e)
+template <bool MASK>
+__device__ __forceinline__ void stats32(const uint32_t (&r)[32], int nvalid, float& m, float& mL, float& l) {
+  float tmax = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float s = u2f(r[i]);
+    if (MASK) s = (i < nvalid) ? s : -INFINITY;
+    tmax = fmaxf(tmax, s);
+  }
+  if (tmax > m) {                                        // online rescale of the running sum
+    const float mLn = __fmul_rn(tmax, kL2E);
+    l = __fmul_rn(l, ex2_fast(__fsub_rn(mL, mLn)));      // first time: mL = -inf -> factor 0 (l is 0 anyway)
+    m = tmax;
+    mL = mLn;
+  }
+  const float nmL = -mL;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float e0 = ex2_fast(__fmaf_rn(u2f(r[i]), kL2E, nmL));
+    float e1 = ex2_fast(__fmaf_rn(u2f(r[i + 1]), kL2E, nmL));
+    float e2 = ex2_fast(__fmaf_rn(u2f(r[i + 2]), kL2E, nmL));
+    float e3 = ex2_fast(__fmaf_rn(u2f(r[i + 3]), kL2E, nmL));
+    if (MASK) {
+      e0 = (i < nvalid) ? e0 : 0.f;
+      e1 = (i + 1 < nvalid) ? e1 : 0.f;
+      e2 = (i + 2 < nvalid) ? e2 : 0.f;
+      e3 = (i + 3 < nvalid) ? e3 : 0.f;
+    }
+    a0 = __fadd_rn(a0, e0);
+    a1 = __fadd_rn(a1, e1);
+    a2 = __fadd_rn(a2, e2);
+    a3 = __fadd_rn(a3, e3);
+  }
+  l = __fadd_rn(l, __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)));
+}
+// l in mL units -> sum of exp(s - m):  multiply by 2^-(m * log2(e) - mL), the product's rounding error recovered by FMA
+__device__ __forceinline__ float stat_fixup(float m, float mL, float l) {
+  if (l == 0.f) return 0.f;                              // slice without a valid key (m = -inf)
+  const float err = __fadd_rn(__fmaf_rn(m, kL2E, -mL), __fmul_rn(m, kL2ELo));
+  return __fmul_rn(l, ex2_fast(-err));
+}
+
+// final probabilities of 32 scores -> two quantised blocks -> swizzled bf16 rows of the P tile
+template <int KIND, bool MASK>
+__device__ __forceinline__ void probs32(const uint32_t (&r)[32], int nvalid, float m, float inv_l, const FmtParams& p,
+                                        uint8_t* prow, int chunk0, int sw) {
+#pragma unroll
+  for (int blk = 0; blk < 2; ++blk) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float e = expf(__fsub_rn(u2f(r[blk * 16 + i]), m));
+      v[i] = __fmul_rn(e, inv_l);
+      if (MASK) v[i] = (blk * 16 + i < nvalid) ? v[i] : 0.f;
+    }
+    uint32_t w[8];
+    quantize_probs16<KIND>(v, p, w);
+    const int chunk = chunk0 + blk * 2;
+    *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(prow + (((chunk + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
@@ -109,29 +222,34 @@ struct Ring {
   }
 };
 
-template <int KIND>
+template <int KIND, int D>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, AttnArgs g) {
+  using Cfg = AtCfg<D>;
+  constexpr int kSub = D / 64;                     // 64-wide sub-tiles along d
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sb = ptx::smem_u32(smem);
-  const uint32_t bar0 = sb + kSmemBar;
+  const uint32_t bar0 = sb + Cfg::kSmemBar;
   // barrier map
-  const uint32_t q_full = bar0, q_empty = bar0 + 8;
-  auto k_full = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (2 + kKStages + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (2 + 2 * kKStages + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (2 + 2 * kKStages + kVStages + s); };
-  const uint32_t bS = bar0 + 8u * (2 + 2 * kKStages + 2 * kVStages);
+  auto q_full = [&](int s) { return bar0 + 8u * s; };
+  auto q_empty = [&](int s) { return bar0 + 8u * (Cfg::kQBufs + s); };
+  const uint32_t bK = bar0 + 8u * (2 * Cfg::kQBufs);
+  auto k_full = [&](int s) { return bK + 8u * s; };
+  auto k_empty = [&](int s) { return bK + 8u * (Cfg::kKStages + s); };
+  const uint32_t bV = bK + 8u * (2 * Cfg::kKStages);
+  auto v_full = [&](int s) { return bV + 8u * s; };
+  auto v_empty = [&](int s) { return bV + 8u * (Cfg::kVStages + s); };
+  const uint32_t bS = bV + 8u * (2 * Cfg::kVStages);
   auto s_full = [&](int s) { return bS + 8u * s; };
   auto s_empty = [&](int s) { return bS + 8u * (2 + s); };
   auto p_full = [&](int s) { return bS + 8u * (4 + s); };
   auto p_empty = [&](int s) { return bS + 8u * (6 + s); };
   const uint32_t o_full = bS + 8u * 8, o_empty = bS + 8u * 9;
   const uint32_t tmem_slot = bS + 8u * 10;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + kNumBars * 8);
-  float* xch = reinterpret_cast<float*>(smem + kSmemX);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kSmemBar + Cfg::kNumBars * 8);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::kSmemX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -140,10 +258,9 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     ptx::prefetch_tmap(&tmV);
   }
   if (warp == 1 && lane == 0) {
-    ptx::mbar_init(q_full, 1);
-    ptx::mbar_init(q_empty, 1);
-    for (int s = 0; s < kKStages; ++s) { ptx::mbar_init(k_full(s), 1); ptx::mbar_init(k_empty(s), 1); }
-    for (int s = 0; s < kVStages; ++s) { ptx::mbar_init(v_full(s), 1); ptx::mbar_init(v_empty(s), 1); }
+    for (int s = 0; s < Cfg::kQBufs; ++s) { ptx::mbar_init(q_full(s), 1); ptx::mbar_init(q_empty(s), 1); }
+    for (int s = 0; s < Cfg::kKStages; ++s) { ptx::mbar_init(k_full(s), 1); ptx::mbar_init(k_empty(s), 1); }
+    for (int s = 0; s < Cfg::kVStages; ++s) { ptx::mbar_init(v_full(s), 1); ptx::mbar_init(v_empty(s), 1); }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(s_full(s), 1);
       ptx::mbar_init(s_empty(s), kSoftmaxWarps);
@@ -160,39 +277,50 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
 
-  const int items = g.B * g.H * g.q_tiles;
-  // heaviest (largest query tile) first; items of one query tile are contiguous
-  auto decode = [&](int w, int& b, int& h, int& qt) {
-    qt = g.q_tiles - 1 - w / (g.B * g.H);
-    const int r = w % (g.B * g.H);
-    b = r / g.H;
-    h = r % g.H;
+  const int T = g.q_tiles;
+  const int pairs = (T + 1) >> 1;
+  const int items = g.B * g.H * pairs;
+  // item -> (b, h, first query tile, number of query tiles); second query tile = T - 1 - first
+  auto decode = [&](int w, int& b, int& h, int& qt_hi, int& nsub) {
+    const int bh = w / pairs, pr = w - bh * pairs;
+    b = bh / g.H;
+    h = bh - b * g.H;
+    qt_hi = T - 1 - pr;
+    nsub = (qt_hi != pr) ? 2 : 1;
   };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      Ring kr, vr;
-      uint32_t qphase = 0;
+      Ring qr, kr, vr;
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
-        int b, h, qt;
-        decode(w, b, h, qt);
-        const int n = qt + 1;
-        ptx::mbar_wait(q_empty, qphase ^ 1);
-        ptx::mbar_expect_tx(q_full, kTileBytes);
-        tma_load_4d(sb + kSmemQ, &tmQ, q_full, 0, h, qt * kAtBM, b);
-        qphase ^= 1;
-        for (int sweep = 0; sweep < 2; ++sweep) {
-          for (int j = 0; j < n; ++j) {
-            ptx::mbar_wait(k_empty(kr.idx), kr.phase ^ 1);
-            ptx::mbar_expect_tx(k_full(kr.idx), kTileBytes);
-            tma_load_4d(sb + kSmemK + kr.idx * kTileBytes, &tmK, k_full(kr.idx), 0, h, j * kAtBN, b);
-            kr.advance(kKStages);
-            if (sweep == 1) {
-              ptx::mbar_wait(v_empty(vr.idx), vr.phase ^ 1);
-              ptx::mbar_expect_tx(v_full(vr.idx), kTileBytes);
-              tma_load_4d(sb + kSmemV + vr.idx * kTileBytes, &tmV, v_full(vr.idx), 0, h, j * kAtBN, b);
-              vr.advance(kVStages);
+        int b, h, qt_hi, nsub;
+        decode(w, b, h, qt_hi, nsub);
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
+          const int n = qt + 1;
+          ptx::mbar_wait(q_empty(qr.idx), qr.phase ^ 1);
+          ptx::mbar_expect_tx(q_full(qr.idx), Cfg::kTile);
+#pragma unroll
+          for (int c = 0; c < kSub; ++c)
+            tma_load_4d(sb + Cfg::kSmemQ + qr.idx * Cfg::kTile + c * kSubTile, &tmQ, q_full(qr.idx), c * 64, h, qt * kAtBM, b);
+          qr.advance(Cfg::kQBufs);
+          for (int sweep = 0; sweep < 2; ++sweep) {
+            for (int j = 0; j < n; ++j) {
+              ptx::mbar_wait(k_empty(kr.idx), kr.phase ^ 1);
+              ptx::mbar_expect_tx(k_full(kr.idx), Cfg::kTile);
+#pragma unroll
+              for (int c = 0; c < kSub; ++c)
+                tma_load_4d(sb + Cfg::kSmemK + kr.idx * Cfg::kTile + c * kSubTile, &tmK, k_full(kr.idx), c * 64, h, j * kAtBN, b);
+              kr.advance(Cfg::kKStages);
+              if (sweep == 1) {
+                ptx::mbar_wait(v_empty(vr.idx), vr.phase ^ 1);
+                ptx::mbar_expect_tx(v_full(vr.idx), Cfg::kTile);
+#pragma unroll
+                for (int c = 0; c < kSub; ++c)
+                  tma_load_4d(sb + Cfg::kSmemV + vr.idx * Cfg::kTile + c * kSubTile, &tmV, v_full(vr.idx), c * 64, h, j * kAtBN, b);
+                vr.advance(Cfg::kVStages);
+              }
             }
           }
         }
@@ -202,53 +330,59 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idS = ptx::idesc_bf16_f32(kAtBM, kAtBN);
-      constexpr uint32_t idO = idesc_bf16_f32_bmn(kAtBM, kAtD);
-      Ring kr, vr, sr, pr;
-      uint32_t qphase = 0, ophase = 0;
-      const uint64_t qdesc = ptx::smem_desc_sw128_kmajor(sb + kSmemQ);
-      auto issue_S = [&]() {
-        ptx::mbar_wait(k_full(kr.idx), kr.phase);
-        ptx::mbar_wait(s_empty(sr.idx), sr.phase ^ 1);
-        ptx::tc_fence_after();
-        const uint64_t kdesc = ptx::smem_desc_sw128_kmajor(sb + kSmemK + kr.idx * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kAtD / 16; ++k)
-          ptx::umma_bf16(tmem + (uint32_t)(sr.idx * kAtBN), qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idS, k != 0);
-        ptx::umma_commit(k_empty(kr.idx));
-        ptx::umma_commit(s_full(sr.idx));
-        kr.advance(kKStages);
-        sr.advance(2);
-      };
+      constexpr uint32_t idO = idesc_bf16_f32_bmn(kAtBM, D);
+      Ring qr, kr, vr, sr, pr;
+      uint32_t ophase = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
-        int b, h, qt;
-        decode(w, b, h, qt);
-        const int n = qt + 1;
-        ptx::mbar_wait(q_full, qphase);
-        qphase ^= 1;
-        for (int j = 0; j < n; ++j) issue_S();                // statistics sweep
-        issue_S();                                            // S(0) of the final sweep
-        for (int j = 0; j < n; ++j) {
-          if (j + 1 < n) issue_S();                           // keep the softmax warps one tile ahead
-          ptx::mbar_wait(v_full(vr.idx), vr.phase);
-          ptx::mbar_wait(p_full(pr.idx), pr.phase);
-          if (j == 0) { ptx::mbar_wait(o_empty, ophase ^ 1); }
-          ptx::tc_fence_after();
-          const uint32_t pbase = sb + kSmemP + pr.idx * 2 * kTileBytes;
-          const uint32_t vbase = sb + kSmemV + vr.idx * kTileBytes;
+        int b, h, qt_hi, nsub;
+        decode(w, b, h, qt_hi, nsub);
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
+          const int n = qt + 1;
+          ptx::mbar_wait(q_full(qr.idx), qr.phase);
+          const uint32_t qbase = sb + Cfg::kSmemQ + qr.idx * Cfg::kTile;
+          auto issue_S = [&]() {
+            ptx::mbar_wait(k_full(kr.idx), kr.phase);
+            ptx::mbar_wait(s_empty(sr.idx), sr.phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t kbase = sb + Cfg::kSmemK + kr.idx * Cfg::kTile;
 #pragma unroll
-          for (int k = 0; k < kAtBN / 16; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128_kmajor(pbase + (k >> 2) * kTileBytes) + (uint64_t)(2 * (k & 3));
-            const uint64_t bdesc = smem_desc_sw128_mnmajor(vbase + k * 16 * 128);
-            ptx::umma_bf16(tmem + kTmemO, adesc, bdesc, idO, (j | k) != 0);
+            for (int k = 0; k < D / 16; ++k) {
+              const uint64_t qdesc = ptx::smem_desc_sw128_kmajor(qbase + (k >> 2) * kSubTile) + (uint64_t)(2 * (k & 3));
+              const uint64_t kdesc = ptx::smem_desc_sw128_kmajor(kbase + (k >> 2) * kSubTile) + (uint64_t)(2 * (k & 3));
+              ptx::umma_bf16(tmem + (uint32_t)(sr.idx * kAtBN), qdesc, kdesc, idS, k != 0);
+            }
+            ptx::umma_commit(k_empty(kr.idx));
+            ptx::umma_commit(s_full(sr.idx));
+            kr.advance(Cfg::kKStages);
+            sr.advance(2);
+          };
+          for (int j = 0; j < n; ++j) issue_S();                // statistics sweep
+          issue_S();                                            // S(0) of the final sweep
+          for (int j = 0; j < n; ++j) {
+            if (j + 1 < n) issue_S();                           // keep the softmax warps one tile ahead
+            ptx::mbar_wait(v_full(vr.idx), vr.phase);
+            ptx::mbar_wait(p_full(pr.idx), pr.phase);
+            if (j == 0) { ptx::mbar_wait(o_empty, ophase ^ 1); }
+            ptx::tc_fence_after();
+            const uint32_t pbase = sb + Cfg::kSmemP + pr.idx * 2 * kSubTile;
+            const uint32_t vbase = sb + Cfg::kSmemV + vr.idx * Cfg::kTile;
+#pragma unroll
+            for (int k = 0; k < kAtBN / 16; ++k) {
+              const uint64_t adesc = ptx::smem_desc_sw128_kmajor(pbase + (k >> 2) * kSubTile) + (uint64_t)(2 * (k & 3));
+              const uint64_t bdesc = smem_desc_sw128_mnmajor(vbase + k * 16 * 128, kSubTile);
+              ptx::umma_bf16(tmem + kTmemO, adesc, bdesc, idO, (j | k) != 0);
+            }
+            ptx::umma_commit(v_empty(vr.idx));
+            ptx::umma_commit(p_empty(pr.idx));
+            vr.advance(Cfg::kVStages);
+            pr.advance(2);
           }
-          ptx::umma_commit(v_empty(vr.idx));
-          ptx::umma_commit(p_empty(pr.idx));
-          vr.advance(kVStages);
-          pr.advance(2);
+          ptx::umma_commit(o_full);
+          ptx::umma_commit(q_empty(qr.idx));
+          qr.advance(Cfg::kQBufs);
+          ophase ^= 1;
         }
-        ptx::umma_commit(o_full);
-        ptx::umma_commit(q_empty);
-        ophase ^= 1;
       }
     }
   } else if (warp >= 4) {
@@ -257,111 +391,125 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int cq = (warp - 4) >> 2;               // which 32 key columns of every tile
     const int r_in = quarter * 32 + lane;         // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int sw = r_in & 7;                      // SWIZZLE_128B: 16-byte chunk index ^= (row & 7)
+    const int chunk0 = (cq & 1) * 4;
     Ring sr, pr;
     uint32_t ophase = 0;
-    const bool scale = (g.score_div != 1.0f);
-    float* xm = xch;                              // [4][128] partial maxima
-    float* xl = xch + 4 * 128;                    // [4][128] partial sums
+    int xbuf = 0;                                 // exchange buffer parity (one per sub-item: no second barrier needed)
+    // On the diagonal tile the 32x32 slice (quarter, cq) is fully visible when cq < quarter, fully masked when
+    // cq > quarter and needs the per-element predicate only when cq == quarter.
+    const bool diag_masked = cq > quarter;
+    const bool diag_partial = cq == quarter;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
-      int b, h, qt;
-      decode(w, b, h, qt);
-      const int n = qt + 1;
-      const int row = qt * kAtBM + r_in;
-      float m = -INFINITY, l = 0.f, inv_l = 0.f;
-      for (int sweep = 0; sweep < 2; ++sweep) {
-        for (int j = 0; j < n; ++j) {
-          ptx::mbar_wait(s_full(sr.idx), sr.phase);
-          ptx::tc_fence_after();
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem + lane_addr + (uint32_t)(sr.idx * kAtBN + cq * 32), r);
-          ptx::tmem_ld_wait();
-          const int cb = j * kAtBN + cq * 32;                 // first key column of this thread's slice
-          const int nvalid = (j == n - 1) ? min(max(row - cb + 1, 0), 32) : 32;   // causal: keys <= row
-          if (scale) {
+      int b, h, qt_hi, nsub;
+      decode(w, b, h, qt_hi, nsub);
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
+        const int n = qt + 1;
+        const int row = qt * kAtBM + r_in;
+        const int nvalid_d = lane + 1;            // cq == quarter: keys [32*cq, 32*cq + lane] of the diagonal tile
+        float* xm = xch + xbuf * (2 * 4 * 128);   // [4][128] partial maxima
+        float* xl = xm + 4 * 128;                 // [4][128] partial sums
+        xbuf ^= 1;
+        float m = -INFINITY, mL = -INFINITY, l = 0.f, inv_l = 0.f;
+        for (int sweep = 0; sweep < 2; ++sweep) {
+          for (int j = 0; j < n; ++j) {
+            const bool diag = (j == n - 1);
+            const bool skip = diag && diag_masked;
+            ptx::mbar_wait(s_full(sr.idx), sr.phase);
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            if (!skip) {
+              ptx::tmem_ld_32x32(tmem + lane_addr + (uint32_t)(sr.idx * kAtBN + cq * 32), r);
+              ptx::tmem_ld_wait();
+            }
+            // the scores are in registers: hand the TMEM buffer back to the MMA warp before the math
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(s_empty(sr.idx));
+            sr.advance(2);
+            if (!skip && g.scale_mode == 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__fdiv_rn(__uint_as_float(r[i]), g.score_div));
+              for (int i = 0; i < 32; ++i) r[i] = f2u(__fmul_rn(u2f(r[i]), g.score_mul));
+            }
+            if (sweep == 0) {
+              if (!skip) {
+                if (!(diag && diag_partial)) stats32<false>(r, 32, m, mL, l);
+                else stats32<true>(r, nvalid_d, m, mL, l);
+              }
+            } else {
+              ptx::mbar_wait(p_empty(pr.idx), pr.phase ^ 1);
+              uint8_t* prow = smem + Cfg::kSmemP + (pr.idx * 2 + (cq >> 1)) * kSubTile + r_in * 128;
+              if (skip) {
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(prow + (((chunk0 + c) ^ sw) << 4)) = z;
+              } else if (!(diag && diag_partial)) {
+                probs32<KIND, false>(r, 32, m, inv_l, g.p, prow, chunk0, sw);
+              } else {
+                probs32<KIND, true>(r, nvalid_d, m, inv_l, g.p, prow, chunk0, sw);
+              }
+              ptx::fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the MMA (async proxy)
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(p_full(pr.idx));
+              pr.advance(2);
+            }
           }
           if (sweep == 0) {
-            float tmax = -INFINITY;
+            // merge the four column quarters of every row:  m = max m_c,  l = sum_c l_c * exp(m_c - m).
+            // Only the four warps that share this lane quarter exchange data: one 128-thread named barrier per quarter.
+            xm[cq * 128 + r_in] = m;
+            xl[cq * 128 + r_in] = stat_fixup(m, mL, l);
+            named_bar_sync(1 + quarter, 128);
+            float mm = xm[r_in];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) tmax = (i < nvalid) ? fmaxf(tmax, __uint_as_float(r[i])) : tmax;
-            if (tmax > m) {                                   // online rescale of the running sum
-              l = __fmul_rn(l, expf(__fsub_rn(m, tmax)));
-              m = tmax;
-            }
-            float acc = 0.f;
+            for (int c = 1; c < 4; ++c) mm = fmaxf(mm, xm[c * 128 + r_in]);
+            float ll = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc = (i < nvalid) ? __fadd_rn(acc, expf(__fsub_rn(__uint_as_float(r[i]), m))) : acc;
-            l = __fadd_rn(l, acc);
+            for (int c = 0; c < 4; ++c) ll = __fadd_rn(ll, __fmul_rn(xl[c * 128 + r_in], expf(__fsub_rn(xm[c * 128 + r_in], mm))));
+            m = mm;
+            l = ll;
+            inv_l = __frcp_rn(l);
+          }
+        }
+        // ---- epilogue: O (128 x D fp32 in TMEM) -> global; this warp owns D/4 of the D columns of its 32 rows
+        ptx::mbar_wait(o_full, ophase);
+        ophase ^= 1;
+        ptx::tc_fence_after();
+        constexpr int kOB = D / 64;                // 16-column blocks per thread
+        uint32_t ro[kOB][16];
+#pragma unroll
+        for (int c = 0; c < kOB; ++c) ptx::tmem_ld_32x16(tmem + lane_addr + kTmemO + (uint32_t)(cq * (D / 4) + c * 16), ro[c]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(o_empty);
+        if (row < g.S) {
+          const int64_t off = ((int64_t)b * g.S + row) * g.ldo + (int64_t)h * D + cq * (D / 4);
+          if (g.out_mode == 0) {
+            float* o = reinterpret_cast<float*>(g.out) + off;
+#pragma unroll
+            for (int c = 0; c < kOB; ++c)
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(o + c * 16 + i) = make_float4(u2f(ro[c][i]), u2f(ro[c][i + 1]), u2f(ro[c][i + 2]), u2f(ro[c][i + 3]));
           } else {
-            ptx::mbar_wait(p_empty(pr.idx), pr.phase ^ 1);
-            // probabilities of 32 keys = two reference blocks; quantise and store as bf16 into the P tile
-            uint8_t* prow = smem + kSmemP + (pr.idx * 2 + (cq >> 1)) * kTileBytes + r_in * 128;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + off;
 #pragma unroll
-            for (int blk = 0; blk < 2; ++blk) {
+            for (int c = 0; c < kOB; ++c) {
               float v[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float e = expf(__fsub_rn(__uint_as_float(r[blk * 16 + i]), m));
-                v[i] = (blk * 16 + i < nvalid) ? __fmul_rn(e, inv_l) : 0.f;
-              }
-              quantize_block16<KIND>(v, g.p);
-              uint32_t w32[8];
+              for (int i = 0; i < 16; ++i) v[i] = u2f(ro[c][i]);
+              quantize_signed16_rt(v, g.po);
+              uint32_t wv[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                w32[i] = *reinterpret_cast<uint32_t*>(&t2);
-              }
-              // 16-byte chunk index inside the 128-byte row, XOR-swizzled by (row & 7)  (SWIZZLE_128B)
-              const int chunk = (cq & 1) * 4 + blk * 2;
-              *reinterpret_cast<uint4*>(prow + ((chunk ^ (r_in & 7)) << 4)) = make_uint4(w32[0], w32[1], w32[2], w32[3]);
-              *reinterpret_cast<uint4*>(prow + (((chunk + 1) ^ (r_in & 7)) << 4)) = make_uint4(w32[4], w32[5], w32[6], w32[7]);
+              for (int i = 0; i < 8; ++i) wv[i] = pack_bf16_rn(v[2 * i], v[2 * i + 1]);
+              *reinterpret_cast<uint4*>(o + c * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+              *reinterpret_cast<uint4*>(o + c * 16 + 8) = make_uint4(wv[4], wv[5], wv[6], wv[7]);
             }
-            ptx::fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the MMA (async proxy)
           }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (sweep == 1) ptx::mbar_arrive(p_full(pr.idx));
-            ptx::mbar_arrive(s_empty(sr.idx));
-          }
-          if (sweep == 1) pr.advance(2);
-          sr.advance(2);
-        }
-        if (sweep == 0) {
-          // merge the four column quarters of every row:  m = max m_c,  l = sum_c l_c * exp(m_c - m)
-          xm[cq * 128 + r_in] = m;
-          xl[cq * 128 + r_in] = l;
-          named_bar_sync(1, kSoftmaxWarps * 32);
-          float mm = xm[r_in];
-#pragma unroll
-          for (int c = 1; c < 4; ++c) mm = fmaxf(mm, xm[c * 128 + r_in]);
-          float ll = 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) ll = __fadd_rn(ll, __fmul_rn(xl[c * 128 + r_in], expf(__fsub_rn(xm[c * 128 + r_in], mm))));
-          m = mm;
-          l = ll;
-          inv_l = __frcp_rn(l);
-          named_bar_sync(1, kSoftmaxWarps * 32);
         }
       }
-      // ---- epilogue: O (128 x 64 fp32 in TMEM) -> global; this warp owns 16 of the 64 columns of its 32 rows
-      ptx::mbar_wait(o_full, ophase);
-      ophase ^= 1;
-      ptx::tc_fence_after();
-      uint32_t r[16];
-      ptx::tmem_ld_32x16(tmem + lane_addr + kTmemO + (uint32_t)(cq * 16), r);
-      ptx::tmem_ld_wait();
-      if (row < g.S) {
-        float* o = g.out + ((int64_t)b * g.S + row) * g.ldo + (int64_t)h * kAtD + cq * 16;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                                                          __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(o_empty);
     }
   }
   ptx::tc_fence_before();
@@ -379,22 +527,63 @@ int make_params(const bq_format* f, FmtParams* p);
 int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, int64_t H, int64_t B, int64_t ld_tok,
                       int box_rows);
 
-template <int KIND>
+template <int KIND, int D>
 static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
                             cudaStream_t st) {
+  using Cfg = AtCfg<D>;
   static bool attr = false;
   if (!attr) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_kernel<KIND, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
     attr = true;
   }
-  const int items = g.B * g.H * g.q_tiles;
+  const int items = g.B * g.H * ((g.q_tiles + 1) / 2);
   const int grid = std::min(items, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
-    attention_causal_kernel<KIND><<<grid, kAtThreads, kAtSmemBytes, st>>>(tq, tk, tv, g);
+    attention_causal_kernel<KIND, D><<<grid, kAtThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
+}
+
+static int attention_impl(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq, void* out,
+                          int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                          float score_div, cudaStream_t st) {
+  if (!fp || B < 0 || H < 0 || S < 0) return BQ_ERR_BAD_ARG;
+  if (B == 0 || H == 0 || S == 0) return BQ_OK;
+  if (!Qq || !Kq || !Vq || !out) return BQ_ERR_BAD_ARG;
+  if (d != 64 && d != 128) return BQ_ERR_UNSUPPORTED;
+  if (fp->kind != BQ_KIND_BLOCK_FP && fp->kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
+  if (fp->block_rows != 1 || fp->block_cols != 16) return BQ_ERR_UNSUPPORTED;
+  if (fo && ((fo->kind != BQ_KIND_BLOCK_FP && fo->kind != BQ_KIND_BLOCK_MINIFLOAT) || fo->block_rows != 1 || fo->block_cols != 16))
+    return BQ_ERR_UNSUPPORTED;
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % (fo ? 8 : 4)) || ((uintptr_t)Qq % 16) || ((uintptr_t)Kq % 16) ||
+      ((uintptr_t)Vq % 16) || ((uintptr_t)out % 16))
+    return BQ_ERR_BAD_ARG;
+  if (!(score_div > 0.f) || !isfinite(score_div)) return BQ_ERR_BAD_ARG;
+  if (B * H * ((S + 127) / 128) > 0x7fffffffll || S > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  AttnArgs g;
+  memset(&g, 0, sizeof(g));
+  int rc = make_params(fp, &g.p);
+  if (rc) return rc;
+  g.p.fold_zero = 0;
+  if (fo) {
+    if ((rc = make_params(fo, &g.po))) return rc;
+    g.po.fold_zero = 0;
+    g.out_mode = 1;
+  }
+  g.out = out; g.B = (int)B; g.H = (int)H; g.S = (int)S; g.ldo = ldo;
+  g.q_tiles = (int)((S + kAtBM - 1) / kAtBM);
+  g.score_mul = 1.0f / score_div;
+  g.scale_mode = (score_div == 1.0f) ? 0 : 1;
+  CUtensorMap tq, tk, tv;
+  if ((rc = make_tmap_bf16_4d(&tq, Qq, d, S, H, B, ldq, kAtBM))) return rc;
+  if ((rc = make_tmap_bf16_4d(&tk, Kq, d, S, H, B, ldk, kAtBN))) return rc;
+  if ((rc = make_tmap_bf16_4d(&tv, Vq, d, S, H, B, ldv, kAtBN))) return rc;
+  const bool bfp = fp->kind == BQ_KIND_BLOCK_FP;
+  if (d == 64) return bfp ? launch_attention<kBlockFP, 64>(tq, tk, tv, g, st) : launch_attention<kBlockMinifloat, 64>(tq, tk, tv, g, st);
+  return bfp ? launch_attention<kBlockFP, 128>(tq, tk, tv, g, st) : launch_attention<kBlockMinifloat, 128>(tq, tk, tv, g, st);
 }
 
 }  // namespace bq
@@ -402,29 +591,12 @@ static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const 
 extern "C" int bq_attention_causal(const bq_format* fp, const void* Qq, const void* Kq, const void* Vq, float* out,
                                    int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv,
                                    int64_t ldo, float score_div, void* stream) {
-  using namespace bq;
-  if (!fp || B < 0 || H < 0 || S < 0) return BQ_ERR_BAD_ARG;
-  if (B == 0 || H == 0 || S == 0) return BQ_OK;
-  if (!Qq || !Kq || !Vq || !out) return BQ_ERR_BAD_ARG;
-  if (d != kAtD) return BQ_ERR_UNSUPPORTED;
-  if (fp->kind != BQ_KIND_BLOCK_FP && fp->kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
-  if (fp->block_rows != 1 || fp->block_cols != 16) return BQ_ERR_UNSUPPORTED;
-  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 4) || ((uintptr_t)Qq % 16) || ((uintptr_t)Kq % 16) ||
-      ((uintptr_t)Vq % 16) || ((uintptr_t)out % 16))
-    return BQ_ERR_BAD_ARG;
-  if (B * H * ((S + 127) / 128) > 0x7fffffffll || S > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
-  AttnArgs g;
-  int rc = make_params(fp, &g.p);
-  if (rc) return rc;
-  g.p.fold_zero = 0;
-  g.out = out; g.B = (int)B; g.H = (int)H; g.S = (int)S; g.ldo = ldo;
-  g.q_tiles = (int)((S + kAtBM - 1) / kAtBM);
-  g.score_div = score_div;
-  CUtensorMap tq, tk, tv;
-  if ((rc = make_tmap_bf16_4d(&tq, Qq, d, S, H, B, ldq, kAtBM))) return rc;
-  if ((rc = make_tmap_bf16_4d(&tk, Kq, d, S, H, B, ldk, kAtBN))) return rc;
-  if ((rc = make_tmap_bf16_4d(&tv, Vq, d, S, H, B, ldv, kAtBN))) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (fp->kind == BQ_KIND_BLOCK_FP) return launch_attention<kBlockFP>(tq, tk, tv, g, st);
-  return launch_attention<kBlockMinifloat>(tq, tk, tv, g, st);
+  return bq::attention_impl(fp, nullptr, Qq, Kq, Vq, out, B, H, S, d, ldq, ldk, ldv, ldo, score_div, (cudaStream_t)stream);
+}
+
+extern "C" int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq,
+                                     void* out_bf16, int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk,
+                                     int64_t ldv, int64_t ldo, float score_div, void* stream) {
+  if (!fo) return BQ_ERR_BAD_ARG;
+  return bq::attention_impl(fp, fo, Qq, Kq, Vq, out_bf16, B, H, S, d, ldq, ldk, ldv, ldo, score_div, (cudaStream_t)stream);
 }

@@ -14,6 +14,7 @@
 //   warp 2   TMEM allocator                       warps 4-7 epilogue (TMEM lane quarter = warp % 4)
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty x2 accumulators (MMA <-> epilogue).
 #include "bq_internal.h"
+#include "bq_blockops.cuh"
 #include "sm100_ptx.cuh"
 
 namespace bq {
@@ -33,6 +34,20 @@ template <int BN> struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStage + kBarBytes + 1024;   // + alignment slack
 };
 
+// Fused epilogue (EPI kernels): v = acc + bias; v *= scale; v = act(v); v = residual + v; v = Q(v); store fp32 / bf16.
+// Replaces the separate ATen / quantizer launches between two quantized Linears of a decoder layer
+// (reference models/opt_quantized/modeling_opt.py:206-225 q*scaling, :412-420 fc2(relu(fc1(x))), residual adds :395,:424,
+// and the x-quantizer of the consuming op, quantized_modules/linear.py:63-71 / quantized_functions/matmul.py:165-193).
+struct EpiArgs {
+  const float* residual;   // fp32 [M][ldr] or nullptr
+  int64_t ldr;
+  float scale;             // 1.0f: skipped
+  int act;                 // 0 none, 1 ReLU
+  int out_bf16;            // 0: fp32 store, 1: bf16 store
+  int qmode;               // 0 none; 1: blocks of 16 along N (one thread's registers); 2: blocks of 16 along M (16 lanes)
+  FmtParams q;
+};
+
 struct GemmArgs {
   float* C;
   const float* bias;
@@ -44,9 +59,78 @@ struct GemmArgs {
   // over the (plane_a, plane_b) pairs below and accumulates every product into the same TMEM accumulator
   int n_terms;
   int8_t term_a[8], term_b[8];
+  EpiArgs epi;
 };
 
-template <int BN>
+// one 32-column chunk of one accumulator row through the fused epilogue
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], int row, int col0, bool row_ok) {
+  const EpiArgs& e = g.epi;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (g.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(g.bias + col0 + j);
+      v[j] = __fadd_rn(v[j], bv.x); v[j + 1] = __fadd_rn(v[j + 1], bv.y);
+      v[j + 2] = __fadd_rn(v[j + 2], bv.z); v[j + 3] = __fadd_rn(v[j + 3], bv.w);
+    }
+  }
+  if (e.scale != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], e.scale);
+  }
+  if (e.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (v[j] < 0.f) ? 0.f : v[j];      // torch relu: NaN propagates
+  }
+  if (e.residual && row_ok) {
+    const float* rr = e.residual + (int64_t)row * e.ldr + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(rr + j);
+      v[j] = __fadd_rn(x.x, v[j]); v[j + 1] = __fadd_rn(x.y, v[j + 1]);
+      v[j + 2] = __fadd_rn(x.z, v[j + 2]); v[j + 3] = __fadd_rn(x.w, v[j + 3]);
+    }
+  }
+  if (e.qmode == 1) {
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+      float t[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t[i] = v[blk * 16 + i];
+      quantize_signed16_rt(t, e.q);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[blk * 16 + i] = t[i];
+    }
+  } else if (e.qmode == 2) {
+    // a block = 16 consecutive rows (lanes 0-15 / 16-31) of one column; M % 16 == 0, so a block is all-valid or all-invalid
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      uint32_t m = __float_as_uint(v[j]) & 0x7fffffffu;
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
+      if (m == 0) v[j] = 0.f;
+      else v[j] = (e.q.kind == kBlockFP) ? quant_with_max<kBlockFP>(v[j], m, e.q) : quant_with_max<kBlockMinifloat>(v[j], m, e.q);
+    }
+  }
+  if (!row_ok) return;
+  if (e.out_bf16) {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(g.C) + (int64_t)row * g.ldc + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8)
+      *reinterpret_cast<uint4*>(c + j) = make_uint4(pack_bf16_rn(v[j], v[j + 1]), pack_bf16_rn(v[j + 2], v[j + 3]),
+                                                    pack_bf16_rn(v[j + 4], v[j + 5]), pack_bf16_rn(v[j + 6], v[j + 7]));
+  } else {
+    float* c = g.C + (int64_t)row * g.ldc + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+}
+
+template <int BN, bool EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
   using Cfg = GemmCfg<BN>;
@@ -155,6 +239,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const int row = mb * kBM + q * 32 + lane;
+      if (EPI) {
+        // fused epilogue (batch == 1, N % 32 == 0, all pointers 16-byte aligned: checked on the host)
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = nb * BN + c * 32;
+          if (col0 >= g.N) break;                 // warp-uniform
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+          ptx::tmem_ld_wait();
+          epilogue_chunk(g, r, row, col0, row < g.M);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
       const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((g.sc & 3) == 0) &&
                           ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
@@ -263,12 +364,12 @@ int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, i
   return BQ_OK;
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, cudaStream_t st) {
+template <int BN, bool EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, cudaStream_t st, int kern_id = kKernGemm) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   g.tiles_m = (g.M + kBM - 1) / kBM;
@@ -277,8 +378,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs 
   if (total > 0x7fffffffll) return BQ_ERR_UNSUPPORTED;
   int grid = (int)std::min<int64_t>(total, num_sms());
   {
-    LaunchScope ls(kKernGemm, st);
-    gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, g);
+    LaunchScope ls(kern_id, st);
+    gemm_bf16_tn_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, g);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
@@ -306,10 +407,60 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
   g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = (int)batch;
   g.ldc = ldc; g.sc = sc; g.tiles_m = g.tiles_n = 0; g.b_broadcast = bcast ? 1 : 0;
   g.n_terms = 0;
+  memset(&g.epi, 0, sizeof(g.epi));
   switch (BN) {
-    case 64: return launch_gemm<64>(tmA, tmB, g, st);
-    case 128: return launch_gemm<128>(tmA, tmB, g, st);
-    default: return launch_gemm<256>(tmA, tmB, g, st);
+    case 64: return launch_gemm<64, false>(tmA, tmB, g, st);
+    case 128: return launch_gemm<128, false>(tmA, tmB, g, st);
+    default: return launch_gemm<256, false>(tmA, tmB, g, st);
+  }
+}
+
+int make_params(const bq_format* f, FmtParams* p);
+
+// GEMM with the fused epilogue (see EpiArgs).  C: fp32 or bf16 [M][ldc].
+int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_epilogue* ep, int64_t M, int64_t N, int64_t K,
+                          int64_t lda, int64_t ldb, int64_t ldc, cudaStream_t st) {
+  if (!ep || M < 0 || N < 0 || K < 0) return BQ_ERR_BAD_ARG;
+  if (M == 0 || N == 0) return BQ_OK;
+  if (!A || !B || !C) return BQ_ERR_BAD_ARG;
+  if (K == 0) return BQ_ERR_UNSUPPORTED;
+  if ((lda % 8) || (ldb % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)C % 16)) return BQ_ERR_BAD_ARG;
+  if (lda < K || ldb < K || ldc < N) return BQ_ERR_BAD_ARG;
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  if (N % 32) return BQ_ERR_UNSUPPORTED;
+  const bool out_bf16 = ep->out_dtype == BQ_BF16;
+  if (ep->out_dtype != BQ_F32 && !out_bf16) return BQ_ERR_BAD_ARG;
+  if (ldc % (out_bf16 ? 8 : 4)) return BQ_ERR_BAD_ARG;
+  if (ep->bias && ((uintptr_t)ep->bias % 16)) return BQ_ERR_BAD_ARG;
+  if (ep->residual && (((uintptr_t)ep->residual % 16) || (ep->ldr % 4) || ep->ldr < N)) return BQ_ERR_BAD_ARG;
+  if (ep->act != 0 && ep->act != 1) return BQ_ERR_UNSUPPORTED;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.epi.residual = ep->residual; g.epi.ldr = ep->ldr; g.epi.scale = ep->scale; g.epi.act = ep->act;
+  g.epi.out_bf16 = out_bf16 ? 1 : 0;
+  if (ep->qfmt) {
+    const bq_format* f = ep->qfmt;
+    if (f->kind != BQ_KIND_BLOCK_FP && f->kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
+    if (f->block_rows != 1 || f->block_cols != 16) return BQ_ERR_UNSUPPORTED;     // block of 16 along the chosen direction
+    if (ep->qdir != 0 && ep->qdir != 1) return BQ_ERR_BAD_ARG;
+    if (ep->qdir == 1 && (M % 16)) return BQ_ERR_UNSUPPORTED;
+    int rc = make_params(f, &g.epi.q);
+    if (rc) return rc;
+    g.epi.q.fold_zero = 0;
+    g.epi.qmode = ep->qdir == 1 ? 2 : 1;
+  }
+  const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, 1, lda, 0, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, 1, ldb, 0, BN);
+  if (rc) return rc;
+  g.C = (float*)C; g.bias = ep->bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = 1;
+  g.ldc = ldc; g.sc = 0; g.b_broadcast = 1; g.n_terms = 0;
+  switch (BN) {
+    case 64: return launch_gemm<64, true>(tmA, tmB, g, st, kKernGemmEpi);
+    case 128: return launch_gemm<128, true>(tmA, tmB, g, st, kKernGemmEpi);
+    default: return launch_gemm<256, true>(tmA, tmB, g, st, kKernGemmEpi);
   }
 }
 
@@ -338,14 +489,20 @@ int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias
     g.term_a[i] = (int8_t)ta[i];
     g.term_b[i] = (int8_t)tb[i];
   }
+  memset(&g.epi, 0, sizeof(g.epi));
   switch (BN) {
-    case 64: return launch_gemm<64>(tmA, tmB, g, st);
-    case 128: return launch_gemm<128>(tmA, tmB, g, st);
-    default: return launch_gemm<256>(tmA, tmB, g, st);
+    case 64: return launch_gemm<64, false>(tmA, tmB, g, st, kKernGemmSplit);
+    case 128: return launch_gemm<128, false>(tmA, tmB, g, st, kKernGemmSplit);
+    default: return launch_gemm<256, false>(tmA, tmB, g, st, kKernGemmSplit);
   }
 }
 
 }  // namespace bq
+
+extern "C" int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_gemm_epilogue* ep, int64_t M, int64_t N,
+                                  int64_t K, int64_t lda, int64_t ldb, int64_t ldc, void* stream) {
+  return bq::gemm_bf16_tn_epi_impl(A, B, C, ep, M, N, K, lda, ldb, ldc, (cudaStream_t)stream);
+}
 
 extern "C" int bq_gemm_split_tn(const void* A_planes, const void* B_planes, float* C, const float* bias, int64_t M, int64_t N,
                                 int64_t K, int32_t planes_a, int32_t planes_b, int32_t n_terms, const int32_t* term_a,

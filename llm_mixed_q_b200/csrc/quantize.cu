@@ -606,6 +606,144 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm + quantize: y_k = Q_k(norm(x)) for up to three operand formats, bf16 out.
+// Replaces `self_attn_layer_norm` / `final_layer_norm` (models/opt_quantized/modeling_opt.py:386,:414;
+// input_layernorm / post_attention_layernorm, models/llama_quantized/modeling_llama.py:386,:399) FOLLOWED BY the
+// x-quantizers of the Linears that read the normalised tensor (q/k/v_proj share one input, modeling_opt.py:206,224-225;
+// fc1; gate/up_proj) — one read of x, one bf16 write per distinct format, instead of an fp32 round trip per consumer.
+// One CTA per row; the row lives in registers (VPT float4 per thread); block of 16 = 4 adjacent lanes.
+// Normalisation arithmetic follows torch's CUDA kernels: LayerNorm  y = fma(gamma, rstd * (x - mean), beta)  with
+// rstd = rsqrtf(var + eps) (layer_norm_kernel.cu); RMSNorm  y = w * (x * rsqrtf(mean(x^2) + eps)).  The statistics are
+// summed in a different order than torch's Welford / reduction kernels (<= 1-2 ulp in mean / rstd), see DESIGN.md.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnThreads = 256;
+struct LnArgs {
+  const float* x;
+  int64_t ldx;
+  const float* gamma;
+  const float* beta;      // nullptr: RMSNorm
+  float eps;
+  int H;
+  int n_out;
+  __nv_bfloat16* out[3];
+  FmtParams f[3];
+};
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5;
+  __syncthreads();                       // protects `red` against the previous use
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = red[0];
+#pragma unroll
+  for (int i = 1; i < kLnThreads / 32; ++i) t = __fadd_rn(t, red[i]);
+  return t;
+}
+template <int VPT>
+__global__ void __launch_bounds__(kLnThreads) norm_quant_kernel(LnArgs a) {
+  __shared__ float red[kLnThreads / 32];
+  const int row = blockIdx.x;
+  const float* xr = a.x + (int64_t)row * a.ldx;
+  const int nslot = a.H >> 2;
+  float4 v[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int s = i * kLnThreads + threadIdx.x;
+    v[i] = (s < nslot) ? ldg_stream4(xr + 4 * s) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invH = 1.0f / (float)a.H;
+  float mean = 0.f, rstd;
+  if (a.beta) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) sum = __fadd_rn(sum, __fadd_rn(__fadd_rn(v[i].x, v[i].y), __fadd_rn(v[i].z, v[i].w)));
+    mean = __fmul_rn(block_sum(sum, red), invH);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int s = i * kLnThreads + threadIdx.x;
+      if (s < nslot) {
+        const float dx = __fsub_rn(v[i].x, mean), dy = __fsub_rn(v[i].y, mean), dz = __fsub_rn(v[i].z, mean), dw = __fsub_rn(v[i].w, mean);
+        sq = __fadd_rn(sq, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fadd_rn(__fmul_rn(dz, dz), __fmul_rn(dw, dw))));
+      }
+    }
+    rstd = rsqrtf(__fadd_rn(__fmul_rn(block_sum(sq, red), invH), a.eps));
+  } else {
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      sq = __fadd_rn(sq, __fadd_rn(__fadd_rn(__fmul_rn(v[i].x, v[i].x), __fmul_rn(v[i].y, v[i].y)),
+                                   __fadd_rn(__fmul_rn(v[i].z, v[i].z), __fmul_rn(v[i].w, v[i].w))));
+    rstd = rsqrtf(__fadd_rn(__fmul_rn(block_sum(sq, red), invH), a.eps));
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int s = i * kLnThreads + threadIdx.x;
+    const bool act = s < nslot;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {
+      const float4 gm = *reinterpret_cast<const float4*>(a.gamma + 4 * s);
+      if (a.beta) {
+        const float4 bt = *reinterpret_cast<const float4*>(a.beta + 4 * s);
+        y.x = __fmaf_rn(gm.x, __fmul_rn(rstd, __fsub_rn(v[i].x, mean)), bt.x);
+        y.y = __fmaf_rn(gm.y, __fmul_rn(rstd, __fsub_rn(v[i].y, mean)), bt.y);
+        y.z = __fmaf_rn(gm.z, __fmul_rn(rstd, __fsub_rn(v[i].z, mean)), bt.z);
+        y.w = __fmaf_rn(gm.w, __fmul_rn(rstd, __fsub_rn(v[i].w, mean)), bt.w);
+      } else {
+        y.x = __fmul_rn(gm.x, __fmul_rn(v[i].x, rstd));
+        y.y = __fmul_rn(gm.y, __fmul_rn(v[i].y, rstd));
+        y.z = __fmul_rn(gm.z, __fmul_rn(v[i].z, rstd));
+        y.w = __fmul_rn(gm.w, __fmul_rn(v[i].w, rstd));
+      }
+    }
+    // block max over the 4 adjacent lanes that hold one block of 16 (H % 16 == 0: a block is all-active or all-inactive)
+    uint32_t m = max(max(absbits(y.x), absbits(y.y)), max(absbits(y.z), absbits(y.w)));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    if (m == 0) m = 0x3f800000u;
+    if (act) {
+      for (int k = 0; k < a.n_out; ++k) {
+        const float4 q = (a.f[k].kind == kBlockFP) ? quant4<kBlockFP>(y, m, a.f[k]) : quant4<kBlockMinifloat>(y, m, a.f[k]);
+        store4<__nv_bfloat16>(a.out[k] + (int64_t)row * a.H + 4 * s, q);
+      }
+    }
+  }
+}
+
+int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, const float* gamma, const float* beta, float eps,
+                       int n_out, const bq_format* fmts, void* const* outs, cudaStream_t st) {
+  if (rows < 0 || H <= 0 || n_out < 1 || n_out > 3 || !fmts || !outs) return BQ_ERR_BAD_ARG;
+  if (rows == 0) return BQ_OK;
+  if (!x || !gamma) return BQ_ERR_BAD_ARG;
+  if ((H % 16) || H > 4 * kLnThreads * 8 || rows > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  if (((uintptr_t)x % 16) || (ldx % 4) || ldx < H || ((uintptr_t)gamma % 16) || (beta && ((uintptr_t)beta % 16))) return BQ_ERR_BAD_ARG;
+  LnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.ldx = ldx; a.gamma = gamma; a.beta = beta; a.eps = eps; a.H = (int)H; a.n_out = n_out;
+  for (int k = 0; k < n_out; ++k) {
+    if (!outs[k] || ((uintptr_t)outs[k] % 8)) return BQ_ERR_BAD_ARG;
+    if (fmts[k].kind != BQ_KIND_BLOCK_FP && fmts[k].kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
+    if (fmts[k].block_rows != 1 || fmts[k].block_cols != 16) return BQ_ERR_UNSUPPORTED;
+    int rc = make_params(&fmts[k], &a.f[k]);
+    if (rc) return rc;
+    a.f[k].fold_zero = 0;
+    a.out[k] = (__nv_bfloat16*)outs[k];
+  }
+  const int vpt = (int)((H / 4 + kLnThreads - 1) / kLnThreads);
+  {
+    LaunchScope ls(kKernLnQuant, st);
+    switch (vpt) {
+      case 1: norm_quant_kernel<1><<<(int)rows, kLnThreads, 0, st>>>(a); break;
+      case 2: norm_quant_kernel<2><<<(int)rows, kLnThreads, 0, st>>>(a); break;
+      case 3: case 4: norm_quant_kernel<4><<<(int)rows, kLnThreads, 0, st>>>(a); break;
+      default: norm_quant_kernel<8><<<(int)rows, kLnThreads, 0, st>>>(a); break;
+    }
+  }
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // exhaustive self-test of the exponent-field shortcuts against libdevice log2f
 // ------------------------------------------------------------------------------------------------
 __global__ void selftest_log2_kernel(unsigned long long* mism) {
@@ -647,6 +785,10 @@ int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream) {
   bq::selftest_log2_kernel<<<bq::num_sms() * 8, 256, 0, st>>>(mismatches_dev3);
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
+}
+int bq_norm_quantize(const float* x, int64_t rows, int64_t H, int64_t ldx, const float* gamma, const float* beta, float eps,
+                     int32_t n_out, const bq_format* fmts, void* const* outs_bf16, void* stream) {
+  return bq::norm_quantize_impl(x, rows, H, ldx, gamma, beta, eps, n_out, fmts, outs_bf16, (cudaStream_t)stream);
 }
 size_t bq_quantize_workspace_bytes(const bq_format* fmt, const bq_tensor3* x) { return bq::quantize_ws_bytes(fmt, x); }
 int bq_quantize(const bq_format* fmt, const bq_tensor3* x_desc, const float* x, void* y, int32_t y_dtype,

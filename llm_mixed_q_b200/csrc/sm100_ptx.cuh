@@ -31,15 +31,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Blocks until the phase with the given parity completes.  try_wait carries a suspend-time hint, so a waiting thread
+// sleeps in hardware (woken by the completing arrive) instead of spinning through issue slots that the math warps of
+// the same SM sub-partition need (ncu: the hint-less loop cost 14 % of all issued instructions in the attention kernel).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
       "@P bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}\n" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 

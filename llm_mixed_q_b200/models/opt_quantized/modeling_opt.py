@@ -21,7 +21,9 @@ from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
 from ..quantize.quantized_functions.fp32_linear import fp32_linear
-from ..quantize.quantized_functions.attention import fusable as _attn_fusable, fused_causal_attention
+from ..quantize.quantized_functions.attention import (fusable as _attn_fusable, fused_causal_attention,
+                                                      fused_causal_attention_q, output_quantizable)
+from ..quantize.quantized_functions.fused_glue import linear_input_format, norm_quantize, row_block16_format
 from .configuration_opt import OPTQuantizedConfig
 
 
@@ -84,6 +86,11 @@ class OPTQauntizedAttention(nn.Module):      # (sic) class name kept from the re
             q = self.q_proj(hidden_states) * self.scaling
             k = self.k_proj(hidden_states)
             v = self.v_proj(hidden_states)
+            if self.out_proj.accepts_prequantized() and output_quantizable(self.out_proj.config, self.embed_dim):
+                # the x-quantizer of out_proj runs in the attention epilogue; out_proj consumes the bf16 operand directly
+                oq = fused_causal_attention(q, k, v, self.quant_config["bmm_0"], self.quant_config["bmm_1"], self.num_heads,
+                                            score_div=1.0, out_cfg=self.out_proj.config)
+                return self.out_proj.forward_prequantized(oq), None
             attn_output = fused_causal_attention(q, k, v, self.quant_config["bmm_0"], self.quant_config["bmm_1"],
                                                  self.num_heads, score_div=1.0)
             return self.out_proj(attn_output), None
@@ -127,12 +134,63 @@ class OPTQuantizedDecoderLayer(nn.Module):
         self.do_layer_norm_before = config.do_layer_norm_before
         self.dropout = config.dropout
         self.activation_fn = ACT2FN[config.activation_function]
+        self.activation_name = config.activation_function
         self.self_attn_layer_norm = nn.LayerNorm(self.embed_dim, elementwise_affine=config.layer_norm_elementwise_affine)
         self.fc1 = get_quantized_cls("linear", qc["fc1"])(self.embed_dim, config.ffn_dim, bias=config.enable_bias, config=qc["fc1"])
         self.fc2 = get_quantized_cls("linear", qc["fc2"])(config.ffn_dim, self.embed_dim, bias=config.enable_bias, config=qc["fc2"])
         self.final_layer_norm = nn.LayerNorm(self.embed_dim, elementwise_affine=config.layer_norm_elementwise_affine)
 
-    def forward(self, hidden_states, attention_mask=None, output_attentions=False, causal_only=False):
+    # ------------------------------------------------------------------ fused layer (PTQ inference, causal mask)
+    def _fused_plan(self, seq_len: int):
+        """Formats for running the whole layer on 8 fused kernels, or None when any piece is not eligible.
+        Each x-quantizer then runs inside the kernel that produces its input: LN->quantize, GEMM epilogues
+        (bias, q scaling, ReLU, residual add, quantize), attention epilogue; every GEMM reads a bf16 operand."""
+        key = seq_len
+        cache = getattr(self, "_plan_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        at = self.self_attn
+        plan = None
+        H, d = self.embed_dim, at.head_dim
+        ok = (self.do_layer_norm_before and getattr(self, "activation_name", None) == "relu" and seq_len % 16 == 0
+              and H % 32 == 0 and self.fc1.out_features % 32 == 0
+              and self.self_attn_layer_norm.elementwise_affine and self.final_layer_norm.elementwise_affine
+              and _attn_fusable(at.quant_config["bmm_0"], at.quant_config["bmm_1"], d, seq_len))
+        if ok:
+            fmts = dict(
+                q_in=linear_input_format(at.q_proj), k_in=linear_input_format(at.k_proj), v_in=linear_input_format(at.v_proj),
+                o_in=linear_input_format(at.out_proj) if output_quantizable(at.out_proj.config, H) else None,
+                fc1_in=linear_input_format(self.fc1), fc2_in=linear_input_format(self.fc2),
+                q_out=row_block16_format(at.quant_config["bmm_0"], "data_in", d),
+                k_out=row_block16_format(at.quant_config["bmm_0"], "weight", seq_len),
+                v_out=row_block16_format(at.quant_config["bmm_1"], "weight", d))
+            if all(v is not None for v in fmts.values()):
+                plan = fmts
+        self._plan_cache = (key, plan)
+        return plan
+
+    @torch.no_grad()
+    def _fused_forward(self, h, plan):
+        B, S, H = h.shape
+        at = self.self_attn
+        ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm
+        xq_q, xq_k, xq_v = norm_quantize(h, ln1.weight, ln1.bias, ln1.eps, [plan["q_in"], plan["k_in"], plan["v_in"]])
+        Qq = at.q_proj.forward_prequantized(xq_q, scale=at.scaling, out_format=plan["q_out"])
+        Kq = at.k_proj.forward_prequantized(xq_k, out_format=plan["k_out"], out_blocks_along_rows=True)
+        Vq = at.v_proj.forward_prequantized(xq_v, out_format=plan["v_out"])
+        oq = fused_causal_attention_q(Qq, Kq, Vq, at.quant_config["bmm_1"], at.num_heads, B, S, 1.0, out_cfg=at.out_proj.config)
+        h2 = at.out_proj.forward_prequantized(oq, residual=h)                         # residual + out_proj(attn)
+        (x1,) = norm_quantize(h2, ln2.weight, ln2.bias, ln2.eps, [plan["fc1_in"]])
+        a = self.fc1.forward_prequantized(x1.view(B * S, H), relu=True, out_format=plan["fc2_in"])
+        h3 = self.fc2.forward_prequantized(a, residual=h2.view(B * S, H))             # residual + fc2(relu(fc1(x)))
+        return h3.view(B, S, H)
+
+    def forward(self, hidden_states, attention_mask=None, output_attentions=False, causal_only=False, fused_glue=False):
+        if (fused_glue and causal_only and not output_attentions and hidden_states.is_cuda and hidden_states.dtype == torch.float32
+                and not torch.is_grad_enabled() and not self.training and hidden_states.ndim == 3):
+            plan = self._fused_plan(hidden_states.shape[1])
+            if plan is not None:
+                return self._fused_forward(hidden_states, plan), None
         residual = hidden_states
         if self.do_layer_norm_before:
             hidden_states = self.self_attn_layer_norm(hidden_states)
@@ -201,6 +259,7 @@ class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
             self.final_layer_norm = None
         self.layers = nn.ModuleList([OPTQuantizedDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
         self.fused_attention = True      # set False to force the op-by-op attention path (QUANTIZED_FUNC_MAP bmm functions)
+        self.fused_glue = True           # set False to run LayerNorm / ReLU / residual / x-quantizers as separate kernels
         self.post_init()
 
     def get_input_embeddings(self):
@@ -229,7 +288,7 @@ class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
             if output_hidden_states:
                 all_h += (hidden_states,)
             hidden_states, attn = layer(hidden_states, attention_mask=causal, output_attentions=output_attentions,
-                                        causal_only=causal_only)
+                                        causal_only=causal_only, fused_glue=self.fused_glue and causal_only)
             if output_attentions:
                 all_a += (attn,)
         if self.final_layer_norm is not None:

@@ -26,7 +26,7 @@ def fusable(cfg0: dict, cfg1: dict, head_dim: int, seq_len: int) -> bool:
     try:
         if cfg0.get("bypass", False) or cfg1.get("bypass", False):
             return False
-        if head_dim != 64:
+        if head_dim not in (64, 128):
             return False
         (qk, qkw, qbs), (kk, kkw, kbs) = operand_format(cfg0, "data_in"), operand_format(cfg0, "weight")
         (pk, pkw, pbs), (vk, vkw, vbs) = operand_format(cfg1, "data_in"), operand_format(cfg1, "weight")
@@ -48,17 +48,26 @@ def fusable(cfg0: dict, cfg1: dict, head_dim: int, seq_len: int) -> bool:
         pb[1] == 1 and pb[2] == 16
 
 
-def fused_causal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cfg0: dict, cfg1: dict, num_heads: int,
-                           score_div: float = 1.0) -> torch.Tensor:
-    """
-    q, k, v: fp32 [B, S, H] projections (q already scaled where the model scales before bmm_0, as OPT does).
-    Returns fp32 [B, S, H] = concat over heads of  Q(softmax(Q(q) Q(k)^T / score_div, causal)) @ Q(v).
-    """
-    lib = L.load()
+def output_quantizable(out_cfg: dict, hidden: int) -> bool:
+    """Can the x-quantizer of the Linear that consumes the attention output run in the attention epilogue?"""
+    try:
+        if out_cfg is None or out_cfg.get("bypass", False) or not out_cfg.get("is_ptq", False):
+            return False
+        ok, okw, obs = operand_format(out_cfg, "data_in")
+    except KeyError:
+        return False
+    if ok not in ("block_fp", "block_minifloat") or obs is None or significant_bits(ok, okw) > 8:
+        return False
+    ob = resolve_block_shape([1, 1, hidden], obs)
+    return ob[1] == 1 and ob[2] == 16
+
+
+def quantize_qkv(q, k, v, cfg0: dict, cfg1: dict, num_heads: int):
+    """fp32 [B, S, H] projections -> the three bf16 [B, S, H] operands of the fused kernel."""
     B, S, H = q.shape
     d = H // num_heads
     (qk, qkw, qbs), (kk, kkw, kbs) = operand_format(cfg0, "data_in"), operand_format(cfg0, "weight")
-    (pk, pkw, pbs), (vk, vkw, vbs) = operand_format(cfg1, "data_in"), operand_format(cfg1, "weight")
+    (vk, vkw, vbs) = operand_format(cfg1, "weight")
     # q / v: blocks along d — identical to blocking the [B*S, H] matrix along H because b1 divides d
     qb = resolve_block_shape([1, S, d], qbs)[2]
     vb = resolve_block_shape([1, S, d], vbs)[2]
@@ -67,9 +76,42 @@ def fused_causal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cf
     # k: the reference quantises k^T, i.e. blocks of consecutive KEY POSITIONS at fixed feature
     kb = resolve_block_shape([1, d, S], kbs)[2]
     Kq = quantize_operand_bf16(k.transpose(1, 2), kk, kkw, [1, kb], True, transpose_out=True)     # -> [B, S, H]
+    return Qq, Kq, Vq
+
+
+def fused_causal_attention_q(Qq: torch.Tensor, Kq: torch.Tensor, Vq: torch.Tensor, cfg1: dict, num_heads: int, B: int, S: int,
+                             score_div: float = 1.0, out_cfg: dict = None) -> torch.Tensor:
+    """Kernel call on already-quantised bf16 operands ([B*S, H] or [B, S, H], unit stride along H).
+    Returns fp32 [B, S, H], or — with `out_cfg` (config of the Linear consuming the result) — its bf16 x-quantised form."""
+    lib = L.load()
+    H = Qq.shape[-1]
+    d = H // num_heads
+    (pk, pkw, pbs) = operand_format(cfg1, "data_in")
     fp = make_format(pk, b0=1, b1=16, **pkw)
-    out = torch.empty((B, S, H), dtype=torch.float32, device=q.device)
-    rc = lib.bq_attention_causal(ctypes.byref(fp), Qq.data_ptr(), Kq.data_ptr(), Vq.data_ptr(), out.data_ptr(), B, num_heads,
-                                 S, d, H, H, H, H, float(score_div), L.stream_ptr(q.device))
-    L.check(rc, "bq_attention_causal")
+    dev = Qq.device
+    ld = lambda t: t.stride(-2)
+    if out_cfg is None:
+        out = torch.empty((B, S, H), dtype=torch.float32, device=dev)
+        rc = lib.bq_attention_causal(ctypes.byref(fp), Qq.data_ptr(), Kq.data_ptr(), Vq.data_ptr(), out.data_ptr(), B, num_heads,
+                                     S, d, ld(Qq), ld(Kq), ld(Vq), H, float(score_div), L.stream_ptr(dev))
+        L.check(rc, "bq_attention_causal")
+        return out
+    ok, okw, _ = operand_format(out_cfg, "data_in")
+    fo = make_format(ok, b0=1, b1=16, **okw)
+    out = torch.empty((B, S, H), dtype=torch.bfloat16, device=dev)
+    rc = lib.bq_attention_causal_q(ctypes.byref(fp), ctypes.byref(fo), Qq.data_ptr(), Kq.data_ptr(), Vq.data_ptr(), out.data_ptr(),
+                                   B, num_heads, S, d, ld(Qq), ld(Kq), ld(Vq), H, float(score_div), L.stream_ptr(dev))
+    L.check(rc, "bq_attention_causal_q")
     return out
+
+
+def fused_causal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cfg0: dict, cfg1: dict, num_heads: int,
+                           score_div: float = 1.0, out_cfg: dict = None) -> torch.Tensor:
+    """
+    q, k, v: fp32 [B, S, H] projections (q already scaled where the model scales before bmm_0, as OPT does).
+    Returns fp32 [B, S, H] = concat over heads of  Q(softmax(Q(q) Q(k)^T / score_div, causal)) @ Q(v)
+    (bf16, x-quantised for the consuming Linear, when `out_cfg` is given).
+    """
+    B, S, H = q.shape
+    Qq, Kq, Vq = quantize_qkv(q, k, v, cfg0, cfg1, num_heads)
+    return fused_causal_attention_q(Qq, Kq, Vq, cfg1, num_heads, B, S, score_div, out_cfg)

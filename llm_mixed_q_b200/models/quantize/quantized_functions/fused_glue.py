@@ -1,0 +1,86 @@
+"""
+Glue fusion between the quantized ops of a decoder layer — host side of bq_norm_quantize and of
+the quantising GEMM / attention epilogues (include/bq.h).
+
+The reference runs every op of a layer as its own torch kernels and round-trips fp32 activations through HBM between
+them (models/opt_quantized/modeling_opt.py:360-441).  In PTQ inference the x-quantizer of an op only depends on the
+tensor it reads, so it can run inside the kernel that PRODUCES that tensor and hand the next GEMM a bf16 operand
+holding the exact quantised values.  These helpers decide when that is legal and build the format descriptors; the
+arithmetic (and its op order) is the reference's.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .... import _lib as L
+from ..quantized_modules.linear import _LinearBase, operand_format, significant_bits
+from ..quantizers.utils import make_format, resolve_block_shape
+
+_EPI_KINDS = ("block_fp", "block_minifloat")
+
+
+def row_block16_format(config: dict, prefix: str, last_dim: int) -> Optional[Tuple[str, dict]]:
+    """(kind, kwargs) when `<prefix>_*` of a config node is a block_fp / block_minifloat format that resolves to blocks of
+    16 along a last dim of size `last_dim` and is exact in bf16 — i.e. something an epilogue can apply — else None."""
+    try:
+        if config is None or config.get("bypass", False):
+            return None
+        kind, kw, bs = operand_format(config, prefix)
+    except KeyError:
+        return None
+    if kind not in _EPI_KINDS or bs is None or significant_bits(kind, kw) > 8:
+        return None
+    b = resolve_block_shape([1, 1, last_dim], bs)
+    if b[1] != 1 or b[2] != 16 or last_dim % 16:
+        return None
+    return kind, kw
+
+
+def linear_input_format(lin, last_dim: Optional[int] = None) -> Optional[Tuple[str, dict]]:
+    """x-quantizer of a quantized Linear as an epilogue format, if the module can take a pre-quantised bf16 input."""
+    if not isinstance(lin, _LinearBase) or not lin.accepts_prequantized():
+        return None
+    return row_block16_format(lin.config, "data_in", lin.in_features if last_dim is None else last_dim)
+
+
+def _same(a, b) -> bool:
+    return a[0] == b[0] and a[1] == b[1]
+
+
+@torch.no_grad()
+def norm_quantize(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float,
+                  formats: Sequence[Tuple[str, dict]]) -> List[torch.Tensor]:
+    """
+    LayerNorm (bias given) or RMSNorm (bias None) of fp32 x [..., H], then one bf16 tensor per entry of `formats` holding
+    Q_format(norm(x)); identical formats share one output tensor (q/k/v_proj usually do).
+    """
+    lib = L.load()
+    H = x.shape[-1]
+    x2 = x.reshape(-1, H)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 4 != 0):
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    distinct: List[Tuple[str, dict]] = []
+    index = []
+    for f in formats:
+        for i, d in enumerate(distinct):
+            if _same(f, d):
+                index.append(i)
+                break
+        else:
+            index.append(len(distinct))
+            distinct.append(f)
+    outs = [torch.empty((rows, H), dtype=torch.bfloat16, device=x.device) for _ in distinct]
+    for lo in range(0, len(distinct), 3):
+        chunk = distinct[lo:lo + 3]
+        fmts = (L.BqFormat * len(chunk))(*[make_format(k, b0=1, b1=16, **kw) for k, kw in chunk])
+        ptrs = (ctypes.c_void_p * len(chunk))(*[o.data_ptr() for o in outs[lo:lo + 3]])
+        rc = lib.bq_norm_quantize(x2.data_ptr(), rows, H, x2.stride(0) if rows > 1 else H, weight.data_ptr(),
+                                  bias.data_ptr() if bias is not None else None, float(eps), len(chunk), fmts, ptrs,
+                                  L.stream_ptr(x.device))
+        L.check(rc, "bq_norm_quantize")
+    shape = tuple(x.shape)
+    return [outs[i].view(shape) for i in index]

@@ -154,17 +154,85 @@ class _LinearBase(nn.Linear):
                 L.check(rc, "bq_gemm_bf16_tn")
         return y.reshape(*x.shape[:-1], N)
 
+    def _ensure_ptq(self):
+        """One-off PTQ overwrite of weight / bias with their quantised values (reference linear.py:66-70)."""
+        if self.weight_requires_quantisation:
+            with torch.no_grad():
+                self.weight.copy_(self.w_quantizer(self.weight.data))
+                if self.bias is not None:
+                    self.bias.copy_(self.b_quantizer(self.bias.data))
+            self.weight_requires_quantisation = False
+            self._wq_bf16 = None
+
+    def accepts_prequantized(self) -> bool:
+        """True when `forward_prequantized` may be used: PTQ mode and a weight format that is exact in bf16."""
+        if self.bypass or not self.is_ptq or self.weight.dtype != torch.float32 or self.in_features % 8 != 0:
+            return False
+        try:
+            wkind, wkw, _ = operand_format(self.config, "weight")
+        except KeyError:
+            return False
+        return significant_bits(wkind, wkw) <= 8
+
+    @torch.no_grad()
+    def forward_prequantized(self, xq: torch.Tensor, *, scale: float = 1.0, relu: bool = False, residual: torch.Tensor = None,
+                             out_format=None, out_blocks_along_rows: bool = False) -> torch.Tensor:
+        """
+        y = F.linear(xq, Wq, bq) for an input that ALREADY went through this module's x-quantizer inside the kernel that
+        produced it (bf16 carrier of the exact quantised values), with the layer glue that follows fused into the GEMM
+        epilogue (bq_gemm_bf16_tn_ex, include/bq.h), in the reference's op order:
+            y = y * scale;  y = relu(y);  y = residual + y;  y = Q_out(y)
+        out_format: None -> fp32 result; (kind, kwargs) of the x-quantizer of the NEXT op (block [1,16]) -> bf16 result
+        holding its exact quantised values.  out_blocks_along_rows: the 16-blocks run over 16 consecutive rows (tokens)
+        instead of 16 consecutive features (the k^T operand of bmm_0).
+        """
+        assert xq.dtype == torch.bfloat16 and xq.is_cuda and xq.shape[-1] == self.in_features
+        self._ensure_ptq()
+        lib = L.load()
+        K, N = self.in_features, self.out_features
+        x2 = xq.reshape(-1, K)
+        if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0):
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        out_dtype = torch.float32 if out_format is None else torch.bfloat16
+        y = torch.empty((M, N), dtype=out_dtype, device=xq.device)
+        if M > 0 and N > 0:
+            wq = self._weight_cache()
+            bias = self.bias.detach() if self.bias is not None else None
+            lda = x2.stride(0) if M > 1 else K
+            plain = scale == 1.0 and not relu and residual is None and out_format is None
+            if plain:
+                rc = lib.bq_gemm_bf16_tn(x2.data_ptr(), wq.data_ptr(), y.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                         1, M, N, K, lda, K, N, 0, 0, 0, L.stream_ptr(xq.device))
+                L.check(rc, "bq_gemm_bf16_tn")
+            else:
+                ep = L.BqGemmEpilogue()
+                ep.bias = bias.data_ptr() if bias is not None else None
+                res2 = None
+                if residual is not None:
+                    res2 = residual.reshape(M, N)
+                    if res2.stride(-1) != 1 or res2.dtype != torch.float32:
+                        res2 = res2.float().contiguous()
+                    ep.residual, ep.ldr = res2.data_ptr(), res2.stride(0) if M > 1 else N
+                ep.scale, ep.act = float(scale), 1 if relu else 0
+                ep.out_dtype = L.BQ_F32 if out_format is None else L.BQ_BF16
+                fmt = None
+                if out_format is not None:
+                    kind, kw = out_format
+                    fmt = make_format(kind, b0=1, b1=16, **kw)
+                    ep.qfmt = ctypes.pointer(fmt)
+                    ep.qdir = 1 if out_blocks_along_rows else 0
+                rc = lib.bq_gemm_bf16_tn_ex(x2.data_ptr(), wq.data_ptr(), y.data_ptr(), ctypes.byref(ep), M, N, K, lda, K, N,
+                                            L.stream_ptr(xq.device))
+                L.check(rc, "bq_gemm_bf16_tn_ex")
+        return y.reshape(*xq.shape[:-1], N)
+
     def forward(self, x):
         if self.bypass:
             return F.linear(x, self.weight, self.bias)
         elif self.is_ptq:
             with torch.no_grad():
-                if self.weight_requires_quantisation:
-                    self.weight.copy_(self.w_quantizer(self.weight.data))
-                    if self.bias is not None:
-                        self.bias.copy_(self.b_quantizer(self.bias.data))
-                    self.weight_requires_quantisation = False
-                    self._wq_bf16 = None
+                self._ensure_ptq()
                 if self._fusable(x):
                     return self._fused_forward(x)
                 x = self.x_quantizer(x)

@@ -211,6 +211,51 @@ def test_fused_causal_attention_vs_op_by_op_oracle(S):
     assert torch.equal(out[:, 0, :], exp0)
 
 
+def test_fused_causal_attention_head_dim_128_and_score_div():
+    """Llama-7B geometry: d = 128, scores divided by sqrt(d) after matmul_0 (modeling_llama.py:309-314).  torch-CUDA
+    evaluates `tensor / python_float` as a multiplication by the fp32 reciprocal; the kernel does the same."""
+    import math
+
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import fusable, fused_causal_attention
+
+    g = torch.Generator(device="cuda").manual_seed(77)
+    B, heads, d, S = 2, 3, 128, 640
+    H = heads * d
+    q = torch.randn(B, S, H, device="cuda", generator=g)
+    k = torch.randn(B, S, H, device="cuda", generator=g)
+    v = torch.randn(B, S, H, device="cuda", generator=g)
+    assert fusable(CFG_BFP6, CFG_BFP6, d, S)
+    out = fused_causal_attention(q, k, v, CFG_BFP6, CFG_BFP6, heads, score_div=math.sqrt(d))
+    ref, _ = _oracle_attention(q, k, v, CFG_BFP6, heads, score_div=math.sqrt(d))
+    err = (out - ref).abs()
+    vmax = float(v.abs().max())
+    assert float(err.max()) <= 2 * (2.0 ** -5) * vmax * 0.25, float(err.max())
+    assert float(err.mean()) <= 2e-4, float(err.mean())
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_fused_attention_quantised_output_equals_quantizer_of_fp32_output(d):
+    """bq_attention_causal_q == x-quantizer(out_proj) applied to bq_attention_causal's fp32 result, bit for bit
+    (the epilogue quantises the same TMEM accumulator the fp32 variant stores)."""
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import fused_causal_attention, output_quantizable
+    from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer
+
+    g = torch.Generator(device="cuda").manual_seed(5 + d)
+    B, heads, S = 2, 2, 384
+    H = heads * d
+    q = torch.randn(B, S, H, device="cuda", generator=g)
+    k = torch.randn(B, S, H, device="cuda", generator=g)
+    v = torch.randn(B, S, H, device="cuda", generator=g)
+    assert output_quantizable(CFG_BFP6, H)
+    o32 = fused_causal_attention(q, k, v, CFG_BFP6, CFG_BFP6, heads)
+    oq = fused_causal_attention(q, k, v, CFG_BFP6, CFG_BFP6, heads, out_cfg=CFG_BFP6)
+    assert oq.dtype == torch.bfloat16
+    want = block_fp_quantizer(o32, 6, 8, 127, [1, 16], True)
+    passthrough = o32.abs() <= 1e-8          # returned UNQUANTISED by the reference (block_fp.py:93-94): the bf16 carrier rounds them
+    assert torch.equal(oq.float()[~passthrough], want[~passthrough])
+    assert torch.equal(oq[passthrough], want[passthrough].to(torch.bfloat16))
+
+
 def test_fp32_equivalent_linear_for_unquantised_layers():
     """lm_head-style fp32 Linear through the split-bf16 tensor-core GEMM: error must stay inside the same
     fp32-accumulation-order bound an fp32 GEMM obeys (the reference's F.linear is checked against it too)."""

@@ -1,0 +1,166 @@
+"""GPU parity of the glue-fusion kernels: quantising GEMM epilogue, LayerNorm/RMSNorm+quantize, and the
+8-kernel fused OPT decoder layer.
+
+The fused kernels apply the reference's ops in the reference's order on the SAME accumulator values the unfused kernels
+produce, so epilogue results are compared BIT-EXACTLY against (plain GEMM -> torch ops -> standalone quantizer); the only
+stated exception are |x| <= 1e-8 pass-through elements, which the bf16 carrier rounds (see test_gpu_consumers.py).
+LayerNorm statistics are summed in a different order than torch's kernel (<= 1-2 ulp in mean / rstd), so a normalised
+value can differ by an ulp before quantisation and, on a rounding boundary, by one quantisation step after it."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import opt_ref
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def bfp_cfg(width=6):
+    d = {"name": "block_fp", "bypass": False, "is_ptq": True}
+    for p in ("data_in", "weight", "bias"):
+        d.update({f"{p}_width": width, f"{p}_exponent_width": 8, f"{p}_exponent_bias": 127,
+                  f"{p}_block_size": [16] if p == "bias" else [1, 16]})
+    return d
+
+
+def assert_bf16_carrier_equal(got_bf16, want_f32, pre_quant_f32):
+    passthrough = pre_quant_f32.abs() <= 1e-8
+    assert torch.equal(got_bf16.float()[~passthrough], want_f32[~passthrough])
+    assert torch.equal(got_bf16[passthrough], want_f32[passthrough].to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (2048, 2048, 512), (1040, 96, 328), (16, 32, 8)])
+def test_gemm_epilogue_matches_unfused_composition(M, N, K):
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer
+    from llm_mixed_q_b200.models.quantize.quantizers.utils import make_format
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    res = torch.randn(M, N, device="cuda", generator=g)
+    plain = torch.empty(M, N, device="cuda")
+    L.check(lib.bq_gemm_bf16_tn(A.data_ptr(), B.data_ptr(), plain.data_ptr(), bias.data_ptr(), 1, M, N, K, K, K, N, 0, 0, 0,
+                                L.stream_ptr()), "gemm")
+
+    def run(out_dtype, scale=1.0, act=0, residual=None, fmt=None, qdir=0, use_bias=True):
+        ep = L.BqGemmEpilogue()
+        ep.bias = bias.data_ptr() if use_bias else None
+        if residual is not None:
+            ep.residual, ep.ldr = residual.data_ptr(), N
+        ep.scale, ep.act, ep.out_dtype = scale, act, (L.BQ_BF16 if out_dtype == torch.bfloat16 else L.BQ_F32)
+        if fmt is not None:
+            ep.qfmt, ep.qdir = ctypes.pointer(fmt), qdir
+        C = torch.full((M, N), float("nan"), device="cuda").to(out_dtype)
+        L.check(lib.bq_gemm_bf16_tn_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), ctypes.byref(ep), M, N, K, K, K, N,
+                                       L.stream_ptr()), "gemm_ex")
+        return C
+
+    f6 = make_format("block_fp", width=6, exponent_width=8, exponent_bias=127, b0=1, b1=16)
+    # 1. bias + residual, fp32 out (out_proj / fc2 of the fused layer)
+    assert torch.equal(run(torch.float32, residual=res), res + plain)
+    # 2. bias, scale, quantise along N, bf16 (q_proj)
+    pre = plain * 0.125
+    assert_bf16_carrier_equal(run(torch.bfloat16, scale=0.125, fmt=f6), block_fp_quantizer(pre, 6, 8, 127, [1, 16], True), pre)
+    # 3. bias, ReLU, quantise along N, bf16 (fc1 -> fc2)
+    pre = torch.relu(plain)
+    assert_bf16_carrier_equal(run(torch.bfloat16, act=1, fmt=f6), block_fp_quantizer(pre, 6, 8, 127, [1, 16], True), pre)
+    # 4. quantise along M: 16 consecutive rows at one column (k_proj -> k^T operand of bmm_0)
+    if M % 16 == 0:
+        want = block_fp_quantizer(plain.t().contiguous(), 6, 8, 127, [1, 16], True).t()
+        assert_bf16_carrier_equal(run(torch.bfloat16, fmt=f6, qdir=1), want, plain)
+    # 5. fp32 output of quantised values (no carrier rounding at all), W4
+    f4 = make_format("block_fp", width=4, exponent_width=8, exponent_bias=127, b0=1, b1=16)
+    got = run(torch.float32, fmt=f4, use_bias=True)
+    want = block_fp_quantizer(plain, 4, 8, 127, [1, 16], True)
+    assert torch.equal(got, want)
+    # 6. block_minifloat epilogue
+    fm = make_format("block_minifloat", width=8, exponent_width=4, exponent_bias_width=8, b0=1, b1=16)
+    pre = plain * 8.0
+    got = run(torch.float32, scale=8.0, fmt=fm)
+    assert torch.equal(got, O.block_minifloat_quantize(pre, 8, 4, 8, [1, 16], True))
+
+
+@pytest.mark.parametrize("H,rows", [(2048, 512), (768, 300), (4096, 64), (64, 1000)])
+def test_layernorm_quantize_vs_torch_layernorm_then_quantizer(H, rows):
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import norm_quantize
+    from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer
+
+    g = torch.Generator(device="cuda").manual_seed(H + rows)
+    x = torch.randn(rows, H, device="cuda", generator=g) * 3 + 0.5
+    w = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    b = 0.1 * torch.randn(H, device="cuda", generator=g)
+    f6 = ("block_fp", dict(width=6, exponent_width=8, exponent_bias=127))
+    f4 = ("block_fp", dict(width=4, exponent_width=8, exponent_bias=127))
+    y6, y4, y6b = norm_quantize(x, w, b, 1e-5, [f6, f4, f6])
+    assert y6b.data_ptr() == y6.data_ptr()                      # identical formats share one output
+    ln = torch.nn.functional.layer_norm(x, (H,), w, b, 1e-5)
+    for got, width in ((y6, 6), (y4, 4)):
+        want = block_fp_quantizer(ln, width, 8, 127, [1, 16], True)
+        diff = (got.float() - want).abs()
+        bad = diff > 0
+        frac = float(bad.float().mean())
+        assert frac <= 2e-3, frac                                # rounding-boundary flips only
+        # a flip is one quantisation step of its block: 2^(E - m) <= 2 * blockmax * 2^-m
+        blockmax = ln.abs().view(rows, H // 16, 16).amax(-1, keepdim=True).expand(rows, H // 16, 16).reshape(rows, H)
+        assert bool((diff <= 2.0 * blockmax * 2.0 ** -(width - 1) + 1e-8).all())
+    # RMSNorm (Llama): y = w * (x * rsqrt(mean(x^2) + eps))
+    (r6,) = norm_quantize(x, w, None, 1e-6, [f6])
+    var = x.pow(2).mean(-1, keepdim=True)
+    rn = w * (x * torch.rsqrt(var + 1e-6))
+    want = block_fp_quantizer(rn, 6, 8, 127, [1, 16], True)
+    assert float(((r6.float() - want).abs() > 0).float().mean()) <= 2e-3
+
+
+def _opt_model(layers=2, hidden=256, heads=4, ffn=512, vocab=512, width=6):
+    from llm_mixed_q_b200.models.opt_quantized import OPTQuantizedConfig, OPTQuantizedForCausalLM
+
+    cfg = OPTQuantizedConfig(hidden_size=hidden, num_hidden_layers=layers, ffn_dim=ffn, num_attention_heads=heads,
+                             vocab_size=vocab, max_position_embeddings=256, quant_config={"default": bfp_cfg(width)})
+    torch.manual_seed(0)
+    model = OPTQuantizedForCausalLM(cfg).eval()
+    with torch.no_grad():          # non-trivial biases / LN parameters so every fused term is exercised
+        for n, p in model.named_parameters():
+            if n.endswith(".bias"):
+                p.normal_(0, 0.02)
+            elif "layer_norm.weight" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    return model.cuda()
+
+
+@pytest.mark.parametrize("width", [6, 4])
+def test_fused_opt_layer_matches_op_by_op_and_oracle(width):
+    """Whole model through the 8-kernel fused layers vs (a) the same modules op by op and (b) the oracle's restatement of
+    the reference forward (torch emulation on the same device).  Statistical tolerance as in test_gpu_models.py."""
+    model = _opt_model(width=width)
+    dec = model.model.decoder
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ids = torch.randint(0, 512, (3, 128), device="cuda", generator=g)
+    with torch.no_grad():
+        dec.fused_glue, dec.fused_attention = False, False
+        ref = model(input_ids=ids, labels=ids)                 # also performs the PTQ weight overwrite
+        dec.fused_glue, dec.fused_attention = True, True
+        assert dec.layers[0]._fused_plan(128) is not None
+        out = model(input_ids=ids, labels=ids)
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        qc = model.config.quant_config
+        o_logits, o_loss = opt_ref.opt_forward(sd, qc, ids, num_layers=2, num_heads=4, labels=ids)
+    spread = float(ref.logits.std())
+    for name, r_logits, r_loss in (("op-by-op", ref.logits, float(ref.loss)), ("oracle", o_logits, float(o_loss))):
+        err = (out.logits - r_logits).abs()
+        assert abs(float(out.loss) - r_loss) <= 2e-3 * abs(r_loss), (name, float(out.loss), r_loss)
+        assert float(err.mean()) <= 0.02 * spread and float(err.max()) <= 0.5 * spread, (name, float(err.mean()), float(err.max()), spread)
+
+
+def test_fused_layer_falls_back_when_not_eligible():
+    model = _opt_model()
+    dec = model.model.decoder
+    assert dec.layers[0]._fused_plan(100) is None              # S % 16 != 0: k^T blocks would straddle rows
+    ids = torch.randint(0, 512, (2, 100), device="cuda")
+    with torch.no_grad():
+        out = model(input_ids=ids, labels=ids)
+    assert torch.isfinite(out.loss)
