@@ -341,7 +341,8 @@ def main():
                                            "tensor_TFLOPs": (6 * flops_head * K / (head_ms / 1e3) / 1e12) if head_ms else None,
                                            "note": "unquantised fp32 lm_head as 6 bf16 plane products (fp32-equivalent)"},
                     "layernorm_quant_kernel": {"share_of_step": ln_ms / step_ms_local, "launches": ln_n,
-                                               "GBs": (T * H * 6 * ln_n / (ln_ms / 1e3) / 1e9) if ln_ms else None},
+                                               "GBs": (T * H * 6 * ln_n / (ln_ms / 1e3) / 1e9) if ln_ms else None,
+                                               "note": "4 B/elem fp32 read + 2 B/elem bf16 write per launch; HBM-bound"},
                     "quantizer_kernels": {"share_of_step": q_ms / step_ms_local}}}
     gpu_launches = sum(launches1.values()) - sum(launches0.values())
 

@@ -468,7 +468,9 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
             for (int c = 0; c < 4; ++c) ll = __fadd_rn(ll, __fmul_rn(xl[c * 128 + r_in], expf(__fsub_rn(xm[c * 128 + r_in], mm))));
             m = mm;
-            l = ll;
+            // the exact sum contains exp(m - m) = 1, so it is >= 1; rounding in the statistics sweep may land an ulp below,
+            // which would make the largest probability exceed 1.0 and jump to the next block exponent
+            l = fmaxf(ll, 1.0f);
             inv_l = __frcp_rn(l);
           }
         }

@@ -163,19 +163,26 @@ __device__ __forceinline__ float quant_elem(float x, const BlockState& s, const 
 constexpr uint32_t kZone = 0x1000u;          // +-2^12 ulps around a cliff
 constexpr uint32_t kSqrt2Mant = 0x3504f3u;   // mantissa field of sqrt(2)
 
+// cold fall-backs (inputs within 2^-11 of a rounding cliff, denormals): kept out of line — every inlined copy of the
+// libdevice log2f polynomial costs ~40 instructions of code, and the fused kernels instantiate these helpers dozens of
+// times per loop body (instruction-cache footprint, see DESIGN.md "code size")
+static __device__ __noinline__ int ceil_log2_slow(float x) { return (int)ceilf(log2f(x)); }
+static __device__ __noinline__ int floor_log2_slow(float x) { return (int)floorf(log2f(x)); }
+static __device__ __noinline__ int rint_log2_slow(float x) { return (int)rintf(log2f(x)); }
+
 __device__ __forceinline__ int ceil_log2_i(float x) {        // == (int)ceilf(log2f(x)) for x > 0 finite
   const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
-  if (ex - 1u >= 254u || ((f + kZone) & 0x7fffffu) < 2 * kZone) return (int)ceilf(log2f(x));
+  if (ex - 1u >= 254u || ((f + kZone) & 0x7fffffu) < 2 * kZone) return ceil_log2_slow(x);
   return (int)ex - 126;
 }
 __device__ __forceinline__ int floor_log2_i(float x) {       // == (int)floorf(log2f(x))
   const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
-  if (ex - 1u >= 254u || ((f + kZone) & 0x7fffffu) < 2 * kZone) return (int)floorf(log2f(x));
+  if (ex - 1u >= 254u || ((f + kZone) & 0x7fffffu) < 2 * kZone) return floor_log2_slow(x);
   return (int)ex - 127;
 }
 __device__ __forceinline__ int rint_log2_i(float x) {        // == (int)rintf(log2f(x))
   const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
-  if (ex - 1u >= 254u || (f - kSqrt2Mant + kZone) < 2 * kZone) return (int)rintf(log2f(x));
+  if (ex - 1u >= 254u || (f - kSqrt2Mant + kZone) < 2 * kZone) return rint_log2_slow(x);
   return (int)ex - 127 + (f > kSqrt2Mant ? 1 : 0);
 }
 __device__ __forceinline__ float pow2_i(int e) { return __int_as_float((e + 127) << 23); }   // e in [-126, 127]

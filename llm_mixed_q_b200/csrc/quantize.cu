@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
 // rstd = rsqrtf(var + eps) (layer_norm_kernel.cu); RMSNorm  y = w * (x * rsqrtf(mean(x^2) + eps)).  The statistics are
 // summed in a different order than torch's Welford / reduction kernels (<= 1-2 ulp in mean / rstd), see DESIGN.md.
 // ------------------------------------------------------------------------------------------------
-constexpr int kLnThreads = 256;
+constexpr int kLnWarps = 4;
 struct LnArgs {
   const float* x;
   int64_t ldx;
@@ -624,76 +624,59 @@ struct LnArgs {
   const float* beta;      // nullptr: RMSNorm
   float eps;
   int H;
+  int rows;
   int n_out;
   __nv_bfloat16* out[3];
   FmtParams f[3];
 };
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-  const int w = threadIdx.x >> 5;
-  __syncthreads();                       // protects `red` against the previous use
-  if ((threadIdx.x & 31) == 0) red[w] = v;
-  __syncthreads();
-  float t = red[0];
-#pragma unroll
-  for (int i = 1; i < kLnThreads / 32; ++i) t = __fadd_rn(t, red[i]);
-  return t;
+// Persistent warps, one row per warp at a time.  The row is fetched by ONE bulk async copy (cp.async.bulk, the 1-D TMA
+// path) into the warp's shared-memory slot, double-buffered so the next row is in flight while this one is processed;
+// the three passes (sum, squared deviations, normalise + quantise + store) then read shared memory in rolled loops —
+// a few hundred instructions of code and ~40 registers, instead of a register-resident row whose fully unrolled
+// quantiser bodies overflowed the instruction cache (measured 1.7 TB/s).
+__device__ __forceinline__ void bulk_load_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
-template <int VPT>
-__global__ void __launch_bounds__(kLnThreads) norm_quant_kernel(LnArgs a) {
-  __shared__ float red[kLnThreads / 32];
-  const int row = blockIdx.x;
-  const float* xr = a.x + (int64_t)row * a.ldx;
-  const int nslot = a.H >> 2;
-  float4 v[VPT];
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int s = i * kLnThreads + threadIdx.x;
-    v[i] = (s < nslot) ? ldg_stream4(xr + 4 * s) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  const float invH = 1.0f / (float)a.H;
-  float mean = 0.f, rstd;
-  if (a.beta) {
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) sum = __fadd_rn(sum, __fadd_rn(__fadd_rn(v[i].x, v[i].y), __fadd_rn(v[i].z, v[i].w)));
-    mean = __fmul_rn(block_sum(sum, red), invH);
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int s = i * kLnThreads + threadIdx.x;
-      if (s < nslot) {
-        const float dx = __fsub_rn(v[i].x, mean), dy = __fsub_rn(v[i].y, mean), dz = __fsub_rn(v[i].z, mean), dw = __fsub_rn(v[i].w, mean);
-        sq = __fadd_rn(sq, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fadd_rn(__fmul_rn(dz, dz), __fmul_rn(dw, dw))));
-      }
-    }
-    rstd = rsqrtf(__fadd_rn(__fmul_rn(block_sum(sq, red), invH), a.eps));
-  } else {
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i)
-      sq = __fadd_rn(sq, __fadd_rn(__fadd_rn(__fmul_rn(v[i].x, v[i].x), __fmul_rn(v[i].y, v[i].y)),
-                                   __fadd_rn(__fmul_rn(v[i].z, v[i].z), __fmul_rn(v[i].w, v[i].w))));
-    rstd = rsqrtf(__fadd_rn(__fmul_rn(block_sum(sq, red), invH), a.eps));
-  }
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int s = i * kLnThreads + threadIdx.x;
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "LN_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
+      "@P bra LN_DONE;\n\t"
+      "bra LN_WAIT;\n\t"
+      "LN_DONE:\n\t}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int KIND>
+__device__ __forceinline__ void norm_emit(const float4* __restrict__ xs, const LnArgs& a, const FmtParams& p, float mean, float rstd,
+                                          __nv_bfloat16* __restrict__ outp, int nslot, int lane) {
+  const int iters = (nslot + 31) >> 5;
+#pragma unroll 2
+  for (int i = 0; i < iters; ++i) {
+    const int s = i * 32 + lane;
     const bool act = s < nslot;
     float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
     if (act) {
+      const float4 xv = xs[s];
       const float4 gm = *reinterpret_cast<const float4*>(a.gamma + 4 * s);
       if (a.beta) {
         const float4 bt = *reinterpret_cast<const float4*>(a.beta + 4 * s);
-        y.x = __fmaf_rn(gm.x, __fmul_rn(rstd, __fsub_rn(v[i].x, mean)), bt.x);
-        y.y = __fmaf_rn(gm.y, __fmul_rn(rstd, __fsub_rn(v[i].y, mean)), bt.y);
-        y.z = __fmaf_rn(gm.z, __fmul_rn(rstd, __fsub_rn(v[i].z, mean)), bt.z);
-        y.w = __fmaf_rn(gm.w, __fmul_rn(rstd, __fsub_rn(v[i].w, mean)), bt.w);
+        y.x = __fmaf_rn(gm.x, __fmul_rn(rstd, __fsub_rn(xv.x, mean)), bt.x);
+        y.y = __fmaf_rn(gm.y, __fmul_rn(rstd, __fsub_rn(xv.y, mean)), bt.y);
+        y.z = __fmaf_rn(gm.z, __fmul_rn(rstd, __fsub_rn(xv.z, mean)), bt.z);
+        y.w = __fmaf_rn(gm.w, __fmul_rn(rstd, __fsub_rn(xv.w, mean)), bt.w);
       } else {
-        y.x = __fmul_rn(gm.x, __fmul_rn(v[i].x, rstd));
-        y.y = __fmul_rn(gm.y, __fmul_rn(v[i].y, rstd));
-        y.z = __fmul_rn(gm.z, __fmul_rn(v[i].z, rstd));
-        y.w = __fmul_rn(gm.w, __fmul_rn(v[i].w, rstd));
+        y.x = __fmul_rn(gm.x, __fmul_rn(xv.x, rstd));
+        y.y = __fmul_rn(gm.y, __fmul_rn(xv.y, rstd));
+        y.z = __fmul_rn(gm.z, __fmul_rn(xv.z, rstd));
+        y.w = __fmul_rn(gm.w, __fmul_rn(xv.w, rstd));
       }
     }
     // block max over the 4 adjacent lanes that hold one block of 16 (H % 16 == 0: a block is all-active or all-inactive)
@@ -701,12 +684,79 @@ __global__ void __launch_bounds__(kLnThreads) norm_quant_kernel(LnArgs a) {
     m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
     m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
     if (m == 0) m = 0x3f800000u;
-    if (act) {
-      for (int k = 0; k < a.n_out; ++k) {
-        const float4 q = (a.f[k].kind == kBlockFP) ? quant4<kBlockFP>(y, m, a.f[k]) : quant4<kBlockMinifloat>(y, m, a.f[k]);
-        store4<__nv_bfloat16>(a.out[k] + (int64_t)row * a.H + 4 * s, q);
+    if (act) store4<__nv_bfloat16>(outp + 4 * s, quant4<KIND>(y, m, p));
+  }
+}
+__global__ void __launch_bounds__(kLnWarps * 32) norm_quant_kernel(LnArgs a) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)a.H * 4u;
+  uint8_t* mybuf = ln_smem + (size_t)warp * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)kLnWarps * 2 * row_bytes) + warp * 2;
+  const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(mybuf);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int nw = gridDim.x * kLnWarps;
+  int row = blockIdx.x * kLnWarps + warp;
+  if (row < a.rows && lane == 0) bulk_load_row(buf0, a.x + (int64_t)row * a.ldx, row_bytes, bar0);
+  const int nslot = a.H >> 2;
+  const float invH = 1.0f / (float)a.H;
+  for (int it = 0; row < a.rows; row += nw, ++it) {
+    const int b = it & 1;
+    const int next = row + nw;
+    if (next < a.rows && lane == 0)
+      bulk_load_row(buf0 + (b ^ 1) * row_bytes, a.x + (int64_t)next * a.ldx, row_bytes, bar0 + 8 * (b ^ 1));
+    mbar_wait_parity(bar0 + 8 * b, (it >> 1) & 1);
+    const float4* xs = reinterpret_cast<const float4*>(mybuf + (size_t)b * row_bytes);
+    float mean = 0.f, rstd;
+    if (a.beta) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int s = lane; s < nslot; s += 64) {
+        const float4 v = xs[s];
+        s0 = __fadd_rn(s0, __fadd_rn(__fadd_rn(v.x, v.y), __fadd_rn(v.z, v.w)));
+        if (s + 32 < nslot) {
+          const float4 w = xs[s + 32];
+          s1 = __fadd_rn(s1, __fadd_rn(__fadd_rn(w.x, w.y), __fadd_rn(w.z, w.w)));
+        }
       }
+      mean = __fmul_rn(warp_sum(__fadd_rn(s0, s1)), invH);
+      float q0 = 0.f, q1 = 0.f;
+      for (int s = lane; s < nslot; s += 64) {
+        const float4 v = xs[s];
+        const float dx = __fsub_rn(v.x, mean), dy = __fsub_rn(v.y, mean), dz = __fsub_rn(v.z, mean), dw = __fsub_rn(v.w, mean);
+        q0 = __fadd_rn(q0, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fadd_rn(__fmul_rn(dz, dz), __fmul_rn(dw, dw))));
+        if (s + 32 < nslot) {
+          const float4 w = xs[s + 32];
+          const float ex = __fsub_rn(w.x, mean), ey = __fsub_rn(w.y, mean), ez = __fsub_rn(w.z, mean), ew = __fsub_rn(w.w, mean);
+          q1 = __fadd_rn(q1, __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fadd_rn(__fmul_rn(ez, ez), __fmul_rn(ew, ew))));
+        }
+      }
+      rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(__fadd_rn(q0, q1)), invH), a.eps));
+    } else {
+      float q0 = 0.f, q1 = 0.f;
+      for (int s = lane; s < nslot; s += 64) {
+        const float4 v = xs[s];
+        q0 = __fadd_rn(q0, __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fadd_rn(__fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w))));
+        if (s + 32 < nslot) {
+          const float4 w = xs[s + 32];
+          q1 = __fadd_rn(q1, __fadd_rn(__fadd_rn(__fmul_rn(w.x, w.x), __fmul_rn(w.y, w.y)), __fadd_rn(__fmul_rn(w.z, w.z), __fmul_rn(w.w, w.w))));
+        }
+      }
+      rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(__fadd_rn(q0, q1)), invH), a.eps));
     }
+#pragma unroll 1
+    for (int k = 0; k < a.n_out; ++k) {
+      const FmtParams& p = (k == 0) ? a.f[0] : ((k == 1) ? a.f[1] : a.f[2]);
+      __nv_bfloat16* outp = ((k == 0) ? a.out[0] : ((k == 1) ? a.out[1] : a.out[2])) + (int64_t)row * a.H;
+      if (p.kind == kBlockFP) norm_emit<kBlockFP>(xs, a, p, mean, rstd, outp, nslot, lane);
+      else norm_emit<kBlockMinifloat>(xs, a, p, mean, rstd, outp, nslot, lane);
+    }
+    __syncwarp();            // every lane is done with buffer b before lane 0 re-arms it two iterations later
   }
 }
 
@@ -715,7 +765,7 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
   if (rows < 0 || H <= 0 || n_out < 1 || n_out > 3 || !fmts || !outs) return BQ_ERR_BAD_ARG;
   if (rows == 0) return BQ_OK;
   if (!x || !gamma) return BQ_ERR_BAD_ARG;
-  if ((H % 16) || H > 4 * kLnThreads * 8 || rows > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  if ((H % 16) || H > 6144 || rows > 0x7fffffff) return BQ_ERR_UNSUPPORTED;      // 4 warps x 2 buffers x H x 4 B of shared memory
   if (((uintptr_t)x % 16) || (ldx % 4) || ldx < H || ((uintptr_t)gamma % 16) || (beta && ((uintptr_t)beta % 16))) return BQ_ERR_BAD_ARG;
   LnArgs a;
   memset(&a, 0, sizeof(a));
@@ -729,15 +779,25 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
     a.f[k].fold_zero = 0;
     a.out[k] = (__nv_bfloat16*)outs[k];
   }
-  const int vpt = (int)((H / 4 + kLnThreads - 1) / kLnThreads);
+  a.rows = (int)rows;
+  const size_t smem = (size_t)kLnWarps * 2 * H * 4 + kLnWarps * 2 * 8;
+  static size_t smem_attr = 0;
+  if (smem > smem_attr) {
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  static int occ_cache_h = 0, occ_cache = 0;
+  if (occ_cache_h != (int)H) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_kernel, kLnWarps * 32, smem) != cudaSuccess || o < 1) o = 1;
+    occ_cache = o;
+    occ_cache_h = (int)H;
+  }
+  const int64_t want = (rows + kLnWarps - 1) / kLnWarps;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * occ_cache);
   {
     LaunchScope ls(kKernLnQuant, st);
-    switch (vpt) {
-      case 1: norm_quant_kernel<1><<<(int)rows, kLnThreads, 0, st>>>(a); break;
-      case 2: norm_quant_kernel<2><<<(int)rows, kLnThreads, 0, st>>>(a); break;
-      case 3: case 4: norm_quant_kernel<4><<<(int)rows, kLnThreads, 0, st>>>(a); break;
-      default: norm_quant_kernel<8><<<(int)rows, kLnThreads, 0, st>>>(a); break;
-    }
+    norm_quant_kernel<<<grid, kLnWarps * 32, smem, st>>>(a);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;

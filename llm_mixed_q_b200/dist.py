@@ -152,8 +152,8 @@ class ColumnParallelLinear(nn.Module):
             local.weight.copy_(linear.weight[lo:hi])
             if has_bias:
                 local.bias.copy_(linear.bias[lo:hi])
-        # a module whose PTQ overwrite already happened holds quantised values: quantising again is idempotent for
-        # the block formats, but keep the flag so no second pass runs
+        # a module whose PTQ overwrite already happened holds quantised values; block_fp is NOT idempotent (a block max that
+        # rounded down onto a power of two would get a smaller exponent), so carry the flag over: no second pass runs
         if hasattr(linear, "weight_requires_quantisation"):
             local.weight_requires_quantisation = linear.weight_requires_quantisation
         local.train(linear.training)

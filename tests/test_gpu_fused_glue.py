@@ -141,12 +141,14 @@ def test_fused_opt_layer_matches_op_by_op_and_oracle(width):
     g = torch.Generator(device="cuda").manual_seed(1)
     ids = torch.randint(0, 512, (3, 128), device="cuda", generator=g)
     with torch.no_grad():
+        # snapshot BEFORE the first forward: PTQ overwrites the parameters, and block_fp is not idempotent (a block max that
+        # rounds down onto a power of two gets a smaller shared exponent the second time) — the reference quantises once
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         dec.fused_glue, dec.fused_attention = False, False
         ref = model(input_ids=ids, labels=ids)                 # also performs the PTQ weight overwrite
         dec.fused_glue, dec.fused_attention = True, True
         assert dec.layers[0]._fused_plan(128) is not None
         out = model(input_ids=ids, labels=ids)
-        sd = {k: v.detach() for k, v in model.state_dict().items()}
         qc = model.config.quant_config
         o_logits, o_loss = opt_ref.opt_forward(sd, qc, ids, num_layers=2, num_heads=4, labels=ids)
     spread = float(ref.logits.std())

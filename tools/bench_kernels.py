@@ -54,3 +54,43 @@ if which in ("all", "gemm"):
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open(f"gpurun_out/bench_kernels_{which}.json", "w"), indent=1)
 print(json.dumps(out, indent=1))
+if which in ("all", "fused"):
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import norm_quantize
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import fused_causal_attention_q
+    out = {}
+    f6 = ("block_fp", dict(width=6, exponent_width=8, exponent_bias=127))
+    for rows, H in [(16384, 2048), (16384, 4096), (16384, 768)]:
+        x = torch.randn(rows, H, device=dev); w = torch.ones(H, device=dev); b = torch.zeros(H, device=dev)
+        ms = timeit(lambda: norm_quantize(x, w, b, 1e-5, [f6, f6, f6]))
+        out[f"ln_quant_{rows}x{H}_us"] = round(ms * 1e3, 1); out[f"ln_quant_{rows}x{H}_GBs"] = round(rows * H * 6 / ms / 1e6, 1)
+        ms = timeit(lambda: norm_quantize(x, w, None, 1e-5, [f6]))
+        out[f"rms_quant_{rows}x{H}_GBs"] = round(rows * H * 6 / ms / 1e6, 1)
+    cfg = {"name": "block_fp", "bypass": False, "is_ptq": True}
+    for p in ("data_in", "weight", "bias"):
+        cfg.update({f"{p}_width": 6, f"{p}_exponent_width": 8, f"{p}_exponent_bias": 127, f"{p}_block_size": [16] if p == "bias" else [1, 16]})
+    for (B, heads, S, d) in [(8, 32, 2048, 64), (2, 32, 2048, 128)]:
+        Hh = heads * d
+        q = torch.randn(B, S, Hh, device=dev).to(torch.bfloat16); k = torch.randn(B, S, Hh, device=dev).to(torch.bfloat16); v = torch.randn(B, S, Hh, device=dev).to(torch.bfloat16)
+        ms = timeit(lambda: fused_causal_attention_q(q, k, v, cfg, heads, B, S, 1.0, out_cfg=cfg), n=10)
+        out[f"attention_B{B}h{heads}S{S}d{d}_ms"] = round(ms, 4)
+        out[f"attention_B{B}h{heads}S{S}d{d}_Gscores_per_s"] = round(B * heads * S * (S + 1) / 2 / ms / 1e6, 1)
+    # GEMM with fused epilogues at the OPT-1.3B layer shapes
+    import ctypes as C
+    from llm_mixed_q_b200.models.quantize.quantizers.utils import make_format
+    fq = make_format("block_fp", width=6, exponent_width=8, exponent_bias=127, b0=1, b1=16)
+    for (M, N, K, mode) in [(16384, 2048, 2048, "plain"), (16384, 2048, 2048, "q_n"), (16384, 2048, 2048, "q_m"), (16384, 2048, 2048, "residual"),
+                            (16384, 8192, 2048, "relu_q_n"), (16384, 2048, 8192, "residual")]:
+        A = torch.randn(M, K, device=dev).to(torch.bfloat16); Bw = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev) * 0.02; res = torch.randn(M, N, device=dev)
+        ep = L.BqGemmEpilogue(); ep.bias = bias.data_ptr(); ep.scale = 1.0
+        bf = mode not in ("plain", "residual")
+        if mode == "residual": ep.residual, ep.ldr = res.data_ptr(), N
+        if "q_" in mode: ep.qfmt = C.pointer(fq); ep.qdir = 1 if mode == "q_m" else 0
+        if "relu" in mode: ep.act = 1
+        ep.out_dtype = 1 if bf else 0
+        Cc = torch.empty(M, N, device=dev, dtype=torch.bfloat16 if bf else torch.float32)
+        ms = timeit(lambda: lib.bq_gemm_bf16_tn_ex(A.data_ptr(), Bw.data_ptr(), Cc.data_ptr(), C.byref(ep), M, N, K, K, K, N, L.stream_ptr()), n=10)
+        out[f"gemm_epi_{mode}_{M}x{N}x{K}_TFLOPs"] = round(2 * M * N * K / ms / 1e9, 1)
+        del A, Bw, Cc, res
+    json.dump(out, open("gpurun_out/bench_kernels_fused.json", "w"), indent=1)
+    print(json.dumps(out, indent=1))
