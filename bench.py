@@ -338,8 +338,8 @@ def main():
                                                 "note": "reference-algorithmic 2*2*B*h*S^2*d FLOP per layer; masked key tiles are skipped and S is computed twice; ALU-issue bound (exp + quantize per score)"},
                     "lm_head_split_gemm": {"share_of_step": head_ms / step_ms_local, "launches": head_n,
                                            "fp32_equivalent_TFLOPs": (flops_head * K / (head_ms / 1e3) / 1e12) if head_ms else None,
-                                           "tensor_TFLOPs": (6 * flops_head * K / (head_ms / 1e3) / 1e12) if head_ms else None,
-                                           "note": "unquantised fp32 lm_head as 6 bf16 plane products (fp32-equivalent)"},
+                                           "tensor_TFLOPs": (3 * flops_head * K / (head_ms / 1e3) / 1e12) if head_ms else None,
+                                           "note": "unquantised fp32 lm_head as 3 products of row-scaled fp16 hi/lo planes (fp32-equivalent: ~2^-21 per product)"},
                     "layernorm_quant_kernel": {"share_of_step": ln_ms / step_ms_local, "launches": ln_n,
                                                "GBs": (T * H * 6 * ln_n / (ln_ms / 1e3) / 1e9) if ln_ms else None,
                                                "note": "4 B/elem fp32 read + 2 B/elem bf16 write per launch; HBM-bound"},

@@ -175,6 +175,15 @@ BQ_API int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_ge
  *   bf16-representable operand is passed as a single plane.
  * ---------------------------------------------------------------------------------------------- */
 BQ_API int bq_split3_bf16(const float* x, void* planes_bf16, int64_t n, void* stream);
+/* Cheaper variant with the same purpose (half the tensor work): per-row scaled fp16 planes.
+ *   bq_split2_f16_rows: x fp32 [rows][K] (row stride ldx) -> fp16 planes [2][rows][K] with x * 2^e(row) = hi + lo up to 2^-22 of
+ *   the row max, and inv_scale[row] = 2^-e(row).
+ *   bq_gemm_split16_tn: C[m][n] = a_inv_scale[m] * b_inv_scale[n] * sum_t A_plane[term_a[t]][m][:] . B_plane[term_b[t]][n][:] (+ bias[n]);
+ *   the three terms (lo,hi), (hi,lo), (hi,hi) give ~2^-21 relative error per product. */
+BQ_API int bq_split2_f16_rows(const float* x, int64_t rows, int64_t K, int64_t ldx, void* planes_f16, float* inv_scale, void* stream);
+BQ_API int bq_gemm_split16_tn(const void* A_planes_f16, const void* B_planes_f16, float* C, const float* bias,
+                              const float* a_inv_scale, const float* b_inv_scale, int64_t M, int64_t N, int64_t K,
+                              int32_t n_terms, const int32_t* term_a, const int32_t* term_b, int64_t ldc, void* stream);
 BQ_API int bq_gemm_split_tn(const void* A_planes, const void* B_planes, float* C, const float* bias, int64_t M, int64_t N,
                             int64_t K, int32_t planes_a, int32_t planes_b, int32_t n_terms, const int32_t* term_a,
                             const int32_t* term_b, int64_t ldc, void* stream);

@@ -111,6 +111,11 @@ def load():
     lib.bq_gemm_split_tn.restype = ctypes.c_int
     lib.bq_gemm_split_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32,
                                      POINTER(c_int32), POINTER(c_int32), c_int64, c_void_p]
+    lib.bq_split2_f16_rows.restype = ctypes.c_int
+    lib.bq_split2_f16_rows.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.bq_gemm_split16_tn.restype = ctypes.c_int
+    lib.bq_gemm_split16_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,
+                                       POINTER(c_int32), POINTER(c_int32), c_int64, c_void_p]
     lib.bq_selftest_log2.restype = ctypes.c_int
     lib.bq_selftest_log2.argtypes = [c_void_p, c_void_p]
     lib.bq_kernel_count.restype = ctypes.c_int

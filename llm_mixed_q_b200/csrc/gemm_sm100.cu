@@ -61,6 +61,9 @@ struct GemmArgs {
   // over the (plane_a, plane_b) pairs below and accumulates every product into the same TMEM accumulator
   int n_terms;
   int8_t term_a[8], term_b[8];
+  int fp16;                    // operands are fp16 (kind::f16 with F16 inputs) instead of bf16
+  const float* row_scale;      // optional exact power-of-two output scales: C = acc * row_scale[m] * col_scale[n] (+ bias)
+  const float* col_scale;
   EpiArgs epi;
 };
 
@@ -239,7 +242,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBM, BN);
+      const uint32_t idesc = g.fp16 ? ptx::idesc_f16_f32(kBM, BN) : ptx::idesc_bf16_f32(kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -314,7 +317,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
       const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((g.sc & 3) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+                          ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.col_scale) & 15) == 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -327,6 +330,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; j += 4) {
               float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                      __uint_as_float(r[j + 3]));
+              if (g.row_scale) {
+                const float rs = g.row_scale[row];
+                const float4 cs = *reinterpret_cast<const float4*>(g.col_scale + col0 + j);
+                o.x *= rs * cs.x; o.y *= rs * cs.y; o.z *= rs * cs.z; o.w *= rs * cs.w;
+              }
               if (g.bias) {
                 const float4 bv = *reinterpret_cast<const float4*>(g.bias + col0 + j);
                 o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
@@ -336,7 +344,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (col0 + j < g.N) crow[col0 + j] = __uint_as_float(r[j]) + (g.bias ? g.bias[col0 + j] : 0.f);
+              if (col0 + j < g.N) {
+                float o = __uint_as_float(r[j]);
+                if (g.row_scale) o *= g.row_scale[row] * g.col_scale[col0 + j];
+                crow[col0 + j] = o + (g.bias ? g.bias[col0 + j] : 0.f);
+              }
             }
           }
         }
@@ -463,6 +475,7 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
   g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = (int)batch;
   g.ldc = ldc; g.sc = sc; g.tiles_m = g.tiles_n = 0; g.b_broadcast = bcast ? 1 : 0;
   g.n_terms = 0;
+  g.fp16 = 0; g.row_scale = g.col_scale = nullptr;
   memset(&g.epi, 0, sizeof(g.epi));
   switch (BN) {
     case 64: return launch_gemm<64, false>(tmA, tmB, g, st);
@@ -524,28 +537,31 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
 // planes, see split3 in quantize.cu) and the six terms {(2,0),(0,2),(1,1),(1,0),(0,1),(0,0)} (smallest first) the
 // result carries ~2^-24 relative error per product, i.e. it stands in for an fp32 GEMM on the tensor cores.
 int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t M, int64_t N, int64_t K,
-                       int planes_a, int planes_b, int n_terms, const int* ta, const int* tb, int64_t ldc, cudaStream_t st) {
+                       int planes_a, int planes_b, int n_terms, const int* ta, const int* tb, int64_t ldc, cudaStream_t st,
+                       int fp16 = 0, const float* row_scale = nullptr, const float* col_scale = nullptr) {
   if (M < 0 || N < 0 || K <= 0 || n_terms < 1 || n_terms > 8 || !ta || !tb) return BQ_ERR_BAD_ARG;
   if (M == 0 || N == 0) return BQ_OK;
   if (!A || !B || !C) return BQ_ERR_BAD_ARG;
   if ((K % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)C % 4) || ldc < N) return BQ_ERR_BAD_ARG;
+  if ((row_scale == nullptr) != (col_scale == nullptr)) return BQ_ERR_BAD_ARG;
   if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
   const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, planes_a, K, M * K, kBM);
+  int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, planes_a, K, M * K, kBM);     // 16-bit elements: the map only moves bytes
   if (rc) return rc;
   rc = make_tmap_bf16_kmajor(&tmB, B, K, N, planes_b, K, N * K, BN);
   if (rc) return rc;
   GemmArgs g;
+  memset(&g, 0, sizeof(g));
   g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = 1;
   g.ldc = ldc; g.sc = 0; g.tiles_m = g.tiles_n = 0; g.b_broadcast = 1;
   g.n_terms = n_terms;
+  g.fp16 = fp16; g.row_scale = row_scale; g.col_scale = col_scale;
   for (int i = 0; i < n_terms; ++i) {
     if (ta[i] < 0 || ta[i] >= planes_a || tb[i] < 0 || tb[i] >= planes_b) return BQ_ERR_BAD_ARG;
     g.term_a[i] = (int8_t)ta[i];
     g.term_b[i] = (int8_t)tb[i];
   }
-  memset(&g.epi, 0, sizeof(g.epi));
   switch (BN) {
     case 64: return launch_gemm<64, false>(tmA, tmB, g, st, kKernGemmSplit);
     case 128: return launch_gemm<128, false>(tmA, tmB, g, st, kKernGemmSplit);
@@ -554,6 +570,14 @@ int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias
 }
 
 }  // namespace bq
+
+extern "C" int bq_gemm_split16_tn(const void* A_planes_f16, const void* B_planes_f16, float* C, const float* bias,
+                                  const float* a_inv_scale, const float* b_inv_scale, int64_t M, int64_t N, int64_t K,
+                                  int32_t n_terms, const int32_t* term_a, const int32_t* term_b, int64_t ldc, void* stream) {
+  if (!a_inv_scale || !b_inv_scale) return BQ_ERR_BAD_ARG;
+  return bq::gemm_split_tn_impl(A_planes_f16, B_planes_f16, C, bias, M, N, K, 2, 2, n_terms, term_a, term_b, ldc,
+                                (cudaStream_t)stream, 1, a_inv_scale, b_inv_scale);
+}
 
 extern "C" int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_gemm_epilogue* ep, int64_t M, int64_t N,
                                   int64_t K, int64_t lda, int64_t ldb, int64_t ldc, void* stream) {

@@ -23,6 +23,7 @@
 #include "bq_numerics.cuh"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace bq {
 
@@ -804,6 +805,56 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 -> two fp16 planes per row with a per-row power-of-two scale:  x * 2^e = hi + lo (+- 2^-22 of the row max),
+// hi = fp16(x * 2^e), lo = fp16(x * 2^e - hi), e chosen so that the row max lands in [2^14, 2^15).
+// Operand format of the fp16-split GEMM that stands in for the reference's UNQUANTISED fp32 matmuls (lm_head): three
+// plane products (lo*hi, hi*lo, hi*hi) reproduce the fp32 product to ~2^-21 relative — below the accumulation-order
+// noise of an fp32 GEMM — at half the tensor work of the 6-term bf16 split.  inv_scale[r] = 2^-e undoes the scaling in
+// the GEMM epilogue (exact).  One warp per row, two passes (the second re-reads the row from L1/L2).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split2_f16_rows_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K,
+                                                               __half* __restrict__ planes, float* __restrict__ inv_scale) {
+  const int lane = threadIdx.x & 31;
+  const int nslot = K >> 2;
+  const int64_t plane = (int64_t)rows * K;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+    const float* xr = x + (int64_t)row * ldx;
+    uint32_t m = 0;
+    for (int s = lane; s < nslot; s += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + 4 * s);
+      m = max(m, max(max(absbits(v.x), absbits(v.y)), max(absbits(v.z), absbits(v.w))));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // exponent of the row max (finite, non-zero rows); scale = 2^(14 - floor(log2 max)), clamped to normal powers of two
+    int ex = (int)(m >> 23) - 127;
+    if (m == 0 || m >= 0x7f800000u) ex = 14;
+    int e = 14 - ex;
+    e = min(max(e, -126), 126);
+    const float sc = __int_as_float((e + 127) << 23);
+    if (lane == 0) inv_scale[row] = __int_as_float((127 - e) << 23);
+    __half* h0 = planes + (int64_t)row * K;
+    __half* h1 = h0 + plane;
+    for (int s = lane; s < nslot; s += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + 4 * s);
+      const float a[4] = {__fmul_rn(v.x, sc), __fmul_rn(v.y, sc), __fmul_rn(v.z, sc), __fmul_rn(v.w, sc)};
+      __half hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hi[j] = __float2half_rn(a[j]);
+        lo[j] = __float2half_rn(__fsub_rn(a[j], __half2float(hi[j])));
+      }
+      uint2 ph, pl;
+      ph.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
+      ph.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
+      pl.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
+      pl.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+      *reinterpret_cast<uint2*>(h0 + 4 * s) = ph;
+      *reinterpret_cast<uint2*>(h1 + 4 * s) = pl;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // exhaustive self-test of the exponent-field shortcuts against libdevice log2f
 // ------------------------------------------------------------------------------------------------
 __global__ void selftest_log2_kernel(unsigned long long* mism) {
@@ -834,6 +885,21 @@ int bq_split3_bf16(const float* x, void* planes_bf16, int64_t n, void* stream) {
   {
     bq::LaunchScope ls(bq::kKernSplit3, st);
     bq::split3_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)planes_bf16, n4, n);
+  }
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
+int bq_split2_f16_rows(const float* x, int64_t rows, int64_t K, int64_t ldx, void* planes_f16, float* inv_scale, void* stream) {
+  if (rows < 0 || K < 0) return BQ_ERR_BAD_ARG;
+  if (rows == 0 || K == 0) return BQ_OK;
+  if (!x || !planes_f16 || !inv_scale || (K % 4) || (ldx % 4) || ldx < K || ((uintptr_t)x % 16) || ((uintptr_t)planes_f16 % 8))
+    return BQ_ERR_BAD_ARG;
+  if (rows > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)bq::num_sms() * 8);
+  {
+    bq::LaunchScope ls(bq::kKernSplit3, st);
+    bq::split2_f16_rows_kernel<<<grid, 256, 0, st>>>(x, ldx, (int)rows, (int)K, (__half*)planes_f16, inv_scale);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;

@@ -259,20 +259,29 @@ def test_fused_attention_quantised_output_equals_quantizer_of_fp32_output(d):
     assert torch.equal(oq[passthrough], want[passthrough].to(torch.bfloat16))
 
 
-def test_fp32_equivalent_linear_for_unquantised_layers():
-    """lm_head-style fp32 Linear through the split-bf16 tensor-core GEMM: error must stay inside the same
+@pytest.mark.parametrize("mode", ["f16x2", "bf16x3"])
+def test_fp32_equivalent_linear_for_unquantised_layers(mode):
+    """lm_head-style fp32 Linear through the split tensor-core GEMMs: error must stay inside the same
     fp32-accumulation-order bound an fp32 GEMM obeys (the reference's F.linear is checked against it too)."""
-    from llm_mixed_q_b200.models.quantize.quantized_functions.fp32_linear import fp32_linear, split3
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fp32_linear import fp32_linear, split2_rows, split3
 
     g = torch.Generator(device="cuda").manual_seed(9)
     x = torch.randn(1024, 2048, device="cuda", generator=g)
+    x[5] *= 1e-6                                    # rows of very different magnitude: the per-row scale must absorb it
+    x[6] *= 3e4
+    x[7] = 0
     w = torch.randn(5000, 2048, device="cuda", generator=g) * 0.02
+    bias = torch.randn(5000, device="cuda", generator=g)
     planes = split3(x).float()
     assert float((planes.sum(0).double() - x.double()).abs().max()) <= 2.0 ** -24 * float(x.abs().max())
-    y = fp32_linear(x, w)
-    exact = x.double() @ w.double().T
-    absprod = x.double().abs() @ w.double().abs().T
+    p2, inv = split2_rows(x)
+    rec = (p2[0].double() + p2[1].double()) * inv.double()[:, None]
+    rowmax = x.abs().amax(1, keepdim=True).double()
+    assert bool(((rec - x.double()).abs() <= 2.0 ** -21 * rowmax + 1e-300).all())
+    y = fp32_linear(x, w, bias, mode=mode)
+    exact = x.double() @ w.double().T + bias.double()
+    absprod = x.double().abs() @ w.double().abs().T + bias.double().abs()
     assert_gemm_close(y, exact, absprod, 2048)
-    assert_gemm_close(torch.nn.functional.linear(x, w), exact, absprod, 2048)
-    rel = float(((y.double() - exact).abs() / absprod).max())
+    assert_gemm_close(torch.nn.functional.linear(x, w, bias), exact, absprod, 2048)
+    rel = float(((y.double() - exact).abs() / absprod.clamp_min(1e-300)).max())
     assert rel < 1e-6, rel
