@@ -22,18 +22,26 @@ namespace bq {
 constexpr int kBM = 128;          // UMMA M (cta_group::1)
 constexpr int kBK = 64;           // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
 
 constexpr int kEpiWarpWords = 32 * 33 + 64 * 4;      // per epilogue warp: 32x33 transpose tile + 64 uint4 block states
-template <int BN, bool EPI = false> struct GemmCfg {
+// BN: tile width; EPI: fused epilogue (8 epilogue warps + scratch) ; CG: CTAs per MMA (cta_group::1 / ::2).
+// With CG == 2 a CTA pair computes a 256 x 256 tile: each CTA owns 128 rows of A and of the accumulator and HALF of the B tile,
+// which the pair's MMA reads from both shared memories — 2/3 of the smem fill traffic and operand reads per FLOP of CG == 1.
+template <int BN, bool EPI = false, int CG = 1> struct GemmCfg {
+  static constexpr int kEpiWarps = EPI ? 8 : 4;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
   static constexpr int kStageA = kBM * kBK * 2;
-  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStageB = (BN / CG) * kBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kEpiBytes = EPI ? kEpiWarps * kEpiWarpWords * 4 : 0;
+  static constexpr int kBudget = 224 * 1024 - 2048 - kEpiBytes;      // 227 KB per CTA minus barriers / alignment slack / scratch
+  static constexpr int kStages = kBudget / kStage > 8 ? 8 : kBudget / kStage;
   static constexpr int kTmemCols = 2 * BN;                     // two accumulators; power of two >= 32
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kEpiOff = kStages * kStage + ((kBarBytes + 15) / 16) * 16;
-  static constexpr int kSmemBytes = kEpiOff + (EPI ? 4 * kEpiWarpWords * 4 : 0) + 1024;   // + alignment slack
+  static constexpr int kSmemBytes = kEpiOff + kEpiBytes + 1024;   // + alignment slack
+  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 // Fused epilogue (EPI kernels): v = acc + bias; v *= scale; v = act(v); v = residual + v; v = Q(v); store fp32 / bf16.
@@ -171,10 +179,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
   }
 }
 
-template <int BN, bool EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, bool EPI, int CG>
+__global__ void __launch_bounds__(GemmCfg<BN, EPI, CG>::kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
-  using Cfg = GemmCfg<BN, EPI>;
+  using Cfg = GemmCfg<BN, EPI, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -188,6 +196,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (CG == 2) ? (int)ptx::cluster_ctarank() : 0;      // 0 = leader (issues the MMAs)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -200,32 +209,42 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 4);      // one arrive per epilogue warp
+      ptx::mbar_init(tempty_bar(a), CG * Cfg::kEpiWarps);      // one arrive per epilogue warp (of both CTAs of a pair)
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (CG == 2) ptx::tmem_alloc_cg2<Cfg::kTmemCols>(tmem_slot);
+    else ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();     // the peer's barriers exist before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int kb_per_term = (g.K + kBK - 1) / kBK;
   const int num_kb = kb_per_term * (g.n_terms > 0 ? g.n_terms : 1);
-  const int tiles_per_batch = g.tiles_m * g.tiles_n;
+  const int tiles_per_batch = g.tiles_m * g.tiles_n;          // CG == 2: tiles_m counts 256-row blocks
   const int total_tiles = tiles_per_batch * g.batch;
+  const int worker = blockIdx.x / CG, num_workers = gridDim.x / CG;
+  // tile -> (batch, first row of THIS CTA, n block)
+  auto decode = [&](int tile, int& b, int& row0, int& nb) {
+    b = tile / tiles_per_batch;
+    const int t = tile - b * tiles_per_batch;
+    const int mb = t / g.tiles_n;                              // n fastest: the workers of a wave share A rows through L2
+    nb = t - mb * g.tiles_n;
+    row0 = (mb * CG + rank) * kBM;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_batch;
-        const int t = tile - b * tiles_per_batch;
-        const int mb = t / g.tiles_n, nb = t - mb * g.tiles_n;   // n fastest: CTAs of a wave share A rows / stream B through L2
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+        int b, row0, nb;
+        decode(tile, b, row0, nb);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-          ptx::mbar_expect_tx(full_bar(stage), Cfg::kStage);
           const uint32_t sa = smem_base + stage * Cfg::kStage;
           int ca = b, cb = g.b_broadcast ? 0 : b, kk = kb;
           if (g.n_terms > 0) {
@@ -234,20 +253,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ca = g.term_a[t];
             cb = g.term_b[t];
           }
-          ptx::tma_load_3d(sa, &tmA, full_bar(stage), kk * kBK, mb * kBM, ca);
-          ptx::tma_load_3d(sa + Cfg::kStageA, &tmB, full_bar(stage), kk * kBK, nb * BN, cb);
+          if (CG == 2) {
+            // the leader's barrier collects the bytes of BOTH CTAs' loads
+            if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * Cfg::kStage);
+            ptx::tma_load_3d_cg2(sa, &tmA, full_bar(stage), kk * kBK, row0, ca);
+            ptx::tma_load_3d_cg2(sa + Cfg::kStageA, &tmB, full_bar(stage), kk * kBK, nb * BN + rank * (BN / 2), cb);
+          } else {
+            ptx::mbar_expect_tx(full_bar(stage), Cfg::kStage);
+            ptx::tma_load_3d(sa, &tmA, full_bar(stage), kk * kBK, row0, ca);
+            ptx::tma_load_3d(sa + Cfg::kStageA, &tmB, full_bar(stage), kk * kBK, nb * BN, cb);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = g.fp16 ? ptx::idesc_f16_f32(kBM, BN) : ptx::idesc_bf16_f32(kBM, BN);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = g.fp16 ? ptx::idesc_f16_f32(kBM * CG, BN) : ptx::idesc_bf16_f32(kBM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -260,41 +287,46 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if (CG == 2) ptx::umma_bf16_cg2(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
-          ptx::umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (CG == 2) ptx::umma_commit_cg2_mc(empty_bar(stage), 3); else ptx::umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(tfull_bar(acc));          // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 2) ptx::umma_commit_cg2_mc(tfull_bar(acc), 3); else ptx::umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int ew = warp - 4;                       // epilogue warp index
+    const int q = ew & 3;                          // TMEM lane quarter this warp may access (== warp % 4)
+    const int c_first = ew >> 2;                   // with 8 epilogue warps the two warps of a quarter take alternate column chunks
+    constexpr int c_step = Cfg::kEpiWarps / 4;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_batch;
-      const int t = tile - b * tiles_per_batch;
-      const int mb = t / g.tiles_n, nb = t - mb * g.tiles_n;
+    for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      int b, row0, nb;
+      decode(tile, b, row0, nb);
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const int row = mb * kBM + q * 32 + lane;
+      const int row = row0 + q * 32 + lane;
       if (EPI) {
         // fused epilogue (batch == 1, N % 32 == 0, all pointers 16-byte aligned: checked on the host)
-        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + Cfg::kEpiOff) + q * kEpiWarpWords;
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + Cfg::kEpiOff) + ew * kEpiWarpWords;
         const bool row_ok = row < g.M;
         const bool has_res = g.epi.residual != nullptr && row_ok;
         const float* rrow = has_res ? g.epi.residual + (int64_t)row * g.epi.ldr + nb * BN : nullptr;
         float4 res_next[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) res_next[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_res && nb * BN < g.N) {
+        if (has_res && nb * BN + c_first * 32 < g.N) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(rrow + 4 * j);
+          for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(rrow + c_first * 32 + 4 * j);
         }
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_first; c < BN / 32; c += c_step) {
           const int col0 = nb * BN + c * 32;
           if (col0 >= g.N) break;                 // warp-uniform
           uint32_t r[32];
@@ -302,52 +334,48 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float4 res[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) res[j] = res_next[j];
-          if (has_res && c + 1 < BN / 32 && col0 + 32 < g.N) {      // residual of the next chunk: in flight during this chunk's math
+          if (has_res && c + c_step < BN / 32 && col0 + c_step * 32 < g.N) {   // next chunk's residual: in flight during this chunk's math
 #pragma unroll
-            for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(rrow + (c + 1) * 32 + 4 * j);
+            for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(rrow + (c + c_step) * 32 + 4 * j);
           }
           ptx::tmem_ld_wait();
           epilogue_chunk(g, r, res, row, col0, row_ok, scratch, lane);
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
-      float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
-      const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((g.sc & 3) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.col_scale) & 15) == 0);
+      } else {
+        float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
+        const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((g.sc & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.col_scale) & 15) == 0);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        ptx::tmem_ld_wait();
-        const int col0 = nb * BN + c * 32;
-        if (row < g.M && col0 < g.N) {
-          if (vec_ok && col0 + 32 <= g.N) {
+        for (int c = c_first; c < BN / 32; c += c_step) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+          ptx::tmem_ld_wait();
+          const int col0 = nb * BN + c * 32;
+          if (row < g.M && col0 < g.N) {
+            if (vec_ok && col0 + 32 <= g.N) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                     __uint_as_float(r[j + 3]));
-              if (g.row_scale) {
-                const float rs = g.row_scale[row];
-                const float4 cs = *reinterpret_cast<const float4*>(g.col_scale + col0 + j);
-                o.x *= rs * cs.x; o.y *= rs * cs.y; o.z *= rs * cs.z; o.w *= rs * cs.w;
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                       __uint_as_float(r[j + 3]));
+                if (g.row_scale) {
+                  const float rs = g.row_scale[row];
+                  const float4 cs = *reinterpret_cast<const float4*>(g.col_scale + col0 + j);
+                  o.x *= rs * cs.x; o.y *= rs * cs.y; o.z *= rs * cs.z; o.w *= rs * cs.w;
+                }
+                if (g.bias) {
+                  const float4 bv = *reinterpret_cast<const float4*>(g.bias + col0 + j);
+                  o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                }
+                *reinterpret_cast<float4*>(crow + col0 + j) = o;
               }
-              if (g.bias) {
-                const float4 bv = *reinterpret_cast<const float4*>(g.bias + col0 + j);
-                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-              }
-              *reinterpret_cast<float4*>(crow + col0 + j) = o;
-            }
-          } else {
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < g.N) {
-                float o = __uint_as_float(r[j]);
-                if (g.row_scale) o *= g.row_scale[row] * g.col_scale[col0 + j];
-                crow[col0 + j] = o + (g.bias ? g.bias[col0 + j] : 0.f);
+              for (int j = 0; j < 32; ++j) {
+                if (col0 + j < g.N) {
+                  float o = __uint_as_float(r[j]);
+                  if (g.row_scale) o *= g.row_scale[row] * g.col_scale[col0 + j];
+                  crow[col0 + j] = o + (g.bias ? g.bias[col0 + j] : 0.f);
+                }
               }
             }
           }
@@ -355,15 +383,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_leader(tempty_bar(acc)); else ptx::mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();     // nobody leaves while the peer may still signal / read this CTA
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CG == 2) ptx::tmem_dealloc_cg2<Cfg::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -432,25 +463,56 @@ int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, i
   return BQ_OK;
 }
 
-template <int BN, bool EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, cudaStream_t st, int kern_id = kKernGemm) {
-  using Cfg = GemmCfg<BN, EPI>;
+template <int BN, bool EPI, int CG>
+static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, cudaStream_t st, int kern_id) {
+  using Cfg = GemmCfg<BN, EPI, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  g.tiles_m = (g.M + kBM - 1) / kBM;
+  g.tiles_m = (g.M + kBM * CG - 1) / (kBM * CG);
   g.tiles_n = (g.N + BN - 1) / BN;
   int64_t total = (int64_t)g.tiles_m * g.tiles_n * g.batch;
   if (total > 0x7fffffffll) return BQ_ERR_UNSUPPORTED;
-  int grid = (int)std::min<int64_t>(total, num_sms());
+  const int grid = CG * (int)std::min<int64_t>(total, num_sms() / CG);
   {
     LaunchScope ls(kern_id, st);
-    gemm_bf16_tn_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, g);
+    if (CG == 1) {
+      gemm_bf16_tn_kernel<BN, EPI, CG><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, g);
+    } else {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(grid, 1, 1);
+      cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
+      cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      BQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, EPI, CG>, tmA, tmB, g));
+    }
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
+}
+
+// CTA pairs need BN == 256, one batch and enough rows; `pair` is decided by the callers (use_pairs) BEFORE the B tensor map
+// is built, because its box holds BN / CG rows.
+static bool g_pairs_enabled = true;
+static bool use_pairs(int64_t batch, int64_t M, int64_t N) { return g_pairs_enabled && batch == 1 && N > 128 && M > 128; }
+
+template <bool EPI>
+static int launch_gemm_any(int BN, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st,
+                           int kern_id) {
+  if (pair) return launch_gemm_cg<256, EPI, 2>(tmA, tmB, g, st, kern_id);
+  switch (BN) {
+    case 64: return launch_gemm_cg<64, EPI, 1>(tmA, tmB, g, st, kern_id);
+    case 128: return launch_gemm_cg<128, EPI, 1>(tmA, tmB, g, st, kern_id);
+    default: return launch_gemm_cg<256, EPI, 1>(tmA, tmB, g, st, kern_id);
+  }
 }
 
 int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M, int64_t N,
@@ -469,7 +531,8 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
   int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, batch, lda, sa, kBM);
   if (rc) return rc;
   const bool bcast = (sb == 0) || batch == 1;
-  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, bcast ? 1 : batch, ldb, sb, BN);
+  const bool pair = use_pairs(batch, M, N);
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, bcast ? 1 : batch, ldb, sb, pair ? 128 : BN);
   if (rc) return rc;
   GemmArgs g;
   g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = (int)batch;
@@ -477,11 +540,7 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
   g.n_terms = 0;
   g.fp16 = 0; g.row_scale = g.col_scale = nullptr;
   memset(&g.epi, 0, sizeof(g.epi));
-  switch (BN) {
-    case 64: return launch_gemm<64, false>(tmA, tmB, g, st);
-    case 128: return launch_gemm<128, false>(tmA, tmB, g, st);
-    default: return launch_gemm<256, false>(tmA, tmB, g, st);
-  }
+  return launch_gemm_any<false>(BN, pair, tmA, tmB, g, st, kKernGemm);
 }
 
 int make_params(const bq_format* f, FmtParams* p);
@@ -522,15 +581,12 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, 1, lda, 0, kBM);
   if (rc) return rc;
-  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, 1, ldb, 0, BN);
+  const bool pair = use_pairs(1, M, N);
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, 1, ldb, 0, pair ? 128 : BN);
   if (rc) return rc;
   g.C = (float*)C; g.bias = ep->bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = 1;
   g.ldc = ldc; g.sc = 0; g.b_broadcast = 1; g.n_terms = 0;
-  switch (BN) {
-    case 64: return launch_gemm<64, true>(tmA, tmB, g, st, kKernGemmEpi);
-    case 128: return launch_gemm<128, true>(tmA, tmB, g, st, kKernGemmEpi);
-    default: return launch_gemm<256, true>(tmA, tmB, g, st, kKernGemmEpi);
-  }
+  return launch_gemm_any<true>(BN, pair, tmA, tmB, g, st, kKernGemmEpi);
 }
 
 // Split-precision GEMM: C = sum over terms (A_plane[ta] @ B_plane[tb]^T) (+ bias).  With x = x0 + x1 + x2 (three bf16
@@ -549,7 +605,8 @@ int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, planes_a, K, M * K, kBM);     // 16-bit elements: the map only moves bytes
   if (rc) return rc;
-  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, planes_b, K, N * K, BN);
+  const bool pair = use_pairs(1, M, N);
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, planes_b, K, N * K, pair ? 128 : BN);
   if (rc) return rc;
   GemmArgs g;
   memset(&g, 0, sizeof(g));
@@ -562,14 +619,13 @@ int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias
     g.term_a[i] = (int8_t)ta[i];
     g.term_b[i] = (int8_t)tb[i];
   }
-  switch (BN) {
-    case 64: return launch_gemm<64, false>(tmA, tmB, g, st, kKernGemmSplit);
-    case 128: return launch_gemm<128, false>(tmA, tmB, g, st, kKernGemmSplit);
-    default: return launch_gemm<256, false>(tmA, tmB, g, st, kKernGemmSplit);
-  }
+  return launch_gemm_any<false>(BN, pair, tmA, tmB, g, st, kKernGemmSplit);
 }
 
 }  // namespace bq
+
+// debugging / measurement switch: 0 forces cta_group::1 tiles everywhere
+extern "C" void bq_set_cta_pairs(int on) { bq::g_pairs_enabled = on != 0; }
 
 extern "C" int bq_gemm_split16_tn(const void* A_planes_f16, const void* B_planes_f16, float* C, const float* bias,
                                   const float* a_inv_scale, const float* b_inv_scale, int64_t M, int64_t N, int64_t K,
