@@ -186,11 +186,16 @@ __device__ __forceinline__ int rint_log2_i(float x) {        // == (int)rintf(lo
   return (int)ex - 127 + (f > kSqrt2Mant ? 1 : 0);
 }
 __device__ __forceinline__ float pow2_i(int e) { return __int_as_float((e + 127) << 23); }   // e in [-126, 127]
+// rintf(t) for |t| < 2^22 as two full-rate FADDs (FRND runs on the quarter-rate conversion pipe): adding 1.5 * 2^23 moves t into
+// a binade whose ulp is 1, the addition itself rounds to nearest-even, the subtraction is exact.
+constexpr float kRintMagic = 12582912.0f;
+__device__ __forceinline__ float rint_small(float t) { return __fsub_rn(__fadd_rn(t, kRintMagic), kRintMagic); }
 
 struct FastState {
   bool ok;
   float f0, f1;   // block_fp: scale 2^(m-E), step 2^(E-m)            block_log: delta, 2^emin
   int i0, i1;     // block_minifloat / block_log: emin, emax (integers)
+  float c0, c1, hi;   // block_fp: 1e-9f * f0, -kRintMagic * f1, kRintMagic + qmax  (all exact)
 };
 
 // host-known part of the validity check lives in FmtParams::fast_fmt (mantissa width / scalar exponent range)
@@ -200,6 +205,7 @@ __device__ __forceinline__ FastState fast_state(uint32_t mbits, const FmtParams&
   s.ok = false;
   s.f0 = s.f1 = 0.f;
   s.i0 = s.i1 = 0;
+  s.c0 = s.c1 = s.hi = 0.f;
   if (!p.fast_fmt || mbits >= 0x7f800000u) return s;           // inf / NaN block max -> literal path
   const float mx = __uint_as_float(mbits);
   if (KIND == kBlockFP) {
@@ -208,6 +214,9 @@ __device__ __forceinline__ FastState fast_state(uint32_t mbits, const FmtParams&
     if (E < -100 || E > 100) return s;
     s.f0 = pow2_i(p.mbits - E);
     s.f1 = pow2_i(E - p.mbits);
+    s.c0 = __fmul_rn(1e-9f, s.f0);
+    s.c1 = -__fmul_rn(kRintMagic, s.f1);
+    s.hi = __fadd_rn(kRintMagic, p.qmax);
     s.ok = true;
   } else if (KIND == kBlockMinifloat) {
     int b = floor_log2_i(mx);
@@ -234,9 +243,11 @@ __device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, co
   const float ax = fabsf(x);
   float out;
   if (KIND == kBlockFP) {
-    const float v = __fadd_rn(ax, 1e-9f);
-    const float q = fminf(rintf(__fmul_rn(v, s.f0)), p.qmax);
-    float y = copysignf(__fmul_rn(q, s.f1), x);
+    // (|x| + 1e-9f) * 2^(m-E) == fma(|x|, f0, 1e-9f * f0): scaling by a power of two commutes with rounding (no under/overflow:
+    // |m - E| <= 122).  Rounding and clamping happen in the magic-shifted domain; (tm - magic) * f1 is exact, so is the fma.
+    const float t = __fmaf_rn(ax, s.f0, s.c0);
+    const float tm = fminf(__fadd_rn(t, kRintMagic), s.hi);
+    float y = copysignf(__fmaf_rn(tm, s.f1, s.c1), x);
     if (p.fold_zero) y = __fadd_rn(y, 0.f);
     return (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
   } else if (KIND == kBlockMinifloat || KIND == kMinifloatIEEE) {
@@ -248,7 +259,7 @@ __device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, co
     const bool normal = (e != emin);
     // one rounding unit for both branches: normal -> rint(ts - 2^M), subnormal -> rint(ts / 2), clamped to [0, 2^M - 1]
     const float r = normal ? __fsub_rn(ts, p.shift) : __fmul_rn(ts, 0.5f);
-    const float frac = __fmul_rn(fminf(fmaxf(rintf(r), 0.f), p.qmax), p.inv_shift);
+    const float frac = __fmul_rn(fminf(fmaxf(rint_small(r), 0.f), p.qmax), p.inv_shift);   // |r| < 2^(mbits+1) <= 2^22... see fast_fmt
     const float mant = normal ? __fadd_rn(1.0f, frac) : __fmul_rn(frac, 2.f);
     const float y = copysignf(__fmul_rn(pow2_i(e), mant), x);
     out = (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
@@ -261,7 +272,7 @@ __device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, co
   } else if (KIND == kMinifloatDenorm) {
     int e = ceil_log2_i(__fadd_rn(ax, 1e-9f));
     e = min(max(e, (int)p.emin), (int)p.emax);
-    const float q = fminf(rintf(__fmul_rn(__fmul_rn(ax, pow2_i(-e)), p.shift)), p.qmax);
+    const float q = fminf(rint_small(__fmul_rn(__fmul_rn(ax, pow2_i(-e)), p.shift)), p.qmax);
     const float y = copysignf(__fmul_rn(pow2_i(e), __fmul_rn(q, p.inv_shift)), x);
     out = (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
   } else {

@@ -112,6 +112,7 @@ __device__ __forceinline__ void quant_rowblocks32(float (&v)[32], const FmtParam
     fs.ok = true;
     fs.f0 = __uint_as_float(s.x); fs.f1 = __uint_as_float(s.y);
     fs.i0 = (int)s.x; fs.i1 = (int)s.y;
+    fs.c0 = __fmul_rn(1e-9f, fs.f0); fs.c1 = -__fmul_rn(kRintMagic, fs.f1); fs.hi = __fadd_rn(kRintMagic, q.qmax);
     float y = 0.f;
     if (s.w == 1u) y = quant_elem_fast<KIND>(v[j], fs, q);
     else if (s.w == 0u) y = quant_literal_1<KIND>(v[j], s.z, q);

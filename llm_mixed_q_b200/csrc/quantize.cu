@@ -655,37 +655,84 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// normalised value of one float4 slot (torch's op order: LayerNorm fma(gamma, rstd * (x - mean), beta); RMSNorm gamma * (x * rstd))
+__device__ __forceinline__ float4 norm_slot(const float4 xv, const float4 gm, const float4 bt, bool layer_norm, float mean, float rstd) {
+  float4 y;
+  if (layer_norm) {
+    y.x = __fmaf_rn(gm.x, __fmul_rn(rstd, __fsub_rn(xv.x, mean)), bt.x);
+    y.y = __fmaf_rn(gm.y, __fmul_rn(rstd, __fsub_rn(xv.y, mean)), bt.y);
+    y.z = __fmaf_rn(gm.z, __fmul_rn(rstd, __fsub_rn(xv.z, mean)), bt.z);
+    y.w = __fmaf_rn(gm.w, __fmul_rn(rstd, __fsub_rn(xv.w, mean)), bt.w);
+  } else {
+    y.x = __fmul_rn(gm.x, __fmul_rn(xv.x, rstd));
+    y.y = __fmul_rn(gm.y, __fmul_rn(xv.y, rstd));
+    y.z = __fmul_rn(gm.z, __fmul_rn(xv.z, rstd));
+    y.w = __fmul_rn(gm.w, __fmul_rn(xv.w, rstd));
+  }
+  return y;
+}
+// generic emit (any supported kind, ragged rows): one slot per lane and iteration, predicated
 template <int KIND>
 __device__ __forceinline__ void norm_emit(const float4* __restrict__ xs, const LnArgs& a, const FmtParams& p, float mean, float rstd,
                                           __nv_bfloat16* __restrict__ outp, int nslot, int lane) {
   const int iters = (nslot + 31) >> 5;
-#pragma unroll 2
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
   for (int i = 0; i < iters; ++i) {
     const int s = i * 32 + lane;
     const bool act = s < nslot;
-    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act) {
-      const float4 xv = xs[s];
-      const float4 gm = *reinterpret_cast<const float4*>(a.gamma + 4 * s);
-      if (a.beta) {
-        const float4 bt = *reinterpret_cast<const float4*>(a.beta + 4 * s);
-        y.x = __fmaf_rn(gm.x, __fmul_rn(rstd, __fsub_rn(xv.x, mean)), bt.x);
-        y.y = __fmaf_rn(gm.y, __fmul_rn(rstd, __fsub_rn(xv.y, mean)), bt.y);
-        y.z = __fmaf_rn(gm.z, __fmul_rn(rstd, __fsub_rn(xv.z, mean)), bt.z);
-        y.w = __fmaf_rn(gm.w, __fmul_rn(rstd, __fsub_rn(xv.w, mean)), bt.w);
-      } else {
-        y.x = __fmul_rn(gm.x, __fmul_rn(xv.x, rstd));
-        y.y = __fmul_rn(gm.y, __fmul_rn(xv.y, rstd));
-        y.z = __fmul_rn(gm.z, __fmul_rn(xv.z, rstd));
-        y.w = __fmul_rn(gm.w, __fmul_rn(xv.w, rstd));
-      }
-    }
+    float4 y = z;
+    if (act) y = norm_slot(xs[s], *reinterpret_cast<const float4*>(a.gamma + 4 * s),
+                           a.beta ? *reinterpret_cast<const float4*>(a.beta + 4 * s) : z, a.beta != nullptr, mean, rstd);
     // block max over the 4 adjacent lanes that hold one block of 16 (H % 16 == 0: a block is all-active or all-inactive)
     uint32_t m = max(max(absbits(y.x), absbits(y.y)), max(absbits(y.z), absbits(y.w)));
     m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
     m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
     if (m == 0) m = 0x3f800000u;
     if (act) store4<__nv_bfloat16>(outp + 4 * s, quant4<KIND>(y, m, p));
+  }
+}
+// block_fp emit for rows whose slot count is a multiple of 32: no predicates, scalars in registers, magic-constant
+// rounding, exponent straight from the max's exponent field; the rare blocks that need the literal arithmetic (cliff zone,
+// non-finite, extreme exponents) go through the generic quant4.
+__device__ __forceinline__ float bfp_fast1(float x, float f0, float c0, float hi, float f1, float c1) {
+  const float ax = fabsf(x);
+  const float t = __fmaf_rn(ax, f0, c0);                          // == (|x| + 1e-9f) * 2^(m-E)   (power-of-two scaling commutes with rounding)
+  const float tm = fminf(__fadd_rn(t, kRintMagic), hi);           // kRintMagic + min(rint(t), qmax)
+  const float y = copysignf(__fmaf_rn(tm, f1, c1), x);            // (tm - kRintMagic) * 2^(E-m), exact
+  return (ax <= 1e-8f) ? x : y;
+}
+__device__ __forceinline__ void norm_emit_bfp32(const float4* __restrict__ xs, const LnArgs& a, const FmtParams& p, float mean, float rstd,
+                                                __nv_bfloat16* __restrict__ outp, int nslot, int lane) {
+  const int iters = nslot >> 5;
+  const bool ln = a.beta != nullptr;
+  const int emin = (int)p.emin, emax = (int)p.emax, mb = p.mbits;
+  const float hi = __fadd_rn(kRintMagic, p.qmax);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int i = 0; i < iters; ++i) {
+    const int s = i * 32 + lane;
+    const float4 y = norm_slot(xs[s], __ldg(reinterpret_cast<const float4*>(a.gamma) + s),
+                               ln ? __ldg(reinterpret_cast<const float4*>(a.beta) + s) : z, ln, mean, rstd);
+    uint32_t m = max(max(absbits(y.x), absbits(y.y)), max(absbits(y.z), absbits(y.w)));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    if (m == 0) m = 0x3f800000u;
+    const uint32_t ex = m >> 23, f = m & 0x7fffffu;
+    int E = min(max((int)ex - 126, emin), emax);                  // ceil(log2(max)) away from the cliff zone
+    const bool fast = (ex - 1u < 254u) && (((f + kZone) & 0x7fffffu) >= 2 * kZone) && E >= -100 && E <= 100 && p.fast_fmt;
+    float4 q;
+    if (fast) {
+      const float f0 = pow2_i(mb - E), f1 = pow2_i(E - mb);
+      const float c0 = __fmul_rn(1e-9f, f0), c1 = -__fmul_rn(kRintMagic, f1);
+      q.x = bfp_fast1(y.x, f0, c0, hi, f1, c1);
+      q.y = bfp_fast1(y.y, f0, c0, hi, f1, c1);
+      q.z = bfp_fast1(y.z, f0, c0, hi, f1, c1);
+      q.w = bfp_fast1(y.w, f0, c0, hi, f1, c1);
+    } else {
+      q = quant4<kBlockFP>(y, m, p);
+    }
+    store4<__nv_bfloat16>(outp + 4 * s, q);
   }
 }
 __global__ void __launch_bounds__(kLnWarps * 32) norm_quant_kernel(LnArgs a) {
@@ -726,36 +773,27 @@ __global__ void __launch_bounds__(kLnWarps * 32) norm_quant_kernel(LnArgs a) {
         }
       }
       mean = __fmul_rn(warp_sum(__fadd_rn(s0, s1)), invH);
-      float q0 = 0.f, q1 = 0.f;
-      for (int s = lane; s < nslot; s += 64) {
+    }
+    {
+      // sum of squared deviations (RMSNorm: mean = 0), fused multiply-adds in four independent chains
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      for (int s = lane; s < nslot; s += 32) {
         const float4 v = xs[s];
         const float dx = __fsub_rn(v.x, mean), dy = __fsub_rn(v.y, mean), dz = __fsub_rn(v.z, mean), dw = __fsub_rn(v.w, mean);
-        q0 = __fadd_rn(q0, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fadd_rn(__fmul_rn(dz, dz), __fmul_rn(dw, dw))));
-        if (s + 32 < nslot) {
-          const float4 w = xs[s + 32];
-          const float ex = __fsub_rn(w.x, mean), ey = __fsub_rn(w.y, mean), ez = __fsub_rn(w.z, mean), ew = __fsub_rn(w.w, mean);
-          q1 = __fadd_rn(q1, __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fadd_rn(__fmul_rn(ez, ez), __fmul_rn(ew, ew))));
-        }
+        q0 = __fmaf_rn(dx, dx, q0); q1 = __fmaf_rn(dy, dy, q1); q2 = __fmaf_rn(dz, dz, q2); q3 = __fmaf_rn(dw, dw, q3);
       }
-      rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(__fadd_rn(q0, q1)), invH), a.eps));
-    } else {
-      float q0 = 0.f, q1 = 0.f;
-      for (int s = lane; s < nslot; s += 64) {
-        const float4 v = xs[s];
-        q0 = __fadd_rn(q0, __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fadd_rn(__fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w))));
-        if (s + 32 < nslot) {
-          const float4 w = xs[s + 32];
-          q1 = __fadd_rn(q1, __fadd_rn(__fadd_rn(__fmul_rn(w.x, w.x), __fmul_rn(w.y, w.y)), __fadd_rn(__fmul_rn(w.z, w.z), __fmul_rn(w.w, w.w))));
-        }
-      }
-      rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(__fadd_rn(q0, q1)), invH), a.eps));
+      rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3))), invH), a.eps));
     }
 #pragma unroll 1
     for (int k = 0; k < a.n_out; ++k) {
       const FmtParams& p = (k == 0) ? a.f[0] : ((k == 1) ? a.f[1] : a.f[2]);
       __nv_bfloat16* outp = ((k == 0) ? a.out[0] : ((k == 1) ? a.out[1] : a.out[2])) + (int64_t)row * a.H;
-      if (p.kind == kBlockFP) norm_emit<kBlockFP>(xs, a, p, mean, rstd, outp, nslot, lane);
-      else norm_emit<kBlockMinifloat>(xs, a, p, mean, rstd, outp, nslot, lane);
+      if (p.kind == kBlockFP) {
+        if ((nslot & 31) == 0) norm_emit_bfp32(xs, a, p, mean, rstd, outp, nslot, lane);
+        else norm_emit<kBlockFP>(xs, a, p, mean, rstd, outp, nslot, lane);
+      } else {
+        norm_emit<kBlockMinifloat>(xs, a, p, mean, rstd, outp, nslot, lane);
+      }
     }
     __syncwarp();            // every lane is done with buffer b before lane 0 re-arms it two iterations later
   }
