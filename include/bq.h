@@ -230,6 +230,9 @@ BQ_API int bq_bmm(const bq_format* fx, const bq_format* fy, const float* x, cons
 BQ_API int bq_attention_causal(const bq_format* fp, const void* Qq, const void* Kq, const void* Vq, float* out, int64_t B,
                                int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
                                float score_div, void* stream);
+/* 1: numerators of the softmax use libdevice expf (bit-identical to torch's exp(x - max)); 0 (default): ex2.approx of a fused
+ * multiply-add argument, ~|x - max| * 1.44 ulp less accurate, 30 % fewer instructions per score. */
+BQ_API void bq_set_attention_precise_exp(int on);
 BQ_API int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq,
                                  void* out_bf16, int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk,
                                  int64_t ldv, int64_t ldo, float score_div, void* stream);

@@ -193,17 +193,26 @@ __device__ __forceinline__ float stat_fixup(float m, float mL, float l) {
   return __fmul_rn(l, ex2_fast(-err));
 }
 
-// final probabilities of 32 scores -> two quantised blocks -> swizzled bf16 rows of the P tile
-template <int KIND, bool MASK>
-__device__ __forceinline__ void probs32(const uint32_t (&r)[32], int nvalid, float m, float inv_l, const FmtParams& p,
+// final probabilities of 32 scores -> two quantised blocks -> swizzled bf16 rows of the P tile.
+// FAST: p = min(ex2.approx(fma(s, log2 e, -mL)) * inv_l, 1) — the exponential of the statistics sweep again (2 instructions
+// instead of libdevice expf's 8 + the subtraction); inv_l already carries the row constant 2^-(m * log2 e - mL).  Relative error
+// of p <= ~(3 + |s - m| * 1.44) ulp instead of <= ~3 ulp; a probability only changes when it sits that close to a rounding
+// boundary.  The clamp keeps the largest probability from crossing 1.0 (next block exponent).
+template <int KIND, bool MASK, bool FAST>
+__device__ __forceinline__ void probs32(const uint32_t (&r)[32], int nvalid, float m, float mL, float inv_l, const FmtParams& p,
                                         uint8_t* prow, int chunk0, int sw) {
+  const float nmL = -mL;
 #pragma unroll
   for (int blk = 0; blk < 2; ++blk) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float e = expf(__fsub_rn(u2f(r[blk * 16 + i]), m));
-      v[i] = __fmul_rn(e, inv_l);
+      if (FAST) {
+        v[i] = fminf(__fmul_rn(ex2_fast(__fmaf_rn(u2f(r[blk * 16 + i]), kL2E, nmL)), inv_l), 1.0f);
+      } else {
+        const float e = expf(__fsub_rn(u2f(r[blk * 16 + i]), m));
+        v[i] = __fmul_rn(e, inv_l);
+      }
       if (MASK) v[i] = (blk * 16 + i < nvalid) ? v[i] : 0.f;
     }
     uint32_t w[8];
@@ -222,7 +231,7 @@ struct Ring {
   }
 };
 
-template <int KIND, int D>
+template <int KIND, int D, bool FAST>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, AttnArgs g) {
@@ -445,9 +454,9 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
                 for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(prow + (((chunk0 + c) ^ sw) << 4)) = z;
               } else if (!(diag && diag_partial)) {
-                probs32<KIND, false>(r, 32, m, inv_l, g.p, prow, chunk0, sw);
+                probs32<KIND, false, FAST>(r, 32, m, mL, inv_l, g.p, prow, chunk0, sw);
               } else {
-                probs32<KIND, true>(r, nvalid_d, m, inv_l, g.p, prow, chunk0, sw);
+                probs32<KIND, true, FAST>(r, nvalid_d, m, mL, inv_l, g.p, prow, chunk0, sw);
               }
               ptx::fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the MMA (async proxy)
               __syncwarp();
@@ -472,6 +481,12 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             // which would make the largest probability exceed 1.0 and jump to the next block exponent
             l = fmaxf(ll, 1.0f);
             inv_l = __frcp_rn(l);
+            if (FAST) {
+              // final sweep evaluates 2^(s * log2 e - mL) with mL = rn(m * log2 e): fold the row constant 2^-(m * log2 e - mL) into 1 / l
+              mL = __fmul_rn(m, kL2E);
+              const float err = __fadd_rn(__fmaf_rn(m, kL2E, -mL), __fmul_rn(m, kL2ELo));
+              inv_l = __fmul_rn(inv_l, ex2_fast(-err));
+            }
           }
         }
         // ---- epilogue: O (128 x D fp32 in TMEM) -> global; this warp owns D/4 of the D columns of its 32 rows
@@ -529,13 +544,15 @@ int make_params(const bq_format* f, FmtParams* p);
 int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, int64_t H, int64_t B, int64_t ld_tok,
                       int box_rows);
 
-template <int KIND, int D>
-static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
-                            cudaStream_t st) {
+static bool g_attn_precise_exp = false;       // true: libdevice expf for the numerators (bit-identical to torch's exp(x - max))
+
+template <int KIND, int D, bool FAST>
+static int launch_attention_f(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
+                              cudaStream_t st) {
   using Cfg = AtCfg<D>;
   static bool attr = false;
   if (!attr) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_kernel<KIND, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_kernel<KIND, D, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr = true;
   }
@@ -543,10 +560,15 @@ static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const 
   const int grid = std::min(items, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
-    attention_causal_kernel<KIND, D><<<grid, kAtThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
+    attention_causal_kernel<KIND, D, FAST><<<grid, kAtThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
+}
+
+template <int KIND, int D>
+static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g, cudaStream_t st) {
+  return g_attn_precise_exp ? launch_attention_f<KIND, D, false>(tq, tk, tv, g, st) : launch_attention_f<KIND, D, true>(tq, tk, tv, g, st);
 }
 
 static int attention_impl(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq, void* out,
@@ -589,6 +611,8 @@ static int attention_impl(const bq_format* fp, const bq_format* fo, const void* 
 }
 
 }  // namespace bq
+
+extern "C" void bq_set_attention_precise_exp(int on) { bq::g_attn_precise_exp = on != 0; }
 
 extern "C" int bq_attention_causal(const bq_format* fp, const void* Qq, const void* Kq, const void* Vq, float* out,
                                    int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv,

@@ -183,8 +183,18 @@ def _oracle_attention(q, k, v, cfg, heads, score_div=1.0):
     return o.view(B, heads, S, d).transpose(1, 2).reshape(B, S, H), p
 
 
+@pytest.fixture(params=[0, 1], ids=["fast_exp", "precise_exp"])
+def attention_exp_mode(request):
+    """Both numerator modes of the fused attention kernel (bq_set_attention_precise_exp)."""
+    from llm_mixed_q_b200 import _lib as L
+
+    L.load().bq_set_attention_precise_exp(request.param)
+    yield request.param
+    L.load().bq_set_attention_precise_exp(0)
+
+
 @pytest.mark.parametrize("S", [128, 200, 1024, 2048])
-def test_fused_causal_attention_vs_op_by_op_oracle(S):
+def test_fused_causal_attention_vs_op_by_op_oracle(S, attention_exp_mode):
     """The fused kernel computes the same function as bmm_0 -> mask -> softmax -> bmm_1.  Scores agree to fp32
     accumulation order; the row sum of the softmax is accumulated in a different order from 2-ulp ex2.approx
     exponentials, so a probability can differ by a few ulp BEFORE quantisation and, when it sits on a rounding boundary,
@@ -213,7 +223,7 @@ def test_fused_causal_attention_vs_op_by_op_oracle(S):
     assert torch.equal(out[:, 0, :], exp0)
 
 
-def test_fused_causal_attention_head_dim_128_and_score_div():
+def test_fused_causal_attention_head_dim_128_and_score_div(attention_exp_mode):
     """Llama-7B geometry: d = 128, scores divided by sqrt(d) after matmul_0 (modeling_llama.py:309-314).  torch-CUDA
     evaluates `tensor / python_float` as a multiplication by the fp32 reciprocal; the kernel does the same."""
     import math
