@@ -170,20 +170,34 @@ static __device__ __noinline__ int ceil_log2_slow(float x) { return (int)ceilf(l
 static __device__ __noinline__ int floor_log2_slow(float x) { return (int)floorf(log2f(x)); }
 static __device__ __noinline__ int rint_log2_slow(float x) { return (int)rintf(log2f(x)); }
 
+// One-sided cliffs (checked exhaustively by bq_selftest_log2): log2f(x) can only land ON an integer k by rounding when x sits
+// just above 2^k (result k instead of k+tiny: matters for ceil) or just below it (k instead of k-tiny: matters for floor).
 __device__ __forceinline__ int ceil_log2_i(float x) {        // == (int)ceilf(log2f(x)) for x > 0 finite
-  const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
-  if (ex - 1u >= 254u || ((f + kZone) & 0x7fffffu) < 2 * kZone) return ceil_log2_slow(x);
+  const uint32_t b = __float_as_uint(x), ex = b >> 23;
+  if (ex - 1u >= 254u || (b & 0x7fffffu) < kZone) return ceil_log2_slow(x);
   return (int)ex - 126;
 }
 __device__ __forceinline__ int floor_log2_i(float x) {       // == (int)floorf(log2f(x))
-  const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
-  if (ex - 1u >= 254u || ((f + kZone) & 0x7fffffu) < 2 * kZone) return floor_log2_slow(x);
+  const uint32_t b = __float_as_uint(x), ex = b >> 23;
+  if (ex - 1u >= 254u || (b | 0xff800000u) >= 0u - kZone) return floor_log2_slow(x);
   return (int)ex - 127;
+}
+// normal finite x only (callers guarantee it): no exponent-range test.  Returns the BIASED value (+127).
+__device__ __forceinline__ int floor_log2_biased_nf(float x) {
+  const uint32_t b = __float_as_uint(x);
+  if ((b | 0xff800000u) >= 0u - kZone) return floor_log2_slow(x) + 127;
+  return (int)(b >> 23);
 }
 __device__ __forceinline__ int rint_log2_i(float x) {        // == (int)rintf(log2f(x))
   const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
   if (ex - 1u >= 254u || (f - kSqrt2Mant + kZone) < 2 * kZone) return rint_log2_slow(x);
   return (int)ex - 127 + (f > kSqrt2Mant ? 1 : 0);
+}
+// finite x > 0; denormal x returns <= 1 (callers clamp from below).  Biased (+127): a mantissa above sqrt(2)'s carries into the exponent.
+__device__ __forceinline__ int rint_log2_biased_f(float x) {
+  const uint32_t b = __float_as_uint(x);
+  if (((b & 0x7fffffu) - kSqrt2Mant + kZone) < 2 * kZone) return (b >> 23) ? rint_log2_slow(x) + 127 : 0;
+  return (int)((b + (0x7fffffu - kSqrt2Mant)) >> 23);
 }
 __device__ __forceinline__ float pow2_i(int e) { return __int_as_float((e + 127) << 23); }   // e in [-126, 127]
 // rintf(t) for |t| < 2^22 as two full-rate FADDs (FRND runs on the quarter-rate conversion pipe): adding 1.5 * 2^23 moves t into
@@ -194,7 +208,7 @@ __device__ __forceinline__ float rint_small(float t) { return __fsub_rn(__fadd_r
 struct FastState {
   bool ok;
   float f0, f1;   // block_fp: scale 2^(m-E), step 2^(E-m)            block_log: delta, 2^emin
-  int i0, i1;     // block_minifloat / block_log: emin, emax (integers)
+  int i0, i1, i2; // block_log: emin, emax (integers); minifloat: biased step-exponent clamp [i0, i1], normal threshold i2
   float c0, c1, hi;   // block_fp: 1e-9f * f0, -kRintMagic * f1, kRintMagic + qmax  (all exact)
 };
 
@@ -204,7 +218,7 @@ __device__ __forceinline__ FastState fast_state(uint32_t mbits, const FmtParams&
   FastState s;
   s.ok = false;
   s.f0 = s.f1 = 0.f;
-  s.i0 = s.i1 = 0;
+  s.i0 = s.i1 = s.i2 = 0;
   s.c0 = s.c1 = s.hi = 0.f;
   if (!p.fast_fmt || mbits >= 0x7f800000u) return s;           // inf / NaN block max -> literal path
   const float mx = __uint_as_float(mbits);
@@ -218,12 +232,25 @@ __device__ __forceinline__ FastState fast_state(uint32_t mbits, const FmtParams&
     s.c1 = -__fmul_rn(kRintMagic, s.f1);
     s.hi = __fadd_rn(kRintMagic, p.qmax);
     s.ok = true;
-  } else if (KIND == kBlockMinifloat) {
-    int b = floor_log2_i(mx);
-    b = min(max(b, 0), (int)p.bias_hi);
-    s.i0 = -b;
-    s.i1 = (int)p.eb_top - b;
-    s.ok = (s.i0 >= -126 && s.i1 <= 126 && s.i1 >= s.i0);
+  } else if (KIND == kBlockMinifloat || KIND == kMinifloatIEEE) {
+    int emin, emax;
+    if (KIND == kBlockMinifloat) {
+      int b = floor_log2_i(mx);
+      b = min(max(b, 0), (int)p.bias_hi);
+      emin = -b;
+      emax = (int)p.eb_top - b;
+    } else {
+      emin = (int)p.emin;
+      emax = (int)p.emax;
+    }
+    // see quant_elem_fast: biased clamp range of the step exponent, "normal" threshold, clamp bounds in the shifted domain
+    s.i0 = emin + 1 + 127;
+    s.i1 = emax + 127;
+    s.i2 = (emax > emin) ? emin + 127 : 0x7fffffff;
+    s.f0 = __fadd_rn(kRintMagic, p.shift);
+    s.f1 = __fadd_rn(s.f0, p.qmax);
+    s.hi = __fadd_rn(kRintMagic, p.qmax);
+    s.ok = (emax >= emin) && (s.i0 - p.mbits >= 1) && (max(s.i1, s.i0) <= 253);
   } else if (KIND == kBlockLog) {
     int b = (int)p.eb_top - ceil_log2_i(mx);
     b = min(max(b, 0), (int)p.bias_hi);
@@ -251,24 +278,25 @@ __device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, co
     if (p.fold_zero) y = __fadd_rn(y, 0.f);
     return (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
   } else if (KIND == kBlockMinifloat || KIND == kMinifloatIEEE) {
-    const int emin = (KIND == kBlockMinifloat) ? s.i0 : (int)p.emin;
-    const int emax = (KIND == kBlockMinifloat) ? s.i1 : (int)p.emax;
-    int e = floor_log2_i(__fadd_rn(ax, 1e-9f));
-    e = min(max(e, emin), emax);
-    const float ts = __fmul_rn(__fmul_rn(ax, pow2_i(-e)), p.shift);
-    const bool normal = (e != emin);
-    // one rounding unit for both branches: normal -> rint(ts - 2^M), subnormal -> rint(ts / 2), clamped to [0, 2^M - 1]
-    const float r = normal ? __fsub_rn(ts, p.shift) : __fmul_rn(ts, 0.5f);
-    const float frac = __fmul_rn(fminf(fmaxf(rint_small(r), 0.f), p.qmax), p.inv_shift);   // |r| < 2^(mbits+1) <= 2^22... see fast_fmt
-    const float mant = normal ? __fadd_rn(1.0f, frac) : __fmul_rn(frac, 2.f);
-    const float y = copysignf(__fmul_rn(pow2_i(e), mant), x);
+    // minifloat.py:172-194 collapsed.  With e = clamp(floor(log2(|x|+1e-9)), emin, emax):
+    //   normal    (e > emin):  y = 2^(e-M)      * clamp(rint(|x| * 2^(M-e)),      2^M, 2^(M+1)-1)   [rint(ts - 2^M) == rint(ts) - 2^M: the
+    //                                                                                 subtraction is exact wherever the clamp does not decide]
+    //   subnormal (e == emin): y = 2^(emin+1-M) * clamp(rint(|x| * 2^(M-emin-1)), 0,   2^M-1)
+    // i.e. one step exponent es = max(e, emin+1), rounded and clamped in the magic-shifted domain; every scaling is by a power of two.
+    const int eb = floor_log2_biased_nf(__fadd_rn(ax, 1e-9f));
+    const bool normal = eb > s.i2;
+    const int es = max(min(eb, s.i1), s.i0);
+    const float inv_step = __int_as_float((254 + p.mbits - es) << 23), step = __int_as_float((es - p.mbits) << 23);
+    const float tm = fminf(fmaxf(__fadd_rn(__fmul_rn(ax, inv_step), kRintMagic), normal ? s.f0 : kRintMagic), normal ? s.f1 : s.hi);
+    const float y = copysignf(__fmul_rn(__fsub_rn(tm, kRintMagic), step), x);
     out = (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
   } else if (KIND == kBlockLog) {
     const float w = __fadd_rn(x, s.f0);
     const float v = __fadd_rn(ax, s.f0);
-    // v < 2^emin (zeros: v = delta, possibly denormal) clamps to emin whatever log2f returns
-    int e = (v < s.f1) ? s.i0 : min(max(rint_log2_i(v), s.i0), s.i1);
-    out = (w == 0.f) ? 0.f : copysignf(pow2_i(e), w);
+    // v is finite (block max is) and every v below 2^emin — zeros (v = delta), denormals — clamps to emin whatever the shortcut
+    // returns for it (its biased result is <= 1 there), so neither an exponent-range test nor a v < 2^emin select is needed.
+    const int eb = min(max(rint_log2_biased_f(v), s.i0 + 127), s.i1 + 127);
+    out = (w == 0.f) ? 0.f : copysignf(__int_as_float(eb << 23), w);
   } else if (KIND == kMinifloatDenorm) {
     int e = ceil_log2_i(__fadd_rn(ax, 1e-9f));
     e = min(max(e, (int)p.emin), (int)p.emax);

@@ -369,10 +369,10 @@ int make_params(const bq_format* f, FmtParams* p) {
   // normal number: mantissa <= 22 bits, scalar exponent ranges inside [-100, 100].
   switch (f->kind) {
     case kBlockFP: p->fast_fmt = (mb <= 22 && p->emin >= -1e6f && p->emax <= 1e6f); break;
-    case kBlockMinifloat: p->fast_fmt = (mb <= 22 && p->eb_top <= 1e6f && p->bias_hi <= 1e6f); break;
+    case kBlockMinifloat: p->fast_fmt = (mb <= 20 && p->eb_top <= 1e6f && p->bias_hi <= 1e6f); break;
     case kBlockLog: p->fast_fmt = (p->eb_top <= 1e6f && p->bias_hi <= 1e6f); break;
-    case kMinifloatDenorm:
-    case kMinifloatIEEE: p->fast_fmt = (mb <= 22 && p->emin >= -100.f && p->emax <= 100.f && p->emax >= p->emin); break;
+    case kMinifloatDenorm: p->fast_fmt = (mb <= 22 && p->emin >= -100.f && p->emax <= 100.f && p->emax >= p->emin); break;
+    case kMinifloatIEEE: p->fast_fmt = (mb <= 20 && p->emin >= -100.f && p->emax <= 100.f && p->emax >= p->emin); break;
     default: p->fast_fmt = 0;
   }
   return BQ_OK;
