@@ -243,6 +243,7 @@ BQ_API int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const
  * additionally brackets each launch with CUDA events on the launching stream; bq_profile_read
  * synchronises those events and returns the summed device time.
  * ---------------------------------------------------------------------------------------------- */
+BQ_API void bq_set_stream_quantizer(int on);           /* 0: force the per-slot quant_rows_kernel instead of the bulk-copy streaming kernel (A/B measurement) */
 BQ_API void bq_set_cta_pairs(int on);                  /* 0: force cta_group::1 GEMM tiles (A/B measurement) */
 BQ_API int bq_kernel_count(void);
 BQ_API const char* bq_kernel_name(int kernel_id);

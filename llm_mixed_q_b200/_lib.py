@@ -113,6 +113,8 @@ def load():
                                      POINTER(c_int32), POINTER(c_int32), c_int64, c_void_p]
     lib.bq_set_attention_precise_exp.restype = None
     lib.bq_set_attention_precise_exp.argtypes = [ctypes.c_int]
+    lib.bq_set_stream_quantizer.restype = None
+    lib.bq_set_stream_quantizer.argtypes = [ctypes.c_int]
     lib.bq_set_cta_pairs.restype = None
     lib.bq_set_cta_pairs.argtypes = [ctypes.c_int]
     lib.bq_split2_f16_rows.restype = ctypes.c_int

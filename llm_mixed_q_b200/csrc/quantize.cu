@@ -196,6 +196,196 @@ __global__ void __launch_bounds__(kThreads) blocklog_fixup_kernel(OutT* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// quant_stream_kernel — the speed path: dense tensors, blocks of 16 along the last dim (every shipped config) and the
+// element-wise kinds.  Measured motivation (profiles/r01_ncu_quant_rows_s5.json): quant_rows_kernel spends 27 (block_fp) to
+// 55 (block_log) instructions per element, ~20 of them on per-slot addressing, predicates, the shuffle reduction and a block
+// state that four lanes each recompute.  Here
+//   * every WARP is its own pipeline: 4 KB tiles (64 blocks of 16) arrive by one bulk async copy (cp.async.bulk, the 1-D TMA
+//     path) into a 3-deep shared-memory ring guarded by mbarriers, are quantised IN PLACE and leave by one bulk store — no
+//     per-thread global addressing, no CTA-wide barrier;
+//   * a lane owns whole blocks (2 per tile): the block max is 8 integer max instructions on its own registers — no shuffles —
+//     and the block state is computed once per 16 elements;
+//   * shared-memory reads are 16-byte accesses at a 64-byte lane stride, made conflict-free by rotating the chunk order with
+//     the lane index (the element math is order-agnostic).
+// ------------------------------------------------------------------------------------------------
+constexpr int kStWarps = 8;
+constexpr int kStNB = 2;                               // blocks per lane per tile
+constexpr int kStTileElems = 32 * kStNB * 16;          // 1024 floats
+constexpr int kStTileBytes = kStTileElems * 4;
+constexpr int kStStages = 3;
+constexpr size_t kStSmem = (size_t)kStWarps * kStStages * kStTileBytes + (size_t)kStWarps * kStStages * 8;
+
+__device__ __forceinline__ void st_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void st_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity), "r"(0x989680u)
+                 : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t absmax4(float4 v) {
+  return max(max(absbits(v.x), absbits(v.y)), max(absbits(v.z), absbits(v.w)));
+}
+// one bit per block -> the 4-bits-per-block (one per 4-float slot) layout of zmask that blocklog_fixup_kernel reads
+__device__ __forceinline__ uint32_t spread_nibbles(uint32_t b8) {
+  uint32_t v = b8 & 0xffu;
+  v = (v | (v << 12)) & 0x000f000fu;
+  v = (v | (v << 6)) & 0x03030303u;
+  v = (v | (v << 3)) & 0x11111111u;
+  return v * 0xfu;
+}
+
+template <int KIND, typename OutT>
+__global__ void __launch_bounds__(kStWarps * 32) quant_stream_kernel(const float* __restrict__ x, OutT* __restrict__ y,
+                                                                      uint64_t n_elems, FmtParams p,
+                                                                      uint32_t* __restrict__ gstate,
+                                                                      uint32_t* __restrict__ zmask) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  constexpr bool kBlocked = IsBlocked<KIND>::value;
+  constexpr bool kBf16 = sizeof(OutT) == 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(st_smem) + (uint32_t)warp * kStStages * kStTileBytes;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(st_smem) + (uint32_t)kStWarps * kStStages * kStTileBytes +
+                        (uint32_t)warp * kStStages * 8;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kStStages; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * k));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint64_t n_tiles = (n_elems + kStTileElems - 1) / kStTileElems;
+  const uint64_t n_words = (n_elems + 127) >> 7;                     // zmask words (32 slots of 4 floats each)
+  const uint64_t nw = (uint64_t)gridDim.x * kStWarps;
+  uint64_t tile = (uint64_t)blockIdx.x * kStWarps + warp;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kStStages - 1; ++k) {
+      const uint64_t t = tile + (uint64_t)k * nw;
+      if (t < n_tiles) {
+        const uint64_t left = n_elems - t * kStTileElems;
+        st_bulk_load(buf0 + k * kStTileBytes, x + t * kStTileElems, (uint32_t)(left < kStTileElems ? left : kStTileElems) * 4u,
+                     bar0 + 8 * k);
+      }
+    }
+  }
+  const uint32_t rot = (uint32_t)(lane >> 1) & 3u;
+  uint32_t run_min = 0xffffffffu;
+  bool saw_zero = false;
+  int s = 0;
+  uint32_t parity = 0;
+  for (; tile < n_tiles; tile += nw) {
+    const uint64_t left = n_elems - tile * kStTileElems;
+    const uint32_t n_here = (uint32_t)(left < kStTileElems ? left : kStTileElems);
+    const uint32_t buf = buf0 + s * kStTileBytes;
+    st_mbar_wait(bar0 + 8 * s, parity);
+    float4 v[kStNB][4];
+#pragma unroll
+    for (int j = 0; j < kStNB; ++j) {
+      const uint32_t base = buf + (uint32_t)(j * 32 + lane) * 64u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[j][c] = lds128(base + (((uint32_t)c + rot) & 3u) * 16u);
+    }
+    if (kBf16) __syncwarp();                        // every lane holds its inputs before the packed in-place writes below
+#pragma unroll
+    for (int j = 0; j < kStNB; ++j) {
+      const uint32_t blk = (uint32_t)(j * 32 + lane);
+      const bool act = blk * 16u < n_here;
+      uint32_t m = max(max(absmax4(v[j][0]), absmax4(v[j][1])), max(absmax4(v[j][2]), absmax4(v[j][3])));
+      bool zero_block = false;
+      bool ok = true;
+      if (kBlocked) {
+        zero_block = act && (m == 0);
+        if (KIND == kBlockLog) {
+          const uint32_t zb = __ballot_sync(0xffffffffu, zero_block);
+          const uint64_t word = tile * (kStTileElems / 128) + (uint64_t)(j * 4 + lane);
+          if (lane < 4 && word < n_words) zmask[word] = spread_nibbles(zb >> (8 * lane));
+          if (act) {
+            if (zero_block) saw_zero = true; else run_min = min(run_min, m);
+          }
+        }
+        if (m == 0) m = 0x3f800000u;
+      } else {
+        ok = m < 0x7f800000u;                        // element-wise kinds: all 16 finite
+        m = 0x3f800000u;
+      }
+      if (act) {
+        if (KIND == kInteger || KIND == kNone) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[j][c] = quant4<KIND>(v[j][c], m, p);
+        } else {
+          const FastState fs = fast_state<KIND>(m, p);
+          if (ok && fs.ok) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              v[j][c] = make_float4(quant_elem_fast<KIND>(v[j][c].x, fs, p), quant_elem_fast<KIND>(v[j][c].y, fs, p),
+                                    quant_elem_fast<KIND>(v[j][c].z, fs, p), quant_elem_fast<KIND>(v[j][c].w, fs, p));
+          } else {
+#pragma unroll                                       // (a rolled loop would index v dynamically and push it to local memory)
+            for (int c = 0; c < 4; ++c) v[j][c] = quant4_literal<KIND>(v[j][c], m, p);
+          }
+        }
+        if (!kBf16) {
+          const uint32_t base = buf + blk * 64u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sts128(base + (((uint32_t)c + rot) & 3u) * 16u, v[j][c]);
+        } else {
+          // chunk c of the lane's rotated order is logical chunk (c + rot) & 3: 8 bytes each, a packed block is 32 bytes
+          const uint32_t base = buf + blk * 32u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(base + (((uint32_t)c + rot) & 3u) * 8u),
+                         "r"(pack_bf16x2(v[j][c].x, v[j][c].y)), "r"(pack_bf16x2(v[j][c].z, v[j][c].w))
+                         : "memory");
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      st_bulk_store(y + tile * kStTileElems, buf, n_here * (uint32_t)sizeof(OutT));
+      // refill the stage whose store was committed one iteration ago (at most this iteration's store may still be reading)
+      const uint64_t nt = tile + (uint64_t)(kStStages - 1) * nw;
+      if (nt < n_tiles) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const int ns = (s == 0) ? kStStages - 1 : s - 1;
+        const uint64_t l2 = n_elems - nt * kStTileElems;
+        st_bulk_load(buf0 + ns * kStTileBytes, x + nt * kStTileElems, (uint32_t)(l2 < kStTileElems ? l2 : kStTileElems) * 4u,
+                     bar0 + 8 * ns);
+      }
+    }
+    if (++s == kStStages) { s = 0; parity ^= 1u; }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (KIND == kBlockLog) {
+    for (int o = 16; o > 0; o >>= 1) run_min = min(run_min, __shfl_xor_sync(0xffffffffu, run_min, o));
+    if (lane == 0 && run_min != 0xffffffffu) atomicMin(&gstate[0], run_min);
+    if (saw_zero) gstate[1] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic path
 // ------------------------------------------------------------------------------------------------
 struct GenGeom {
@@ -465,6 +655,8 @@ static int make_plan(const bq_format* f, const bq_tensor3* t, int transpose_out,
 }
 
 static int g_num_sms = 0;
+static int g_stream_enabled = 1;
+void set_stream_quantizer(int on) { g_stream_enabled = on ? 1 : 0; }
 int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0, n = 0;
@@ -497,7 +689,24 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
       occ = (e == cudaSuccess && o > 0) ? o : 4;
     }
     int grid = (int)std::min<uint64_t>(tiles, (uint64_t)sms * occ);
-    {
+    const bool stream = g_stream_enabled && pl.rg.flat && (!kBlocked || pl.rg.lpb == 4) && ((uintptr_t)x % 16 == 0) &&
+                        ((uintptr_t)y % 16 == 0);
+    if (stream) {
+      static bool attr_set = false;
+      static int occ_st = 0;
+      if (!attr_set) {
+        BQ_CUDA_CHECK(cudaFuncSetAttribute(quant_stream_kernel<KIND, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmem));
+        int o = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, quant_stream_kernel<KIND, OutT>, kStWarps * 32, kStSmem);
+        occ_st = (e == cudaSuccess && o > 0) ? o : 1;
+        attr_set = true;
+      }
+      const uint64_t n_elems = pl.rg.total_slots * 4;
+      const uint64_t wt = (n_elems + kStTileElems - 1) / kStTileElems;
+      const int g = (int)std::min<uint64_t>((wt + kStWarps - 1) / kStWarps, (uint64_t)sms * occ_st);
+      LaunchScope ls(kKernQuantStream, st);
+      quant_stream_kernel<KIND, OutT><<<g, kStWarps * 32, kStSmem, st>>>(x, y, n_elems, p, gstate, aux);
+    } else {
       LaunchScope ls(kKernQuantRows, st);
       if (pl.rg.flat) quant_rows_kernel<KIND, OutT, true><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux);
       else quant_rows_kernel<KIND, OutT, false><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux);
@@ -942,6 +1151,7 @@ int bq_split2_f16_rows(const float* x, int64_t rows, int64_t K, int64_t ldx, voi
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
 }
+void bq_set_stream_quantizer(int on) { bq::set_stream_quantizer(on); }
 int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream) {
   if (!mismatches_dev3) return BQ_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;

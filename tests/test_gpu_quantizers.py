@@ -196,3 +196,48 @@ def test_ste_backward():
     y = block_fp_quantizer(x, 6, 8, 127, [1, 16], True)
     y.sum().backward()
     assert torch.equal(x.grad, torch.ones_like(x))
+
+
+def test_stream_kernel_matches_rows_kernel_and_oracle():
+    """The bulk-copy streaming kernel (dense, block 16 / element-wise) against the per-slot rows kernel and the oracle:
+    ragged tile tails (a tile is 1024 elements), single blocks, zero blocks, fp32 and bf16 outputs, launch counters."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.quantize.quantizers import minifloat_denorm_quantizer
+    from llm_mixed_q_b200.models.quantize.quantizers.utils import canonicalise, launch_quantize, make_format
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(99)
+    names = [lib.bq_kernel_name(i).decode() for i in range(lib.bq_kernel_count())]
+    sid, rid = names.index("quant_stream_kernel"), names.index("quant_rows_kernel")
+    try:
+        for n_blocks in (1, 2, 63, 64, 65, 127, 1000, 8 * 148 * 64 * 3 + 17):
+            x = torch.randn(n_blocks, 16, device="cuda", generator=g) * 4
+            x.view(-1)[::11] = 0
+            x[::5] = 0                                   # all-zero blocks (block_log: tensor-global min)
+            for name, kw in FORMATS:
+                lib.bq_set_stream_quantizer(1)
+                s0 = lib.bq_launch_count(sid)
+                y, yo = both(name, kw, x, [1, 16], True)
+                assert lib.bq_launch_count(sid) == s0 + 1, "dense block-16 input must take the streaming kernel"
+                lib.bq_set_stream_quantizer(0)
+                r0 = lib.bq_launch_count(rid)
+                y2 = product(name)(x, block_size=[1, 16], skip_first_dim=True, **kw)
+                assert lib.bq_launch_count(rid) == r0 + 1
+                assert n_bits_diff(y, yo) == 0 and n_bits_diff(y2, yo) == 0, (n_blocks, name)
+                # bf16 output of the same call (exact for <= 8 significant bits; block_log values are powers of two)
+                lib.bq_set_stream_quantizer(1)
+                canon = canonicalise(x, [1, 16], True, blocked=True)
+                fkw = dict(kw)
+                if "exponent_bias" in fkw and fkw["exponent_bias"] is None:
+                    fkw["exponent_bias"] = 2 ** (fkw["exponent_width"] - 1) - 1
+                fmt = make_format(name, b0=canon.b0, b1=canon.b1, fold=canon.fold, **fkw)
+                yb = launch_quantize(x, fmt, canon, out_dtype=torch.bfloat16)
+                assert torch.equal(yb.float(), yo.to(torch.bfloat16).float()), (n_blocks, name, "bf16")
+        # element-wise kind: sizes that are multiples of 4 but not of 16
+        for n in (4, 20, 1028, 4096 + 12, 3 * 1024 * 1184 + 4):
+            x = torch.randn(n, device="cuda", generator=g)
+            lib.bq_set_stream_quantizer(1)
+            y = minifloat_denorm_quantizer(x, 8, 4, 7)
+            assert n_bits_diff(y, O.minifloat_denorm_quantize(x, 8, 4, 7)) == 0, n
+    finally:
+        lib.bq_set_stream_quantizer(1)
