@@ -160,7 +160,7 @@ __device__ __forceinline__ float quant_elem(float x, const BlockState& s, const 
 //     bool*float blends collapse to selects.  All of this is valid only while every intermediate is a
 //     finite normal number — FastState::ok says so per block, otherwise the literal path above runs.
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kZone = 0x1000u;          // +-2^12 ulps around a cliff
+constexpr uint32_t kZone = 0x200u;           // 2^9 ulps around a cliff (needed: ~0.7 |k| + a few ulps of log2f error, |k| <= 128)
 constexpr uint32_t kSqrt2Mant = 0x3504f3u;   // mantissa field of sqrt(2)
 
 // cold fall-backs (inputs within 2^-11 of a rounding cliff, denormals): kept out of line — every inlined copy of the
@@ -182,21 +182,34 @@ __device__ __forceinline__ int floor_log2_i(float x) {       // == (int)floorf(l
   if (ex - 1u >= 254u || (b | 0xff800000u) >= 0u - kZone) return floor_log2_slow(x);
   return (int)ex - 127;
 }
-// normal finite x only (callers guarantee it): no exponent-range test.  Returns the BIASED value (+127).
-__device__ __forceinline__ int floor_log2_biased_nf(float x) {
-  const uint32_t b = __float_as_uint(x);
-  if ((b | 0xff800000u) >= 0u - kZone) return floor_log2_slow(x) + 127;
-  return (int)(b >> 23);
-}
 __device__ __forceinline__ int rint_log2_i(float x) {        // == (int)rintf(log2f(x))
   const uint32_t b = __float_as_uint(x), ex = b >> 23, f = b & 0x7fffffu;
   if (ex - 1u >= 254u || (f - kSqrt2Mant + kZone) < 2 * kZone) return rint_log2_slow(x);
   return (int)ex - 127 + (f > kSqrt2Mant ? 1 : 0);
 }
-// finite x > 0; denormal x returns <= 1 (callers clamp from below).  Biased (+127): a mantissa above sqrt(2)'s carries into the exponent.
-__device__ __forceinline__ int rint_log2_biased_f(float x) {
-  const uint32_t b = __float_as_uint(x);
-  if (((b & 0x7fffffu) - kSqrt2Mant + kZone) < 2 * kZone) return (b >> 23) ? rint_log2_slow(x) + 127 : 0;
+// ---- per-element variants for the fast paths.  NC = false: checked (cliff zone -> libdevice, out of line).  NC = true ("no check"):
+// always the shortcut, and the element's distance from the cliff is min-accumulated into `zacc`; the caller tests
+// zone_hit(zacc) ONCE per block and redoes the block through the checked path if any element was close (rare: 16 * 2^-14).
+// All return the BIASED value (+127) and require a finite argument.
+template <int KIND> __device__ __forceinline__ constexpr uint32_t zone_thr() { return KIND == kBlockLog ? 2 * kZone : kZone; }
+template <int KIND> __device__ __forceinline__ bool zone_hit(uint32_t zacc) { return zacc < zone_thr<KIND>(); }
+template <bool NC> __device__ __forceinline__ int floor_log2_biased_nf(float x, uint32_t& zacc) {   // normal x
+  const uint32_t b = __float_as_uint(x), key = ~b & 0x7fffffu;       // ulps below the next power of two, minus one
+  if (NC) { zacc = min(zacc, key); return (int)(b >> 23); }
+  if (key < kZone) return floor_log2_slow(x) + 127;
+  return (int)(b >> 23);
+}
+template <bool NC> __device__ __forceinline__ int ceil_log2_biased_nf(float x, uint32_t& zacc) {    // normal x
+  const uint32_t b = __float_as_uint(x), key = b & 0x7fffffu;        // ulps above the power of two
+  if (NC) { zacc = min(zacc, key); return (int)(b >> 23) + 1; }
+  if (key < kZone) return ceil_log2_slow(x) + 127;
+  return (int)(b >> 23) + 1;
+}
+// denormal x returns <= 1 (callers clamp from below).  A mantissa above sqrt(2)'s carries into the exponent.
+template <bool NC> __device__ __forceinline__ int rint_log2_biased_f(float x, uint32_t& zacc) {
+  const uint32_t b = __float_as_uint(x), key = (b & 0x7fffffu) - kSqrt2Mant + kZone;
+  if (NC) zacc = min(zacc, key);
+  else if (key < 2 * kZone) return (b >> 23) ? rint_log2_slow(x) + 127 : 0;
   return (int)((b + (0x7fffffu - kSqrt2Mant)) >> 23);
 }
 __device__ __forceinline__ float pow2_i(int e) { return __int_as_float((e + 127) << 23); }   // e in [-126, 127]
@@ -259,14 +272,19 @@ __device__ __forceinline__ FastState fast_state(uint32_t mbits, const FmtParams&
     s.ok = (s.i0 >= -126 && s.i1 <= 127 && s.i1 >= s.i0);
     s.f1 = pow2_i(s.i0 < -126 ? -126 : s.i0);
     s.f0 = __fmul_rn(s.f1, 0.1f);
+  } else if (KIND == kMinifloatDenorm) {
+    s.i0 = (int)p.emin + 127;                                    // format-level range check: FmtParams::fast_fmt
+    s.i1 = (int)p.emax + 127;
+    s.hi = __fadd_rn(kRintMagic, p.qmax);
+    s.ok = true;
   } else {
-    s.ok = true;                                                 // element-wise kinds: format-level check only
+    s.ok = true;
   }
   return s;
 }
 
-template <int KIND>
-__device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, const FmtParams& p) {
+template <int KIND, bool NC>
+__device__ __forceinline__ float quant_elem_fast_impl(float x, const FastState& s, const FmtParams& p, uint32_t& zacc) {
   const float ax = fabsf(x);
   float out;
   if (KIND == kBlockFP) {
@@ -283,7 +301,7 @@ __device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, co
     //                                                                                 subtraction is exact wherever the clamp does not decide]
     //   subnormal (e == emin): y = 2^(emin+1-M) * clamp(rint(|x| * 2^(M-emin-1)), 0,   2^M-1)
     // i.e. one step exponent es = max(e, emin+1), rounded and clamped in the magic-shifted domain; every scaling is by a power of two.
-    const int eb = floor_log2_biased_nf(__fadd_rn(ax, 1e-9f));
+    const int eb = floor_log2_biased_nf<NC>(__fadd_rn(ax, 1e-9f), zacc);
     const bool normal = eb > s.i2;
     const int es = max(min(eb, s.i1), s.i0);
     const float inv_step = __int_as_float((254 + p.mbits - es) << 23), step = __int_as_float((es - p.mbits) << 23);
@@ -295,19 +313,26 @@ __device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, co
     const float v = __fadd_rn(ax, s.f0);
     // v is finite (block max is) and every v below 2^emin — zeros (v = delta), denormals — clamps to emin whatever the shortcut
     // returns for it (its biased result is <= 1 there), so neither an exponent-range test nor a v < 2^emin select is needed.
-    const int eb = min(max(rint_log2_biased_f(v), s.i0 + 127), s.i1 + 127);
+    const int eb = min(max(rint_log2_biased_f<NC>(v, zacc), s.i0 + 127), s.i1 + 127);
     out = (w == 0.f) ? 0.f : copysignf(__int_as_float(eb << 23), w);
   } else if (KIND == kMinifloatDenorm) {
-    int e = ceil_log2_i(__fadd_rn(ax, 1e-9f));
-    e = min(max(e, (int)p.emin), (int)p.emax);
-    const float q = fminf(rint_small(__fmul_rn(__fmul_rn(ax, pow2_i(-e)), p.shift)), p.qmax);
-    const float y = copysignf(__fmul_rn(pow2_i(e), __fmul_rn(q, p.inv_shift)), x);
+    // minifloat.py:60-80 with e = clamp(ceil(log2(|x|+1e-9)), emin, emax):  y = 2^(e-M) * min(rint(|x| * 2^(M-e)), 2^M - 1)
+    const int eb = min(max(ceil_log2_biased_nf<NC>(__fadd_rn(ax, 1e-9f), zacc), s.i0), s.i1);
+    const float inv_step = __int_as_float((254 + p.mbits - eb) << 23), step = __int_as_float((eb - p.mbits) << 23);
+    const float tm = fminf(__fadd_rn(__fmul_rn(ax, inv_step), kRintMagic), s.hi);
+    const float y = copysignf(__fmul_rn(__fsub_rn(tm, kRintMagic), step), x);
     out = (ax <= 1e-8f) ? __fadd_rn(x, 0.f) : y;
   } else {
     out = x;
   }
   if (p.fold_zero) out = __fadd_rn(out, 0.f);
   return out;
+}
+
+template <int KIND>
+__device__ __forceinline__ float quant_elem_fast(float x, const FastState& s, const FmtParams& p) {
+  uint32_t unused = 0xffffffffu;
+  return quant_elem_fast_impl<KIND, false>(x, s, p, unused);
 }
 
 template <int KIND> struct IsBlocked { static constexpr bool value = (KIND == kBlockFP || KIND == kBlockMinifloat || KIND == kBlockLog); };

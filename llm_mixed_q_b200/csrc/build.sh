@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fa
 mkdir -p "${HERE}/build"
 pids=()
 for f in common quantize gemm_sm100 ops attention_sm100; do
-  "${NVCC}" "${FLAGS[@]}" ${BQ_PTXAS_V:+-Xptxas -v} -c "${HERE}/${f}.cu" -o "${HERE}/build/${f}.o" &
+  "${NVCC}" "${FLAGS[@]}" ${BQ_EXTRA_FLAGS:-} ${BQ_PTXAS_V:+-Xptxas -v} -c "${HERE}/${f}.cu" -o "${HERE}/build/${f}.o" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done

@@ -99,6 +99,13 @@ __device__ __noinline__ float4 quant4_literal(float4 v, uint32_t mbits, const Fm
   return make_float4(quant_elem<KIND>(v.x, st, p), quant_elem<KIND>(v.y, st, p), quant_elem<KIND>(v.z, st, p),
                      quant_elem<KIND>(v.w, st, p));
 }
+// fast arithmetic with per-element cliff checks, out of line (redo path of the streaming kernel; the block's state is valid)
+template <int KIND>
+__device__ __noinline__ float4 quant4_checked(float4 v, uint32_t mbits, const FmtParams& p) {
+  const FastState fs = fast_state<KIND>(mbits, p);
+  return make_float4(quant_elem_fast<KIND>(v.x, fs, p), quant_elem_fast<KIND>(v.y, fs, p), quant_elem_fast<KIND>(v.z, fs, p),
+                     quant_elem_fast<KIND>(v.w, fs, p));
+}
 template <int KIND>
 __device__ __forceinline__ float4 quant4(float4 v, uint32_t mbits, const FmtParams& p) {
   if (KIND == kInteger || KIND == kNone) {
@@ -209,10 +216,16 @@ __global__ void __launch_bounds__(kThreads) blocklog_fixup_kernel(OutT* __restri
 //     the lane index (the element math is order-agnostic).
 // ------------------------------------------------------------------------------------------------
 constexpr int kStWarps = 8;
-constexpr int kStNB = 2;                               // blocks per lane per tile
+#ifndef BQ_ST_NB
+#define BQ_ST_NB 2
+#endif
+#ifndef BQ_ST_STAGES
+#define BQ_ST_STAGES 3
+#endif
+constexpr int kStNB = BQ_ST_NB;                        // blocks per lane per tile
 constexpr int kStTileElems = 32 * kStNB * 16;          // 1024 floats
 constexpr int kStTileBytes = kStTileElems * 4;
-constexpr int kStStages = 3;
+constexpr int kStStages = BQ_ST_STAGES;
 constexpr size_t kStSmem = (size_t)kStWarps * kStStages * kStTileBytes + (size_t)kStWarps * kStStages * 8;
 
 __device__ __forceinline__ void st_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -337,10 +350,20 @@ __global__ void __launch_bounds__(kStWarps * 32) quant_stream_kernel(const float
         } else {
           const FastState fs = fast_state<KIND>(m, p);
           if (ok && fs.ok) {
+            // straight-line shortcut arithmetic for all 16 elements; one test per block for "some element sat within kZone ulps
+            // of a log2 rounding cliff", in which case the block is redone through the per-element checked path (out of line)
+            uint32_t zacc = 0xffffffffu;
+            float4 q[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              v[j][c] = make_float4(quant_elem_fast<KIND>(v[j][c].x, fs, p), quant_elem_fast<KIND>(v[j][c].y, fs, p),
-                                    quant_elem_fast<KIND>(v[j][c].z, fs, p), quant_elem_fast<KIND>(v[j][c].w, fs, p));
+              q[c] = make_float4(quant_elem_fast_impl<KIND, true>(v[j][c].x, fs, p, zacc), quant_elem_fast_impl<KIND, true>(v[j][c].y, fs, p, zacc),
+                                 quant_elem_fast_impl<KIND, true>(v[j][c].z, fs, p, zacc), quant_elem_fast_impl<KIND, true>(v[j][c].w, fs, p, zacc));
+            if (zone_hit<KIND>(zacc)) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) q[c] = quant4_checked<KIND>(v[j][c], m, p);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[j][c] = q[c];
           } else {
 #pragma unroll                                       // (a rolled loop would index v dynamically and push it to local memory)
             for (int c = 0; c < 4; ++c) v[j][c] = quant4_literal<KIND>(v[j][c], m, p);
@@ -1110,9 +1133,23 @@ __global__ void selftest_log2_kernel(unsigned long long* mism) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const float x = __uint_as_float((uint32_t)i);
     const float l = log2f(x);
-    bad0 += (ceil_log2_i(x) != (int)ceilf(l));
-    bad1 += (floor_log2_i(x) != (int)floorf(l));
-    bad2 += (rint_log2_i(x) != (int)rintf(l));
+    const int c = (int)ceilf(l), f = (int)floorf(l), r = (int)rintf(l);
+    bad0 += (ceil_log2_i(x) != c);
+    bad1 += (floor_log2_i(x) != f);
+    bad2 += (rint_log2_i(x) != r);
+    // biased per-element variants: checked == exact; unchecked == exact whenever the zone key says "not near a cliff"
+    uint32_t z0 = 0xffffffffu, z1 = 0xffffffffu, z2 = 0xffffffffu, zu = 0xffffffffu;
+    if (i >= 0x00800000ull) {
+      bad0 += (ceil_log2_biased_nf<false>(x, zu) != c + 127);
+      bad1 += (floor_log2_biased_nf<false>(x, zu) != f + 127);
+      bad2 += (rint_log2_biased_f<false>(x, zu) != r + 127);
+      const int cn = ceil_log2_biased_nf<true>(x, z0), fn = floor_log2_biased_nf<true>(x, z1), rn = rint_log2_biased_f<true>(x, z2);
+      bad0 += (!zone_hit<kMinifloatDenorm>(z0) && cn != c + 127);
+      bad1 += (!zone_hit<kBlockMinifloat>(z1) && fn != f + 127);
+      bad2 += (!zone_hit<kBlockLog>(z2) && rn != r + 127);
+    } else {
+      bad2 += (rint_log2_biased_f<false>(x, zu) > 1) + (rint_log2_biased_f<true>(x, z2) > 1);   // denormals: anything <= 1
+    }
   }
   if (bad0) atomicAdd(&mism[0], bad0);
   if (bad1) atomicAdd(&mism[1], bad1);
