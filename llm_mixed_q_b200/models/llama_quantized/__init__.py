@@ -1,4 +1,4 @@
 from .configuration_llama import LlamaQuantizedConfig
 from .modeling_llama import (LlamaQuantizedAttention, LlamaQuantizedDecoderLayer, LlamaQuantizedForCausalLM,
-                             LlamaQuantizedMLP, LlamaQuantizedModel)
+                             LlamaQuantizedForSequenceClassification, LlamaQuantizedMLP, LlamaQuantizedModel)
 from .quant_config_llama import parse_llama_quantized_config

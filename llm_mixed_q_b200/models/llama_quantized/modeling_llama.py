@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 from torch.nn import CrossEntropyLoss
 from transformers.activations import ACT2FN
-from transformers.modeling_outputs import CausalLMOutputWithPast
+from transformers.modeling_outputs import CausalLMOutputWithPast, SequenceClassifierOutputWithPast
 from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
@@ -248,3 +248,33 @@ class LlamaQuantizedForCausalLM(LlamaQuantizedPreTrainedModel):
             out = (logits, None, all_h, all_a)
             return ((loss,) + out) if loss is not None else out
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=all_h, attentions=all_a)
+
+
+class LlamaQuantizedForSequenceClassification(LlamaQuantizedPreTrainedModel):
+    """reference modeling_llama.py:955-1080 — MODEL_MAP["llama"]["cls"]; `score` is an unquantised bias-free nn.Linear."""
+
+    def __init__(self, config: LlamaQuantizedConfig):
+        super().__init__(config)
+        self.num_labels = config.num_labels
+        self.model = LlamaQuantizedModel(config)
+        self.score = nn.Linear(config.hidden_size, self.num_labels, bias=False)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.model.embed_tokens = value
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, inputs_embeds=None, labels=None,
+                output_attentions=False, output_hidden_states=False, return_dict=True, **unused):
+        from ..opt_quantized.modeling_opt import sequence_classification_head
+
+        hidden, all_h, all_a = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                                          inputs_embeds=inputs_embeds, output_attentions=output_attentions,
+                                          output_hidden_states=output_hidden_states)
+        pooled, loss = sequence_classification_head(self.config, self.score(hidden), input_ids, inputs_embeds, labels, self.num_labels)
+        if not return_dict:
+            out = (pooled, None, all_h, all_a)
+            return ((loss,) + out) if loss is not None else out
+        return SequenceClassifierOutputWithPast(loss=loss, logits=pooled, past_key_values=None, hidden_states=all_h, attentions=all_a)

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 from torch.nn import CrossEntropyLoss
 from transformers.activations import ACT2FN
-from transformers.modeling_outputs import CausalLMOutputWithPast
+from transformers.modeling_outputs import CausalLMOutputWithPast, SequenceClassifierOutputWithPast
 from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
@@ -355,3 +355,60 @@ class OPTQuantizedForCausalLM(OPTQuantizedPreTrainedModel):
             out = (logits, None, all_h, all_a)
             return ((loss,) + out) if loss is not None else out
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=all_h, attentions=all_a)
+
+
+def sequence_classification_head(config, logits, input_ids, inputs_embeds, labels, num_labels):
+    """Shared by OPT / Llama ForSequenceClassification (reference modeling_opt.py:1221-1273, modeling_llama.py:1010-1063):
+    pool the logits of the last non-pad token of every sequence, then HF problem-type dispatch for the loss."""
+    from torch.nn import BCEWithLogitsLoss, MSELoss
+
+    batch_size = input_ids.shape[0] if input_ids is not None else inputs_embeds.shape[0]
+    if config.pad_token_id is None or input_ids is None:
+        sequence_lengths = -1
+    else:
+        sequence_lengths = (torch.ne(input_ids, config.pad_token_id).sum(-1) - 1).to(logits.device)
+    pooled = logits[torch.arange(batch_size, device=logits.device), sequence_lengths]
+    loss = None
+    if labels is not None:
+        if config.problem_type is None:
+            if num_labels == 1:
+                config.problem_type = "regression"
+            elif num_labels > 1 and labels.dtype in (torch.long, torch.int):
+                config.problem_type = "single_label_classification"
+            else:
+                config.problem_type = "multi_label_classification"
+        if config.problem_type == "regression":
+            loss = MSELoss()(pooled.squeeze(), labels.squeeze()) if num_labels == 1 else MSELoss()(pooled, labels)
+        elif config.problem_type == "single_label_classification":
+            loss = CrossEntropyLoss()(pooled.view(-1, num_labels), labels.view(-1))
+        else:
+            loss = BCEWithLogitsLoss()(pooled, labels)
+    return pooled, loss
+
+
+class OPTQuantizedForSequenceClassification(OPTQuantizedPreTrainedModel):
+    """reference modeling_opt.py:1163-1290 — MODEL_MAP["opt"]["cls"]; `score` is an unquantised bias-free nn.Linear."""
+
+    def __init__(self, config: OPTQuantizedConfig):
+        super().__init__(config)
+        self.num_labels = config.num_labels
+        self.model = OPTQuantizedModel(config)
+        self.score = nn.Linear(config.word_embed_proj_dim, self.num_labels, bias=False)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.model.decoder.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.model.decoder.embed_tokens = value
+
+    def forward(self, input_ids=None, attention_mask=None, inputs_embeds=None, labels=None, output_attentions=False,
+                output_hidden_states=False, return_dict=True, **unused):
+        hidden, all_h, all_a = self.model.decoder(input_ids=input_ids, attention_mask=attention_mask,
+                                                  inputs_embeds=inputs_embeds, output_attentions=output_attentions,
+                                                  output_hidden_states=output_hidden_states)
+        pooled, loss = sequence_classification_head(self.config, self.score(hidden), input_ids, inputs_embeds, labels, self.num_labels)
+        if not return_dict:
+            out = (pooled, None, all_h, all_a)
+            return ((loss,) + out) if loss is not None else out
+        return SequenceClassifierOutputWithPast(loss=loss, logits=pooled, past_key_values=None, hidden_states=all_h, attentions=all_a)

@@ -79,3 +79,23 @@ def load_models():
     ns.llama = importlib.import_module("llm_mixed_q.models.llama_quantized.modeling_llama")
     ns.llama_qc = importlib.import_module("llm_mixed_q.models.llama_quantized.quant_config_llama")
     return ns
+
+
+def load_bert():
+    """Reference BERT quantized model + config (after load_models()).  transformers 5.5 removed two helpers the
+    reference's 4.31-era file expects; both are shimmed WITHOUT touching the reference: `find_pruneable_heads_and_indices`
+    (import-time only, head pruning is never called) and `get_head_mask` (returns [None]*L when no head mask is given)."""
+    ns = load_models()
+    import transformers.pytorch_utils as pu
+
+    if not hasattr(pu, "find_pruneable_heads_and_indices"):
+        def _unsupported(*a, **k):
+            raise NotImplementedError("head pruning is not part of the golden run")
+        pu.find_pruneable_heads_and_indices = _unsupported
+    _stub("llm_mixed_q.models.bert_quantized", f"{SRC}/llm_mixed_q/models/bert_quantized")
+    ns.bert_cfg = importlib.import_module("llm_mixed_q.models.bert_quantized.configuration_bert")
+    ns.bert = importlib.import_module("llm_mixed_q.models.bert_quantized.modeling_bert")
+    ns.bert_qc = importlib.import_module("llm_mixed_q.models.bert_quantized.quant_config_bert")
+    if not hasattr(ns.bert.BertQuantizedModel, "get_head_mask"):
+        ns.bert.BertQuantizedModel.get_head_mask = lambda self, head_mask, n, *a, **k: [None] * n
+    return ns
