@@ -112,6 +112,17 @@ BQ_API int bq_quantize(const bq_format* fmt, const bq_tensor3* x_desc, const flo
                 int32_t transpose_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SiLU(gate) * up + quantize.  y = Q_fmt( silu(gate) * up ), the input of Llama's down_proj:
+ * `self.down_proj(self.act_fn(self.gate_proj(x)) * self.up_proj(x))` (models/llama_quantized/modeling_llama.py:246) followed by
+ * down_proj's x-quantizer (quantized_modules/linear.py:63-71).  gate and up share the layout `desc`; blocks [1, b] along
+ * the last dim, block_fp / block_minifloat / block_log; other layouts return BQ_ERR_UNSUPPORTED (the caller then composes
+ * torch silu/mul with bq_quantize).  silu(g) = g / (1 + expf(-g)) as torch-CUDA evaluates it, so fp32 results are
+ * bit-identical to F.silu(gate) * up followed by the quantizer.  Workspace as for bq_quantize.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API int bq_silu_mul_quantize(const bq_format* fmt, const bq_tensor3* desc, const float* gate, const float* up, void* y,
+                                int32_t y_dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * LayerNorm / RMSNorm + quantize.  y_k = Q_fmts[k]( norm(x) ), k < n_out <= 3, each written as bf16 [rows][H].
  * Replaces nn.LayerNorm (models/opt_quantized/modeling_opt.py:386,:414) / LlamaRMSNorm
  * (models/llama_quantized/modeling_llama.py:79-92) followed by the x-quantizers (quantized_modules/linear.py:63-71) of

@@ -85,6 +85,9 @@ def load():
     lib.bq_quantize.restype = ctypes.c_int
     lib.bq_quantize.argtypes = [POINTER(BqFormat), POINTER(BqTensor3), c_void_p, c_void_p, c_int32, c_int32, c_void_p,
                                 c_size_t, c_void_p]
+    lib.bq_silu_mul_quantize.restype = ctypes.c_int
+    lib.bq_silu_mul_quantize.argtypes = [POINTER(BqFormat), POINTER(BqTensor3), c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                         c_size_t, c_void_p]
     lib.bq_gemm_bf16_tn.restype = ctypes.c_int
     lib.bq_gemm_bf16_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 10 + [c_void_p]
     lib.bq_gemm_bf16_tn_ex.restype = ctypes.c_int

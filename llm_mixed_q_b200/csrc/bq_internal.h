@@ -13,13 +13,13 @@ namespace bq {
 void set_last_cuda_error(const char* what, const char* file, int line);
 int num_sms();
 int quantize_impl(const bq_format* fmt, const bq_tensor3* t, const float* x, void* y, int y_dtype, int transpose_out,
-                  void* ws, size_t ws_bytes, cudaStream_t st);
+                  void* ws, size_t ws_bytes, cudaStream_t st, const float* x2 = nullptr);
 size_t quantize_ws_bytes(const bq_format* fmt, const bq_tensor3* t);
 int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M, int64_t N,
                       int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc,
                       cudaStream_t st);
 enum KernelId { kKernQuantRows = 0, kKernBlockLogFixup, kKernQuantTile, kKernGenericMax, kKernGenericMin, kKernGenericQuant,
-                kKernGemm, kKernAttention, kKernSplit3, kKernGemmEpi, kKernGemmSplit, kKernLnQuant, kKernQuantStream, kKernCount };
+                kKernGemm, kKernAttention, kKernSplit3, kKernGemmEpi, kKernGemmSplit, kKernLnQuant, kKernQuantStream, kKernSiluMulQuant, kKernCount };
 // RAII launch bracket: counts the launch; records start/stop events on `st` when profiling is enabled.
 struct LaunchScope {
   LaunchScope(int id, cudaStream_t st);

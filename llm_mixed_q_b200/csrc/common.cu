@@ -17,7 +17,8 @@ void set_last_cuda_error(const char* what, const char* file, int line) {
 static const char* kKernelNames[kKernCount] = {"quant_rows_kernel", "blocklog_fixup_kernel", "quant_tile_kernel",
                                                "generic_blockmax_kernel", "generic_gmin_kernel", "generic_quant_kernel",
                                                "gemm_bf16_tn_kernel", "attention_causal_kernel", "split3_kernel",
-                                               "gemm_bf16_tn_kernel<epilogue>", "gemm_bf16_tn_kernel<split>", "layernorm_quant_kernel", "quant_stream_kernel"};
+                                               "gemm_bf16_tn_kernel<epilogue>", "gemm_bf16_tn_kernel<split>", "layernorm_quant_kernel", "quant_stream_kernel",
+                                               "silu_mul_quant_kernel"};
 static std::atomic<int64_t> g_launches[kKernCount];
 static std::atomic<int> g_profiling{0};
 struct EventPair { int id; cudaEvent_t a, b; };

@@ -127,10 +127,16 @@ __device__ __forceinline__ float4 quant4(float4 v, uint32_t mbits, const FmtPara
 }
 
 // gstate[0]: min over non-zero block maxima (uint bits, init 0xffffffff); gstate[1]: 0xffffffff until a zero block is seen
-template <int KIND, typename OutT, bool FLAT>
+// PRE: the element fed to the quantizer is silu(x) * x2 (Llama MLP: act_fn(gate_proj(h)) * up_proj(h), reference
+// modeling_llama.py:246) in torch-CUDA's op order: silu(g) = g / (1 + expf(-g)) (ActivationSiluKernel.cu), then one multiply.
+__device__ __forceinline__ float silu_mul1(float g, float u) {
+  return __fmul_rn(__fdiv_rn(g, __fadd_rn(1.0f, expf(-g))), u);
+}
+template <int KIND, typename OutT, bool FLAT, bool PRE = false>
 __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const float* __restrict__ x, OutT* __restrict__ y, RowsGeom g,
                                                                FmtParams p, uint32_t* __restrict__ gstate,
-                                                               uint32_t* __restrict__ zmask) {
+                                                               uint32_t* __restrict__ zmask,
+                                                               const float* __restrict__ x2 = nullptr) {
   constexpr bool kBlocked = IsBlocked<KIND>::value;
   constexpr uint32_t tile = kThreads * kUnroll;
   const uint32_t total = (uint32_t)g.total_slots;
@@ -148,6 +154,10 @@ __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const float* __res
       yoff[u] = 0;
       act[u] = (base64 + u * kThreads + threadIdx.x < g.total_slots) && slot_addr<FLAT>(g, slot, total, xo, yoff[u]);
       v[u] = act[u] ? ldg_stream4(x + xo) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (PRE) {
+        const float4 w = act[u] ? ldg_stream4(x2 + xo) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u] = make_float4(silu_mul1(v[u].x, w.x), silu_mul1(v[u].y, w.y), silu_mul1(v[u].z, w.z), silu_mul1(v[u].w, w.w));
+      }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -691,11 +701,13 @@ int num_sms() {
 }
 
 template <int KIND, typename OutT>
-static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT* y, uint32_t* ws, cudaStream_t st) {
+static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT* y, uint32_t* ws, cudaStream_t st,
+                       const float* x2 = nullptr) {
   constexpr bool kBlocked = IsBlocked<KIND>::value;
   uint32_t* gstate = ws;
   uint32_t* aux = ws + 4;
   const int sms = num_sms();
+  if (x2 && !(pl.fast && kBlocked)) return BQ_ERR_UNSUPPORTED;      // silu*mul prologue: streaming rows layout, block formats
   if (pl.fast) {
     if (pl.rg.total_slots == 0) return BQ_OK;
     if (KIND == kBlockLog) BQ_CUDA_CHECK(cudaMemsetAsync(gstate, 0xff, 8, st));
@@ -712,9 +724,15 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
       occ = (e == cudaSuccess && o > 0) ? o : 4;
     }
     int grid = (int)std::min<uint64_t>(tiles, (uint64_t)sms * occ);
-    const bool stream = g_stream_enabled && pl.rg.flat && (!kBlocked || pl.rg.lpb == 4) && ((uintptr_t)x % 16 == 0) &&
+    const bool stream = g_stream_enabled && !x2 && pl.rg.flat && (!kBlocked || pl.rg.lpb == 4) && ((uintptr_t)x % 16 == 0) &&
                         ((uintptr_t)y % 16 == 0);
-    if (stream) {
+    if (x2) {
+      if constexpr (kBlocked) {
+        LaunchScope ls(kKernSiluMulQuant, st);
+        if (pl.rg.flat) quant_rows_kernel<KIND, OutT, true, true><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux, x2);
+        else quant_rows_kernel<KIND, OutT, false, true><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux, x2);
+      }
+    } else if (stream) {
       static bool attr_set = false;
       static int occ_st = 0;
       if (!attr_set) {
@@ -765,11 +783,12 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
 }
 
 template <typename OutT>
-static int launch_dtype(const Plan& pl, const FmtParams& p, const float* x, OutT* y, uint32_t* ws, cudaStream_t st) {
+static int launch_dtype(const Plan& pl, const FmtParams& p, const float* x, OutT* y, uint32_t* ws, cudaStream_t st,
+                        const float* x2 = nullptr) {
   switch (p.kind) {
-    case kBlockFP: return launch_kind<kBlockFP, OutT>(pl, p, x, y, ws, st);
-    case kBlockMinifloat: return launch_kind<kBlockMinifloat, OutT>(pl, p, x, y, ws, st);
-    case kBlockLog: return launch_kind<kBlockLog, OutT>(pl, p, x, y, ws, st);
+    case kBlockFP: return launch_kind<kBlockFP, OutT>(pl, p, x, y, ws, st, x2);
+    case kBlockMinifloat: return launch_kind<kBlockMinifloat, OutT>(pl, p, x, y, ws, st, x2);
+    case kBlockLog: return launch_kind<kBlockLog, OutT>(pl, p, x, y, ws, st, x2);
     case kMinifloatDenorm: return launch_kind<kMinifloatDenorm, OutT>(pl, p, x, y, ws, st);
     case kMinifloatIEEE: return launch_kind<kMinifloatIEEE, OutT>(pl, p, x, y, ws, st);
     case kInteger: return launch_kind<kInteger, OutT>(pl, p, x, y, ws, st);
@@ -779,7 +798,7 @@ static int launch_dtype(const Plan& pl, const FmtParams& p, const float* x, OutT
 }
 
 int quantize_impl(const bq_format* fmt, const bq_tensor3* t, const float* x, void* y, int y_dtype, int transpose_out,
-                  void* ws, size_t ws_bytes, cudaStream_t st) {
+                  void* ws, size_t ws_bytes, cudaStream_t st, const float* x2) {
   if (!fmt || !t) return BQ_ERR_BAD_ARG;
   FmtParams p;
   int rc = make_params(fmt, &p);
@@ -796,8 +815,9 @@ int quantize_impl(const bq_format* fmt, const bq_tensor3* t, const float* x, voi
     if (!ws || ws_bytes < pl.ws_bytes) return BQ_ERR_WORKSPACE;
     if ((uintptr_t)ws % 16) return BQ_ERR_BAD_ARG;
   }
-  if (y_dtype == BQ_F32) return launch_dtype<float>(pl, p, x, (float*)y, (uint32_t*)ws, st);
-  return launch_dtype<__nv_bfloat16>(pl, p, x, (__nv_bfloat16*)y, (uint32_t*)ws, st);
+  if (x2 && (((uintptr_t)x2 % 16) || !is_blocked(fmt->kind))) return BQ_ERR_UNSUPPORTED;
+  if (y_dtype == BQ_F32) return launch_dtype<float>(pl, p, x, (float*)y, (uint32_t*)ws, st, x2);
+  return launch_dtype<__nv_bfloat16>(pl, p, x, (__nv_bfloat16*)y, (uint32_t*)ws, st, x2);
 }
 
 size_t quantize_ws_bytes(const bq_format* fmt, const bq_tensor3* t) {
@@ -1205,5 +1225,10 @@ size_t bq_quantize_workspace_bytes(const bq_format* fmt, const bq_tensor3* x) { 
 int bq_quantize(const bq_format* fmt, const bq_tensor3* x_desc, const float* x, void* y, int32_t y_dtype,
                 int32_t transpose_out, void* ws, size_t ws_bytes, void* stream) {
   return bq::quantize_impl(fmt, x_desc, x, y, y_dtype, transpose_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+int bq_silu_mul_quantize(const bq_format* fmt, const bq_tensor3* desc, const float* gate, const float* up, void* y, int32_t y_dtype,
+                         void* ws, size_t ws_bytes, void* stream) {
+  if (!up) return BQ_ERR_BAD_ARG;
+  return bq::quantize_impl(fmt, desc, gate, y, y_dtype, 0, ws, ws_bytes, (cudaStream_t)stream, up);
 }
 }

@@ -19,7 +19,13 @@ from transformers.modeling_outputs import CausalLMOutputWithPast, SequenceClassi
 from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
+from ..quantize.quantized_functions.attention import (fusable as _attn_fusable, fused_causal_attention_q, output_quantizable,
+                                                       quantize_qkv)
 from ..quantize.quantized_functions.fp32_linear import fp32_linear
+from ..quantize.quantized_functions.fused_glue import (linear_input_format, norm_quantize, row_block16_format,
+                                                        silu_mul_quantize)
+from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major as _rope_token_major
+from ..quantize.quantized_modules.linear import operand_format, quantize_operand_bf16
 from .configuration_llama import LlamaQuantizedConfig
 
 
@@ -68,6 +74,7 @@ class LlamaQuantizedMLP(nn.Module):
         self.down_proj = get_quantized_cls("linear", qc["down_proj"])(intermediate_size, hidden_size, bias=False, config=qc["down_proj"])
         self.up_proj = get_quantized_cls("linear", qc["up_proj"])(hidden_size, intermediate_size, bias=False, config=qc["up_proj"])
         self.act_fn = ACT2FN[hidden_act]
+        self.hidden_act = hidden_act
         self.quant_config = qc
 
     def forward(self, x):
@@ -129,7 +136,59 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         self.input_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
-    def forward(self, hidden_states, attention_mask=None, position_ids=None, output_attentions=False):
+    # ------------------------------------------------------------------ fused layer (PTQ inference, causal mask)
+    def _fused_plan(self, seq_len: int):
+        """Formats for running the layer on fused kernels (same idea as OPTQuantizedDecoderLayer._fused_plan): RMSNorm+quantize,
+        GEMMs that read bf16 operands and apply the next op's x-quantizer / the residual add in their epilogue, one attention
+        kernel.  None when any piece is not eligible (block_log, odd block shapes, > 8 significant bits, QAT...)."""
+        cache = getattr(self, "_plan_cache", None)
+        if cache is not None and cache[0] == seq_len:
+            return cache[1]
+        at, mlp = self.self_attn, self.mlp
+        H, d = self.hidden_size, at.head_dim
+        plan = None
+        qc = at.quant_config
+        if (seq_len % 16 == 0 and H % 32 == 0 and mlp.gate_proj.out_features % 16 == 0 and mlp.hidden_act == "silu"
+                and _attn_fusable(qc["matmul_0"], qc["matmul_1"], d, seq_len) and output_quantizable(at.o_proj.config, H)):
+            fmts = dict(q_in=linear_input_format(at.q_proj), k_in=linear_input_format(at.k_proj), v_in=linear_input_format(at.v_proj),
+                        o_in=linear_input_format(at.o_proj), gate_in=linear_input_format(mlp.gate_proj),
+                        up_in=linear_input_format(mlp.up_proj), down_in=linear_input_format(mlp.down_proj),
+                        v_out=row_block16_format(qc["matmul_1"], "weight", d))
+            if all(v is not None for v in fmts.values()):
+                plan = fmts
+        self._plan_cache = (seq_len, plan)
+        return plan
+
+    @torch.no_grad()
+    def _fused_forward(self, h, position_ids, plan):
+        B, S, H = h.shape
+        at, mlp = self.self_attn, self.mlp
+        n1, n2 = self.input_layernorm, self.post_attention_layernorm
+        qc = at.quant_config
+        xq, xk, xv = norm_quantize(h, n1.weight, None, n1.variance_epsilon, [plan["q_in"], plan["k_in"], plan["v_in"]])
+        q = at.q_proj.forward_prequantized(xq)                                   # fp32: RoPE runs on unquantised projections
+        k = at.k_proj.forward_prequantized(xk)
+        Vq = at.v_proj.forward_prequantized(xv, out_format=plan["v_out"])        # bmm_1's y-quantizer in the GEMM epilogue
+        cos, sin = at.rotary_emb(q, seq_len=S)
+        q4, k4 = _rope_token_major(q.view(B, S, at.num_heads, at.head_dim), k.view(B, S, at.num_heads, at.head_dim), cos, sin,
+                                   position_ids, qc["rotary_positional_encoding"])
+        Qq, Kq, _ = quantize_qkv(q4.view(B, S, H), k4.view(B, S, H), None, qc["matmul_0"], qc["matmul_1"], at.num_heads)
+        oq = fused_causal_attention_q(Qq, Kq, Vq, qc["matmul_1"], at.num_heads, B, S, math.sqrt(at.head_dim),
+                                      out_cfg=at.o_proj.config)
+        h2 = at.o_proj.forward_prequantized(oq, residual=h)                      # residual + o_proj(attn)
+        xg, xu = norm_quantize(h2, n2.weight, None, n2.variance_epsilon, [plan["gate_in"], plan["up_in"]])
+        g = mlp.gate_proj.forward_prequantized(xg)
+        u = mlp.up_proj.forward_prequantized(xu)
+        a = silu_mul_quantize(g.view(B * S, -1), u.view(B * S, -1), plan["down_in"])   # Q_down(silu(gate) * up), one kernel
+        h3 = mlp.down_proj.forward_prequantized(a, residual=h2.view(B * S, H))   # residual + down(silu(gate) * up)
+        return h3.view(B, S, H)
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, output_attentions=False, causal_only=False):
+        if (causal_only and not output_attentions and hidden_states.is_cuda and hidden_states.dtype == torch.float32
+                and not torch.is_grad_enabled() and not self.training and hidden_states.ndim == 3):
+            plan = self._fused_plan(hidden_states.shape[1])
+            if plan is not None:
+                return self._fused_forward(hidden_states, position_ids, plan), None
         residual = hidden_states
         hidden_states = self.input_layernorm(hidden_states)
         hidden_states, attn = self.self_attn(hidden_states, attention_mask=attention_mask, position_ids=position_ids,
@@ -180,6 +239,7 @@ class LlamaQuantizedModel(LlamaQuantizedPreTrainedModel):
         self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size, self.padding_idx)
         self.layers = nn.ModuleList([LlamaQuantizedDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
         self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.fused_glue = True           # set False to force the op-by-op module path (QUANTIZED_MODULE_MAP / QUANTIZED_FUNC_MAP)
         self.post_init()
 
     def get_input_embeddings(self):
@@ -196,13 +256,14 @@ class LlamaQuantizedModel(LlamaQuantizedPreTrainedModel):
         if position_ids is None:
             position_ids = torch.arange(q_len, dtype=torch.long, device=inputs_embeds.device).unsqueeze(0).view(-1, q_len)
         mask = _causal_mask(attention_mask, bsz, q_len, inputs_embeds.dtype, inputs_embeds.device)
+        causal_only = self.fused_glue and (attention_mask is None or bool(attention_mask.all()))
         hidden_states = inputs_embeds
         all_h, all_a = (), ()
         for layer in self.layers:
             if output_hidden_states:
                 all_h += (hidden_states,)
             hidden_states, attn = layer(hidden_states, attention_mask=mask, position_ids=position_ids,
-                                        output_attentions=output_attentions)
+                                        output_attentions=output_attentions, causal_only=causal_only)
             if output_attentions:
                 all_a += (attn,)
         hidden_states = self.norm(hidden_states)

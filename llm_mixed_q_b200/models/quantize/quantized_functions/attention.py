@@ -72,7 +72,7 @@ def quantize_qkv(q, k, v, cfg0: dict, cfg1: dict, num_heads: int):
     qb = resolve_block_shape([1, S, d], qbs)[2]
     vb = resolve_block_shape([1, S, d], vbs)[2]
     Qq = quantize_operand_bf16(q.reshape(B * S, H), qk, qkw, [1, qb], True)
-    Vq = quantize_operand_bf16(v.reshape(B * S, H), vk, vkw, [1, vb], True)
+    Vq = quantize_operand_bf16(v.reshape(B * S, H), vk, vkw, [1, vb], True) if v is not None else None
     # k: the reference quantises k^T, i.e. blocks of consecutive KEY POSITIONS at fixed feature
     kb = resolve_block_shape([1, d, S], kbs)[2]
     Kq = quantize_operand_bf16(k.transpose(1, 2), kk, kkw, [1, kb], True, transpose_out=True)     # -> [B, S, H]

@@ -24,6 +24,18 @@ def _apply(q, k, cos, sin, position_ids, table_quantizer):
     return (q * cos) + (_rotate_half(q) * sin), (k * cos) + (_rotate_half(k) * sin)
 
 
+def apply_token_major(q, k, cos, sin, position_ids, config):
+    """Same arithmetic as `_apply` on token-major operands: q, k [B, S, h, d] (views of the [B, S, H] projections) instead of
+    [B, h, S, d].  Element-wise, so the results are bit-identical to the head-major call; it saves the two transposes the
+    fused attention kernel does not need (it reads [B, S, H] directly)."""
+    tq = _table_quantizer(config, config["name"])
+    cos = tq(cos.squeeze(1).squeeze(0))
+    sin = tq(sin.squeeze(1).squeeze(0))
+    cos = cos[position_ids].unsqueeze(2)               # [bs, seq_len, 1, dim]
+    sin = sin[position_ids].unsqueeze(2)
+    return (q * cos) + (_rotate_half(q) * sin), (k * cos) + (_rotate_half(k) * sin)
+
+
 def _table_quantizer(config, name):
     if config.get("bypass", False):
         return lambda t: t

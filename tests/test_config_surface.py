@@ -123,3 +123,45 @@ def test_quantizer_signatures_match_reference():
     assert sig(block_log_quantizer) == [("x", E), ("width", E), ("exponent_bias_width", None), ("block_size", [16]),
                                         ("skip_first_dim", False)]
     assert sig(minifloat_denorm_quantizer) == [("x", E), ("width", E), ("exponent_width", E), ("exponent_bias", None)]
+
+
+def test_dict_tools_docstring_examples_and_search_roundtrip(golden_configs):
+    """flatten/expand known answers are the worked examples in reference utils/dict_tools.py:1-75; the round trip is the
+    search's save path (search/search.py:873-897): nested -> "root:..." flat params -> nested -> TOML -> parser."""
+    from llm_mixed_q_b200.models.opt_quantized import parse_opt_quantized_config
+    from llm_mixed_q_b200.utils.dict_tools import expand_dict, flatten_dict, parse_ast_literal, resolve_ast_literals
+
+    nested = {"a": 1, "b": {"c": 2, "d": {"e": 3, "f": 4}}}
+    flat = {}
+    flatten_dict(nested, flat, join=":", name="root")
+    assert flat == {"root:a": 1, "root:b:c": 2, "root:b:d:e": 3, "root:b:d:f": 4}
+    back = {}
+    expand_dict(flat, back, join=":", name="root")
+    assert back == nested
+    with pytest.raises(ValueError):
+        expand_dict({"root:a": 1, "root:a:b": 2}, {"a": 1})
+    assert parse_ast_literal("!ast![1, 16]") == [1, 16] and parse_ast_literal("!ast!None") is None
+    assert parse_ast_literal("block_fp") == "block_fp" and parse_ast_literal(6) == 6
+    assert resolve_ast_literals({"x": ["!ast!True", 5], "y": {"z": "!ast!(1, 2)"}}) == {"x": [True, 5], "y": {"z": (1, 2)}}
+    mixed = convert_str_na_to_none(clone(golden_configs["mixed_raw"]))
+    flat, back = {}, {}
+    flatten_dict(mixed, flat)
+    assert "root:model_layer_0:self_attn:q_proj:data_in_width" in flat
+    expand_dict(flat, back)
+    assert parse_opt_quantized_config(back, 3) == golden_configs["mixed_opt"]
+
+
+def test_shipped_configs_parse():
+    from llm_mixed_q_b200.models.llama_quantized import parse_llama_quantized_config
+    from llm_mixed_q_b200.models.opt_quantized import parse_opt_quantized_config
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs")
+    q = parse_opt_quantized_config(os.path.join(root, "opt_6.7b_mixed_bfp.toml"), 32)
+    widths = {q[f"model_layer_{i}"]["fc1"]["weight_width"] for i in range(32)}
+    assert widths <= {5, 4, 3, 2} and len(widths) > 1
+    assert q["model_layer_0"]["self_attn"]["bmm_0"]["data_in_exponent_bias"] is None
+    for name, kind in (("llama_w4a4_block_minifloat.toml", "block_minifloat"), ("llama_w4a4_block_log.toml", "block_log")):
+        q = parse_llama_quantized_config(os.path.join(root, name), 2)
+        assert q["model_layer_1"]["mlp"]["down_proj"]["name"] == kind
+        assert q["model_layer_1"]["mlp"]["down_proj"]["weight_width"] == 4
+        assert q["model_layer_0"]["self_attn"]["rotary_positional_encoding"]["name"] == "integer"

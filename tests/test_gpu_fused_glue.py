@@ -166,3 +166,56 @@ def test_fused_layer_falls_back_when_not_eligible():
     with torch.no_grad():
         out = model(input_ids=ids, labels=ids)
     assert torch.isfinite(out.loss)
+
+
+@pytest.mark.parametrize("tomlname,init", [("bfp_6bit.toml", 0.02), ("block_minifloat.toml", 1.5)])
+def test_fused_llama_layer_matches_op_by_op(tomlname, init):
+    """Llama through the fused layer (RMSNorm+quantize, prequantised GEMMs with residual / v-quantiser epilogues, token-major
+    RoPE, one attention kernel with the post-matmul 1/sqrt(d), SiLU*up quantised for down_proj) vs the same modules op by op."""
+    import json
+    import os
+
+    from conftest import GOLD
+    from llm_mixed_q_b200.models.llama_quantized import LlamaQuantizedConfig, LlamaQuantizedForCausalLM
+
+    with open(os.path.join(GOLD, "configs.json")) as f:
+        qc = json.load(f)["raw"][tomlname]
+    torch.manual_seed(0)
+    cfg = LlamaQuantizedConfig(hidden_size=128, intermediate_size=352, num_hidden_layers=2, num_attention_heads=2, vocab_size=512,
+                               max_position_embeddings=128, initializer_range=init, quant_config=qc)
+    model = LlamaQuantizedForCausalLM(cfg).eval().cuda()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "layernorm.weight" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    ids = torch.randint(0, 512, (3, 128), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    with torch.no_grad():
+        model.model.fused_glue = False
+        ref = model(input_ids=ids, labels=ids)                 # also performs the PTQ weight overwrite
+        model.model.fused_glue = True
+        assert model.model.layers[0]._fused_plan(128) is not None
+        out = model(input_ids=ids, labels=ids)
+        # a padded batch must take the op-by-op path and still agree with itself
+        am = torch.ones_like(ids)
+        am[0, :5] = 0
+        padded = model(input_ids=ids, attention_mask=am, labels=ids)
+    assert torch.isfinite(padded.loss)
+    spread = float(ref.logits.std())
+    err = (out.logits - ref.logits).abs()
+    assert abs(float(out.loss) - float(ref.loss)) <= 5e-3 * abs(float(ref.loss)), (float(out.loss), float(ref.loss))
+    assert float(err.mean()) <= 0.03 * spread and float(err.max()) <= 0.75 * spread, (float(err.mean()), float(err.max()), spread)
+
+
+def test_fused_llama_not_eligible_for_block_log():
+    import json
+    import os
+
+    from conftest import GOLD
+    from llm_mixed_q_b200.models.llama_quantized import LlamaQuantizedConfig, LlamaQuantizedForCausalLM
+
+    with open(os.path.join(GOLD, "configs.json")) as f:
+        qc = json.load(f)["raw"]["block_log.toml"]
+    cfg = LlamaQuantizedConfig(hidden_size=128, intermediate_size=352, num_hidden_layers=1, num_attention_heads=2, vocab_size=512,
+                               max_position_embeddings=128, quant_config=qc)
+    model = LlamaQuantizedForCausalLM(cfg).eval().cuda()
+    assert model.model.layers[0]._fused_plan(128) is None      # tensor-global zero-block rule: stays op by op

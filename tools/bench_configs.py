@@ -1,0 +1,211 @@
+#!/usr/bin/env python
+"""
+Secondary measurements for BASELINE.json configs[3] and configs[4] (bench.py stays the headline, configs[2]).
+
+  python tools/bench_configs.py --config 4 [--format block_minifloat|block_log|both] [--batch 2]
+      Llama-7B shape (32 layers, H 4096, I 11008, h 32, d 128, vocab 32000), random init, W4A4 block_minifloat /
+      block_log (configs/llama_w4a4_*.toml), seq 2048, full forward incl. fp32 lm_head + shifted CE loss.
+      Data-parallel: every rank runs its own replica (weak scaling, no data-path collective).  tokens/s.
+  python tools/bench_configs.py --config 5 [--tokens 4096]
+      OPT-6.7B layer GEMMs (H 4096, F 16384) under the per-layer mixed-precision block_fp config
+      (configs/opt_6.7b_mixed_bfp.toml, section-4.4 search format), column-parallel over the ranks of the job:
+      quantize x -> tcgen05 GEMM on this rank's N/g rows -> all-gather of the fp32 column slabs.
+      Checks the gathered result is BIT-IDENTICAL to the one-GPU module, then times it (CUDA events, max over ranks).
+
+Launch N>1 as:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_configs.py ...
+Each run prints one JSON line per measurement on rank 0 and appends it to gpurun_out/bench_configs.jsonl.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+SEQ = 2048
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def emit(line, rank):
+    if rank != 0:
+        return
+    print(json.dumps(line), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "bench_configs.jsonl"), "a") as f:
+        f.write(json.dumps(line) + "\n")
+
+
+def setup():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return world, rank, dev
+
+
+def max_over_ranks(ms, world, dev):
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def barrier(world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------
+def config4(args, world, rank, dev):
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.llama_quantized import LlamaQuantizedConfig, LlamaQuantizedForCausalLM
+
+    kinds = ["block_minifloat", "block_log"] if args.format == "both" else [args.format]
+    for kind in kinds:
+        toml_path = os.path.join(ROOT, "configs", f"llama_w4a4_{kind}.toml")
+        # N(0,0.02) weights all quantise to 0 under block_minifloat (shared bias clamps at >= 0):
+        # the timed run uses the x64-scaled init so the arithmetic is not degenerate
+        init = 1.28 if kind == "block_minifloat" else 0.02
+        cfg = LlamaQuantizedConfig(quant_config=toml_path, initializer_range=init,
+                                   num_hidden_layers=args.layers or 32)
+        torch.manual_seed(0)
+        t0 = time.time()
+        with torch.device(dev):
+            model = LlamaQuantizedForCausalLM(cfg).eval()
+        g = torch.Generator(device="cpu").manual_seed(rank)
+        ids = torch.randint(0, cfg.vocab_size, (args.batch, SEQ), generator=g).to(dev)
+        K, W = args.steps, max(args.warmup, 2)
+        with torch.no_grad():
+            for _ in range(W):
+                out = model(input_ids=ids, labels=ids)
+            barrier(world)
+            l0 = sum(L.launch_counts().values())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                out = model(input_ids=ids, labels=ids)
+            e1.record()
+            barrier(world)
+        ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / K
+        launches = sum(L.launch_counts().values()) - l0
+        tokens = args.batch * SEQ * world
+        # algorithmic FLOPs per token: 7 Linears + 2 matmuls per layer + lm_head
+        H, I, Lyr, V, h, d = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.vocab_size, 32, 128
+        flops = 2 * args.batch * SEQ * (Lyr * (4 * H * H + 3 * H * I) + H * V) + Lyr * 2 * 2 * args.batch * h * SEQ * SEQ * d
+        _, burst, sus, src = peaks()
+        emit({"metric": f"W4A4-{kind} fwd tokens/s (Llama-7B)", "value": tokens / (ms / 1e3), "unit": "tokens/s", "n_gpus": world,
+              "steps": K, "warmup": W, "ms_per_step": ms, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+              "config": {"workload": f"Llama-7B shape W4A4 {kind} (block 16) full forward, seq 2048, batch {args.batch} per GPU",
+                         "toml": os.path.relpath(toml_path, ROOT), "layers": Lyr, "init_std": init,
+                         "parallelism": f"dp{world} (independent replicas)", "loss": float(out.loss)},
+              "algorithmic_TFLOPs": flops * world / (ms / 1e3) / 1e12, "frac_of_bf16_sustained": flops / (ms / 1e3) / 1e12 / sus,
+              "peak_source": src, "gpu_launches_per_step": launches // K, "build_s": round(time.time() - t0, 1)}, rank)
+        del model, out
+        torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------------
+def config5(args, world, rank, dev):
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.dist import ColumnParallelLinear
+    from llm_mixed_q_b200.models.opt_quantized import parse_opt_quantized_config
+    from llm_mixed_q_b200.models.quantize import get_quantized_cls
+
+    qc = parse_opt_quantized_config(os.path.join(ROOT, "configs", "opt_6.7b_mixed_bfp.toml"), 32)
+    H, F_ = 4096, 16384
+    M = args.tokens
+    shapes = [("self_attn.q_proj", H, H), ("self_attn.k_proj", H, H), ("self_attn.v_proj", H, H), ("self_attn.out_proj", H, H),
+              ("fc1", H, F_), ("fc2", F_, H)]
+    _, burst, sus, src = peaks()
+    layer = args.layer
+    total_ms, total_flops, total_gemm_ms = 0.0, 0, 0.0
+    for name, K, N in shapes:
+        node = qc[f"model_layer_{layer}"]
+        for part in name.split("."):
+            node = node[part]
+        torch.manual_seed(1234)                     # every rank builds the SAME full module and input
+        with torch.device(dev):
+            full = get_quantized_cls("linear", node)(K, N, bias=True, config=node).eval()
+            full.bias.data.normal_(0, 0.02)
+        x = torch.randn(M, K, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        cp = ColumnParallelLinear.from_linear(full)          # shards BEFORE the PTQ overwrite: blocks never cross the cut
+        cp_local = ColumnParallelLinear(cp.local, N, gather_output=False)
+        with torch.no_grad():
+            y_full = full(x)
+            y_cp = cp(x)
+        identical = bool(torch.equal(y_full.view(torch.int32), y_cp.view(torch.int32)))
+        del y_full, y_cp
+
+        def timed(fn, iters=args.steps):
+            with torch.no_grad():
+                for _ in range(max(args.warmup, 3)):
+                    fn()
+                barrier(world)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(iters):
+                    fn()
+                b.record()
+                barrier(world)
+            return max_over_ranks(a.elapsed_time(b), world, dev) / iters
+
+        ms = timed(lambda: cp(x))
+        ms_local = timed(lambda: cp_local(x))
+        flops = 2 * M * N * K
+        total_ms += ms
+        total_gemm_ms += ms_local
+        total_flops += flops
+        emit({"metric": "column-parallel q-GEMM TFLOP/s (OPT-6.7B mixed block_fp)", "op": name, "M": M, "K": K, "N": N, "n_gpus": world,
+              "x_width": node["data_in_width"], "w_width": node["weight_width"], "ms": ms, "ms_quantize_plus_gemm": ms_local,
+              "ms_all_gather": ms - ms_local, "value": flops / (ms / 1e3) / 1e12, "unit": "TFLOP/s (whole job)",
+              "frac_of_bf16_sustained_x_gpus": flops / (ms / 1e3) / 1e12 / (sus * world),
+              "gemm_only_frac": flops / (ms_local / 1e3) / 1e12 / (sus * world), "bit_identical_to_1gpu": identical,
+              "all_gather_bytes_per_rank": M * (N // world) * 4 * (world - 1), "peak_source": src}, rank)
+        assert identical, f"{name}: column-parallel result differs from the 1-GPU module"
+        del full, cp, cp_local, x
+        torch.cuda.empty_cache()
+    emit({"metric": "column-parallel q-GEMM TFLOP/s (OPT-6.7B mixed block_fp)", "op": "layer total (6 Linears)", "M": M, "n_gpus": world,
+          "layer": layer, "ms": total_ms, "ms_quantize_plus_gemm": total_gemm_ms, "value": total_flops / (total_ms / 1e3) / 1e12,
+          "unit": "TFLOP/s (whole job)", "frac_of_bf16_sustained_x_gpus": total_flops / (total_ms / 1e3) / 1e12 / (sus * world),
+          "scaling": "strong", "gpu_launches": sum(L.launch_counts().values())}, rank)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True, choices=[4, 5])
+    ap.add_argument("--format", default="both", choices=["block_minifloat", "block_log", "both"])
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers")
+    ap.add_argument("--tokens", type=int, default=4096)
+    ap.add_argument("--layer", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    args = ap.parse_args()
+    world, rank, dev = setup()
+    from llm_mixed_q_b200 import _lib as L
+
+    L.load()
+    (config4 if args.config == 4 else config5)(args, world, rank, dev)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
