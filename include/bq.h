@@ -249,6 +249,23 @@ BQ_API int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const
                                  int64_t ldv, int64_t ldo, float score_div, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Token cross-entropy (perplexity numerator).  Replaces the loss tail of the reference's causal-LM forward,
+ *     shift_logits = logits[..., :-1, :].contiguous(); shift_labels = labels[..., 1:].contiguous()
+ *     loss = CrossEntropyLoss()(shift_logits.view(-1, V), shift_labels.view(-1))
+ * (models/opt_quantized/modeling_opt.py:1086-1098, models/llama_quantized/modeling_llama.py:867-879; the number
+ * eval/eval_lm.py:41-63 turns into perplexity) with ONE streaming read of the logits — no shifted copy, no
+ * log-softmax tensor.  logits: fp32 [n_seq, seq_len, vocab], row stride ld; labels: int64 [n_seq, seq_len] contiguous.
+ * shift = 1: row (b, t), t < seq_len - 1, is scored against labels[b, t + 1]; shift = 0: against labels[b, t].
+ * Rows whose target equals ignore_index are skipped (mean over the others, like reduction="mean"); targets outside
+ * [0, vocab) — a device assert in torch — are skipped as well.  out2[0] = mean loss (NaN when no row is valid),
+ * out2[1] = number of valid rows.  ws: bq_token_ce_workspace_bytes(n_seq, seq_len) bytes (one fp32 per row).
+ * Deterministic (fixed reduction order).  Log-sum-exp differs from torch's by <= ~1e-6 absolute (ex2.approx).
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API size_t bq_token_ce_workspace_bytes(int64_t n_seq, int64_t seq_len);
+BQ_API int bq_token_ce_mean(const float* logits, int64_t n_seq, int64_t seq_len, int64_t vocab, int64_t ld, const int64_t* labels,
+                            int32_t shift, int64_t ignore_index, float* out2, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Launch accounting (measurement support for bench.py; no reference counterpart).
  * Every kernel this library launches is counted per kernel id.  With profiling enabled the library
  * additionally brackets each launch with CUDA events on the launching stream; bq_profile_read

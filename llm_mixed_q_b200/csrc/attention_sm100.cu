@@ -109,22 +109,82 @@ __device__ __forceinline__ float ex2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t bf16x2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_min(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// kMagicB = 1.5 * 2^23 + 0x4300: (t + kMagicB) - kMagicB == rintf(t) like kMagic, and the LOW 16 bits of the sum are
+// 0x4300 + q — the bf16 encoding of 128 + q (q <= 128).  Two such halves byte-permuted into one word are a bf16x2 pair on
+// which the clamp to qmax and the de-quantisation q * 2^(E-m) = fma(128 + q, step, -128 * step) run packed (every value
+// exact in bf16: q has <= 7 bits).
+constexpr float kMagicB = 12600064.0f;
+
 // Quantise 16 consecutive NON-NEGATIVE values (one reference block of probabilities) and pack them as bf16.
-template <int KIND>
-__device__ __forceinline__ void quantize_probs16(float (&v)[16], const FmtParams& p, uint32_t (&w)[8]) {
-  float mx = v[0];
+// SCALED: v holds the UN-normalised exponentials e_i and the probabilities are p_i = rn(e_i * inv_l); the common path never
+// forms p_i: block max / min scale once (rounding is monotonic) and the normalisation rides on the quantiser's scale,
+// t_i = fma(e_i, inv_l * 2^(m-E), c0) — one rounding instead of rn(rn(e_i * inv_l) * 2^(m-E) + c0), i.e. <= 1 ulp of t_i, the
+// same class of deviation as the approximate exponential itself.  !SCALED: v holds p_i, inv_l unused.
+// Probabilities are <= 1 mathematically; an approximate exponential may overshoot by an ulp, so the BLOCK MAX is clamped to
+// 1.0 before the shared exponent is derived (an overshooting element then saturates at qmax exactly like the reference's 1.0).
+template <int KIND, bool SCALED>
+__device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, const FmtParams& p, uint32_t (&w)[8]) {
+  float mx = v[0], mn = v[0];
 #pragma unroll
   for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[i]);
+  if (SCALED) mx = __fmul_rn(mx, inv_l);
   if (mx == 0.f) {                                      // all-zero block -> zeros (pass-through)
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = 0u;
     return;
   }
+  mx = fminf(mx, 1.0f);
   const uint32_t mbits = f2u(mx);
   const FastState fs = fast_state<KIND>(mbits, p);
+  if (KIND == kBlockFP && fs.ok && p.mbits <= 7) {
+#pragma unroll
+    for (int i = 1; i < 16; ++i) mn = fminf(mn, v[i]);
+    if (SCALED) mn = __fmul_rn(mn, inv_l);
+    if (mn > 1e-8f) {
+      // no pass-through element in this block (the common case): rounding in fp32, clamp + de-quantisation packed in bf16
+      const float c0 = __fmul_rn(1e-9f, fs.f0);         // exact: f0 is a power of two
+      const float g0 = SCALED ? __fmul_rn(inv_l, fs.f0) : fs.f0;      // exact (power-of-two factor, |E| <= 100)
+      const uint32_t step2 = pack_bf16_trunc(fs.f1, fs.f1);
+      const float nb = -__fmul_rn(128.0f, fs.f1);
+      const uint32_t base2 = pack_bf16_trunc(nb, nb);
+      const float top = __fadd_rn(128.0f, p.qmax);
+      const uint32_t top2 = pack_bf16_trunc(top, top);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t0 = __fadd_rn(__fmaf_rn(v[2 * i], g0, c0), kMagicB);            // kMagicB + rint((p + 1e-9f) * 2^(m-E))
+        const float t1 = __fadd_rn(__fmaf_rn(v[2 * i + 1], g0, c0), kMagicB);
+        const uint32_t q2 = bf16x2_min(__byte_perm(f2u(t0), f2u(t1), 0x5410), top2);   // {128 + q0, 128 + q1}, clamped to 128 + qmax
+        w[i] = bf16x2_fma(q2, step2, base2);
+      }
+      return;
+    }
+  }
+  if (SCALED) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], inv_l);
+  }
   if (fs.ok) {
     if (KIND == kBlockFP) {
-      const float c0 = __fmul_rn(1e-9f, fs.f0);         // exact: f0 is a power of two
+      const float c0 = __fmul_rn(1e-9f, fs.f0);
       const float hi = __fadd_rn(kMagic, p.qmax);       // clamp bound in the magic-shifted domain (exact integer)
       const float c1 = -__fmul_rn(kMagic, fs.f1);       // exact: f1 is a power of two
 #pragma unroll
@@ -194,13 +254,13 @@ __device__ __forceinline__ float stat_fixup(float m, float mL, float l) {
 }
 
 // final probabilities of 32 scores -> two quantised blocks -> swizzled bf16 rows of the P tile.
-// FAST: p = min(ex2.approx(fma(s, log2 e, -mL)) * inv_l, 1) — the exponential of the statistics sweep again (2 instructions
+// FAST: p = ex2.approx(fma(s, log2 e, -mL)) * inv_l (the product folded into the quantiser's scale) — the exponential of the statistics sweep again (2 instructions
 // instead of libdevice expf's 8 + the subtraction); inv_l already carries the row constant 2^-(m * log2 e - mL).  Relative error
 // of p <= ~(3 + |s - m| * 1.44) ulp instead of <= ~3 ulp; a probability only changes when it sits that close to a rounding
-// boundary.  The clamp keeps the largest probability from crossing 1.0 (next block exponent).
+// boundary.  The largest probability may overshoot 1.0 by an ulp: quantize_probs16 clamps the block max.
 template <int KIND, bool MASK, bool FAST>
 __device__ __forceinline__ void probs32(const uint32_t (&r)[32], int nvalid, float m, float mL, float inv_l, const FmtParams& p,
-                                        uint8_t* prow, int chunk0, int sw) {
+                                        uint32_t prow, int chunk0, int sw) {
   const float nmL = -mL;
 #pragma unroll
   for (int blk = 0; blk < 2; ++blk) {
@@ -208,7 +268,7 @@ __device__ __forceinline__ void probs32(const uint32_t (&r)[32], int nvalid, flo
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       if (FAST) {
-        v[i] = fminf(__fmul_rn(ex2_fast(__fmaf_rn(u2f(r[blk * 16 + i]), kL2E, nmL)), inv_l), 1.0f);
+        v[i] = ex2_fast(__fmaf_rn(u2f(r[blk * 16 + i]), kL2E, nmL));       // normalised inside quantize_probs16
       } else {
         const float e = expf(__fsub_rn(u2f(r[blk * 16 + i]), m));
         v[i] = __fmul_rn(e, inv_l);
@@ -216,10 +276,10 @@ __device__ __forceinline__ void probs32(const uint32_t (&r)[32], int nvalid, flo
       if (MASK) v[i] = (blk * 16 + i < nvalid) ? v[i] : 0.f;
     }
     uint32_t w[8];
-    quantize_probs16<KIND>(v, p, w);
+    quantize_probs16<KIND, FAST>(v, inv_l, p, w);
     const int chunk = chunk0 + blk * 2;
-    *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(prow + (((chunk + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+    sts_v4(prow + ((chunk ^ sw) << 4), w[0], w[1], w[2], w[3]);
+    sts_v4(prow + (((chunk + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
   }
 }
 
@@ -237,9 +297,11 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         const __grid_constant__ CUtensorMap tmV, AttnArgs g) {
   using Cfg = AtCfg<D>;
   constexpr int kSub = D / 64;                     // 64-wide sub-tiles along d
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sb = ptx::smem_u32(smem);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // all shared-memory traffic of this kernel uses 32-bit shared-space addresses (no generic pointers: their window base is
+  // re-derived from special registers wherever the compiler rematerialises them — measured 15 instructions per 32-score slice)
+  uint32_t sb = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  asm volatile("mov.u32 %0, %0;" : "+r"(sb));            // opaque: keep the base in a register instead of re-deriving it per use
   const uint32_t bar0 = sb + Cfg::kSmemBar;
   // barrier map
   auto q_full = [&](int s) { return bar0 + 8u * s; };
@@ -257,8 +319,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   auto p_empty = [&](int s) { return bS + 8u * (6 + s); };
   const uint32_t o_full = bS + 8u * 8, o_empty = bS + 8u * 9;
   const uint32_t tmem_slot = bS + 8u * 10;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kSmemBar + Cfg::kNumBars * 8);
-  float* xch = reinterpret_cast<float*>(smem + Cfg::kSmemX);
+  const uint32_t xch = sb + Cfg::kSmemX;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -284,7 +345,8 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
   const int T = g.q_tiles;
   const int pairs = (T + 1) >> 1;
@@ -417,8 +479,8 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int n = qt + 1;
         const int row = qt * kAtBM + r_in;
         const int nvalid_d = lane + 1;            // cq == quarter: keys [32*cq, 32*cq + lane] of the diagonal tile
-        float* xm = xch + xbuf * (2 * 4 * 128);   // [4][128] partial maxima
-        float* xl = xm + 4 * 128;                 // [4][128] partial sums
+        const uint32_t xm = xch + xbuf * (2 * 4 * 128 * 4);   // [4][128] partial maxima
+        const uint32_t xl = xm + 4 * 128 * 4;                 // [4][128] partial sums
         xbuf ^= 1;
         float m = -INFINITY, mL = -INFINITY, l = 0.f, inv_l = 0.f;
         for (int sweep = 0; sweep < 2; ++sweep) {
@@ -448,11 +510,10 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               }
             } else {
               ptx::mbar_wait(p_empty(pr.idx), pr.phase ^ 1);
-              uint8_t* prow = smem + Cfg::kSmemP + (pr.idx * 2 + (cq >> 1)) * kSubTile + r_in * 128;
+              const uint32_t prow = sb + Cfg::kSmemP + (pr.idx * 2 + (cq >> 1)) * kSubTile + r_in * 128;
               if (skip) {
-                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(prow + (((chunk0 + c) ^ sw) << 4)) = z;
+                for (int c = 0; c < 4; ++c) sts_v4(prow + (((chunk0 + c) ^ sw) << 4), 0u, 0u, 0u, 0u);
               } else if (!(diag && diag_partial)) {
                 probs32<KIND, false, FAST>(r, 32, m, mL, inv_l, g.p, prow, chunk0, sw);
               } else {
@@ -467,15 +528,16 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           if (sweep == 0) {
             // merge the four column quarters of every row:  m = max m_c,  l = sum_c l_c * exp(m_c - m).
             // Only the four warps that share this lane quarter exchange data: one 128-thread named barrier per quarter.
-            xm[cq * 128 + r_in] = m;
-            xl[cq * 128 + r_in] = stat_fixup(m, mL, l);
+            sts_f32(xm + (cq * 128 + r_in) * 4, m);
+            sts_f32(xl + (cq * 128 + r_in) * 4, stat_fixup(m, mL, l));
             named_bar_sync(1 + quarter, 128);
-            float mm = xm[r_in];
+            float mc[4];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) mm = fmaxf(mm, xm[c * 128 + r_in]);
+            for (int c = 0; c < 4; ++c) mc[c] = lds_f32(xm + (c * 128 + r_in) * 4);
+            const float mm = fmaxf(fmaxf(mc[0], mc[1]), fmaxf(mc[2], mc[3]));
             float ll = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) ll = __fadd_rn(ll, __fmul_rn(xl[c * 128 + r_in], expf(__fsub_rn(xm[c * 128 + r_in], mm))));
+            for (int c = 0; c < 4; ++c) ll = __fadd_rn(ll, __fmul_rn(lds_f32(xl + (c * 128 + r_in) * 4), expf(__fsub_rn(mc[c], mm))));
             m = mm;
             // the exact sum contains exp(m - m) = 1, so it is >= 1; rounding in the statistics sweep may land an ulp below,
             // which would make the largest probability exceed 1.0 and jump to the next block exponent

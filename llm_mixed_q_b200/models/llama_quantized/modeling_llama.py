@@ -22,6 +22,7 @@ from ..quantize import get_quantized_cls, get_quantized_func
 from ..quantize.quantized_functions.attention import (fusable as _attn_fusable, fused_causal_attention_q, output_quantizable,
                                                        quantize_qkv)
 from ..quantize.quantized_functions.fp32_linear import fp32_linear
+from ..quantize.quantized_functions.loss import causal_lm_loss
 from ..quantize.quantized_functions.fused_glue import (linear_input_format, norm_quantize, row_block16_format,
                                                         silu_mul_quantize)
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major as _rope_token_major
@@ -302,9 +303,8 @@ class LlamaQuantizedForCausalLM(LlamaQuantizedPreTrainedModel):
         logits = fp32_linear(hidden, self.lm_head.weight, self.lm_head.bias)
         loss = None
         if labels is not None:
-            shift_logits = logits[..., :-1, :].contiguous()
-            shift_labels = labels[..., 1:].contiguous().to(logits.device)
-            loss = CrossEntropyLoss()(shift_logits.view(-1, self.config.vocab_size), shift_labels.view(-1))
+            # shifted CE (modeling_llama.py:867-879) in one streaming read of the logits: bq_token_ce_mean
+            loss = causal_lm_loss(logits, labels, shift=True)
         if not return_dict:
             out = (logits, None, all_h, all_a)
             return ((loss,) + out) if loss is not None else out

@@ -21,6 +21,7 @@ from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
 from ..quantize.quantized_functions.fp32_linear import fp32_linear
+from ..quantize.quantized_functions.loss import causal_lm_loss
 from ..quantize.quantized_functions.attention import (fusable as _attn_fusable, fused_causal_attention,
                                                       fused_causal_attention_q, output_quantizable)
 from ..quantize.quantized_functions.fused_glue import linear_input_format, norm_quantize, row_block16_format
@@ -347,10 +348,8 @@ class OPTQuantizedForCausalLM(OPTQuantizedPreTrainedModel):
         logits = fp32_linear(hidden, self.lm_head.weight, self.lm_head.bias)
         loss = None
         if labels is not None:
-            labels = labels.to(logits.device)
-            shift_logits = logits[..., :-1, :].contiguous()
-            shift_labels = labels[..., 1:].contiguous()
-            loss = CrossEntropyLoss()(shift_logits.view(-1, self.config.vocab_size), shift_labels.view(-1))
+            # shifted CE (modeling_opt.py:1086-1098) in one streaming read of the logits: bq_token_ce_mean
+            loss = causal_lm_loss(logits, labels, shift=True)
         if not return_dict:
             out = (logits, None, all_h, all_a)
             return ((loss,) + out) if loss is not None else out
