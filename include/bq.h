@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BQ_ABI_VERSION 1
+#define BQ_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define BQ_API __attribute__((visibility("default")))
@@ -172,7 +172,14 @@ typedef struct bq_gemm_epilogue {
   int32_t out_dtype;       /* bq_dtype of C                                 */
   const bq_format* qfmt;   /* NULL = no quantisation                        */
   int32_t qdir;            /* 0: blocks along N, 1: blocks along M          */
+  /* Fused all-gather (column-parallel Linear): every output tile is ALSO stored to the same [m][n] position of
+   * n_replicas further buffers with the same ldc and dtype as C — peer GPUs' copies of the gathered output, mapped with
+   * bq_ipc_import, written over NVLink from the epilogue while the other tiles are still being multiplied.  The caller
+   * passes pointers already offset to this rank's first column and orders visibility with bq_peer_barrier. */
+  int32_t n_replicas;      /* 0..BQ_MAX_REPLICAS                            */
+  void* replicas[7];
 } bq_gemm_epilogue;
+#define BQ_MAX_REPLICAS 7
 BQ_API int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_gemm_epilogue* ep, int64_t M, int64_t N, int64_t K,
                               int64_t lda, int64_t ldb, int64_t ldc, void* stream);
 
@@ -278,6 +285,33 @@ BQ_API const char* bq_kernel_name(int kernel_id);
 BQ_API int64_t bq_launch_count(int kernel_id);          /* launches since load (kernel_id < 0: all kernels) */
 BQ_API void bq_profile_enable(int on);                  /* turning it on clears earlier records */
 BQ_API int bq_profile_read(int kernel_id, double* total_ms, int64_t* launches);
+
+/* ------------------------------------------------------------------------------------------------
+ * Peer memory over NVLink / NVSwitch — the one exchange step of the path (column-parallel Linear).
+ * The reference has no counterpart (single device).  One process per GPU; buffers stay owned by the caller (torch):
+ *   bq_ipc_export   handle of the cudaMalloc allocation that contains dev_ptr, plus dev_ptr's offset inside it
+ *   bq_ipc_import   maps a peer process's allocation (peer access enabled lazily); *base = start of the mapping,
+ *                   *ptr = base + offset.  One mapping per (process, allocation): callers cache it.
+ *   bq_ipc_release  unmaps (pass *base).
+ *   bq_peer_barrier stream-ordered barrier between the `world` processes of a job, on flags that live in peer-mapped
+ *                   memory: signals[r] points at rank r's flag block (BQ_PEER_FLAG_WORDS x uint32, zeroed once);
+ *                   rank `rank` release-increments word [rank] of every peer's block and acquire-waits until its own
+ *                   block shows `epoch` arrivals from every peer (epoch = number of barriers so far, counted by the
+ *                   caller identically on all ranks).  All writes issued by earlier work on `stream` (including
+ *                   epilogue stores into peers) are visible to the peers' later work.  A wait longer than
+ *                   timeout_ms sets word [BQ_PEER_FLAG_TIMEOUT] of the own block and returns (never hangs the GPU).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bq_ipc_handle {
+  unsigned char reserved[64];   /* cudaIpcMemHandle_t */
+  int64_t offset;               /* of dev_ptr inside the allocation */
+  int64_t size;                 /* of the allocation */
+} bq_ipc_handle;
+#define BQ_PEER_FLAG_WORDS 64
+#define BQ_PEER_FLAG_TIMEOUT 32
+BQ_API int bq_ipc_export(const void* dev_ptr, bq_ipc_handle* out);
+BQ_API int bq_ipc_import(const bq_ipc_handle* h, void** base, void** ptr);
+BQ_API int bq_ipc_release(void* base);
+BQ_API int bq_peer_barrier(void* const* signals, int32_t rank, int32_t world, uint32_t epoch, int32_t timeout_ms, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,12 @@ class BqTensor3(Structure):
 
 class BqGemmEpilogue(Structure):
     _fields_ = [("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64), ("scale", ctypes.c_float), ("act", c_int32),
-                ("out_dtype", c_int32), ("qfmt", POINTER(BqFormat)), ("qdir", c_int32)]
+                ("out_dtype", c_int32), ("qfmt", POINTER(BqFormat)), ("qdir", c_int32), ("n_replicas", c_int32),
+                ("replicas", c_void_p * 7)]
+
+
+class BqIpcHandle(Structure):
+    _fields_ = [("reserved", ctypes.c_ubyte * 64), ("offset", c_int64), ("size", c_int64)]
 
 
 class BqError(RuntimeError):
@@ -130,6 +135,14 @@ def load():
     lib.bq_token_ce_mean.restype = ctypes.c_int
     lib.bq_token_ce_mean.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int32, c_int64, c_void_p, c_void_p,
                                      c_size_t, c_void_p]
+    lib.bq_ipc_export.restype = ctypes.c_int
+    lib.bq_ipc_export.argtypes = [c_void_p, POINTER(BqIpcHandle)]
+    lib.bq_ipc_import.restype = ctypes.c_int
+    lib.bq_ipc_import.argtypes = [POINTER(BqIpcHandle), POINTER(c_void_p), POINTER(c_void_p)]
+    lib.bq_ipc_release.restype = ctypes.c_int
+    lib.bq_ipc_release.argtypes = [c_void_p]
+    lib.bq_peer_barrier.restype = ctypes.c_int
+    lib.bq_peer_barrier.argtypes = [POINTER(c_void_p), c_int32, c_int32, ctypes.c_uint32, c_int32, c_void_p]
     lib.bq_selftest_log2.restype = ctypes.c_int
     lib.bq_selftest_log2.argtypes = [c_void_p, c_void_p]
     lib.bq_kernel_count.restype = ctypes.c_int

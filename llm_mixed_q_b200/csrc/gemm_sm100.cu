@@ -56,6 +56,9 @@ struct EpiArgs {
   int out_bf16;            // 0: fp32 store, 1: bf16 store
   int qmode;               // 0 none; 1: blocks of 16 along N (one thread's registers); 2: blocks of 16 along M (16 lanes)
   FmtParams q;
+  // fused all-gather: the tile is also stored to the same position of n_rep peer-mapped copies of C (NVLink stores)
+  int n_rep;
+  void* rep[BQ_MAX_REPLICAS];
 };
 
 struct GemmArgs {
@@ -167,16 +170,32 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     else quant_rowblocks32<kBlockMinifloat>(v, e.q, scratch, lane);
   }
   if (!row_ok) return;
+  const int64_t off = (int64_t)row * g.ldc + col0;
   if (e.out_bf16) {
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(g.C) + (int64_t)row * g.ldc + col0;
+    uint4 o[4];
 #pragma unroll
-    for (int j = 0; j < 32; j += 8)
-      *reinterpret_cast<uint4*>(c + j) = make_uint4(pack_bf16_rn(v[j], v[j + 1]), pack_bf16_rn(v[j + 2], v[j + 3]),
-                                                    pack_bf16_rn(v[j + 4], v[j + 5]), pack_bf16_rn(v[j + 6], v[j + 7]));
+    for (int j = 0; j < 4; ++j)
+      o[j] = make_uint4(pack_bf16_rn(v[8 * j], v[8 * j + 1]), pack_bf16_rn(v[8 * j + 2], v[8 * j + 3]),
+                        pack_bf16_rn(v[8 * j + 4], v[8 * j + 5]), pack_bf16_rn(v[8 * j + 6], v[8 * j + 7]));
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(g.C) + off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(c)[j] = o[j];
+#pragma unroll 1
+    for (int p = 0; p < e.n_rep; ++p) {                          // peers' copies of the gathered output
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(e.rep[p]) + off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(cp)[j] = o[j];
+    }
   } else {
-    float* c = g.C + (int64_t)row * g.ldc + col0;
+    float* c = g.C + off;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+#pragma unroll 1
+    for (int p = 0; p < e.n_rep; ++p) {
+      float* cp = reinterpret_cast<float*>(e.rep[p]) + off;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
   }
 }
 
@@ -577,6 +596,12 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
     if (rc) return rc;
     g.epi.q.fold_zero = 0;
     g.epi.qmode = ep->qdir == 1 ? 2 : 1;
+  }
+  if (ep->n_replicas < 0 || ep->n_replicas > BQ_MAX_REPLICAS) return BQ_ERR_BAD_ARG;
+  g.epi.n_rep = ep->n_replicas;
+  for (int i = 0; i < ep->n_replicas; ++i) {
+    if (!ep->replicas[i] || ((uintptr_t)ep->replicas[i] % 16)) return BQ_ERR_BAD_ARG;
+    g.epi.rep[i] = ep->replicas[i];
   }
   const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
   CUtensorMap tmA, tmB;

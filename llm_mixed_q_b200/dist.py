@@ -14,10 +14,16 @@ emulation on one device, or lets `accelerate` place layers (`cli/eval_lm.py`), w
    values to quantising the full matrix, because no block crosses the cut), computes its column slab
    of y from the replicated x, and the slabs are all-gathered.  The K-reduction of every output element is
    done by the same kernel in the same order as on one GPU, so the result is bit-identical to 1 GPU.
-   `ColumnParallelLinear`.
+   `ColumnParallelLinear`.  Two exchange implementations behind the same module:
+     * `all_gather_columns` — NCCL all-gather of the slabs + one permute (the library baseline), and
+     * `PeerArena` (fused, the default on NVLink-connected GPUs) — the GEMM epilogue stores every output tile into all
+       ranks' gathered [M, N] buffers while the remaining tiles are still being multiplied (bq_gemm_bf16_tn_ex
+       `replicas`, include/bq.h), followed by one flag barrier over peer memory (bq_peer_barrier).  No NCCL call, no
+       staging slab, no permute; the bytes that cross NVLink are the all-gather's own (M*N/g*4*(g-1) per rank).
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Iterable, List, Optional, Sequence, Tuple
 
@@ -114,6 +120,129 @@ def all_gather_columns(y_local: torch.Tensor, group=None) -> torch.Tensor:
     return buf.view(world, m, nl).permute(1, 0, 2).reshape(*lead, world * nl)
 
 
+# peer allocations mapped into this process: (peer rank, 64-byte IPC handle) -> [base address, users].  CUDA maps an
+# allocation once per process; two arenas that torch carved out of the same cudaMalloc block share the mapping.
+_IPC_MAPPINGS: dict = {}
+
+
+def _ipc_import(lib, L, peer_rank: int, raw: bytes):
+    h = L.BqIpcHandle.from_buffer_copy(raw)
+    key = (peer_rank, bytes(h.reserved))
+    ent = _IPC_MAPPINGS.get(key)
+    if ent is None:
+        base, ptr = ctypes.c_void_p(), ctypes.c_void_p()
+        L.check(lib.bq_ipc_import(ctypes.byref(h), ctypes.byref(base), ctypes.byref(ptr)), "bq_ipc_import")
+        ent = _IPC_MAPPINGS[key] = [base.value, 0]
+    ent[1] += 1
+    return key, ent[0] + h.offset
+
+
+def _ipc_release(lib, key):
+    ent = _IPC_MAPPINGS.get(key)
+    if ent is None:
+        return
+    ent[1] -= 1
+    if ent[1] <= 0:
+        lib.bq_ipc_release(ent[0])
+        del _IPC_MAPPINGS[key]
+
+
+class PeerArena:
+    """
+    Symmetric, peer-mapped output memory for the fused all-gather: every rank owns `slots` buffers of `slot_bytes`
+    plus one flag block, allocated by torch (one fresh allocation) and mapped into every other rank with CUDA IPC
+    (bq_ipc_export / bq_ipc_import).  Handles travel through `torch.distributed` (all_gather_object), never the data.
+
+    Protocol of one use (`ColumnParallelLinear._forward_fused`): take the next slot (round-robin over >= 2 slots), let the
+    GEMM epilogue write this rank's column slab into the slot of EVERY rank, then `barrier()`.  After the barrier the
+    local slot holds the complete [M, N] result.  Reusing a slot is safe without a second barrier: a rank starts writing
+    slot s of call k only after it passed the barrier of call k-1, which every peer enters only after (stream order) the
+    consumers of its call k-2 result — the previous user of slot s — were enqueued ahead of it.
+    """
+
+    TIMEOUT_MS = 20000
+
+    def __init__(self, slot_bytes: int, device, group=None, slots: int = 2):
+        from . import _lib as L
+
+        if slots < 2:
+            raise ValueError("PeerArena needs at least two slots (see the reuse argument in the class docstring)")
+        self.group = group
+        self.world, self.rank = _world(group)
+        if self.world > 8:
+            raise ValueError("PeerArena spans one NVSwitch domain (<= 8 GPUs)")
+        self.device = torch.device(device)
+        self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
+        self.slots = slots
+        self._flag_bytes = 1024
+        self.lib = L.load()
+        self._L = L
+        # one private allocation: flags first, then the slots (>= 1 MB so torch gives it its own cudaMalloc block)
+        total = self._flag_bytes + self.slots * self.slot_bytes
+        self.buf = torch.zeros(max(total, 2 << 20), dtype=torch.uint8, device=self.device)
+        torch.cuda.synchronize(self.device)
+        h = L.BqIpcHandle()
+        L.check(self.lib.bq_ipc_export(self.buf.data_ptr(), ctypes.byref(h)), "bq_ipc_export")
+        mine = bytes(h)
+        gathered = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(gathered, mine, group=group)
+        else:
+            gathered[0] = mine
+        self._bases = []
+        self.ptrs = []
+        for r, raw in enumerate(gathered):
+            if r == self.rank:
+                self.ptrs.append(self.buf.data_ptr())
+                continue
+            key, ptr = _ipc_import(self.lib, L, r, raw)
+            self._bases.append(key)
+            self.ptrs.append(ptr)
+        self._signals = (ctypes.c_void_p * self.world)(*self.ptrs)
+        self.epoch = 0
+        self._next = 0
+        # nobody signals into a flag block before its owner zeroed it
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def take(self, shape, dtype=torch.float32):
+        """Next slot as a local tensor of `shape`, and the address of the same slot on every rank."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if nbytes > self.slot_bytes:
+            raise ValueError(f"result of {nbytes} bytes does not fit a PeerArena slot of {self.slot_bytes} bytes")
+        off = self._flag_bytes + self._next * self.slot_bytes
+        self._next = (self._next + 1) % self.slots
+        local = self.buf[off:off + nbytes].view(dtype).view(*shape)
+        return local, [p + off for p in self.ptrs]
+
+    def barrier(self):
+        """Stream-ordered flag barrier over peer memory (one tiny kernel; no NCCL)."""
+        self.epoch += 1
+        if self.world == 1:
+            return
+        L = self._L
+        L.check(self.lib.bq_peer_barrier(self._signals, self.rank, self.world, self.epoch & 0xFFFFFFFF, self.TIMEOUT_MS,
+                                         L.stream_ptr(self.device)), "bq_peer_barrier")
+
+    def timed_out(self) -> bool:
+        """True if any barrier on this rank gave up waiting (synchronises the device)."""
+        return bool(self.buf[:self._flag_bytes].view(torch.int32)[32].item())
+
+    def close(self):
+        for key in self._bases:
+            _ipc_release(self.lib, key)
+        self._bases = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ColumnParallelLinear(nn.Module):
     """
     Column-parallel wrapper around any quantized Linear class of QUANTIZED_MODULE_MAP.
@@ -125,17 +254,19 @@ class ColumnParallelLinear(nn.Module):
     `gather_output=False` returns the local slab (for a following row-independent op).
     """
 
-    def __init__(self, local: nn.Linear, out_features: int, group=None, gather_output: bool = True):
+    def __init__(self, local: nn.Linear, out_features: int, group=None, gather_output: bool = True,
+                 arena: Optional[PeerArena] = None):
         super().__init__()
         self.local = local
         self.in_features = local.in_features
         self.out_features = out_features
         self.group = group
         self.gather_output = gather_output
+        self.arena = arena            # set -> fused all-gather (epilogue stores into the peers), else NCCL all-gather
 
     @classmethod
     def from_linear(cls, linear: nn.Linear, group=None, gather_output: bool = True, world: Optional[int] = None,
-                    rank: Optional[int] = None):
+                    rank: Optional[int] = None, arena: Optional[PeerArena] = None):
         w_, r_ = _world(group)
         world = w_ if world is None else world
         rank = r_ if rank is None else rank
@@ -157,15 +288,41 @@ class ColumnParallelLinear(nn.Module):
         if hasattr(linear, "weight_requires_quantisation"):
             local.weight_requires_quantisation = linear.weight_requires_quantisation
         local.train(linear.training)
-        return cls(local, linear.out_features, group=group, gather_output=gather_output)
+        return cls(local, linear.out_features, group=group, gather_output=gather_output, arena=arena)
+
+    def _fused_ok(self, x) -> bool:
+        loc = self.local
+        return (self.arena is not None and self.gather_output and x.is_cuda and x.dtype == torch.float32
+                and getattr(loc, "accepts_prequantized", lambda: False)() and loc.out_features % 32 == 0
+                and getattr(loc, "_fusable", lambda _x: False)(x))
+
+    @torch.no_grad()
+    def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
+        """quantize x -> GEMM whose epilogue writes this rank's slab into every rank's [M, N] buffer -> flag barrier.
+        The returned tensor lives in the arena: it stays valid until `slots - 1` further calls on the same arena."""
+        from .models.quantize.quantized_modules.linear import operand_format, quantize_operand_bf16
+
+        loc, arena = self.local, self.arena
+        kind, kw, block_size = operand_format(loc.config, "data_in")
+        xq = quantize_operand_bf16(x, kind, kw, block_size, True).reshape(-1, self.in_features)
+        m, nl = xq.shape[0], loc.out_features
+        full, bases = arena.take((m, self.out_features))
+        col0 = arena.rank * nl
+        peers = [b + col0 * 4 for r, b in enumerate(bases) if r != arena.rank]
+        loc.forward_prequantized(xq, out=full[:, col0:col0 + nl], peer_out_ptrs=peers)
+        arena.barrier()
+        return full.view(*x.shape[:-1], self.out_features)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._fused_ok(x):
+            return self._forward_fused(x)
         y = self.local(x)
         return all_gather_columns(y, self.group) if self.gather_output else y
 
     def extra_repr(self) -> str:
         world, rank = _world(self.group)
-        return f"in_features={self.in_features}, out_features={self.out_features}, shard={rank}/{world}"
+        how = "peer-store epilogue" if self.arena is not None else "nccl all-gather"
+        return f"in_features={self.in_features}, out_features={self.out_features}, shard={rank}/{world}, gather={how}"
 
 
 def column_parallelize(model: nn.Module, names: Iterable[str], group=None) -> List[str]:

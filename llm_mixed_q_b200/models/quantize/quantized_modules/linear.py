@@ -176,7 +176,8 @@ class _LinearBase(nn.Linear):
 
     @torch.no_grad()
     def forward_prequantized(self, xq: torch.Tensor, *, scale: float = 1.0, relu: bool = False, residual: torch.Tensor = None,
-                             out_format=None, out_blocks_along_rows: bool = False) -> torch.Tensor:
+                             out_format=None, out_blocks_along_rows: bool = False, out: torch.Tensor = None,
+                             peer_out_ptrs=None) -> torch.Tensor:
         """
         y = F.linear(xq, Wq, bq) for an input that ALREADY went through this module's x-quantizer inside the kernel that
         produced it (bf16 carrier of the exact quantised values), with the layer glue that follows fused into the GEMM
@@ -185,6 +186,9 @@ class _LinearBase(nn.Linear):
         out_format: None -> fp32 result; (kind, kwargs) of the x-quantizer of the NEXT op (block [1,16]) -> bf16 result
         holding its exact quantised values.  out_blocks_along_rows: the 16-blocks run over 16 consecutive rows (tokens)
         instead of 16 consecutive features (the k^T operand of bmm_0).
+        out: optional preallocated [M, N] destination (row stride >= N: e.g. this rank's column slab of a gathered
+        [M, N_total] buffer).  peer_out_ptrs: device addresses of the SAME slab in up to 7 peer-mapped buffers with the same
+        row stride — the epilogue stores every tile there too (fused all-gather of the column-parallel Linear, dist.py).
         """
         assert xq.dtype == torch.bfloat16 and xq.is_cuda and xq.shape[-1] == self.in_features
         self._ensure_ptq()
@@ -195,15 +199,22 @@ class _LinearBase(nn.Linear):
             x2 = x2.contiguous()
         M = x2.shape[0]
         out_dtype = torch.float32 if out_format is None else torch.bfloat16
-        y = torch.empty((M, N), dtype=out_dtype, device=xq.device)
+        if out is None:
+            y = torch.empty((M, N), dtype=out_dtype, device=xq.device)
+        else:
+            y = out
+            if tuple(y.shape) != (M, N) or y.dtype != out_dtype or y.device != xq.device or (N > 1 and y.stride(1) != 1):
+                raise ValueError(f"out must be a [{M}, {N}] {out_dtype} tensor with unit column stride on {xq.device}")
+        ldc = y.stride(0) if M > 1 else max(N, y.stride(0))
+        peers = list(peer_out_ptrs or [])
         if M > 0 and N > 0:
             wq = self._weight_cache()
             bias = self.bias.detach() if self.bias is not None else None
             lda = x2.stride(0) if M > 1 else K
-            plain = scale == 1.0 and not relu and residual is None and out_format is None
+            plain = scale == 1.0 and not relu and residual is None and out_format is None and not peers
             if plain:
                 rc = lib.bq_gemm_bf16_tn(x2.data_ptr(), wq.data_ptr(), y.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                         1, M, N, K, lda, K, N, 0, 0, 0, L.stream_ptr(xq.device))
+                                         1, M, N, K, lda, K, ldc, 0, 0, 0, L.stream_ptr(xq.device))
                 L.check(rc, "bq_gemm_bf16_tn")
             else:
                 ep = L.BqGemmEpilogue()
@@ -222,10 +233,15 @@ class _LinearBase(nn.Linear):
                     fmt = make_format(kind, b0=1, b1=16, **kw)
                     ep.qfmt = ctypes.pointer(fmt)
                     ep.qdir = 1 if out_blocks_along_rows else 0
-                rc = lib.bq_gemm_bf16_tn_ex(x2.data_ptr(), wq.data_ptr(), y.data_ptr(), ctypes.byref(ep), M, N, K, lda, K, N,
+                if len(peers) > 7:
+                    raise ValueError("at most 7 peer replicas (8 GPUs per NVSwitch domain)")
+                ep.n_replicas = len(peers)
+                for i, ptr in enumerate(peers):
+                    ep.replicas[i] = int(ptr)
+                rc = lib.bq_gemm_bf16_tn_ex(x2.data_ptr(), wq.data_ptr(), y.data_ptr(), ctypes.byref(ep), M, N, K, lda, K, ldc,
                                             L.stream_ptr(xq.device))
                 L.check(rc, "bq_gemm_bf16_tn_ex")
-        return y.reshape(*xq.shape[:-1], N)
+        return y if out is not None else y.reshape(*xq.shape[:-1], N)
 
     def forward(self, x):
         if self.bypass:

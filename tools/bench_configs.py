@@ -124,7 +124,7 @@ def config4(args, world, rank, dev):
 # ---------------------------------------------------------------------------------------------------
 def config5(args, world, rank, dev):
     from llm_mixed_q_b200 import _lib as L
-    from llm_mixed_q_b200.dist import ColumnParallelLinear
+    from llm_mixed_q_b200.dist import ColumnParallelLinear, PeerArena
     from llm_mixed_q_b200.models.opt_quantized import parse_opt_quantized_config
     from llm_mixed_q_b200.models.quantize import get_quantized_cls
 
@@ -135,7 +135,13 @@ def config5(args, world, rank, dev):
               ("fc1", H, F_), ("fc2", F_, H)]
     _, burst, sus, src = peaks()
     layer = args.layer
-    total_ms, total_flops, total_gemm_ms = 0.0, 0, 0.0
+    total_ms, total_flops, total_gemm_ms, total_fused_ms = 0.0, 0, 0.0, 0.0
+    arena = None
+    if not args.no_peer:
+        try:
+            arena = PeerArena(M * F_ * 4, dev)          # two slots of the largest gathered output (fc1)
+        except Exception as e:                          # e.g. IPC not permitted in this container: NCCL numbers still print
+            print(f"[rank {rank}] PeerArena unavailable: {type(e).__name__}: {e}", flush=True)
     for name, K, N in shapes:
         node = qc[f"model_layer_{layer}"]
         for part in name.split("."):
@@ -147,10 +153,18 @@ def config5(args, world, rank, dev):
         x = torch.randn(M, K, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
         cp = ColumnParallelLinear.from_linear(full)          # shards BEFORE the PTQ overwrite: blocks never cross the cut
         cp_local = ColumnParallelLinear(cp.local, N, gather_output=False)
+        cp_fused = ColumnParallelLinear(cp.local, N, arena=arena) if arena is not None else None
         with torch.no_grad():
             y_full = full(x)
             y_cp = cp(x)
-        identical = bool(torch.equal(y_full.view(torch.int32), y_cp.view(torch.int32)))
+            identical = bool(torch.equal(y_full.view(torch.int32), y_cp.view(torch.int32)))
+            fused_identical = None
+            if cp_fused is not None:
+                assert cp_fused._fused_ok(x)
+                y_f = cp_fused(x)
+                torch.cuda.synchronize()
+                fused_identical = bool(torch.equal(y_full.view(torch.int32), y_f.view(torch.int32))) and not arena.timed_out()
+                del y_f
         del y_full, y_cp
 
         def timed(fn, iters=args.steps):
@@ -168,21 +182,28 @@ def config5(args, world, rank, dev):
 
         ms = timed(lambda: cp(x))
         ms_local = timed(lambda: cp_local(x))
+        ms_fused = timed(lambda: cp_fused(x)) if cp_fused is not None else None
         flops = 2 * M * N * K
         total_ms += ms
         total_gemm_ms += ms_local
+        total_fused_ms += ms_fused or 0.0
         total_flops += flops
         emit({"metric": "column-parallel q-GEMM TFLOP/s (OPT-6.7B mixed block_fp)", "op": name, "M": M, "K": K, "N": N, "n_gpus": world,
               "x_width": node["data_in_width"], "w_width": node["weight_width"], "ms": ms, "ms_quantize_plus_gemm": ms_local,
               "ms_all_gather": ms - ms_local, "value": flops / (ms / 1e3) / 1e12, "unit": "TFLOP/s (whole job)",
               "frac_of_bf16_sustained_x_gpus": flops / (ms / 1e3) / 1e12 / (sus * world),
               "gemm_only_frac": flops / (ms_local / 1e3) / 1e12 / (sus * world), "bit_identical_to_1gpu": identical,
+              "ms_fused_peer_store": ms_fused, "fused_TFLOPs": (flops / (ms_fused / 1e3) / 1e12) if ms_fused else None,
+              "fused_bit_identical_to_1gpu": fused_identical, "fused_timed_out": arena.timed_out() if arena is not None else None,
               "all_gather_bytes_per_rank": M * (N // world) * 4 * (world - 1), "peak_source": src}, rank)
         assert identical, f"{name}: column-parallel result differs from the 1-GPU module"
-        del full, cp, cp_local, x
+        assert fused_identical in (None, True), f"{name}: fused peer-store result differs from the 1-GPU module"
+        del full, cp, cp_local, cp_fused, x
         torch.cuda.empty_cache()
     emit({"metric": "column-parallel q-GEMM TFLOP/s (OPT-6.7B mixed block_fp)", "op": "layer total (6 Linears)", "M": M, "n_gpus": world,
           "layer": layer, "ms": total_ms, "ms_quantize_plus_gemm": total_gemm_ms, "value": total_flops / (total_ms / 1e3) / 1e12,
+          "ms_fused_peer_store": total_fused_ms or None,
+          "fused_TFLOPs": (total_flops / (total_fused_ms / 1e3) / 1e12) if total_fused_ms else None,
           "unit": "TFLOP/s (whole job)", "frac_of_bf16_sustained_x_gpus": total_flops / (total_ms / 1e3) / 1e12 / (sus * world),
           "scaling": "strong", "gpu_launches": sum(L.launch_counts().values())}, rank)
 
@@ -195,6 +216,7 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers")
     ap.add_argument("--tokens", type=int, default=4096)
     ap.add_argument("--layer", type=int, default=0)
+    ap.add_argument("--no-peer", action="store_true", help="config 5: skip the fused peer-store path (NCCL all-gather only)")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
