@@ -21,6 +21,7 @@
 //                         workspace.  Correctness path, not a speed path.
 #include "bq_internal.h"
 #include "bq_numerics.cuh"
+#include "bq_blockops.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -864,12 +865,25 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
 // input_layernorm / post_attention_layernorm, models/llama_quantized/modeling_llama.py:386,:399) FOLLOWED BY the
 // x-quantizers of the Linears that read the normalised tensor (q/k/v_proj share one input, modeling_opt.py:206,224-225;
 // fc1; gate/up_proj) — one read of x, one bf16 write per distinct format, instead of an fp32 round trip per consumer.
-// One CTA per row; the row lives in registers (VPT float4 per thread); block of 16 = 4 adjacent lanes.
 // Normalisation arithmetic follows torch's CUDA kernels: LayerNorm  y = fma(gamma, rstd * (x - mean), beta)  with
 // rstd = rsqrtf(var + eps) (layer_norm_kernel.cu); RMSNorm  y = w * (x * rsqrtf(mean(x^2) + eps)).  The statistics are
 // summed in a different order than torch's Welford / reduction kernels (<= 1-2 ulp in mean / rstd), see DESIGN.md.
+//
+// Layout (v5): one ROW per CTA at a time, one BLOCK of 16 per thread (H/16 threads, rounded up to whole warps).
+//   * rows arrive by one bulk async copy (cp.async.bulk, the 1-D TMA path) into a two-slot shared-memory ring: the next row is
+//     in flight while this one is processed; several CTAs per SM cover each other's barriers;
+//   * a thread reads its 16 floats ONCE (four 16-byte accesses, chunk order rotated with the lane so that the 64-byte lane
+//     stride is conflict-free) and keeps them in registers through all three phases; gamma / beta of the thread's block are
+//     loaded once per kernel and live in registers too;
+//   * the block max is taken on the thread's own registers and the block state is computed once per block (no shuffles);
+//   * the bf16 row is assembled in shared memory and leaves by one bulk store.
+// v4 (one row per warp, three rolled passes over shared memory, block = 4 lanes) spent 34 instructions per element and kept 12
+// warps per SM (4 at H = 4096): 2.0 TB/s at H = 2048, 1.2 TB/s at H = 4096 (profiles/r01_ncu_micro_s7.json).
 // ------------------------------------------------------------------------------------------------
-constexpr int kLnWarps = 4;
+constexpr int kLnMaxThreads = 512;
+constexpr int kLnMaxWarps = kLnMaxThreads / 32;
+constexpr int kLnStages = 4;             // input ring: three rows in flight per CTA while one is processed (2 slots left the
+                                         // kernel latency-bound: 4 CTAs x 8 KB per SM in flight, 3.8 TB/s)
 struct LnArgs {
   const float* x;
   int64_t ldx;
@@ -882,173 +896,129 @@ struct LnArgs {
   __nv_bfloat16* out[3];
   FmtParams f[3];
 };
-// Persistent warps, one row per warp at a time.  The row is fetched by ONE bulk async copy (cp.async.bulk, the 1-D TMA
-// path) into the warp's shared-memory slot, double-buffered so the next row is in flight while this one is processed;
-// the three passes (sum, squared deviations, normalise + quantise + store) then read shared memory in rolled loops —
-// a few hundred instructions of code and ~40 registers, instead of a register-resident row whose fully unrolled
-// quantiser bodies overflowed the instruction cache (measured 1.7 TB/s).
 __device__ __forceinline__ void bulk_load_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "LN_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
-      "@P bra LN_DONE;\n\t"
-      "bra LN_WAIT;\n\t"
-      "LN_DONE:\n\t}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)
-      : "memory");
-}
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// normalised value of one float4 slot (torch's op order: LayerNorm fma(gamma, rstd * (x - mean), beta); RMSNorm gamma * (x * rstd))
-__device__ __forceinline__ float4 norm_slot(const float4 xv, const float4 gm, const float4 bt, bool layer_norm, float mean, float rstd) {
-  float4 y;
-  if (layer_norm) {
-    y.x = __fmaf_rn(gm.x, __fmul_rn(rstd, __fsub_rn(xv.x, mean)), bt.x);
-    y.y = __fmaf_rn(gm.y, __fmul_rn(rstd, __fsub_rn(xv.y, mean)), bt.y);
-    y.z = __fmaf_rn(gm.z, __fmul_rn(rstd, __fsub_rn(xv.z, mean)), bt.z);
-    y.w = __fmaf_rn(gm.w, __fmul_rn(rstd, __fsub_rn(xv.w, mean)), bt.w);
-  } else {
-    y.x = __fmul_rn(gm.x, __fmul_rn(xv.x, rstd));
-    y.y = __fmul_rn(gm.y, __fmul_rn(xv.y, rstd));
-    y.z = __fmul_rn(gm.z, __fmul_rn(xv.z, rstd));
-    y.w = __fmul_rn(gm.w, __fmul_rn(xv.w, rstd));
-  }
-  return y;
+__device__ __forceinline__ float cta_sum(float v, float* red, int warp, int lane, int nwarp) {
+  v = warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = red[0];
+  for (int w = 1; w < nwarp; ++w) t = __fadd_rn(t, red[w]);
+  return t;
 }
-// generic emit (any supported kind, ragged rows): one slot per lane and iteration, predicated
-template <int KIND>
-__device__ __forceinline__ void norm_emit(const float4* __restrict__ xs, const LnArgs& a, const FmtParams& p, float mean, float rstd,
-                                          __nv_bfloat16* __restrict__ outp, int nslot, int lane) {
-  const int iters = (nslot + 31) >> 5;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-  for (int i = 0; i < iters; ++i) {
-    const int s = i * 32 + lane;
-    const bool act = s < nslot;
-    float4 y = z;
-    if (act) y = norm_slot(xs[s], *reinterpret_cast<const float4*>(a.gamma + 4 * s),
-                           a.beta ? *reinterpret_cast<const float4*>(a.beta + 4 * s) : z, a.beta != nullptr, mean, rstd);
-    // block max over the 4 adjacent lanes that hold one block of 16 (H % 16 == 0: a block is all-active or all-inactive)
-    uint32_t m = max(max(absbits(y.x), absbits(y.y)), max(absbits(y.z), absbits(y.w)));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    if (m == 0) m = 0x3f800000u;
-    if (act) store4<__nv_bfloat16>(outp + 4 * s, quant4<KIND>(y, m, p));
-  }
-}
-// block_fp emit for rows whose slot count is a multiple of 32: no predicates, scalars in registers, magic-constant
-// rounding, exponent straight from the max's exponent field; the rare blocks that need the literal arithmetic (cliff zone,
-// non-finite, extreme exponents) go through the generic quant4.
-__device__ __forceinline__ float bfp_fast1(float x, float f0, float c0, float hi, float f1, float c1) {
-  const float ax = fabsf(x);
-  const float t = __fmaf_rn(ax, f0, c0);                          // == (|x| + 1e-9f) * 2^(m-E)   (power-of-two scaling commutes with rounding)
-  const float tm = fminf(__fadd_rn(t, kRintMagic), hi);           // kRintMagic + min(rint(t), qmax)
-  const float y = copysignf(__fmaf_rn(tm, f1, c1), x);            // (tm - kRintMagic) * 2^(E-m), exact
-  return (ax <= 1e-8f) ? x : y;
-}
-__device__ __forceinline__ void norm_emit_bfp32(const float4* __restrict__ xs, const LnArgs& a, const FmtParams& p, float mean, float rstd,
-                                                __nv_bfloat16* __restrict__ outp, int nslot, int lane) {
-  const int iters = nslot >> 5;
-  const bool ln = a.beta != nullptr;
-  const int emin = (int)p.emin, emax = (int)p.emax, mb = p.mbits;
-  const float hi = __fadd_rn(kRintMagic, p.qmax);
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-  for (int i = 0; i < iters; ++i) {
-    const int s = i * 32 + lane;
-    const float4 y = norm_slot(xs[s], __ldg(reinterpret_cast<const float4*>(a.gamma) + s),
-                               ln ? __ldg(reinterpret_cast<const float4*>(a.beta) + s) : z, ln, mean, rstd);
-    uint32_t m = max(max(absbits(y.x), absbits(y.y)), max(absbits(y.z), absbits(y.w)));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    if (m == 0) m = 0x3f800000u;
-    const uint32_t ex = m >> 23, f = m & 0x7fffffu;
-    int E = min(max((int)ex - 126, emin), emax);                  // ceil(log2(max)) away from the cliff zone
-    const bool fast = (ex - 1u < 254u) && (((f + kZone) & 0x7fffffu) >= 2 * kZone) && E >= -100 && E <= 100 && p.fast_fmt;
-    float4 q;
-    if (fast) {
-      const float f0 = pow2_i(mb - E), f1 = pow2_i(E - mb);
-      const float c0 = __fmul_rn(1e-9f, f0), c1 = -__fmul_rn(kRintMagic, f1);
-      q.x = bfp_fast1(y.x, f0, c0, hi, f1, c1);
-      q.y = bfp_fast1(y.y, f0, c0, hi, f1, c1);
-      q.z = bfp_fast1(y.z, f0, c0, hi, f1, c1);
-      q.w = bfp_fast1(y.w, f0, c0, hi, f1, c1);
-    } else {
-      q = quant4<kBlockFP>(y, m, p);
-    }
-    store4<__nv_bfloat16>(outp + 4 * s, q);
-  }
-}
-__global__ void __launch_bounds__(kLnWarps * 32) norm_quant_kernel(LnArgs a) {
+__global__ void __launch_bounds__(kLnMaxThreads) norm_quant_kernel(LnArgs a) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t row_bytes = (uint32_t)a.H * 4u;
-  uint8_t* mybuf = ln_smem + (size_t)warp * 2 * row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)kLnWarps * 2 * row_bytes) + warp * 2;
-  const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(mybuf);
-  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  const uint32_t row_bytes = (uint32_t)a.H * 4u, out_bytes = (uint32_t)a.H * 2u;
+  const uint32_t in0 = (uint32_t)__cvta_generic_to_shared(ln_smem);
+  const uint32_t outb = in0 + (uint32_t)kLnStages * row_bytes;
+  float* red = reinterpret_cast<float*>(ln_smem + (size_t)kLnStages * row_bytes + out_bytes);      // [2][kLnMaxWarps]
+  const uint32_t bar0 = outb + out_bytes + 2u * kLnMaxWarps * 4u;
+  const int stride = gridDim.x;
+  int row = blockIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < kLnStages; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * k));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const int nw = gridDim.x * kLnWarps;
-  int row = blockIdx.x * kLnWarps + warp;
-  if (row < a.rows && lane == 0) bulk_load_row(buf0, a.x + (int64_t)row * a.ldx, row_bytes, bar0);
-  const int nslot = a.H >> 2;
-  const float invH = 1.0f / (float)a.H;
-  for (int it = 0; row < a.rows; row += nw, ++it) {
-    const int b = it & 1;
-    const int next = row + nw;
-    if (next < a.rows && lane == 0)
-      bulk_load_row(buf0 + (b ^ 1) * row_bytes, a.x + (int64_t)next * a.ldx, row_bytes, bar0 + 8 * (b ^ 1));
-    mbar_wait_parity(bar0 + 8 * b, (it >> 1) & 1);
-    const float4* xs = reinterpret_cast<const float4*>(mybuf + (size_t)b * row_bytes);
-    float mean = 0.f, rstd;
-    if (a.beta) {
-      float s0 = 0.f, s1 = 0.f;
-      for (int s = lane; s < nslot; s += 64) {
-        const float4 v = xs[s];
-        s0 = __fadd_rn(s0, __fadd_rn(__fadd_rn(v.x, v.y), __fadd_rn(v.z, v.w)));
-        if (s + 32 < nslot) {
-          const float4 w = xs[s + 32];
-          s1 = __fadd_rn(s1, __fadd_rn(__fadd_rn(w.x, w.y), __fadd_rn(w.z, w.w)));
-        }
-      }
-      mean = __fmul_rn(warp_sum(__fadd_rn(s0, s1)), invH);
+#pragma unroll
+    for (int k = 0; k < kLnStages - 1; ++k) {
+      const int64_t r = (int64_t)row + (int64_t)k * stride;
+      if (r < a.rows) bulk_load_row(in0 + (uint32_t)k * row_bytes, a.x + r * a.ldx, row_bytes, bar0 + 8u * k);
     }
+  }
+  __syncthreads();
+  const bool act = tid * 16 < a.H;                       // H % 16 == 0: a thread's block is whole or absent
+  const bool ln = a.beta != nullptr;
+  // chunk c of the thread's registers holds logical chunk (c + rot) & 3 of its block: conflict-free for the 16-byte loads at a
+  // 64-byte lane stride (quarter-warps) AND for the 8-byte packed stores at a 32-byte lane stride (half-warps)
+  const uint32_t rot = (uint32_t)((lane >> 1) + (lane >> 3)) & 3u;
+  float g[16], bt[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int off = tid * 16 + (int)(((uint32_t)c + rot) & 3u) * 4;
+    const float4 gv = act ? __ldg(reinterpret_cast<const float4*>(a.gamma + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bv = (act && ln) ? __ldg(reinterpret_cast<const float4*>(a.beta + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    g[4 * c] = gv.x; g[4 * c + 1] = gv.y; g[4 * c + 2] = gv.z; g[4 * c + 3] = gv.w;
+    bt[4 * c] = bv.x; bt[4 * c + 1] = bv.y; bt[4 * c + 2] = bv.z; bt[4 * c + 3] = bv.w;
+  }
+  const float invH = 1.0f / (float)a.H;
+  int b = 0;
+  uint32_t parity = 0;
+  for (; row < a.rows; row += stride) {
+    // the slot refilled here held the previous iteration's row: every thread copied it to registers before that iteration's barriers
+    const int64_t next = (int64_t)row + (int64_t)(kLnStages - 1) * stride;
+    if (tid == 0 && next < a.rows) {
+      const uint32_t nb = (uint32_t)(b == 0 ? kLnStages - 1 : b - 1);
+      bulk_load_row(in0 + nb * row_bytes, a.x + next * a.ldx, row_bytes, bar0 + 8u * nb);
+    }
+    st_mbar_wait(bar0 + 8u * b, parity);
+    float v[16];
     {
-      // sum of squared deviations (RMSNorm: mean = 0), fused multiply-adds in four independent chains
-      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-      for (int s = lane; s < nslot; s += 32) {
-        const float4 v = xs[s];
-        const float dx = __fsub_rn(v.x, mean), dy = __fsub_rn(v.y, mean), dz = __fsub_rn(v.z, mean), dw = __fsub_rn(v.w, mean);
-        q0 = __fmaf_rn(dx, dx, q0); q1 = __fmaf_rn(dy, dy, q1); q2 = __fmaf_rn(dz, dz, q2); q3 = __fmaf_rn(dw, dw, q3);
+      const uint32_t base = in0 + (uint32_t)b * row_bytes + (uint32_t)tid * 64u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 t = act ? lds128(base + (((uint32_t)c + rot) & 3u) * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
       }
-      rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3))), invH), a.eps));
+    }
+    // the previous row's bulk store must have finished READING the output slot before anyone rewrites it (after the next barrier)
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (ln) {
+      float s[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] = __fadd_rn(__fadd_rn(v[4 * c], v[4 * c + 1]), __fadd_rn(v[4 * c + 2], v[4 * c + 3]));
+      const float mean = __fmul_rn(cta_sum(__fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3])), red, warp, lane, nwarp), invH);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __fsub_rn(v[i], mean);
+    }
+    float rstd;
+    {
+      float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) q[i & 3] = __fmaf_rn(v[i], v[i], q[i & 3]);
+      const float qs = act ? __fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3])) : 0.f;
+      rstd = rsqrtf(__fadd_rn(__fmul_rn(cta_sum(qs, red + kLnMaxWarps, warp, lane, nwarp), invH), a.eps));
     }
 #pragma unroll 1
     for (int k = 0; k < a.n_out; ++k) {
       const FmtParams& p = (k == 0) ? a.f[0] : ((k == 1) ? a.f[1] : a.f[2]);
       __nv_bfloat16* outp = ((k == 0) ? a.out[0] : ((k == 1) ? a.out[1] : a.out[2])) + (int64_t)row * a.H;
-      if (p.kind == kBlockFP) {
-        if ((nslot & 31) == 0) norm_emit_bfp32(xs, a, p, mean, rstd, outp, nslot, lane);
-        else norm_emit<kBlockFP>(xs, a, p, mean, rstd, outp, nslot, lane);
-      } else {
-        norm_emit<kBlockMinifloat>(xs, a, p, mean, rstd, outp, nslot, lane);
+      if (k > 0) {
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
       }
+      if (act) {
+        float y[16];
+        if (ln) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = __fmaf_rn(g[i], __fmul_rn(rstd, v[i]), bt[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = __fmul_rn(g[i], __fmul_rn(v[i], rstd));
+        }
+        quantize_signed16_rt(y, p);
+        const uint32_t base = outb + (uint32_t)tid * 32u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(base + (((uint32_t)c + rot) & 3u) * 8u),
+                       "r"(pack_bf16x2(y[4 * c], y[4 * c + 1])), "r"(pack_bf16x2(y[4 * c + 2], y[4 * c + 3]))
+                       : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) st_bulk_store(outp, outb, out_bytes);
     }
-    __syncwarp();            // every lane is done with buffer b before lane 0 re-arms it two iterations later
+    if (++b == kLnStages) { b = 0; parity ^= 1u; }
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, const float* gamma, const float* beta, float eps,
@@ -1056,13 +1026,13 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
   if (rows < 0 || H <= 0 || n_out < 1 || n_out > 3 || !fmts || !outs) return BQ_ERR_BAD_ARG;
   if (rows == 0) return BQ_OK;
   if (!x || !gamma) return BQ_ERR_BAD_ARG;
-  if ((H % 16) || H > 6144 || rows > 0x7fffffff) return BQ_ERR_UNSUPPORTED;      // 4 warps x 2 buffers x H x 4 B of shared memory
+  if ((H % 16) || H > 16 * kLnMaxThreads || rows > 0x7fffffff) return BQ_ERR_UNSUPPORTED;      // one block of 16 per thread
   if (((uintptr_t)x % 16) || (ldx % 4) || ldx < H || ((uintptr_t)gamma % 16) || (beta && ((uintptr_t)beta % 16))) return BQ_ERR_BAD_ARG;
   LnArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x; a.ldx = ldx; a.gamma = gamma; a.beta = beta; a.eps = eps; a.H = (int)H; a.n_out = n_out;
   for (int k = 0; k < n_out; ++k) {
-    if (!outs[k] || ((uintptr_t)outs[k] % 8)) return BQ_ERR_BAD_ARG;
+    if (!outs[k] || ((uintptr_t)outs[k] % 16)) return BQ_ERR_BAD_ARG;
     if (fmts[k].kind != BQ_KIND_BLOCK_FP && fmts[k].kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
     if (fmts[k].block_rows != 1 || fmts[k].block_cols != 16) return BQ_ERR_UNSUPPORTED;
     int rc = make_params(&fmts[k], &a.f[k]);
@@ -1071,7 +1041,8 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
     a.out[k] = (__nv_bfloat16*)outs[k];
   }
   a.rows = (int)rows;
-  const size_t smem = (size_t)kLnWarps * 2 * H * 4 + kLnWarps * 2 * 8;
+  const int threads = (int)((H / 16 + 31) / 32) * 32;
+  const size_t smem = (size_t)kLnStages * H * 4 + (size_t)H * 2 + 2 * kLnMaxWarps * 4 + kLnStages * 8;
   static size_t smem_attr = 0;
   if (smem > smem_attr) {
     BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1080,20 +1051,20 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
   static int occ_cache_h = 0, occ_cache = 0;
   if (occ_cache_h != (int)H) {
     int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_kernel, kLnWarps * 32, smem) != cudaSuccess || o < 1) o = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_kernel, threads, smem) != cudaSuccess || o < 1) o = 1;
     occ_cache = o;
     occ_cache_h = (int)H;
   }
-  const int64_t want = (rows + kLnWarps - 1) / kLnWarps;
-  const int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * occ_cache);
+  const int grid = (int)std::min<int64_t>(rows, (int64_t)num_sms() * occ_cache);
   {
     LaunchScope ls(kKernLnQuant, st);
-    norm_quant_kernel<<<grid, kLnWarps * 32, smem, st>>>(a);
+    norm_quant_kernel<<<grid, threads, smem, st>>>(a);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // fp32 -> two fp16 planes per row with a per-row power-of-two scale:  x * 2^e = hi + lo (+- 2^-22 of the row max),
 // hi = fp16(x * 2^e), lo = fp16(x * 2^e - hi), e chosen so that the row max lands in [2^14, 2^15).

@@ -1,7 +1,7 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list into per-kernel shares of ONE steady-state step.
 
 usage: python tools/summarize_launches.py gpurun_out/launches.csv [out.json]
-A step is delimited by the loss kernel (nll_loss_forward) that ends every forward; the last complete step is used
+A step is delimited by the loss kernel (bq::ce_mean_kernel, or torch's nll_loss_forward) that ends every forward; the last complete step is used
 (step 1 holds the one-off PTQ weight quantisation and is never chosen when a later one exists).
 ncu's per-launch times are cold-cache and serialised: compare SHARES with bench.py's event-timed shares, not absolutes."""
 import csv
@@ -34,7 +34,7 @@ def main():
         unit = r["Metric Unit"]
         us = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
         rows.append((int(r["ID"]), r["Kernel Name"], us, r["Grid Size"], r["Block Size"]))
-    ends = [i for i, r in enumerate(rows) if "nll_loss_forward_reduce" in r[1]]
+    ends = [i for i, r in enumerate(rows) if "nll_loss_forward_reduce" in r[1] or "ce_mean_kernel" in r[1]]
     if len(ends) >= 2:
         lo, hi = ends[-2] + 1, ends[-1] + 1
         which = f"launches {rows[lo][0]}..{rows[hi - 1][0]} (step {len(ends)} of {len(ends)} seen)"
