@@ -53,6 +53,23 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def gemm_traffic_from_profile():
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, averaged over the six
+    quantized-Linear launches of one OPT-1.3B layer in the committed `ncu --set full` capture (tools/ncu_layer.py, same shapes
+    as this bench).  Returns (bytes_per_launch or None, source)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_layer_s9.json")
+    try:
+        d = json.load(open(path))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ur, uw = scale[d["units"]["dram__bytes_read.sum"]], scale[d["units"]["dram__bytes_write.sum"]]
+        rows = [l for l in d["launches"] if "gemm_bf16_tn_kernel<256, 1, 2>" in l["kernel"]]
+        if not rows:
+            return None, None
+        return sum(l["dram__bytes_read.sum"] * ur + l["dram__bytes_write.sum"] * uw for l in rows) / len(rows), os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------------
@@ -326,10 +343,16 @@ def main():
     gemm_flops = flops_linear + (0 if attn_n else flops_bmm)
     flops_head = 2 * T * H * OPT13B["vocab_size"]
     achieved = gemm_flops * K / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic, traffic_src = gemm_traffic_from_profile()
+    # minimum operand traffic of the six Linears of a layer, per launch: bf16 A + bf16 B + the output each epilogue writes
+    # (q/k/v/fc1: bf16 quantised operand of the next op; out_proj/fc2: fp32 residual stream in and out)
+    alg_bytes = (4 * (T * H * 2 + H * H * 2) + (T * H * 2 + H * F_ * 2) + (T * F_ * 2 + H * F_ * 2)      # A + B
+                 + 3 * T * H * 2 + T * F_ * 2 + 2 * (2 * T * H * 4)) / 6                                   # C (+ residual read)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (plain + fused-epilogue instances; the six quantized Linears per layer)",
                 "achieved": achieved, "peak": pk["tf_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "peak_source": pk["source"] + ", sustained bf16",
-                "traffic": None, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu --set full)", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "share_of_step": gemm_ms / step_ms_local, "algorithmic_flops_per_step": gemm_flops,
                 "other_kernels": {
                     "attention_causal_kernel": {"share_of_step": attn_ms / step_ms_local, "launches": attn_n,

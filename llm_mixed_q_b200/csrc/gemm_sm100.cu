@@ -67,6 +67,7 @@ struct GemmArgs {
   int M, N, K, batch;
   int64_t ldc, sc;
   int tiles_m, tiles_n;
+  int band_m;        // > 0: tiles are walked M-fastest inside bands of band_m row blocks (B too large to stay in L2), else N-fastest
   int b_broadcast;   // B has no batch dim (weights)
   // split-precision mode (n_terms > 0, batch == 1): A and B are stacks of bf16 planes [planes][rows][K]; the K loop runs
   // over the (plane_a, plane_b) pairs below and accumulates every product into the same TMEM accumulator
@@ -251,8 +252,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto decode = [&](int tile, int& b, int& row0, int& nb) {
     b = tile / tiles_per_batch;
     const int t = tile - b * tiles_per_batch;
-    const int mb = t / g.tiles_n;                              // n fastest: the workers of a wave share A rows through L2
-    nb = t - mb * g.tiles_n;
+    int mb;
+    if (g.band_m > 0) {
+      // banded raster for a B operand that cannot stay in L2 (lm_head: 412 MB of planes): a band's A rows (<= 32 MB) stay in L2
+      // while the N blocks stream past once per band; the ~74 tiles in flight share 16 A blocks and ~5 B blocks
+      const int per_band = g.band_m * g.tiles_n;
+      const int band = t / per_band, r = t - band * per_band, m0 = band * g.band_m;
+      const int bm = min(g.band_m, g.tiles_m - m0);
+      nb = r / bm;
+      mb = m0 + (r - nb * bm);
+    } else {
+      mb = t / g.tiles_n;                                      // n fastest: the workers of a wave share A rows through L2
+      nb = t - mb * g.tiles_n;
+    }
     row0 = (mb * CG + rank) * kBM;
   };
 
@@ -495,6 +507,15 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmAr
   g.tiles_n = (g.N + BN - 1) / BN;
   int64_t total = (int64_t)g.tiles_m * g.tiles_n * g.batch;
   if (total > 0x7fffffffll) return BQ_ERR_UNSUPPORTED;
+  g.band_m = 0;
+  if (g.batch == 1) {
+    int pa = 1, pb = 1;
+    for (int t = 0; t < g.n_terms; ++t) { pa = std::max(pa, g.term_a[t] + 1); pb = std::max(pb, g.term_b[t] + 1); }
+    const int64_t bytes_b = (int64_t)g.N * g.K * 2 * pb;
+    const int64_t bytes_a_block = (int64_t)kBM * CG * g.K * 2 * pa;
+    if (bytes_b > (40ll << 20) && g.tiles_m > 1)
+      g.band_m = (int)std::min<int64_t>(g.tiles_m, std::max<int64_t>(1, (32ll << 20) / bytes_a_block));
+  }
   const int grid = CG * (int)std::min<int64_t>(total, num_sms() / CG);
   {
     LaunchScope ls(kern_id, st);

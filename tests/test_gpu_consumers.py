@@ -38,7 +38,8 @@ def test_gemm_kernel_vs_fp64():
     lib = L.load()
     g = torch.Generator(device="cuda").manual_seed(0)
     for (b, M, N, K) in [(1, 128, 256, 64), (1, 4096, 4096, 4096), (1, 1000, 520, 328), (3, 200, 136, 64), (4, 512, 64, 512),
-                         (2, 300, 100, 1000), (1, 1, 8, 8), (1, 129, 257, 72), (5, 2048, 2048, 64), (2, 2048, 64, 2048)]:
+                         (2, 300, 100, 1000), (1, 1, 8, 8), (1, 129, 257, 72), (5, 2048, 2048, 64), (2, 2048, 64, 2048),
+                         (1, 4864, 5200, 4096)]:       # last: B > 40 MB -> banded raster, bands of 16 + 3 row blocks, ragged N
         A = torch.randn(b, M, K, device="cuda", generator=g).to(torch.bfloat16)
         B = torch.randn(b, N, K, device="cuda", generator=g).to(torch.bfloat16)
         bias = torch.randn(N, device="cuda", generator=g)
