@@ -170,6 +170,37 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     if (e.q.kind == kBlockFP) quant_rowblocks32<kBlockFP>(v, e.q, scratch, lane);
     else quant_rowblocks32<kBlockMinifloat>(v, e.q, scratch, lane);
   }
+  if (e.n_rep > 0 && !e.out_bf16) {                                // warp-uniform
+    // fused all-gather (fp32): peers' copies are written over NVLink, where a lane-per-row store pattern (32 rows x 16 bytes
+    // per instruction) moves 16-byte packets — measured 163 GB/s at 2 GPUs.  Transpose the 32x32 chunk through the warp's
+    // scratch so that every store instruction covers four full 128-byte row segments.
+    float* sc = reinterpret_cast<float*>(scratch);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = v[j];
+    __syncwarp();
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4, wrow0 = row - lane;
+    float4 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* s4 = sc + (i * 4 + rsub) * 33 + c4;
+      o[i] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+    }
+    __syncwarp();                                                  // scratch is reused by the next chunk
+#pragma unroll 1
+    for (int p = 0; p < e.n_rep; ++p) {
+      float* cp = reinterpret_cast<float*>(e.rep[p]) + col0 + c4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = wrow0 + i * 4 + rsub;
+        if (rr < g.M) *reinterpret_cast<float4*>(cp + (int64_t)rr * g.ldc) = o[i];
+      }
+    }
+    if (!row_ok) return;
+    float* c = g.C + (int64_t)row * g.ldc + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    return;
+  }
   if (!row_ok) return;
   const int64_t off = (int64_t)row * g.ldc + col0;
   if (e.out_bf16) {
@@ -191,12 +222,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     float* c = g.C + off;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-#pragma unroll 1
-    for (int p = 0; p < e.n_rep; ++p) {
-      float* cp = reinterpret_cast<float*>(e.rep[p]) + off;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
   }
 }
 

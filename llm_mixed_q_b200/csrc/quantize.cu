@@ -882,8 +882,7 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnMaxThreads = 512;
 constexpr int kLnMaxWarps = kLnMaxThreads / 32;
-constexpr int kLnStages = 4;             // input ring: three rows in flight per CTA while one is processed (2 slots left the
-                                         // kernel latency-bound: 4 CTAs x 8 KB per SM in flight, 3.8 TB/s)
+constexpr int kLnMaxStages = 4;          // input ring of 2..4 row slots (LnArgs::stages): the host takes the depth that keeps the most CTAs resident
 struct LnArgs {
   const float* x;
   int64_t ldx;
@@ -893,6 +892,7 @@ struct LnArgs {
   int H;
   int rows;
   int n_out;
+  int stages;
   __nv_bfloat16* out[3];
   FmtParams f[3];
 };
@@ -914,22 +914,23 @@ __device__ __forceinline__ float cta_sum(float v, float* red, int warp, int lane
   for (int w = 1; w < nwarp; ++w) t = __fadd_rn(t, red[w]);
   return t;
 }
-__global__ void __launch_bounds__(kLnMaxThreads) norm_quant_kernel(LnArgs a) {
+__global__ void __maxnreg__(80) norm_quant_kernel(LnArgs a) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
   const uint32_t row_bytes = (uint32_t)a.H * 4u, out_bytes = (uint32_t)a.H * 2u;
   const uint32_t in0 = (uint32_t)__cvta_generic_to_shared(ln_smem);
-  const uint32_t outb = in0 + (uint32_t)kLnStages * row_bytes;
-  float* red = reinterpret_cast<float*>(ln_smem + (size_t)kLnStages * row_bytes + out_bytes);      // [2][kLnMaxWarps]
+  const int stages = a.stages;
+  const uint32_t outb = in0 + (uint32_t)stages * row_bytes;
+  float* red = reinterpret_cast<float*>(ln_smem + (size_t)stages * row_bytes + out_bytes);      // [2][kLnMaxWarps]
   const uint32_t bar0 = outb + out_bytes + 2u * kLnMaxWarps * 4u;
+  const uint32_t gam0 = bar0 + 8u * kLnMaxStages;         // 16-byte aligned: gamma [H], then beta [H]
   const int stride = gridDim.x;
   int row = blockIdx.x;
   if (tid == 0) {
 #pragma unroll
-    for (int k = 0; k < kLnStages; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * k));
+    for (int k = 0; k < kLnMaxStages; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * k));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < kLnStages - 1; ++k) {
+    for (int k = 0; k < stages - 1; ++k) {
       const int64_t r = (int64_t)row + (int64_t)k * stride;
       if (r < a.rows) bulk_load_row(in0 + (uint32_t)k * row_bytes, a.x + r * a.ldx, row_bytes, bar0 + 8u * k);
     }
@@ -940,23 +941,25 @@ __global__ void __launch_bounds__(kLnMaxThreads) norm_quant_kernel(LnArgs a) {
   // chunk c of the thread's registers holds logical chunk (c + rot) & 3 of its block: conflict-free for the 16-byte loads at a
   // 64-byte lane stride (quarter-warps) AND for the 8-byte packed stores at a 32-byte lane stride (half-warps)
   const uint32_t rot = (uint32_t)((lane >> 1) + (lane >> 3)) & 3u;
-  float g[16], bt[16];
+  // gamma / beta of the thread's block are parked in shared memory (same rotated chunk order; written and read by the same
+  // thread, so no barrier) — holding them in registers cost 32 registers and a CTA of occupancy
+  const uint32_t myg = gam0 + (uint32_t)tid * 64u, myb = myg + row_bytes;
+  if (act) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int off = tid * 16 + (int)(((uint32_t)c + rot) & 3u) * 4;
-    const float4 gv = act ? __ldg(reinterpret_cast<const float4*>(a.gamma + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 bv = (act && ln) ? __ldg(reinterpret_cast<const float4*>(a.beta + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    g[4 * c] = gv.x; g[4 * c + 1] = gv.y; g[4 * c + 2] = gv.z; g[4 * c + 3] = gv.w;
-    bt[4 * c] = bv.x; bt[4 * c + 1] = bv.y; bt[4 * c + 2] = bv.z; bt[4 * c + 3] = bv.w;
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t cl = ((uint32_t)c + rot) & 3u;
+      sts128(myg + cl * 16u, __ldg(reinterpret_cast<const float4*>(a.gamma + tid * 16 + (int)cl * 4)));
+      if (ln) sts128(myb + cl * 16u, __ldg(reinterpret_cast<const float4*>(a.beta + tid * 16 + (int)cl * 4)));
+    }
   }
   const float invH = 1.0f / (float)a.H;
   int b = 0;
   uint32_t parity = 0;
   for (; row < a.rows; row += stride) {
     // the slot refilled here held the previous iteration's row: every thread copied it to registers before that iteration's barriers
-    const int64_t next = (int64_t)row + (int64_t)(kLnStages - 1) * stride;
+    const int64_t next = (int64_t)row + (int64_t)(stages - 1) * stride;
     if (tid == 0 && next < a.rows) {
-      const uint32_t nb = (uint32_t)(b == 0 ? kLnStages - 1 : b - 1);
+      const uint32_t nb = (uint32_t)(b == 0 ? stages - 1 : b - 1);
       bulk_load_row(in0 + nb * row_bytes, a.x + next * a.ldx, row_bytes, bar0 + 8u * nb);
     }
     st_mbar_wait(bar0 + 8u * b, parity);
@@ -997,12 +1000,22 @@ __global__ void __launch_bounds__(kLnMaxThreads) norm_quant_kernel(LnArgs a) {
       }
       if (act) {
         float y[16];
-        if (ln) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = __fmaf_rn(g[i], __fmul_rn(rstd, v[i]), bt[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = __fmul_rn(g[i], __fmul_rn(v[i], rstd));
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t cl = ((uint32_t)c + rot) & 3u;
+          const float4 gv = lds128(myg + cl * 16u);
+          if (ln) {
+            const float4 bv = lds128(myb + cl * 16u);
+            y[4 * c] = __fmaf_rn(gv.x, __fmul_rn(rstd, v[4 * c]), bv.x);
+            y[4 * c + 1] = __fmaf_rn(gv.y, __fmul_rn(rstd, v[4 * c + 1]), bv.y);
+            y[4 * c + 2] = __fmaf_rn(gv.z, __fmul_rn(rstd, v[4 * c + 2]), bv.z);
+            y[4 * c + 3] = __fmaf_rn(gv.w, __fmul_rn(rstd, v[4 * c + 3]), bv.w);
+          } else {
+            y[4 * c] = __fmul_rn(gv.x, __fmul_rn(v[4 * c], rstd));
+            y[4 * c + 1] = __fmul_rn(gv.y, __fmul_rn(v[4 * c + 1], rstd));
+            y[4 * c + 2] = __fmul_rn(gv.z, __fmul_rn(v[4 * c + 2], rstd));
+            y[4 * c + 3] = __fmul_rn(gv.w, __fmul_rn(v[4 * c + 3], rstd));
+          }
         }
         quantize_signed16_rt(y, p);
         const uint32_t base = outb + (uint32_t)tid * 32u;
@@ -1016,7 +1029,7 @@ __global__ void __launch_bounds__(kLnMaxThreads) norm_quant_kernel(LnArgs a) {
       __syncthreads();
       if (tid == 0) st_bulk_store(outp, outb, out_bytes);
     }
-    if (++b == kLnStages) { b = 0; parity ^= 1u; }
+    if (++b == stages) { b = 0; parity ^= 1u; }
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -1042,19 +1055,27 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
   }
   a.rows = (int)rows;
   const int threads = (int)((H / 16 + 31) / 32) * 32;
-  const size_t smem = (size_t)kLnStages * H * 4 + (size_t)H * 2 + 2 * kLnMaxWarps * 4 + kLnStages * 8;
+  auto smem_for = [&](int stages) { return (size_t)stages * H * 4 + (size_t)H * 2 + 2 * kLnMaxWarps * 4 + kLnMaxStages * 8 + (size_t)2 * H * 4; };
   static size_t smem_attr = 0;
-  if (smem > smem_attr) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
+  if (smem_for(kLnMaxStages) > smem_attr) {
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(kLnMaxStages)));
+    smem_attr = smem_for(kLnMaxStages);
   }
-  static int occ_cache_h = 0, occ_cache = 0;
+  // ring depth: the deepest of 4 / 3 / 2 slots that does not cost a resident CTA
+  static int occ_cache_h = 0, occ_cache = 0, stages_cache = 2;
   if (occ_cache_h != (int)H) {
-    int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_kernel, threads, smem) != cudaSuccess || o < 1) o = 1;
-    occ_cache = o;
+    int best = 0, best_s = 2;
+    for (int s = kLnMaxStages; s >= 2; --s) {
+      int o = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_kernel, threads, smem_for(s)) != cudaSuccess) o = 0;
+      if (o > best) { best = o; best_s = s; }
+    }
+    occ_cache = std::max(best, 1);
+    stages_cache = best_s;
     occ_cache_h = (int)H;
   }
+  a.stages = stages_cache;
+  const size_t smem = smem_for(a.stages);
   const int grid = (int)std::min<int64_t>(rows, (int64_t)num_sms() * occ_cache);
   {
     LaunchScope ls(kKernLnQuant, st);
