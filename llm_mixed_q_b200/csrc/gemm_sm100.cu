@@ -81,8 +81,12 @@ struct GemmArgs {
 
 // Blocks of 16 consecutive ROWS (qmode 2): the 32x32 chunk of |v| bit patterns is transposed through shared memory so that
 // lane c reduces column c (two blocks: rows 0-15, 16-31) and evaluates the per-block state ONCE; the states are then
-// broadcast-read by the row-owning lanes.  (The first version reduced with 4 shuffles per element and re-derived the
-// block state in all 16 lanes of a block: 45 instructions per element, epilogue-bound at 238 TFLOP/s.)
+// broadcast-read by the row-owning lanes.  Common case (every block of the chunk on the fast path, one warp vote): a straight-line
+// loop — 32 independent state loads and element chains, no per-element branch.  (v1 reduced with 4 shuffles per element and
+// re-derived the state in all 16 lanes: 238 TFLOP/s; v2 tested a per-element state flag, which serialised the 32 elements behind
+// 32 dependent load -> branch -> math chains: k_proj 152 us against 97 us for q_proj, ncu.)
+template <int KIND>
+__device__ __noinline__ float quant_with_max_cold(float x, uint32_t mbits, FmtParams p) { return quant_with_max<KIND>(x, mbits, p); }
 template <int KIND>
 __device__ __forceinline__ void quant_rowblocks32(float (&v)[32], const FmtParams& q, uint32_t* tb, int lane) {
   uint4* st = reinterpret_cast<uint4*>(tb + 32 * 33);
@@ -95,32 +99,66 @@ __device__ __forceinline__ void quant_rowblocks32(float (&v)[32], const FmtParam
     m0 = max(m0, tb[r * 33 + lane]);
     m1 = max(m1, tb[(r + 16) * 33 + lane]);
   }
+  uint4 sf[2], ss[2];
+  bool fast = true;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const uint32_t m = h ? m1 : m0;
-    uint4 s = make_uint4(0u, 0u, m, 2u);                       // w: 2 = all-zero block, 1 = fast path, 0 = literal path
-    if (m != 0) {
-      const FastState fs = fast_state<KIND>(m, q);
-      s.w = fs.ok ? 1u : 0u;
-      if (KIND == kBlockFP) { s.x = __float_as_uint(fs.f0); s.y = __float_as_uint(fs.f1); }
-      else { s.x = (uint32_t)fs.i0; s.y = (uint32_t)fs.i1; }
-    }
-    st[h * 32 + lane] = s;
+    const uint32_t mraw = h ? m1 : m0;
+    const uint32_t m = mraw ? mraw : 0x3f800000u;                // all-zero block: every element is +-0 and passes through as +0
+    const FastState fs = fast_state<KIND>(m, q);
+    fast = fast && fs.ok;
+    if (KIND == kBlockFP) sf[h] = make_uint4(__float_as_uint(fs.f0), __float_as_uint(fs.f1), __float_as_uint(fs.c0), __float_as_uint(fs.c1));
+    else sf[h] = make_uint4((uint32_t)fs.i0, (uint32_t)fs.i1, (uint32_t)fs.i2, 0u);
+    ss[h] = make_uint4(m, mraw ? 0u : 2u, 0u, 0u);
   }
-  __syncwarp();
+  const bool all_fast = __all_sync(0xffffffffu, fast);
   const int half = lane >> 4;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const uint4 s = st[half * 32 + j];
+  if (all_fast) {
+    st[lane] = sf[0];
+    st[32 + lane] = sf[1];
+    __syncwarp();
     FastState fs;
     fs.ok = true;
-    fs.f0 = __uint_as_float(s.x); fs.f1 = __uint_as_float(s.y);
-    fs.i0 = (int)s.x; fs.i1 = (int)s.y;
-    fs.c0 = __fmul_rn(1e-9f, fs.f0); fs.c1 = -__fmul_rn(kRintMagic, fs.f1); fs.hi = __fadd_rn(kRintMagic, q.qmax);
-    float y = 0.f;
-    if (s.w == 1u) y = quant_elem_fast<KIND>(v[j], fs, q);
-    else if (s.w == 0u) y = quant_literal_1<KIND>(v[j], s.z, q);
-    v[j] = y;
+    fs.f0 = fs.f1 = fs.c0 = fs.c1 = 0.f;
+    fs.i0 = fs.i1 = fs.i2 = 0;
+    fs.hi = __fadd_rn(kRintMagic, q.qmax);
+    if (KIND != kBlockFP) { fs.f0 = __fadd_rn(kRintMagic, q.shift); fs.f1 = __fadd_rn(fs.f0, q.qmax); }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const uint4 s = st[half * 32 + j];
+      if (KIND == kBlockFP) {
+        fs.f0 = __uint_as_float(s.x); fs.f1 = __uint_as_float(s.y); fs.c0 = __uint_as_float(s.z); fs.c1 = __uint_as_float(s.w);
+      } else {
+        fs.i0 = (int)s.x; fs.i1 = (int)s.y; fs.i2 = (int)s.z;
+      }
+      v[j] = quant_elem_fast<KIND>(v[j], fs, q);
+    }
+  } else {
+    st[lane] = ss[0];
+    st[32 + lane] = ss[1];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {                               // rare: out-of-line per element
+      const uint4 s = st[half * 32 + j];
+      v[j] = (s.y == 2u) ? 0.f : quant_with_max_cold<KIND>(v[j], s.x, q);
+    }
+  }
+  __syncwarp();                                                  // scratch is reused by the next chunk
+}
+
+// 32x32 fp32 chunk, row-per-lane registers -> "coalesced" registers: o[i] = columns 4*(lane&7)..+3 of row 4*i + (lane>>3), through the
+// warp's scratch as 16-byte accesses whose chunk position is XOR-swizzled with the row (conflict-free both ways).  A store
+// instruction then covers four full 128-byte row segments instead of 32 rows x 16 bytes.
+__device__ __forceinline__ void chunk_to_coalesced(const float (&v)[32], float4 (&o)[8], uint32_t* scratch, int lane) {
+  float4* sc = reinterpret_cast<float4*>(scratch);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sc[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int rsub = lane >> 3, c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    o[i] = sc[r * 8 + (c ^ (r & 7))];
   }
   __syncwarp();                                                  // scratch is reused by the next chunk
 }
@@ -148,6 +186,39 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (v[j] < 0.f) ? 0.f : v[j];      // torch relu: NaN propagates
   }
+  if (e.qmode == 0 && !e.out_bf16) {                               // warp-uniform
+    // fp32 output without a quantiser (out_proj / fc2 residual epilogues, plain Linear, fused all-gather): residual read, local
+    // store and the peers' copies all run in the coalesced layout.  (Lane-per-row 16-byte accesses made the K = 2048 residual
+    // epilogue longer than its mainloop — 133 us against 97 us — and moved 16-byte packets over NVLink: 163 GB/s.)
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4, wrow0 = row - lane;
+    float4 rs[8];
+    if (e.residual) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = wrow0 + i * 4 + rsub;
+        rs[i] = rr < g.M ? *reinterpret_cast<const float4*>(e.residual + (int64_t)rr * e.ldr + col0 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float4 o[8];
+    chunk_to_coalesced(v, o, scratch, lane);
+    if (e.residual) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i].x = __fadd_rn(rs[i].x, o[i].x); o[i].y = __fadd_rn(rs[i].y, o[i].y);
+        o[i].z = __fadd_rn(rs[i].z, o[i].z); o[i].w = __fadd_rn(rs[i].w, o[i].w);
+      }
+    }
+#pragma unroll 1
+    for (int p = -1; p < e.n_rep; ++p) {                           // -1: this rank's C, then the peers' copies of the gathered output
+      float* cp = (p < 0 ? g.C : reinterpret_cast<float*>(e.rep[p])) + col0 + c4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = wrow0 + i * 4 + rsub;
+        if (rr < g.M) *reinterpret_cast<float4*>(cp + (int64_t)rr * g.ldc) = o[i];
+      }
+    }
+    return;
+  }
   if (e.residual) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -170,37 +241,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     if (e.q.kind == kBlockFP) quant_rowblocks32<kBlockFP>(v, e.q, scratch, lane);
     else quant_rowblocks32<kBlockMinifloat>(v, e.q, scratch, lane);
   }
-  if (e.n_rep > 0 && !e.out_bf16) {                                // warp-uniform
-    // fused all-gather (fp32): peers' copies are written over NVLink, where a lane-per-row store pattern (32 rows x 16 bytes
-    // per instruction) moves 16-byte packets — measured 163 GB/s at 2 GPUs.  Transpose the 32x32 chunk through the warp's
-    // scratch so that every store instruction covers four full 128-byte row segments.
-    float* sc = reinterpret_cast<float*>(scratch);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = v[j];
-    __syncwarp();
-    const int rsub = lane >> 3, c4 = (lane & 7) * 4, wrow0 = row - lane;
-    float4 o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float* s4 = sc + (i * 4 + rsub) * 33 + c4;
-      o[i] = make_float4(s4[0], s4[1], s4[2], s4[3]);
-    }
-    __syncwarp();                                                  // scratch is reused by the next chunk
-#pragma unroll 1
-    for (int p = 0; p < e.n_rep; ++p) {
-      float* cp = reinterpret_cast<float*>(e.rep[p]) + col0 + c4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = wrow0 + i * 4 + rsub;
-        if (rr < g.M) *reinterpret_cast<float4*>(cp + (int64_t)rr * g.ldc) = o[i];
-      }
-    }
-    if (!row_ok) return;
-    float* c = g.C + (int64_t)row * g.ldc + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    return;
-  }
   if (!row_ok) return;
   const int64_t off = (int64_t)row * g.ldc + col0;
   if (e.out_bf16) {
@@ -222,6 +262,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     float* c = g.C + off;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+#pragma unroll 1
+    for (int p = 0; p < e.n_rep; ++p) {                          // (quantised fp32 output: not a configuration the host issues)
+      float* cp = reinterpret_cast<float*>(e.rep[p]) + off;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
   }
 }
 
@@ -373,7 +419,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // fused epilogue (batch == 1, N % 32 == 0, all pointers 16-byte aligned: checked on the host)
         uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + Cfg::kEpiOff) + ew * kEpiWarpWords;
         const bool row_ok = row < g.M;
-        const bool has_res = g.epi.residual != nullptr && row_ok;
+        const bool has_res = g.epi.residual != nullptr && row_ok && !(g.epi.qmode == 0 && !g.epi.out_bf16);   // coalesced path reads it itself
         const float* rrow = has_res ? g.epi.residual + (int64_t)row * g.epi.ldr + nb * BN : nullptr;
         float4 res_next[8];
 #pragma unroll

@@ -83,6 +83,44 @@ def test_gemm_epilogue_matches_unfused_composition(M, N, K):
     pre = plain * 8.0
     got = run(torch.float32, scale=8.0, fmt=fm)
     assert torch.equal(got, O.block_minifloat_quantize(pre, 8, 4, 8, [1, 16], True))
+    if M % 16 == 0:
+        # 7. block_minifloat along M (fp32 out: no carrier rounding), and the rare per-element path: zero blocks, an inf, a
+        #    block whose maximum sits within the log2 cliff zone is still on the fast path; NaN/inf blocks take the literal one
+        got = run(torch.float32, scale=8.0, fmt=fm, qdir=1)
+        want = O.block_minifloat_quantize(pre.t().contiguous(), 8, 4, 8, [1, 16], True).t()
+        assert torch.equal(got, want)
+        got = run(torch.float32, fmt=f6, qdir=1)
+        want = block_fp_quantizer(plain.t().contiguous(), 6, 8, 127, [1, 16], True).t()
+        assert torch.equal(got, want)
+
+
+def test_gemm_epilogue_row_blocks_rare_path_with_nonfinite_values():
+    """Quantising along M with blocks that cannot take the fast path (inf / NaN block maxima) and all-zero blocks: the
+    per-element out-of-line path must give what the quantizer gives on the transposed fp32 result."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer
+    from llm_mixed_q_b200.models.quantize.quantizers.utils import make_format
+
+    lib = L.load()
+    M, N, K = 256, 128, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    A[3, 5] = float("inf")            # row 3 of C: +-inf
+    A[40, 1] = float("nan")           # row 40: NaN
+    A[64:80] = 0                      # 16 zero rows: all-zero blocks at every column
+    plain = torch.empty(M, N, device="cuda")
+    L.check(lib.bq_gemm_bf16_tn(A.data_ptr(), B.data_ptr(), plain.data_ptr(), None, 1, M, N, K, K, K, N, 0, 0, 0, L.stream_ptr()), "gemm")
+    f6 = make_format("block_fp", width=6, exponent_width=8, exponent_bias=127, b0=1, b1=16)
+    ep = L.BqGemmEpilogue()
+    ep.scale, ep.act, ep.out_dtype = 1.0, 0, L.BQ_F32
+    ep.qfmt, ep.qdir = ctypes.pointer(f6), 1
+    C = torch.full((M, N), 7.0, device="cuda")
+    L.check(lib.bq_gemm_bf16_tn_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), ctypes.byref(ep), M, N, K, K, K, N, L.stream_ptr()), "gemm_ex")
+    want = block_fp_quantizer(plain.t().contiguous(), 6, 8, 127, [1, 16], True).t()
+    assert torch.equal(torch.isnan(C), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(C, nan=1.0), torch.nan_to_num(want, nan=1.0))
+    assert bool((C[64:80] == 0).all())
 
 
 @pytest.mark.parametrize("H,rows", [(2048, 512), (768, 300), (4096, 64), (64, 1000)])
