@@ -25,9 +25,13 @@ constexpr int kUmmaK = 16;
 
 constexpr int kEpiWarpWords = 32 * 33 + 64 * 4;      // per epilogue warp: 32x33 transpose tile + 64 uint4 block states
 // BN: tile width; EPI: fused epilogue (8 epilogue warps + scratch) ; CG: CTAs per MMA (cta_group::1 / ::2).
+// EPI: 0 none; 1 generic (every EpiArgs combination, runtime dispatch); specialised instances of the same code with the mode
+// fixed at compile time (each path gets its own register allocation — in the generic instance the fp32 / row-block paths cost the
+// bf16 column-block path 7 %): 2 = fp32 out, no quantiser (coalesced store / residual / replicas); 3 = blocks along N, bf16 out;
+// 4 = blocks along M, bf16 out (3, 4: no residual, no replicas).
 // With CG == 2 a CTA pair computes a 256 x 256 tile: each CTA owns 128 rows of A and of the accumulator and HALF of the B tile,
 // which the pair's MMA reads from both shared memories — 2/3 of the smem fill traffic and operand reads per FLOP of CG == 1.
-template <int BN, bool EPI = false, int CG = 1> struct GemmCfg {
+template <int BN, int EPI = 0, int CG = 1> struct GemmCfg {
   static constexpr int kEpiWarps = EPI ? 8 : 4;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
   static constexpr int kStageA = kBM * kBK * 2;
@@ -164,9 +168,14 @@ __device__ __forceinline__ void chunk_to_coalesced(const float (&v)[32], float4 
 }
 
 // one 32-column chunk of one accumulator row through the fused epilogue
+template <int EM>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], const float4 (&res)[8], int row, int col0,
                                                bool row_ok, uint32_t* scratch, int lane) {
   const EpiArgs& e = g.epi;
+  const int qmode = (EM == 1) ? e.qmode : (EM == 2 ? 0 : (EM == 3 ? 1 : 2));
+  const bool out_bf16 = (EM == 1) ? (e.out_bf16 != 0) : (EM != 2);
+  const bool has_residual = (EM == 1 || EM == 2) && e.residual != nullptr;
+  const int n_rep = (EM == 1 || EM == 2) ? e.n_rep : 0;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -186,13 +195,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (v[j] < 0.f) ? 0.f : v[j];      // torch relu: NaN propagates
   }
-  if (e.qmode == 0 && !e.out_bf16) {                               // warp-uniform
+  if (qmode == 0 && !out_bf16) {                               // warp-uniform
     // fp32 output without a quantiser (out_proj / fc2 residual epilogues, plain Linear, fused all-gather): residual read, local
     // store and the peers' copies all run in the coalesced layout.  (Lane-per-row 16-byte accesses made the K = 2048 residual
     // epilogue longer than its mainloop — 133 us against 97 us — and moved 16-byte packets over NVLink: 163 GB/s.)
     const int rsub = lane >> 3, c4 = (lane & 7) * 4, wrow0 = row - lane;
     float4 rs[8];
-    if (e.residual) {
+    if (has_residual) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = wrow0 + i * 4 + rsub;
@@ -201,7 +210,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     }
     float4 o[8];
     chunk_to_coalesced(v, o, scratch, lane);
-    if (e.residual) {
+    if (has_residual) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         o[i].x = __fadd_rn(rs[i].x, o[i].x); o[i].y = __fadd_rn(rs[i].y, o[i].y);
@@ -209,7 +218,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       }
     }
 #pragma unroll 1
-    for (int p = -1; p < e.n_rep; ++p) {                           // -1: this rank's C, then the peers' copies of the gathered output
+    for (int p = -1; p < n_rep; ++p) {                           // -1: this rank's C, then the peers' copies of the gathered output
       float* cp = (p < 0 ? g.C : reinterpret_cast<float*>(e.rep[p])) + col0 + c4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -219,14 +228,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     }
     return;
   }
-  if (e.residual) {
+  if (has_residual) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[4 * j] = __fadd_rn(res[j].x, v[4 * j]); v[4 * j + 1] = __fadd_rn(res[j].y, v[4 * j + 1]);
       v[4 * j + 2] = __fadd_rn(res[j].z, v[4 * j + 2]); v[4 * j + 3] = __fadd_rn(res[j].w, v[4 * j + 3]);
     }
   }
-  if (e.qmode == 1) {
+  if (qmode == 1) {
 #pragma unroll
     for (int blk = 0; blk < 2; ++blk) {
       float t[16];
@@ -236,14 +245,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[blk * 16 + i] = t[i];
     }
-  } else if (e.qmode == 2) {
+  } else if (qmode == 2) {
     // a block = 16 consecutive rows (lanes 0-15 / 16-31) of one column; M % 16 == 0, so a block is all-valid or all-invalid
     if (e.q.kind == kBlockFP) quant_rowblocks32<kBlockFP>(v, e.q, scratch, lane);
     else quant_rowblocks32<kBlockMinifloat>(v, e.q, scratch, lane);
   }
   if (!row_ok) return;
   const int64_t off = (int64_t)row * g.ldc + col0;
-  if (e.out_bf16) {
+  if (out_bf16) {
     uint4 o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -253,7 +262,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 #pragma unroll
     for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(c)[j] = o[j];
 #pragma unroll 1
-    for (int p = 0; p < e.n_rep; ++p) {                          // peers' copies of the gathered output
+    for (int p = 0; p < n_rep; ++p) {                          // peers' copies of the gathered output
       __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(e.rep[p]) + off;
 #pragma unroll
       for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(cp)[j] = o[j];
@@ -263,7 +272,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
 #pragma unroll 1
-    for (int p = 0; p < e.n_rep; ++p) {                          // (quantised fp32 output: not a configuration the host issues)
+    for (int p = 0; p < n_rep; ++p) {                          // (quantised fp32 output: not a configuration the host issues)
       float* cp = reinterpret_cast<float*>(e.rep[p]) + off;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -271,7 +280,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
   }
 }
 
-template <int BN, bool EPI, int CG>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GemmCfg<BN, EPI, CG>::kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
   using Cfg = GemmCfg<BN, EPI, CG>;
@@ -419,7 +428,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // fused epilogue (batch == 1, N % 32 == 0, all pointers 16-byte aligned: checked on the host)
         uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + Cfg::kEpiOff) + ew * kEpiWarpWords;
         const bool row_ok = row < g.M;
-        const bool has_res = g.epi.residual != nullptr && row_ok && !(g.epi.qmode == 0 && !g.epi.out_bf16);   // coalesced path reads it itself
+        // row-per-lane residual prefetch: only the generic instance's quantising paths use it (the coalesced path reads it itself)
+        const bool has_res = EPI == 1 && g.epi.residual != nullptr && row_ok && !(g.epi.qmode == 0 && !g.epi.out_bf16);
         const float* rrow = has_res ? g.epi.residual + (int64_t)row * g.epi.ldr + nb * BN : nullptr;
         float4 res_next[8];
 #pragma unroll
@@ -442,7 +452,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(rrow + (c + c_step) * 32 + 4 * j);
           }
           ptx::tmem_ld_wait();
-          epilogue_chunk(g, r, res, row, col0, row_ok, scratch, lane);
+          epilogue_chunk<EPI>(g, r, res, row, col0, row_ok, scratch, lane);
         }
       } else {
         float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
@@ -566,7 +576,7 @@ int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, i
   return BQ_OK;
 }
 
-template <int BN, bool EPI, int CG>
+template <int BN, int EPI, int CG>
 static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, cudaStream_t st, int kern_id) {
   using Cfg = GemmCfg<BN, EPI, CG>;
   static bool attr_set = false;
@@ -619,11 +629,20 @@ static bool use_pairs(int64_t batch, int64_t M, int64_t N) { return g_pairs_enab
 template <bool EPI>
 static int launch_gemm_any(int BN, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st,
                            int kern_id) {
-  if (pair) return launch_gemm_cg<256, EPI, 2>(tmA, tmB, g, st, kern_id);
+  if (pair) {
+    if (!EPI) return launch_gemm_cg<256, 0, 2>(tmA, tmB, g, st, kern_id);
+    const EpiArgs& e = g.epi;
+    if (e.qmode == 0 && !e.out_bf16) return launch_gemm_cg<256, 2, 2>(tmA, tmB, g, st, kern_id);
+    if (e.out_bf16 && !e.residual && e.n_rep == 0) {
+      if (e.qmode == 1) return launch_gemm_cg<256, 3, 2>(tmA, tmB, g, st, kern_id);
+      if (e.qmode == 2) return launch_gemm_cg<256, 4, 2>(tmA, tmB, g, st, kern_id);
+    }
+    return launch_gemm_cg<256, 1, 2>(tmA, tmB, g, st, kern_id);
+  }
   switch (BN) {
-    case 64: return launch_gemm_cg<64, EPI, 1>(tmA, tmB, g, st, kern_id);
-    case 128: return launch_gemm_cg<128, EPI, 1>(tmA, tmB, g, st, kern_id);
-    default: return launch_gemm_cg<256, EPI, 1>(tmA, tmB, g, st, kern_id);
+    case 64: return launch_gemm_cg<64, EPI ? 1 : 0, 1>(tmA, tmB, g, st, kern_id);
+    case 128: return launch_gemm_cg<128, EPI ? 1 : 0, 1>(tmA, tmB, g, st, kern_id);
+    default: return launch_gemm_cg<256, EPI ? 1 : 0, 1>(tmA, tmB, g, st, kern_id);
   }
 }
 
