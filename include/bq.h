@@ -202,6 +202,14 @@ BQ_API int bq_split2_f16_rows(const float* x, int64_t rows, int64_t K, int64_t l
 BQ_API int bq_gemm_split16_tn(const void* A_planes_f16, const void* B_planes_f16, float* C, const float* bias,
                               const float* a_inv_scale, const float* b_inv_scale, int64_t M, int64_t N, int64_t K,
                               int32_t n_terms, const int32_t* term_a, const int32_t* term_b, int64_t ldc, void* stream);
+/* Batched form for matmul / bmm whose operands are not bf16-exact — generic_matmul_block_log leaves y unquantised in fp32
+ * (quantized_functions/matmul.py:293-296), formats wider than 8 significant bits — instead of an fp32 SIMT library GEMM:
+ *   C[b][m][n] = a_inv_scale[b*M+m] * b_inv_scale[b*N+n] * sum_t A_plane[term_a[t]][b][m][:] . B_plane[term_b[t]][b][n][:]
+ * planes are fp16 [2][batch][rows][K] as written by ONE bq_split2_f16_rows call over batch*rows rows; C row stride ldc, batch
+ * stride sc (elements). */
+BQ_API int bq_bmm_split16_tn(const void* A_planes_f16, const void* B_planes_f16, float* C, const float* a_inv_scale,
+                             const float* b_inv_scale, int64_t batch, int64_t M, int64_t N, int64_t K, int32_t n_terms,
+                             const int32_t* term_a, const int32_t* term_b, int64_t ldc, int64_t sc, void* stream);
 BQ_API int bq_gemm_split_tn(const void* A_planes, const void* B_planes, float* C, const float* bias, int64_t M, int64_t N,
                             int64_t K, int32_t planes_a, int32_t planes_b, int32_t n_terms, const int32_t* term_a,
                             const int32_t* term_b, int64_t ldc, void* stream);

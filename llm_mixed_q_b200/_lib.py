@@ -130,6 +130,9 @@ def load():
     lib.bq_gemm_split16_tn.restype = ctypes.c_int
     lib.bq_gemm_split16_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,
                                        POINTER(c_int32), POINTER(c_int32), c_int64, c_void_p]
+    lib.bq_bmm_split16_tn.restype = ctypes.c_int
+    lib.bq_bmm_split16_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
+                                      POINTER(c_int32), POINTER(c_int32), c_int64, c_int64, c_void_p]
     lib.bq_token_ce_workspace_bytes.restype = c_size_t
     lib.bq_token_ce_workspace_bytes.argtypes = [c_int64, c_int64]
     lib.bq_token_ce_mean.restype = ctypes.c_int

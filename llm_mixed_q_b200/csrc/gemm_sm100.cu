@@ -362,8 +362,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (g.n_terms > 0) {
             const int t = kb / kb_per_term;
             kk = kb - t * kb_per_term;
-            ca = g.term_a[t];
-            cb = g.term_b[t];
+            ca = g.term_a[t] * g.batch + b;                       // planes are stacked outside the batch: [plane][batch][rows][K]
+            cb = g.term_b[t] * (g.b_broadcast ? 1 : g.batch) + (g.b_broadcast ? 0 : b);
           }
           if (CG == 2) {
             // the leader's barrier collects the bytes of BOTH CTAs' loads
@@ -457,7 +457,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else {
         float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
         const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((g.sc & 3) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.col_scale) & 15) == 0);
+                            ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.col_scale) & 15) == 0) &&
+                            (g.batch == 1 || (g.N & 3) == 0);
 #pragma unroll 1
         for (int c = c_first; c < BN / 32; c += c_step) {
           uint32_t r[32];
@@ -471,8 +472,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                        __uint_as_float(r[j + 3]));
                 if (g.row_scale) {
-                  const float rs = g.row_scale[row];
-                  const float4 cs = *reinterpret_cast<const float4*>(g.col_scale + col0 + j);
+                  const float rs = g.row_scale[(int64_t)b * g.M + row];
+                  const float4 cs = *reinterpret_cast<const float4*>(g.col_scale + (g.b_broadcast ? 0 : (int64_t)b * g.N) + col0 + j);
                   o.x *= rs * cs.x; o.y *= rs * cs.y; o.z *= rs * cs.z; o.w *= rs * cs.w;
                 }
                 if (g.bias) {
@@ -486,7 +487,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 32; ++j) {
                 if (col0 + j < g.N) {
                   float o = __uint_as_float(r[j]);
-                  if (g.row_scale) o *= g.row_scale[row] * g.col_scale[col0 + j];
+                  if (g.row_scale) o *= g.row_scale[(int64_t)b * g.M + row] * g.col_scale[(g.b_broadcast ? 0 : (int64_t)b * g.N) + col0 + j];
                   crow[col0 + j] = o + (g.bias ? g.bias[col0 + j] : 0.f);
                 }
               }
@@ -731,24 +732,26 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
 // result carries ~2^-24 relative error per product, i.e. it stands in for an fp32 GEMM on the tensor cores.
 int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t M, int64_t N, int64_t K,
                        int planes_a, int planes_b, int n_terms, const int* ta, const int* tb, int64_t ldc, cudaStream_t st,
-                       int fp16 = 0, const float* row_scale = nullptr, const float* col_scale = nullptr) {
-  if (M < 0 || N < 0 || K <= 0 || n_terms < 1 || n_terms > 8 || !ta || !tb) return BQ_ERR_BAD_ARG;
-  if (M == 0 || N == 0) return BQ_OK;
+                       int fp16 = 0, const float* row_scale = nullptr, const float* col_scale = nullptr, int64_t batch = 1,
+                       int64_t sc = 0) {
+  if (M < 0 || N < 0 || K <= 0 || n_terms < 1 || n_terms > 8 || !ta || !tb || batch < 0) return BQ_ERR_BAD_ARG;
+  if (M == 0 || N == 0 || batch == 0) return BQ_OK;
+  if (batch > 1 && (sc < M * ldc || planes_a * batch > 0x7fffffff || planes_b * batch > 0x7fffffff)) return BQ_ERR_BAD_ARG;
   if (!A || !B || !C) return BQ_ERR_BAD_ARG;
   if ((K % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)C % 4) || ldc < N) return BQ_ERR_BAD_ARG;
   if ((row_scale == nullptr) != (col_scale == nullptr)) return BQ_ERR_BAD_ARG;
   if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
   const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, planes_a, K, M * K, kBM);     // 16-bit elements: the map only moves bytes
+  int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, planes_a * batch, K, M * K, kBM);     // 16-bit elements: the map only moves bytes
   if (rc) return rc;
-  const bool pair = use_pairs(1, M, N);
-  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, planes_b, K, N * K, pair ? 128 : BN);
+  const bool pair = use_pairs(batch, M, N);
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, planes_b * batch, K, N * K, pair ? 128 : BN);
   if (rc) return rc;
   GemmArgs g;
   memset(&g, 0, sizeof(g));
-  g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = 1;
-  g.ldc = ldc; g.sc = 0; g.tiles_m = g.tiles_n = 0; g.b_broadcast = 1;
+  g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = (int)batch;
+  g.ldc = ldc; g.sc = batch > 1 ? sc : 0; g.tiles_m = g.tiles_n = 0; g.b_broadcast = batch > 1 ? 0 : 1;
   g.n_terms = n_terms;
   g.fp16 = fp16; g.row_scale = row_scale; g.col_scale = col_scale;
   for (int i = 0; i < n_terms; ++i) {
@@ -770,6 +773,14 @@ extern "C" int bq_gemm_split16_tn(const void* A_planes_f16, const void* B_planes
   if (!a_inv_scale || !b_inv_scale) return BQ_ERR_BAD_ARG;
   return bq::gemm_split_tn_impl(A_planes_f16, B_planes_f16, C, bias, M, N, K, 2, 2, n_terms, term_a, term_b, ldc,
                                 (cudaStream_t)stream, 1, a_inv_scale, b_inv_scale);
+}
+
+extern "C" int bq_bmm_split16_tn(const void* A_planes_f16, const void* B_planes_f16, float* C, const float* a_inv_scale,
+                                const float* b_inv_scale, int64_t batch, int64_t M, int64_t N, int64_t K, int32_t n_terms,
+                                const int32_t* term_a, const int32_t* term_b, int64_t ldc, int64_t sc, void* stream) {
+  if (!a_inv_scale || !b_inv_scale) return BQ_ERR_BAD_ARG;
+  return bq::gemm_split_tn_impl(A_planes_f16, B_planes_f16, C, nullptr, M, N, K, 2, 2, n_terms, term_a, term_b, ldc,
+                                (cudaStream_t)stream, 1, a_inv_scale, b_inv_scale, batch, sc);
 }
 
 extern "C" int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_gemm_epilogue* ep, int64_t M, int64_t N,

@@ -69,11 +69,52 @@ def _generic_matmul(x, y, config, style, quantize_y=True):
             out = _fused_bmm(x3, y3 if y3.ndim == 3 else y3.unsqueeze(0), config, xk, xkw, xbs, yk, ykw, ybs)
             return out.reshape(*x.shape[:-1], y.shape[-1])
 
-    # general route: reference op order with our quantizer kernels, fp32 library matmul
+    # general route: reference op order with our quantizer kernels, then an fp32(-equivalent) matmul
     x_shape, y_shape = list(x.shape), list(y.shape)
     xq = _quantize_fp32(_flatten3(x), xk, xkw, xbs, x_multi).reshape(x_shape)
     yq = _quantize_fp32(_flatten3(y), yk, ykw, ybs, y_multi).reshape(y_shape) if quantize_y else y
+    if (SPLIT_BMM and xq.is_cuda and yq.is_cuda and xq.dtype == torch.float32 and yq.dtype == torch.float32
+            and xq.ndim >= 2 and yq.ndim >= 2 and xq.shape[-1] == yq.shape[-2] and xq.shape[-1] % 8 == 0
+            and (xq.shape[:-2] == yq.shape[:-2] or yq.ndim == 2) and xq.numel() > 0 and yq.numel() > 0
+            and (not torch.is_grad_enabled() or not (xq.requires_grad or yq.requires_grad))):
+        # x is a power of two under block_log: its low fp16 plane is identically zero, two products suffice
+        return _split_bmm(xq, yq, x_lo_is_zero=(xk == "block_log"))
     return matmul(xq, yq)
+
+
+SPLIT_BMM = True        # False: fp32 library matmul on the general route (A/B measurement, tests)
+
+
+def _split_bmm(xq, yq, x_lo_is_zero=False):
+    """matmul(xq, yq) for fp32 operands that are not bf16-exact, on the tensor cores: every row of xq and every column of yq is
+    scaled by a power of two and split into two fp16 planes (bq_split2_f16_rows), the plane products are accumulated in fp32
+    (bq_bmm_split16_tn) — ~2^-21 relative error per product, inside the accumulation-order noise of the fp32 matmul the reference
+    runs here (quantized_functions/matmul.py:196, :293-296).  Stands in for the SIMT SGEMM torch.matmul would launch."""
+    from .fp32_linear import split2_rows
+
+    lib = L.load()
+    out_shape = tuple(xq.shape[:-1]) + (yq.shape[-1],)
+    x3 = _flatten3(xq)
+    if x3.ndim == 2:
+        x3 = x3.unsqueeze(0)
+    batch, M, K = x3.shape
+    N = yq.shape[-1]
+    y3 = _flatten3(yq)
+    if y3.ndim == 2:                                    # one weight-like matrix for every batch: fold the batch into M
+        x3 = x3.reshape(1, batch * M, K)
+        y3 = y3.unsqueeze(0)
+        batch, M = 1, batch * M
+    yt = y3.transpose(1, 2).contiguous()               # [batch, N, K]; a no-op for the k^T views the attention passes
+    ap, a_inv = split2_rows(x3.reshape(batch * M, K).contiguous())
+    bp, b_inv = split2_rows(yt.reshape(batch * N, K))
+    out = torch.empty((batch, M, N), dtype=torch.float32, device=xq.device)
+    terms = [(0, 1), (0, 0)] if x_lo_is_zero else [(1, 0), (0, 1), (0, 0)]        # smallest magnitude first
+    ta = (ctypes.c_int32 * len(terms))(*[t[0] for t in terms])
+    tb = (ctypes.c_int32 * len(terms))(*[t[1] for t in terms])
+    rc = lib.bq_bmm_split16_tn(ap.data_ptr(), bp.data_ptr(), out.data_ptr(), a_inv.data_ptr(), b_inv.data_ptr(), batch, M, N, K,
+                               len(terms), ta, tb, N, M * N, L.stream_ptr(xq.device))
+    L.check(rc, "bq_bmm_split16_tn")
+    return out.reshape(out_shape)
 
 
 def _fused_bmm(x3, y3, config, xk, xkw, xbs, yk, ykw, ybs):

@@ -167,6 +167,49 @@ def test_block_log_matmul_leaves_y_unquantised():
     assert get_quantized_func("bmm", {"name": "log"}) is get_quantized_func("bmm", cfg)
 
 
+@pytest.mark.parametrize("name", ["block_log", "block_fp12"])
+def test_general_route_matmul_runs_on_the_split_tensor_core_gemm(name):
+    """Operands that are not bf16-exact (block_log: y unquantised fp32; formats wider than 8 significant bits) go through the
+    batched fp16-plane split GEMM: same fp32-accumulation-order bound as the fp32 matmul of the reference, k^T views, ragged
+    shapes, 2-D y, and no SIMT library GEMM launched."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.quantize import get_quantized_func
+
+    if name == "block_log":
+        cfg = {"name": "block_log", "bypass": False, "data_in_width": 4, "data_in_exponent_bias_width": 8,
+               "data_in_block_size": [1, 16], "weight_width": 4, "weight_exponent_bias_width": 8, "weight_block_size": [1, 16]}
+        qx = lambda t, multi: O.block_log_quantize(t, 4, 8, [1, 16], multi)
+        qy = lambda t, multi: t
+    else:
+        cfg = {"name": "block_fp", "bypass": False}
+        for p in ("data_in", "weight"):
+            cfg.update({f"{p}_width": 12, f"{p}_exponent_width": 8, f"{p}_exponent_bias": 127, f"{p}_block_size": [1, 16]})
+        qx = qy = lambda t, multi: O.block_fp_quantize(t, 12, 8, 127, [1, 16], multi)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n0 = L.launch_counts()["gemm_bf16_tn_kernel<split>"]
+    cases = [("bmm", (8, 512, 128), (8, 128, 512), True), ("bmm", (8, 512, 512), (8, 512, 128), False),
+             ("bmm", (3, 300, 1000), (3, 1000, 100), False), ("matmul", (2, 5, 64, 48), (2, 5, 48, 40), False),
+             ("matmul", (4, 200, 64), (64, 72), False)]
+    for style, xs, ys, kt in cases:
+        x = torch.randn(*xs, device="cuda", generator=g)
+        if kt:
+            y = torch.randn(ys[0], ys[2], ys[1], device="cuda", generator=g).transpose(1, 2)      # k^T view
+        else:
+            y = torch.randn(*ys, device="cuda", generator=g)
+        x[..., 3, :] *= 1e-5
+        x[..., 4, :] = 0
+        out = get_quantized_func(style, cfg)(x, y, config=copy.deepcopy(cfg))
+        f3 = lambda t: torch.flatten(t, 0, -3) if t.ndim > 2 else t                   # reference matmul.py:166-190: flatten, quantise, restore
+        xq = qx(f3(x).contiguous(), x.ndim > 2).reshape(x.shape)
+        yq = qy(f3(y).contiguous(), y.ndim > 2).reshape(y.shape)
+        exact = xq.double() @ yq.double()
+        absprod = xq.double().abs() @ yq.double().abs()
+        assert out.shape == exact.shape
+        assert_gemm_close(out, exact, absprod, xs[-1])
+        assert_gemm_close(torch.matmul(xq, yq), exact, absprod, xs[-1])            # the reference's own route obeys the same bound
+    assert L.launch_counts()["gemm_bf16_tn_kernel<split>"] - n0 == len(cases)
+
+
 def _oracle_attention(q, k, v, cfg, heads, score_div=1.0):
     """op-by-op reference composition (modeling_opt.py:237-323) with the oracle's quantizers, on the same device."""
     B, S, H = q.shape
