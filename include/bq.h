@@ -287,6 +287,7 @@ BQ_API int bq_token_ce_mean(const float* logits, int64_t n_seq, int64_t seq_len,
  * synchronises those events and returns the summed device time.
  * ---------------------------------------------------------------------------------------------- */
 BQ_API void bq_set_stream_quantizer(int on);           /* 0: force the per-slot quant_rows_kernel instead of the bulk-copy streaming kernel (A/B measurement) */
+BQ_API void bq_set_norm_warp_rows(int on);             /* 0: force the row-per-CTA norm_quant_kernel for H <= 2048 too (A/B measurement, tests) */
 BQ_API void bq_set_cta_pairs(int on);                  /* 0: force cta_group::1 GEMM tiles (A/B measurement) */
 BQ_API int bq_kernel_count(void);
 BQ_API const char* bq_kernel_name(int kernel_id);

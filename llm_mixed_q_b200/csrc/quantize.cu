@@ -1034,6 +1034,164 @@ __global__ void __maxnreg__(80) norm_quant_kernel(LnArgs a) {
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// v6, rows of at most 2048 elements, one kind for every output: one ROW per WARP, a lane owns NB whole blocks (blocks lane,
+// lane + 32, ...) and holds them in registers.  No CTA barrier and no cross-warp traffic at all: the statistics are two warp
+// shuffle trees, the row slot is handed back to the bulk-copy engine as soon as the row is in registers (the next row lands
+// while this one is processed), gamma / beta are read from one shared copy per CTA.  ~16 instructions per element against 33
+// for v5 (whose per-row CTA barriers, partial-sum exchange and thread-0 bookkeeping are per-row costs paid by 4 warps).
+constexpr int kLwWarps = 8;
+template <int KIND, int NB>
+__global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArgs a) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)a.H * 4u, out_bytes = (uint32_t)a.H * 2u;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ln_smem);
+  const uint32_t gam0 = sbase, bet0 = sbase + row_bytes;
+  const uint32_t in0 = sbase + 2u * row_bytes + (uint32_t)warp * (row_bytes + out_bytes);
+  const uint32_t outb = in0 + row_bytes;
+  const uint32_t bar = sbase + 2u * row_bytes + (uint32_t)kLwWarps * (row_bytes + out_bytes) + 8u * (uint32_t)warp;
+  const bool ln = a.beta != nullptr;
+  const int nblk = a.H >> 4;
+  const int stride = gridDim.x * kLwWarps;
+  int row = blockIdx.x * kLwWarps + warp;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (row < a.rows) bulk_load_row(in0, a.x + (int64_t)row * a.ldx, row_bytes, bar);
+  }
+  for (int i = threadIdx.x; i < (a.H >> 2); i += kLwWarps * 32) {
+    sts128(gam0 + 16u * i, __ldg(reinterpret_cast<const float4*>(a.gamma) + i));
+    if (ln) sts128(bet0 + 16u * i, __ldg(reinterpret_cast<const float4*>(a.beta) + i));
+  }
+  __syncthreads();
+  const uint32_t rot = (uint32_t)((lane >> 1) + (lane >> 3)) & 3u;
+  const float invH = 1.0f / (float)a.H;
+  uint32_t parity = 0;
+  for (; row < a.rows; row += stride) {
+    st_mbar_wait(bar, parity);
+    parity ^= 1u;
+    float v[NB][16];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int blk = j * 32 + lane;
+      const uint32_t base = in0 + (uint32_t)blk * 64u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 t = blk < nblk ? lds128(base + (((uint32_t)c + rot) & 3u) * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j][4 * c] = t.x; v[j][4 * c + 1] = t.y; v[j][4 * c + 2] = t.z; v[j][4 * c + 3] = t.w;
+      }
+    }
+    __syncwarp();                                        // the row is in registers: refill the slot while it is processed
+    if (lane == 0) {
+      const int64_t next = (int64_t)row + stride;
+      if (next < a.rows) bulk_load_row(in0, a.x + next * a.ldx, row_bytes, bar);
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous row's store has left the output slot
+    }
+    float mean = 0.f;
+    if (ln) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        float t[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t[c] = __fadd_rn(__fadd_rn(v[j][4 * c], v[j][4 * c + 1]), __fadd_rn(v[j][4 * c + 2], v[j][4 * c + 3]));
+        s = __fadd_rn(s, __fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])));
+      }
+      mean = __fmul_rn(warp_sum(s), invH);
+    }
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[j][i] = __fsub_rn(v[j][i], mean);
+        t[i & 3] = __fmaf_rn(v[j][i], v[j][i], t[i & 3]);
+      }
+      if (j * 32 + lane < nblk) q = __fadd_rn(q, __fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])));
+    }
+    const float rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(q), invH), a.eps));     // (warp_sum's shuffles also order lane 0's wait above)
+#pragma unroll 1
+    for (int k = 0; k < a.n_out; ++k) {
+      const FmtParams& p = (k == 0) ? a.f[0] : ((k == 1) ? a.f[1] : a.f[2]);
+      __nv_bfloat16* outp = ((k == 0) ? a.out[0] : ((k == 1) ? a.out[1] : a.out[2])) + (int64_t)row * a.H;
+      if (k > 0) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int blk = j * 32 + lane;
+        if (blk < nblk) {
+          float y[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t cl = ((uint32_t)c + rot) & 3u;
+            const float4 gv = lds128(gam0 + (uint32_t)blk * 64u + cl * 16u);
+            if (ln) {
+              const float4 bv = lds128(bet0 + (uint32_t)blk * 64u + cl * 16u);
+              y[4 * c] = __fmaf_rn(gv.x, __fmul_rn(rstd, v[j][4 * c]), bv.x);
+              y[4 * c + 1] = __fmaf_rn(gv.y, __fmul_rn(rstd, v[j][4 * c + 1]), bv.y);
+              y[4 * c + 2] = __fmaf_rn(gv.z, __fmul_rn(rstd, v[j][4 * c + 2]), bv.z);
+              y[4 * c + 3] = __fmaf_rn(gv.w, __fmul_rn(rstd, v[j][4 * c + 3]), bv.w);
+            } else {
+              y[4 * c] = __fmul_rn(gv.x, __fmul_rn(v[j][4 * c], rstd));
+              y[4 * c + 1] = __fmul_rn(gv.y, __fmul_rn(v[j][4 * c + 1], rstd));
+              y[4 * c + 2] = __fmul_rn(gv.z, __fmul_rn(v[j][4 * c + 2], rstd));
+              y[4 * c + 3] = __fmul_rn(gv.w, __fmul_rn(v[j][4 * c + 3], rstd));
+            }
+          }
+          quantize_signed16<KIND>(y, p);
+          const uint32_t base = outb + (uint32_t)blk * 32u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(base + (((uint32_t)c + rot) & 3u) * 8u),
+                         "r"(pack_bf16x2(y[4 * c], y[4 * c + 1])), "r"(pack_bf16x2(y[4 * c + 2], y[4 * c + 3]))
+                         : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) st_bulk_store(outp, outb, out_bytes);
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int KIND, int NB>
+static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)2 * a.H * 4 + (size_t)kLwWarps * ((size_t)a.H * 6) + kLwWarps * 8;
+  static size_t smem_attr = 0;
+  if (smem > smem_attr) {
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_warp_kernel<KIND, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  static int occ_h = 0, occ = 1;
+  if (occ_h != a.H) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_warp_kernel<KIND, NB>, kLwWarps * 32, smem) != cudaSuccess || o < 1) o = 1;
+    occ = o;
+    occ_h = a.H;
+  }
+  const int64_t want = ((int64_t)a.rows + kLwWarps - 1) / kLwWarps;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * occ);
+  {
+    LaunchScope ls(kKernLnQuant, st);
+    norm_quant_warp_kernel<KIND, NB><<<grid, kLwWarps * 32, smem, st>>>(a);
+  }
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
+template <int KIND>
+static int launch_norm_quant_warp_nb(const LnArgs& a, cudaStream_t st) {
+  const int nblk = a.H / 16;
+  if (nblk <= 32) return launch_norm_quant_warp<KIND, 1>(a, st);
+  if (nblk <= 64) return launch_norm_quant_warp<KIND, 2>(a, st);
+  return launch_norm_quant_warp<KIND, 4>(a, st);
+}
+static bool g_ln_warp_rows = true;
+void set_ln_warp_rows(int on) { g_ln_warp_rows = on != 0; }
+
 int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, const float* gamma, const float* beta, float eps,
                        int n_out, const bq_format* fmts, void* const* outs, cudaStream_t st) {
   if (rows < 0 || H <= 0 || n_out < 1 || n_out > 3 || !fmts || !outs) return BQ_ERR_BAD_ARG;
@@ -1054,6 +1212,14 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
     a.out[k] = (__nv_bfloat16*)outs[k];
   }
   a.rows = (int)rows;
+  if (g_ln_warp_rows && H <= 2048) {
+    bool same = true;
+    for (int k = 1; k < n_out; ++k) same = same && fmts[k].kind == fmts[0].kind;
+    if (same) {
+      a.stages = 1;
+      return fmts[0].kind == BQ_KIND_BLOCK_FP ? launch_norm_quant_warp_nb<kBlockFP>(a, st) : launch_norm_quant_warp_nb<kBlockMinifloat>(a, st);
+    }
+  }
   const int threads = (int)((H / 16 + 31) / 32) * 32;
   auto smem_for = [&](int stages) { return (size_t)stages * H * 4 + (size_t)H * 2 + 2 * kLnMaxWarps * 4 + kLnMaxStages * 8 + (size_t)2 * H * 4; };
   static size_t smem_attr = 0;
@@ -1201,6 +1367,7 @@ int bq_split2_f16_rows(const float* x, int64_t rows, int64_t K, int64_t ldx, voi
   return BQ_OK;
 }
 void bq_set_stream_quantizer(int on) { bq::set_stream_quantizer(on); }
+void bq_set_norm_warp_rows(int on) { bq::set_ln_warp_rows(on); }
 int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream) {
   if (!mismatches_dev3) return BQ_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;

@@ -123,10 +123,22 @@ def test_gemm_epilogue_row_blocks_rare_path_with_nonfinite_values():
     assert bool((C[64:80] == 0).all())
 
 
-@pytest.mark.parametrize("H,rows", [(2048, 512), (768, 300), (4096, 64), (64, 1000)])
-def test_layernorm_quantize_vs_torch_layernorm_then_quantizer(H, rows):
+@pytest.mark.parametrize("warp_rows", [1, 0])
+@pytest.mark.parametrize("H,rows", [(2048, 512), (768, 300), (4096, 64), (64, 1000), (1024, 1), (2048, 8 * 148 * 2 + 3)])
+def test_layernorm_quantize_vs_torch_layernorm_then_quantizer(H, rows, warp_rows):
+    """Both norm+quantize kernels: row-per-warp (H <= 2048, default) and row-per-CTA (any H; forced by the A/B switch)."""
+    from llm_mixed_q_b200 import _lib as L
     from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import norm_quantize
     from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer
+
+    L.load().bq_set_norm_warp_rows(warp_rows)
+    try:
+        _layernorm_quantize_case(H, rows, norm_quantize, block_fp_quantizer)
+    finally:
+        L.load().bq_set_norm_warp_rows(1)
+
+
+def _layernorm_quantize_case(H, rows, norm_quantize, block_fp_quantizer):
 
     g = torch.Generator(device="cuda").manual_seed(H + rows)
     x = torch.randn(rows, H, device="cuda", generator=g) * 3 + 0.5
@@ -152,6 +164,16 @@ def test_layernorm_quantize_vs_torch_layernorm_then_quantizer(H, rows):
     rn = w * (x * torch.rsqrt(var + 1e-6))
     want = block_fp_quantizer(rn, 6, 8, 127, [1, 16], True)
     assert float(((r6.float() - want).abs() > 0).float().mean()) <= 2e-3
+    # block_minifloat outputs (Llama W4A4 / W8A8), zero rows and a zero block inside a row
+    x2 = x.clone()
+    x2[0] = 0
+    x2[-1, :16] = 0
+    fm = ("block_minifloat", dict(width=8, exponent_width=4, exponent_bias_width=8))
+    (m8,) = norm_quantize(x2, w, None, 1e-6, [fm])
+    rn2 = w * (x2 * torch.rsqrt(x2.pow(2).mean(-1, keepdim=True) + 1e-6))
+    want = O.block_minifloat_quantize(rn2, 8, 4, 8, [1, 16], True)
+    assert float(((m8.float() - want).abs() > 0).float().mean()) <= 2e-3
+    assert bool((m8[0] == 0).all())
 
 
 def _opt_model(layers=2, hidden=256, heads=4, ffn=512, vocab=512, width=6):
