@@ -321,7 +321,11 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t tmem_slot = bS + 8u * 10;
   const uint32_t xch = sb + Cfg::kSmemX;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // opaque copy of the thread index: under the 102-register cap the compiler otherwise re-reads SR_TID.X (S2R, ~20 cycles in front
+  // of a dependent chain) inside the per-slice loop — 3 % of the kernel's stall samples sat on that chain (ncu source view)
+  int tid_reg = (int)threadIdx.x;
+  if (D == 64) asm volatile("mov.u32 %0, %0;" : "+r"(tid_reg));      // (d = 128 has no register to spare: pinning spills 350 bytes there)
+  const int warp = tid_reg >> 5, lane = tid_reg & 31;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);

@@ -599,6 +599,8 @@ int make_params(const bq_format* f, FmtParams* p) {
     case kMinifloatIEEE: p->fast_fmt = (mb <= 20 && p->emin >= -100.f && p->emax <= 100.f && p->emax >= p->emin); break;
     default: p->fast_fmt = 0;
   }
+  auto to_i = [](float v) { return (int)fmaxf(fminf(v, 2.0e9f), -2.0e9f); };
+  p->emin_i = to_i(p->emin); p->emax_i = to_i(p->emax); p->bias_hi_i = to_i(p->bias_hi); p->eb_top_i = to_i(p->eb_top);
   return BQ_OK;
 }
 
