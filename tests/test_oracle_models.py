@@ -25,3 +25,27 @@ def test_opt_ref_matches_reference(tag, cfgkey):
         logits, loss = opt_ref.opt_forward(sd, qc, ids, num_layers=2, num_heads=4, labels=ids)
     torch.testing.assert_close(logits, torch.from_numpy(z["logits"]), rtol=1e-4, atol=1e-4)
     assert abs(float(loss) - float(z["loss"])) < 1e-5
+
+
+def test_opt125m_seeded_init_matches_the_reference_checksums():
+    """BASELINE configs[0]: the 125 M weights of the golden run are not stored; the mirror's model built under seed 0 must
+    reproduce every reference tensor (per-tensor sum and abs-sum recorded by oracle/gen_golden_opt125m.py)."""
+    import json
+    import os
+
+    import numpy as np
+    import torch
+
+    from conftest import GOLD
+    from llm_mixed_q_b200.models.opt_quantized import OPTQuantizedConfig, OPTQuantizedForCausalLM
+
+    z = np.load(os.path.join(GOLD, "opt125m_bfp6.npz"))
+    qc = json.load(open(os.path.join(GOLD, "configs.json")))["raw"]["bfp_6bit.toml"]
+    torch.manual_seed(0)
+    model = OPTQuantizedForCausalLM(OPTQuantizedConfig(quant_config=qc, tie_word_embeddings=False))
+    sd = model.state_dict()
+    assert len(z["checksum_keys"]) == len(sd) == 197
+    for k, (s, a) in zip(z["checksum_keys"], z["checksum_vals"]):
+        v = sd[str(k)].double()
+        assert abs(float(v.sum()) - s) <= 1e-9 * (a + 1e-30) and abs(float(v.abs().sum()) - a) <= 1e-9 * a, str(k)
+    assert abs(float(z["loss"]) - 10.991276) < 1e-5

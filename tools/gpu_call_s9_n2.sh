@@ -1,8 +1,12 @@
-# session-9 two-GPU call: peer tests on two real devices, config-5 column-parallel at 2 GPUs, LN kernel check
+# multi-GPU sanity: bench.py under torchrun at N GPUs (N = number of visible devices)
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_peer.py tests/test_gpu_fused_glue.py -x -q 2>&1 | tail -4
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/bench_configs.py --config 5 > gpurun_out/s9_cfg5_n2.log 2>&1
-grep -E "layer total|fc1" gpurun_out/s9_cfg5_n2.log | cut -c1-900
-timeout 300 python tools/bench_kernels.py fused 2>&1 | head -12
+N=$(nvidia-smi -L | wc -l)
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/s9_bench_n$N.json 2> gpurun_out/s9_bench_n$N.err
+tail -c 300 gpurun_out/s9_bench_n$N.json; tail -3 gpurun_out/s9_bench_n$N.err
+python - <<P
+import json
+d=json.loads(open('gpurun_out/s9_bench_n$N.json').read().strip().splitlines()[-1])
+print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])
+P
