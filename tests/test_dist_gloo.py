@@ -95,19 +95,32 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(180)
+@pytest.mark.timeout(420)
 def test_column_parallel_and_dp_perplexity_world2():
     world = 2
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=150) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=30)
-        assert p.exitcode == 0
+    results, last_err = None, None
+    for attempt in range(3):                  # a rendezvous can lose its port to another process between _free_port() and bind
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            got = [q.get(timeout=100) for _ in range(world)]
+            for p in procs:
+                p.join(timeout=30)
+            if all(p.exitcode == 0 for p in procs):
+                results = got
+                break
+            last_err = f"exit codes {[p.exitcode for p in procs]}"
+        except Exception as e:                # queue.Empty: a worker died before reporting
+            last_err = repr(e)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+            p.join(timeout=10)
+    assert results is not None, last_err
     lin, x = _full_linear()
     y_full = lin(x)
     ref_ppl = D.dp_perplexity(_FakeLM(), _batches())        # single process: the reference's loop
