@@ -136,6 +136,17 @@ BQ_API int bq_norm_quantize(const float* x, int64_t rows, int64_t H, int64_t ldx
 /* Exhaustive device self-test: compares the exponent-field shortcuts the quantizers use for
  * ceil/floor/rint(log2f(x)) with libdevice's log2f on every positive finite fp32 bit pattern.
  * Writes three mismatch counters (ceil, floor, rint) to mismatches_dev3 (device memory, 3 x uint64). */
+/* Rotary position embedding + the two operand quantizers of matmul_0, token-major (Llama).  Replaces apply_rotary_pos_emb_*
+ * (quantized_functions/rotary_positional_encoding.py:142-167) followed by the x- / y-quantizers of the QK^T matmul
+ * (models/llama_quantized/modeling_llama.py:309-314 -> quantized_functions/matmul.py:166-196):
+ *   Qq[b,s,h,:] = Q_fq(q * cos[pos] + rotate_half(q) * sin[pos])   blocks of 16 along head_dim
+ *   Kq[b,s,h,e] = Q_fk(k * cos[pos] + rotate_half(k) * sin[pos])   blocks of 16 consecutive positions s at fixed (h, e)  (= blocks of k^T)
+ * q, k fp32 [B][S][heads*head_dim] with token strides ldq / ldk; cos / sin tables fp32 [table_rows][head_dim] ALREADY quantised by
+ * the rotary table quantizer; position_ids int64 [B][S] or NULL (position = s).  Outputs dense bf16 [B][S][heads*head_dim].
+ * Formats: block_fp / block_minifloat, blocks [1,16]; head_dim % 32 == 0, S % 16 == 0. */
+BQ_API int bq_rope_quantize(const float* q, const float* k, const float* cos_table, const float* sin_table, const int64_t* position_ids,
+                            int64_t table_rows, int64_t B, int64_t S, int32_t heads, int32_t head_dim, int64_t ldq, int64_t ldk,
+                            const bq_format* fq, const bq_format* fk, void* Qq_bf16, void* Kq_bf16, void* stream);
 BQ_API int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -121,6 +121,9 @@ def load():
                                      POINTER(c_int32), POINTER(c_int32), c_int64, c_void_p]
     lib.bq_set_attention_precise_exp.restype = None
     lib.bq_set_attention_precise_exp.argtypes = [ctypes.c_int]
+    lib.bq_rope_quantize.restype = ctypes.c_int
+    lib.bq_rope_quantize.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
+                                     c_int64, c_int64, POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_void_p]
     lib.bq_set_norm_warp_rows.restype = None
     lib.bq_set_norm_warp_rows.argtypes = [ctypes.c_int]
     lib.bq_set_stream_quantizer.restype = None

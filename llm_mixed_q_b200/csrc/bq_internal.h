@@ -19,7 +19,7 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
                       int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc,
                       cudaStream_t st);
 enum KernelId { kKernQuantRows = 0, kKernBlockLogFixup, kKernQuantTile, kKernGenericMax, kKernGenericMin, kKernGenericQuant,
-                kKernGemm, kKernAttention, kKernSplit3, kKernGemmEpi, kKernGemmSplit, kKernLnQuant, kKernQuantStream, kKernSiluMulQuant, kKernTokenCe, kKernTokenCeMean, kKernPeerBarrier, kKernCount };
+                kKernGemm, kKernAttention, kKernSplit3, kKernGemmEpi, kKernGemmSplit, kKernLnQuant, kKernQuantStream, kKernSiluMulQuant, kKernTokenCe, kKernTokenCeMean, kKernPeerBarrier, kKernRopeQuant, kKernCount };
 // RAII launch bracket: counts the launch; records start/stop events on `st` when profiling is enabled.
 struct LaunchScope {
   LaunchScope(int id, cudaStream_t st);

@@ -1255,6 +1255,126 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
 
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
+// Rotary position embedding + the x / y quantizers of matmul_0, token-major (Llama).  Replaces apply_rotary_pos_emb
+// (quantized_functions/rotary_positional_encoding.py:142-167: q_embed = (q * cos) + (rotate_half(q) * sin) with the already
+// quantised cos / sin tables gathered by position_ids) FOLLOWED BY the two operand quantizers of the QK^T matmul
+// (models/llama_quantized/modeling_llama.py:309-314, quantized_functions/matmul.py:166-196): q in blocks of 16 along d,
+// k^T in blocks of 16 consecutive key positions at a fixed feature.  The reference runs ~12 element-wise kernels (two gathers, four
+// multiplies, two negations, two concatenations, two additions) and two quantizer calls over [B, S, H] fp32 tensors; here q and k
+// are read once and the bf16 operands of the attention kernel are written once.  Same arithmetic, same order: rn(rn(x * cos) +
+// rn(rot * sin)), rot = -x[i + d/2] for i < d/2 and x[i - d/2] otherwise (negation commutes with the rounding of the product).
+// ------------------------------------------------------------------------------------------------
+struct RopeArgs {
+  const float* q;
+  const float* k;
+  const float* cs;            // cos table [rows][d]
+  const float* sn;            // sin table [rows][d]
+  const int64_t* pos;         // [B][S] or nullptr (position = s)
+  __nv_bfloat16* Qq;
+  __nv_bfloat16* Kq;
+  int B, S, heads, d;
+  int64_t ldq, ldk;           // token strides of q / k (elements); outputs are dense [B*S][heads*d]
+  FmtParams fq, fk;
+};
+// q: one thread per block of 16 along d
+__global__ void __launch_bounds__(256) rope_quant_q_kernel(RopeArgs a) {
+  const int H = a.heads * a.d, bpt = H >> 4, half = a.d >> 1;
+  const int64_t nblk = (int64_t)a.B * a.S * bpt;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nblk; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tok = i / bpt;
+    const int f0 = (int)(i - tok * bpt) << 4;              // first feature of the block
+    const int e0 = f0 % a.d;                               // position inside the head
+    const bool lo = e0 < half;
+    const int64_t p = a.pos ? a.pos[tok] : (tok % a.S);
+    const float* x = a.q + tok * a.ldq + f0;
+    const float* xp = x + (lo ? half : -half);
+    const float* c = a.cs + p * a.d + e0;
+    const float* s = a.sn + p * a.d + e0;
+    float y[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + 4 * j), pv = *reinterpret_cast<const float4*>(xp + 4 * j);
+      const float4 cv = __ldg(reinterpret_cast<const float4*>(c + 4 * j)), sv = __ldg(reinterpret_cast<const float4*>(s + 4 * j));
+      const float r0 = lo ? -pv.x : pv.x, r1 = lo ? -pv.y : pv.y, r2 = lo ? -pv.z : pv.z, r3 = lo ? -pv.w : pv.w;
+      y[4 * j] = __fadd_rn(__fmul_rn(xv.x, cv.x), __fmul_rn(r0, sv.x));
+      y[4 * j + 1] = __fadd_rn(__fmul_rn(xv.y, cv.y), __fmul_rn(r1, sv.y));
+      y[4 * j + 2] = __fadd_rn(__fmul_rn(xv.z, cv.z), __fmul_rn(r2, sv.z));
+      y[4 * j + 3] = __fadd_rn(__fmul_rn(xv.w, cv.w), __fmul_rn(r3, sv.w));
+    }
+    quantize_signed16_rt(y, a.fq);
+    uint4* o = reinterpret_cast<uint4*>(a.Qq + tok * H + f0);
+    o[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    o[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
+  }
+}
+// k: one thread per (16 consecutive key positions, feature); a warp covers 32 consecutive features, so every access is a
+// coalesced 128-byte (fp32) or 64-byte (bf16) row segment
+__global__ void __launch_bounds__(256) rope_quant_k_kernel(RopeArgs a) {
+  const int H = a.heads * a.d, half = a.d >> 1, sblk = a.S >> 4;
+  const int64_t n = (int64_t)a.B * sblk * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % H);
+    const int64_t bs = i / H;                              // (batch, block of 16 positions)
+    const int b = (int)(bs / sblk), s0 = (int)(bs - (int64_t)b * sblk) << 4;
+    const int e = f % a.d;
+    const bool lo = e < half;
+    const int fp = lo ? f + half : f - half;
+    float y[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int64_t tok = (int64_t)b * a.S + s0 + t;
+      const int64_t p = a.pos ? a.pos[tok] : (int64_t)(s0 + t);
+      const float xv = a.k[tok * a.ldk + f], pv = a.k[tok * a.ldk + fp];
+      const float cv = __ldg(a.cs + p * a.d + e), sv = __ldg(a.sn + p * a.d + e);
+      y[t] = __fadd_rn(__fmul_rn(xv, cv), __fmul_rn(lo ? -pv : pv, sv));
+    }
+    quantize_signed16_rt(y, a.fk);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) a.Kq[((int64_t)b * a.S + s0 + t) * H + f] = __float2bfloat16_rn(y[t]);
+  }
+}
+
+int rope_quantize_impl(const float* q, const float* k, const float* cos_t, const float* sin_t, const int64_t* pos, int64_t table_rows,
+                       int64_t B, int64_t S, int heads, int d, int64_t ldq, int64_t ldk, const bq_format* fq, const bq_format* fk,
+                       void* Qq, void* Kq, cudaStream_t st) {
+  if (B < 0 || S < 0 || heads <= 0 || d <= 0 || !fq || !fk) return BQ_ERR_BAD_ARG;
+  if (B == 0 || S == 0) return BQ_OK;
+  if (!q || !k || !cos_t || !sin_t || !Qq || !Kq) return BQ_ERR_BAD_ARG;
+  if ((d % 32) || (S % 16)) return BQ_ERR_UNSUPPORTED;              // a block of 16 stays inside one half of a head / inside the sequence
+  if (!pos && table_rows < S) return BQ_ERR_BAD_ARG;
+  const int64_t H = (int64_t)heads * d;
+  if (ldq < H || ldk < H || (ldq % 4) || (ldk % 4) || ((uintptr_t)q % 16) || ((uintptr_t)k % 16) || ((uintptr_t)cos_t % 16) ||
+      ((uintptr_t)sin_t % 16) || ((uintptr_t)Qq % 16) || ((uintptr_t)Kq % 2))
+    return BQ_ERR_BAD_ARG;
+  if (B * S * H > 0x7fffffffffffll || H > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  RopeArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < 2; ++i) {
+    const bq_format* f = i ? fk : fq;
+    if (f->kind != BQ_KIND_BLOCK_FP && f->kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
+    if (f->block_rows != 1 || f->block_cols != 16) return BQ_ERR_UNSUPPORTED;
+    int rc = make_params(f, i ? &a.fk : &a.fq);
+    if (rc) return rc;
+    (i ? a.fk : a.fq).fold_zero = 0;
+  }
+  a.q = q; a.k = k; a.cs = cos_t; a.sn = sin_t; a.pos = pos; a.Qq = (__nv_bfloat16*)Qq; a.Kq = (__nv_bfloat16*)Kq;
+  a.B = (int)B; a.S = (int)S; a.heads = heads; a.d = d; a.ldq = ldq; a.ldk = ldk;
+  const int64_t nq = B * S * (H / 16), nk = B * (S / 16) * H;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  {
+    LaunchScope ls(kKernRopeQuant, st);
+    rope_quant_q_kernel<<<(int)std::min<int64_t>((nq + 255) / 256, cap), 256, 0, st>>>(a);
+  }
+  BQ_CUDA_CHECK(cudaGetLastError());
+  {
+    LaunchScope ls(kKernRopeQuant, st);
+    rope_quant_k_kernel<<<(int)std::min<int64_t>((nk + 255) / 256, cap), 256, 0, st>>>(a);
+  }
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 -> two fp16 planes per row with a per-row power-of-two scale:  x * 2^e = hi + lo (+- 2^-22 of the row max),
 // hi = fp16(x * 2^e), lo = fp16(x * 2^e - hi), e chosen so that the row max lands in [2^14, 2^15).
 // Operand format of the fp16-split GEMM that stands in for the reference's UNQUANTISED fp32 matmuls (lm_head): three
@@ -1370,6 +1490,12 @@ int bq_split2_f16_rows(const float* x, int64_t rows, int64_t K, int64_t ldx, voi
 }
 void bq_set_stream_quantizer(int on) { bq::set_stream_quantizer(on); }
 void bq_set_norm_warp_rows(int on) { bq::set_ln_warp_rows(on); }
+int bq_rope_quantize(const float* q, const float* k, const float* cos_table, const float* sin_table, const int64_t* position_ids,
+                     int64_t table_rows, int64_t B, int64_t S, int32_t heads, int32_t head_dim, int64_t ldq, int64_t ldk,
+                     const bq_format* fq, const bq_format* fk, void* Qq_bf16, void* Kq_bf16, void* stream) {
+  return bq::rope_quantize_impl(q, k, cos_table, sin_table, position_ids, table_rows, B, S, heads, head_dim, ldq, ldk, fq, fk, Qq_bf16,
+                                Kq_bf16, (cudaStream_t)stream);
+}
 int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream) {
   if (!mismatches_dev3) return BQ_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;

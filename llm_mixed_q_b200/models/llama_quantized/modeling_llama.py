@@ -26,6 +26,7 @@ from ..quantize.quantized_functions.loss import causal_lm_loss
 from ..quantize.quantized_functions.fused_glue import (linear_input_format, norm_quantize, row_block16_format,
                                                         silu_mul_quantize)
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major as _rope_token_major
+from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major_quantized as _rope_token_major_quantized
 from ..quantize.quantized_modules.linear import operand_format, quantize_operand_bf16
 from .configuration_llama import LlamaQuantizedConfig
 
@@ -136,6 +137,7 @@ class LlamaQuantizedDecoderLayer(nn.Module):
                                      config.quant_config[f"model_layer_{layer_id}"]["mlp"])
         self.input_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.fused_rope = True           # False: RoPE with torch ops + separate q / k^T quantizer launches (A/B, tests)
 
     # ------------------------------------------------------------------ fused layer (PTQ inference, causal mask)
     def _fused_plan(self, seq_len: int):
@@ -171,9 +173,14 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         k = at.k_proj.forward_prequantized(xk)
         Vq = at.v_proj.forward_prequantized(xv, out_format=plan["v_out"])        # bmm_1's y-quantizer in the GEMM epilogue
         cos, sin = at.rotary_emb(q, seq_len=S)
-        q4, k4 = _rope_token_major(q.view(B, S, at.num_heads, at.head_dim), k.view(B, S, at.num_heads, at.head_dim), cos, sin,
-                                   position_ids, qc["rotary_positional_encoding"])
-        Qq, Kq, _ = quantize_qkv(q4.view(B, S, H), k4.view(B, S, H), None, qc["matmul_0"], qc["matmul_1"], at.num_heads)
+        fusedqk = _rope_token_major_quantized(q.view(B, S, H), k.view(B, S, H), cos, sin, position_ids,
+                                              qc["rotary_positional_encoding"], qc["matmul_0"], at.num_heads) if self.fused_rope else None
+        if fusedqk is not None:                                                  # RoPE + both matmul_0 operand quantizers: 2 kernels
+            Qq, Kq = fusedqk
+        else:
+            q4, k4 = _rope_token_major(q.view(B, S, at.num_heads, at.head_dim), k.view(B, S, at.num_heads, at.head_dim), cos, sin,
+                                       position_ids, qc["rotary_positional_encoding"])
+            Qq, Kq, _ = quantize_qkv(q4.view(B, S, H), k4.view(B, S, H), None, qc["matmul_0"], qc["matmul_1"], at.num_heads)
         oq = fused_causal_attention_q(Qq, Kq, Vq, qc["matmul_1"], at.num_heads, B, S, math.sqrt(at.head_dim),
                                       out_cfg=at.o_proj.config)
         h2 = at.o_proj.forward_prequantized(oq, residual=h)                      # residual + o_proj(attn)

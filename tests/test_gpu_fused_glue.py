@@ -266,6 +266,46 @@ def test_fused_llama_layer_matches_op_by_op(tomlname, init):
     assert float(err.mean()) <= 0.03 * spread and float(err.max()) <= 0.75 * spread, (float(err.mean()), float(err.max()), spread)
 
 
+@pytest.mark.parametrize("kind", ["block_fp", "block_minifloat"])
+@pytest.mark.parametrize("heads,d", [(4, 64), (2, 128)])
+def test_rope_quantize_kernel_is_bit_identical_to_rope_ops_plus_quantizers(kind, heads, d):
+    """bq_rope_quantize == apply_rotary_pos_emb (torch ops on the quantised tables) followed by the q / k^T quantizers of matmul_0."""
+    from llm_mixed_q_b200.models.llama_quantized.modeling_llama import LlamaRotaryEmbedding
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import quantize_qkv
+    from llm_mixed_q_b200.models.quantize.quantized_functions.rotary_positional_encoding import (apply_token_major,
+                                                                                                  apply_token_major_quantized)
+
+    B, S, H = 3, 96, heads * d
+    if kind == "block_fp":
+        m0 = {"name": "block_fp", "bypass": False}
+        for p in ("data_in", "weight"):
+            m0.update({f"{p}_width": 6, f"{p}_exponent_width": 8, f"{p}_exponent_bias": 127, f"{p}_block_size": [1, 16]})
+    else:
+        m0 = {"name": "block_minifloat", "bypass": False}
+        for p in ("data_in", "weight"):
+            m0.update({f"{p}_width": 8, f"{p}_exponent_width": 4, f"{p}_exponent_bias_width": 8, f"{p}_block_size": [1, 16]})
+    rope_cfg = {"name": "integer", "bypass": False, "data_in_width": 8, "data_in_frac_width": 7}
+    g = torch.Generator(device="cuda").manual_seed(heads * d)
+    q = torch.randn(B, S, H, device="cuda", generator=g) * 2
+    k = torch.randn(B, S, H, device="cuda", generator=g) * 2
+    q[0, 3] = 0
+    k[1, 16:32, :d] = 0                                     # all-zero k^T blocks
+    k[2, 5, 7] = 1e-9                                       # pass-through element
+    rot = LlamaRotaryEmbedding(d, max_position_embeddings=256).cuda()
+    cos, sin = rot(q, seq_len=S)
+    for pos in (torch.arange(S, device="cuda")[None].expand(B, S), torch.randint(0, S, (B, S), device="cuda", generator=g), None):
+        pid = pos if pos is not None else torch.arange(S, device="cuda")[None]
+        q4, k4 = apply_token_major(q.view(B, S, heads, d), k.view(B, S, heads, d), cos, sin, pid, rope_cfg)
+        Qr, Kr, _ = quantize_qkv(q4.reshape(B, S, H), k4.reshape(B, S, H), None, m0, m0, heads)
+        got = apply_token_major_quantized(q, k, cos, sin, pid if pos is not None else None, rope_cfg, m0, heads)
+        assert got is not None
+        assert torch.equal(got[0].view(torch.int16), Qr.reshape(B, S, H).view(torch.int16))
+        assert torch.equal(got[1].view(torch.int16), Kr.reshape(B, S, H).view(torch.int16))
+    # not eligible: block sizes other than [1,16] -> None, the caller falls back
+    m_odd = dict(m0, data_in_block_size=[1, 32])
+    assert apply_token_major_quantized(q, k, cos, sin, None, rope_cfg, m_odd, heads) is None
+
+
 def test_fused_llama_not_eligible_for_block_log():
     import json
     import os
