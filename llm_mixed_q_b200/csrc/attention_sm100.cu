@@ -616,7 +616,8 @@ template <int KIND, int D, bool FAST>
 static int launch_attention_f(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
                               cudaStream_t st) {
   using Cfg = AtCfg<D>;
-  static bool attr = false;
+  static PerDevice<bool> attr_pd;
+  bool& attr = attr_pd.get();
   if (!attr) {
     BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_kernel<KIND, D, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));

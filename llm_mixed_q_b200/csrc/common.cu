@@ -14,6 +14,11 @@ void set_last_cuda_error(const char* what, const char* file, int line) {
 // ---------------------------------------------------------------------------------------------
 // launch accounting
 // ---------------------------------------------------------------------------------------------
+int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return 0;
+  return d;
+}
 static const char* kKernelNames[kKernCount] = {"quant_rows_kernel", "blocklog_fixup_kernel", "quant_tile_kernel",
                                                "generic_blockmax_kernel", "generic_gmin_kernel", "generic_quant_kernel",
                                                "gemm_bf16_tn_kernel", "attention_causal_kernel", "split3_kernel",

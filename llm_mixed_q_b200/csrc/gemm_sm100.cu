@@ -580,7 +580,8 @@ int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, i
 template <int BN, int EPI, int CG>
 static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, cudaStream_t st, int kern_id) {
   using Cfg = GemmCfg<BN, EPI, CG>;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_pd;
+  bool& attr_set = attr_pd.get();
   if (!attr_set) {
     BQ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;

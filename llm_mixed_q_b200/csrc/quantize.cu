@@ -289,10 +289,15 @@ __global__ void __launch_bounds__(kStWarps * 32) quant_stream_kernel(const float
   extern __shared__ __align__(128) uint8_t st_smem[];
   constexpr bool kBlocked = IsBlocked<KIND>::value;
   constexpr bool kBf16 = sizeof(OutT) == 2;
+  constexpr uint32_t kStageBytes = kStTileBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(st_smem) + (uint32_t)warp * kStStages * kStTileBytes;
-  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(st_smem) + (uint32_t)kStWarps * kStStages * kStTileBytes +
+  const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(st_smem) + (uint32_t)warp * kStStages * kStageBytes;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(st_smem) + (uint32_t)kStWarps * kStStages * kStageBytes +
                         (uint32_t)warp * kStStages * 8;
+  auto load_tile = [&](uint32_t dst, uint64_t t, uint32_t bar) {
+    const uint64_t left = n_elems - t * kStTileElems;
+    st_bulk_load(dst, x + t * kStTileElems, (uint32_t)(left < kStTileElems ? left : kStTileElems) * 4u, bar);
+  };
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < kStStages; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * k));
@@ -307,11 +312,7 @@ __global__ void __launch_bounds__(kStWarps * 32) quant_stream_kernel(const float
 #pragma unroll
     for (int k = 0; k < kStStages - 1; ++k) {
       const uint64_t t = tile + (uint64_t)k * nw;
-      if (t < n_tiles) {
-        const uint64_t left = n_elems - t * kStTileElems;
-        st_bulk_load(buf0 + k * kStTileBytes, x + t * kStTileElems, (uint32_t)(left < kStTileElems ? left : kStTileElems) * 4u,
-                     bar0 + 8 * k);
-      }
+      if (t < n_tiles) load_tile(buf0 + k * kStageBytes, t, bar0 + 8 * k);
     }
   }
   const uint32_t rot = (uint32_t)(lane >> 1) & 3u;
@@ -322,14 +323,16 @@ __global__ void __launch_bounds__(kStWarps * 32) quant_stream_kernel(const float
   for (; tile < n_tiles; tile += nw) {
     const uint64_t left = n_elems - tile * kStTileElems;
     const uint32_t n_here = (uint32_t)(left < kStTileElems ? left : kStTileElems);
-    const uint32_t buf = buf0 + s * kStTileBytes;
+    const uint32_t buf = buf0 + s * kStageBytes;
     st_mbar_wait(bar0 + 8 * s, parity);
     float4 v[kStNB][4];
 #pragma unroll
     for (int j = 0; j < kStNB; ++j) {
       const uint32_t base = buf + (uint32_t)(j * 32 + lane) * 64u;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[j][c] = lds128(base + (((uint32_t)c + rot) & 3u) * 16u);
+      for (int c = 0; c < 4; ++c) {
+        v[j][c] = lds128(base + (((uint32_t)c + rot) & 3u) * 16u);
+      }
     }
     if (kBf16) __syncwarp();                        // every lane holds its inputs before the packed in-place writes below
 #pragma unroll
@@ -404,9 +407,7 @@ __global__ void __launch_bounds__(kStWarps * 32) quant_stream_kernel(const float
       if (nt < n_tiles) {
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         const int ns = (s == 0) ? kStStages - 1 : s - 1;
-        const uint64_t l2 = n_elems - nt * kStTileElems;
-        st_bulk_load(buf0 + ns * kStTileBytes, x + nt * kStTileElems, (uint32_t)(l2 < kStTileElems ? l2 : kStTileElems) * 4u,
-                     bar0 + 8 * ns);
+        load_tile(buf0 + ns * kStageBytes, nt, bar0 + 8 * ns);
       }
     }
     if (++s == kStStages) { s = 0; parity ^= 1u; }
@@ -690,10 +691,11 @@ static int make_plan(const bq_format* f, const bq_tensor3* t, int transpose_out,
   return BQ_OK;
 }
 
-static int g_num_sms = 0;
+static PerDevice<int> g_num_sms_pd;
 static int g_stream_enabled = 1;
 void set_stream_quantizer(int on) { g_stream_enabled = on ? 1 : 0; }
 int num_sms() {
+  int& g_num_sms = g_num_sms_pd.get();
   if (g_num_sms == 0) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -717,8 +719,8 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
     const uint64_t tile = (uint64_t)kThreads * kUnroll;
     uint64_t tiles = (pl.rg.total_slots + tile - 1) / tile;
     // persistent grid: exactly the number of CTAs that are co-resident (one wave), so the grid-stride loop balances
-    static int occ_flat = 0, occ_rows = 0;
-    int& occ = pl.rg.flat ? occ_flat : occ_rows;
+    static PerDevice<int> occ_flat_pd, occ_rows_pd;
+    int& occ = pl.rg.flat ? occ_flat_pd.get() : occ_rows_pd.get();
     if (occ == 0) {
       int o = 0;
       cudaError_t e = pl.rg.flat
@@ -736,8 +738,10 @@ static int launch_kind(const Plan& pl, const FmtParams& p, const float* x, OutT*
         else quant_rows_kernel<KIND, OutT, false, true><<<grid, kThreads, 0, st>>>(x, y, pl.rg, p, gstate, aux, x2);
       }
     } else if (stream) {
-      static bool attr_set = false;
-      static int occ_st = 0;
+      static PerDevice<bool> attr_pd;
+      static PerDevice<int> occ_st_pd;
+      bool& attr_set = attr_pd.get();
+      int& occ_st = occ_st_pd.get();
       if (!attr_set) {
         BQ_CUDA_CHECK(cudaFuncSetAttribute(quant_stream_kernel<KIND, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmem));
         int o = 0;
@@ -1042,7 +1046,8 @@ __global__ void __maxnreg__(80) norm_quant_kernel(LnArgs a) {
 // while this one is processed), gamma / beta are read from one shared copy per CTA.  ~16 instructions per element against 33
 // for v5 (whose per-row CTA barriers, partial-sum exchange and thread-0 bookkeeping are per-row costs paid by 4 warps).
 constexpr int kLwWarps = 8;
-template <int KIND, int NB>
+// FULL: the row has exactly NB * 32 blocks (H = 512 * NB), no per-block predicate anywhere
+template <int KIND, int NB, bool FULL>
 __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArgs a) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1079,7 +1084,7 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
       const uint32_t base = in0 + (uint32_t)blk * 64u;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float4 t = blk < nblk ? lds128(base + (((uint32_t)c + rot) & 3u) * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t = (FULL || blk < nblk) ? lds128(base + (((uint32_t)c + rot) & 3u) * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
         v[j][4 * c] = t.x; v[j][4 * c + 1] = t.y; v[j][4 * c + 2] = t.z; v[j][4 * c + 3] = t.w;
       }
     }
@@ -1110,7 +1115,7 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
         v[j][i] = __fsub_rn(v[j][i], mean);
         t[i & 3] = __fmaf_rn(v[j][i], v[j][i], t[i & 3]);
       }
-      if (j * 32 + lane < nblk) q = __fadd_rn(q, __fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])));
+      if (FULL || j * 32 + lane < nblk) q = __fadd_rn(q, __fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])));
     }
     const float rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(q), invH), a.eps));     // (warp_sum's shuffles also order lane 0's wait above)
 #pragma unroll 1
@@ -1124,7 +1129,7 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const int blk = j * 32 + lane;
-        if (blk < nblk) {
+        if (FULL || blk < nblk) {
           float y[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -1160,18 +1165,21 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int KIND, int NB>
+template <int KIND, int NB, bool FULL>
 static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)2 * a.H * 4 + (size_t)kLwWarps * ((size_t)a.H * 6) + kLwWarps * 8;
-  static size_t smem_attr = 0;
+  static PerDevice<size_t> smem_attr_pd;
+  size_t& smem_attr = smem_attr_pd.get();
   if (smem > smem_attr) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_warp_kernel<KIND, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_warp_kernel<KIND, NB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
-  static int occ_h = 0, occ = 1;
+  static PerDevice<int> occ_h_pd, occ_pd;
+  int& occ_h = occ_h_pd.get();
+  int& occ = occ_pd.get();
   if (occ_h != a.H) {
     int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_warp_kernel<KIND, NB>, kLwWarps * 32, smem) != cudaSuccess || o < 1) o = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_warp_kernel<KIND, NB, FULL>, kLwWarps * 32, smem) != cudaSuccess || o < 1) o = 1;
     occ = o;
     occ_h = a.H;
   }
@@ -1179,7 +1187,7 @@ static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
   const int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * occ);
   {
     LaunchScope ls(kKernLnQuant, st);
-    norm_quant_warp_kernel<KIND, NB><<<grid, kLwWarps * 32, smem, st>>>(a);
+    norm_quant_warp_kernel<KIND, NB, FULL><<<grid, kLwWarps * 32, smem, st>>>(a);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
@@ -1187,9 +1195,11 @@ static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
 template <int KIND>
 static int launch_norm_quant_warp_nb(const LnArgs& a, cudaStream_t st) {
   const int nblk = a.H / 16;
-  if (nblk <= 32) return launch_norm_quant_warp<KIND, 1>(a, st);
-  if (nblk <= 64) return launch_norm_quant_warp<KIND, 2>(a, st);
-  return launch_norm_quant_warp<KIND, 4>(a, st);
+  if (nblk == 128) return launch_norm_quant_warp<KIND, 4, true>(a, st);
+  if (nblk == 64) return launch_norm_quant_warp<KIND, 2, true>(a, st);
+  if (nblk <= 32) return launch_norm_quant_warp<KIND, 1, false>(a, st);
+  if (nblk <= 64) return launch_norm_quant_warp<KIND, 2, false>(a, st);
+  return launch_norm_quant_warp<KIND, 4, false>(a, st);
 }
 static bool g_ln_warp_rows = true;
 void set_ln_warp_rows(int on) { g_ln_warp_rows = on != 0; }
@@ -1224,13 +1234,17 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
   }
   const int threads = (int)((H / 16 + 31) / 32) * 32;
   auto smem_for = [&](int stages) { return (size_t)stages * H * 4 + (size_t)H * 2 + 2 * kLnMaxWarps * 4 + kLnMaxStages * 8 + (size_t)2 * H * 4; };
-  static size_t smem_attr = 0;
+  static PerDevice<size_t> smem_attr_pd;
+  size_t& smem_attr = smem_attr_pd.get();
   if (smem_for(kLnMaxStages) > smem_attr) {
     BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(kLnMaxStages)));
     smem_attr = smem_for(kLnMaxStages);
   }
   // ring depth: the deepest of 4 / 3 / 2 slots that does not cost a resident CTA
-  static int occ_cache_h = 0, occ_cache = 0, stages_cache = 2;
+  static PerDevice<int> occ_cache_h_pd, occ_cache_pd, stages_cache_pd;
+  int& occ_cache_h = occ_cache_h_pd.get();
+  int& occ_cache = occ_cache_pd.get();
+  int& stages_cache = stages_cache_pd.get();
   if (occ_cache_h != (int)H) {
     int best = 0, best_s = 2;
     for (int s = kLnMaxStages; s >= 2; --s) {

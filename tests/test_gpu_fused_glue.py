@@ -306,6 +306,39 @@ def test_rope_quantize_kernel_is_bit_identical_to_rope_ops_plus_quantizers(kind,
     assert apply_token_major_quantized(q, k, cos, sin, None, rope_cfg, m_odd, heads) is None
 
 
+@pytest.mark.parametrize("stream", [1, 0])
+@pytest.mark.parametrize("kind", ["block_fp", "block_minifloat"])
+def test_silu_mul_quantize_is_bit_identical_to_torch_silu_mul_then_quantizer(kind, stream):
+    """Q(silu(gate) * up) in one kernel == torch's silu, multiply, then the quantizer (the A/B switch must not change the result:
+    the silu*mul prologue lives in the per-slot kernel — a bulk-copy streaming variant holding both tiles in shared memory was
+    measured slower, 0.316 vs 0.188 ms at 4096 x 11008: one CTA of 8 warps per SM cannot hide expf + IEEE division)."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import silu_mul_quantize
+    from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer, block_minifloat_quantizer
+
+    if kind == "block_fp":
+        fmt, qz = ("block_fp", dict(width=6, exponent_width=8, exponent_bias=127)), lambda t: block_fp_quantizer(t, 6, 8, 127, [1, 16], True)
+    else:
+        fmt = ("block_minifloat", dict(width=8, exponent_width=4, exponent_bias_width=8))
+        qz = lambda t: block_minifloat_quantizer(t, 8, 4, 8, [1, 16], True)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    L.load().bq_set_stream_quantizer(stream)
+    try:
+        for rows, I in [(300, 11008), (64, 352), (5, 16), (1030, 1024)]:
+            gate = torch.randn(rows, I, device="cuda", generator=g) * 3
+            up = torch.randn(rows, I, device="cuda", generator=g)
+            gate[0, :16] = 0
+            up[1, 16:32] = 0
+            gate[2, 5] = -100.0                          # silu underflows to -0
+            want = qz(torch.nn.functional.silu(gate) * up)
+            got = silu_mul_quantize(gate, up, fmt)
+            assert_bf16_carrier_equal(got, want, torch.nn.functional.silu(gate) * up)
+            got32 = silu_mul_quantize(gate, up, fmt, out_dtype=torch.float32)
+            assert torch.equal(got32, want)
+    finally:
+        L.load().bq_set_stream_quantizer(1)
+
+
 def test_fused_llama_not_eligible_for_block_log():
     import json
     import os
