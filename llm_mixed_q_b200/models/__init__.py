@@ -1,14 +1,15 @@
 """llm_mixed_q_b200.models — quantize/ (registries, kernels) and the quantized OPT / Llama / BERT module classes.
 
 Same lookup surface as reference models/__init__.py:26-108 for the entries that sit on the quantized forward path
-(model / config / quant-config-parser maps).  The tokenizer, profiler, sampler and statistic-hook maps belong to the
+(model / config / quant-config-parser / analytic-profiler maps).  The tokenizer, sampler and statistic-hook maps belong to the
 search / training drivers, which SURVEY.md §8 marks out of scope.
 """
-from .bert_quantized import BertQuantizedConfig, BertQuantizedForSequenceClassification, parse_bert_quantized_config
+from .bert_quantized import (BertQuantizedConfig, BertQuantizedForSequenceClassification, parse_bert_quantized_config,
+                             profile_bert_quantized)
 from .llama_quantized import (LlamaQuantizedConfig, LlamaQuantizedForCausalLM, LlamaQuantizedForSequenceClassification,
-                              parse_llama_quantized_config)
+                              parse_llama_quantized_config, profile_llama_quantized)
 from .opt_quantized import (OPTQuantizedConfig, OPTQuantizedForCausalLM, OPTQuantizedForSequenceClassification,
-                            parse_opt_quantized_config)
+                            parse_opt_quantized_config, profile_opt_quantized)
 
 MODEL_MAP = {
     "bert": {"cls": BertQuantizedForSequenceClassification},
@@ -18,6 +19,7 @@ MODEL_MAP = {
 CONFIG_MAP = {"bert": BertQuantizedConfig, "llama": LlamaQuantizedConfig, "opt": OPTQuantizedConfig}
 QUANT_CONFIG_PARSER_MAP = {"bert": parse_bert_quantized_config, "llama": parse_llama_quantized_config,
                            "opt": parse_opt_quantized_config}
+PROFILER_MAP = {"bert": profile_bert_quantized, "llama": profile_llama_quantized, "opt": profile_opt_quantized}
 
 
 def get_model_cls(arch: str, task: str):
@@ -34,3 +36,8 @@ def get_config_cls(arch: str):
 def get_quant_config_parser(arch: str):
     assert arch in QUANT_CONFIG_PARSER_MAP, f"arch {arch} not supported"
     return QUANT_CONFIG_PARSER_MAP[arch]
+
+
+def get_model_profiler(arch: str):
+    assert arch in PROFILER_MAP, f"arch {arch} not supported"
+    return PROFILER_MAP[arch]
