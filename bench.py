@@ -353,6 +353,8 @@ def main():
                 "achieved": achieved, "peak": pk["tf_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long, power-capped step)",
                 "frac_of_burst_peak": achieved / pk["tf_burst"], "burst_peak": pk["tf_burst"],
+                "frac_note": "the sustained figure is a GEMM-only loop at the power cap; inside the step the GEMMs alternate with lower-power "
+                             "kernels (attention, norm) and clock higher than that loop, so frac can exceed 1 — frac_of_burst_peak is the hard ceiling",
                 "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu --set full)", "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "share_of_step": gemm_ms / step_ms_local, "algorithmic_flops_per_step": gemm_flops,
