@@ -140,3 +140,30 @@ def test_opt125m_config1_fused_and_op_by_op_match_reference_forward():
         assert d_lse <= 0.01, (name, d_lse)
     # the fused layers must not be further from the reference than the op-by-op path (bit-exact quantizers + same GEMM kernel) is
     assert results["fused"][1] <= 1.5 * results["op-by-op"][1] + 1e-3, results
+
+
+@pytest.mark.timeout(600)
+def test_opt_1p3b_headline_shape_fused_matches_op_by_op():
+    """BASELINE configs[2] shape (OPT-1.3B, W6A6 block_fp on every Linear and both bmms, seq 2048; batch 2 to bound the op-by-op
+    path's 4 GB of fp32 scores per layer): the 8-kernel fused layers against the same modules run op by op (bit-exact quantizer
+    kernels, one GEMM kernel, torch softmax) on the synthetic token stream bench.py uses — loss to 2e-4 relative."""
+    import bench
+
+    model = bench.build_model(torch.device("cuda", 0))
+    dec = model.model.decoder
+    ids = torch.randint(0, bench.OPT13B["vocab_size"], (2, bench.SEQ), generator=torch.Generator().manual_seed(0)).cuda()
+    with torch.no_grad():
+        assert dec.layers[0]._fused_plan(bench.SEQ) is not None
+        fused = model(input_ids=ids, labels=ids)                       # also performs the one-off PTQ weight overwrite
+        lf, logits_f = float(fused.loss), fused.logits[:, ::64, ::97].float().cpu()
+        del fused
+        dec.fused_glue, dec.fused_attention = False, False
+        ref = model(input_ids=ids, labels=ids)
+        lr, logits_r = float(ref.loss), ref.logits[:, ::64, ::97].float().cpu()
+        spread = float(ref.logits.std())
+        del ref
+    dec.fused_glue, dec.fused_attention = True, True
+    err = (logits_f - logits_r).abs()
+    print("opt-1.3b fused vs op-by-op: loss", lf, lr, "mean|dlogit|", float(err.mean()), "max", float(err.max()), "logit std", spread)
+    assert abs(lf - lr) <= 2e-4 * abs(lr), (lf, lr)
+    assert float(err.mean()) <= 0.08 * spread and float(err.max()) <= 0.6 * spread, (float(err.mean()), float(err.max()), spread)

@@ -1,4 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest tests/test_gpu_consumers.py tests/test_gpu_models.py tests/test_gpu_fused_glue.py -x -q -k "not opt125m" > gpurun_out/s9_sanitizer_rest.log 2>&1; echo "rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|misaligned" gpurun_out/s9_sanitizer_rest.log | head -8
+timeout 600 python -m pytest tests/test_gpu_models.py -x -q -s -k "1p3b" > gpurun_out/s9_opt13b_parity.log 2>&1
+grep -n "opt-1.3b fused\|passed\|failed\|Error" gpurun_out/s9_opt13b_parity.log | cut -c1-400
