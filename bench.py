@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer decoder layers (result is then INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true")
+    ap.add_argument("--eager-e2e", action="store_true", help="end-to-end region through the eager forward instead of graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -310,15 +311,31 @@ def main():
         prof = L.profile_read()
         loss_val = float(out.loss)
         # ---- end-to-end: pinned host ids -> H2D, forward, loss D2H, every step ---------------
+        # through the package's graph-replay runner (llm_mixed_q_b200.utils.graphs.GraphedForward: the forward captured once in a CUDA
+        # graph — every step copies the ids from pinned host memory, replays, and reads the loss back), eager if capture is refused
+        from llm_mixed_q_b200.utils.graphs import GraphedForward
+
+        runner = None if args.eager_e2e else GraphedForward(model, BATCH, SEQ, device)
+        e2e_mode = "cuda-graph replay" if (runner is not None and runner.graph is not None) else "eager"
+        if runner is not None:
+            e2e_loss = float(runner(ids_host))                                         # one untimed replay; must reproduce the eager loss
+            assert abs(e2e_loss - loss_val) <= 1e-6 * abs(loss_val), (e2e_loss, loss_val)
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
-            ids_dev = ids_host.to(device, non_blocking=True)
-            o = model(input_ids=ids_dev, labels=ids_dev)
-            _ = o.loss.item()
+            if runner is not None:
+                _ = runner(ids_host).item()
+            else:
+                ids_dev = ids_host.to(device, non_blocking=True)
+                o = model(input_ids=ids_dev, labels=ids_dev)
+                _ = o.loss.item()
         e1.record()
         barrier()
+        clocks_e2e = sampler2.stop() if rank == 0 else None
         e2e_ms = max_over_ranks(e0.elapsed_time(e1))
 
     tokens_per_step = BATCH * SEQ * world
@@ -401,7 +418,8 @@ def main():
                        "loss": loss_val, "layers": Lyr},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * ids_host.element_size(),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K},
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K, "mode": e2e_mode,
+                    "capture_error": getattr(runner, "error", None) if runner is not None else None, "clocks": clocks_e2e},
             "gpu_launches": gpu_launches, "clocks": clocks, "launches_by_kernel": {k: launches1[k] - launches0[k] for k in launches1},
             "sub_metrics": extra}
     if args.layers:

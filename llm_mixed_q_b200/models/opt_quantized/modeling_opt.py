@@ -42,12 +42,15 @@ class OPTLearnedPositionalEmbedding(nn.Embedding):
         return super().forward(positions + self.offset)
 
 
-def _causal_additive_mask(attention_mask, bsz, tgt_len, dtype, device):
-    """[bsz, 1, tgt, src] additive mask: finfo.min above the diagonal and on padded keys (reference :520-548)."""
+def _causal_additive_mask(attention_mask, bsz, tgt_len, dtype, device, all_ones=None):
+    """[bsz, 1, tgt, src] additive mask: finfo.min above the diagonal and on padded keys (reference :520-548).
+    `all_ones`: the caller already knows whether the mask has no padding (None: look — a device-to-host synchronisation)."""
     neg = torch.finfo(dtype).min
     mask = torch.full((tgt_len, tgt_len), neg, device=device, dtype=dtype)
     mask = torch.triu(mask, diagonal=1)[None, None].expand(bsz, 1, tgt_len, tgt_len)
-    if attention_mask is not None and not bool(attention_mask.all()):
+    if all_ones is None:
+        all_ones = attention_mask is None or bool(attention_mask.all())
+    if attention_mask is not None and not all_ones:
         pad = (1.0 - attention_mask[:, None, None, :].to(dtype)).masked_fill(attention_mask[:, None, None, :] == 0, 1.0)
         pad = pad.masked_fill(pad.bool(), neg)
         mask = mask + pad
@@ -274,11 +277,13 @@ class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
         if inputs_embeds is None:
             inputs_embeds = self.embed_tokens(input_ids)
         bsz, seq_len = inputs_embeds.shape[:2]
-        causal_only = attention_mask is None or bool(attention_mask.all())
+        # no padding: known without looking when no mask was passed (the look is a device-to-host synchronisation that would drain
+        # the launch queue at the start of every forward and cannot be captured in a CUDA graph)
+        no_padding = attention_mask is None or bool(attention_mask.all())
         if attention_mask is None:
             attention_mask = torch.ones(bsz, seq_len, dtype=torch.bool, device=inputs_embeds.device)
-        causal_only = causal_only and self.fused_attention
-        causal = _causal_additive_mask(attention_mask, bsz, seq_len, inputs_embeds.dtype, inputs_embeds.device)
+        causal_only = no_padding and self.fused_attention
+        causal = _causal_additive_mask(attention_mask, bsz, seq_len, inputs_embeds.dtype, inputs_embeds.device, all_ones=no_padding)
         pos_embeds = self.embed_positions(attention_mask, 0)
         if self.project_in is not None:
             inputs_embeds = self.project_in(inputs_embeds)

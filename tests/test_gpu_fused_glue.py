@@ -218,6 +218,25 @@ def test_fused_opt_layer_matches_op_by_op_and_oracle(width):
         assert float(err.mean()) <= 0.02 * spread and float(err.max()) <= 0.5 * spread, (name, float(err.mean()), float(err.max()), spread)
 
 
+def test_graphed_forward_replays_the_eager_result():
+    """llm_mixed_q_b200.utils.graphs.GraphedForward: the whole fused forward captured in one CUDA graph (every kernel of the C ABI is
+    a plain stream launch) reproduces the eager forward bit for bit, for new token ids on every replay."""
+    from llm_mixed_q_b200.utils.graphs import GraphedForward
+
+    model = _opt_model()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ids = [torch.randint(0, 512, (3, 128), device="cuda", generator=g) for _ in range(3)]
+    with torch.no_grad():
+        eager = [model(input_ids=i, labels=i) for i in ids]
+    runner = GraphedForward(model, 3, 128)
+    assert runner.graph is not None, runner.error
+    for i, e in zip(ids, eager):
+        loss = runner(i.cpu().pin_memory())                    # host ids: the H2D copy is part of the call
+        assert torch.equal(loss, e.loss) and torch.equal(runner.logits, e.logits)
+    # a model whose forward needs a host-side decision (padding mask -> op-by-op path) still works through the eager fallback
+    assert float(runner(ids[0])) == float(eager[0].loss)
+
+
 def test_fused_layer_falls_back_when_not_eligible():
     model = _opt_model()
     dec = model.model.decoder
