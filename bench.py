@@ -317,9 +317,13 @@ def main():
 
         runner = None if args.eager_e2e else GraphedForward(model, BATCH, SEQ, device)
         e2e_mode = "cuda-graph replay" if (runner is not None and runner.graph is not None) else "eager"
+        replay_ok = None
         if runner is not None:
             e2e_loss = float(runner(ids_host))                                         # one untimed replay; must reproduce the eager loss
-            assert abs(e2e_loss - loss_val) <= 1e-6 * abs(loss_val), (e2e_loss, loss_val)
+            replay_ok = bool(abs(e2e_loss - loss_val) <= 1e-6 * abs(loss_val))
+            if not replay_ok:                                                          # never observed; measure the eager call then
+                print(f"[bench] graph replay loss {e2e_loss} != eager loss {loss_val}: falling back to the eager e2e", file=sys.stderr)
+                runner, e2e_mode = None, "eager (graph replay mismatch)"
         sampler2 = ClockSampler(local_rank)
         if rank == 0:
             sampler2.start()
@@ -419,7 +423,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * ids_host.element_size(),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K, "mode": e2e_mode,
-                    "capture_error": getattr(runner, "error", None) if runner is not None else None, "clocks": clocks_e2e},
+                    "capture_error": getattr(runner, "error", None) if runner is not None else None, "clocks": clocks_e2e, "replay_reproduces_eager_loss": replay_ok},
             "gpu_launches": gpu_launches, "clocks": clocks, "launches_by_kernel": {k: launches1[k] - launches0[k] for k in launches1},
             "sub_metrics": extra}
     if args.layers:
