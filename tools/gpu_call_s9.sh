@@ -1,16 +1,13 @@
+# session-9 final validation: full GPU tests, smoke, bench (+ reference arm)
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_fused_glue.py -x -q -k "graphed or fused_opt_layer" 2>&1 | tail -12
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub > gpurun_out/s9_bench.json 2> gpurun_out/s9_bench.err; tail -5 gpurun_out/s9_bench.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/s9_gpu_tests.log; tail -2 gpurun_out/s9_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/s9_bench.json 2> gpurun_out/s9_bench.err; tail -3 gpurun_out/s9_bench.err
 python - <<'P'
 import json
 d=json.load(open('gpurun_out/s9_bench.json'))
-print(d['value'], d['ms_per_step'], d['e2e'], d['clocks'])
+print(d['value'], d['ms_per_step'], d['e2e'], d['clocks'], d['roofline']['achieved'], d['roofline']['frac'], d['gpu_launches'])
 P
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub --eager-e2e > gpurun_out/s9_bench_eager.json 2>/dev/null
-python - <<'P'
-import json
-d=json.load(open('gpurun_out/s9_bench_eager.json'))
-print(d['value'], d['ms_per_step'], d['e2e'])
-P
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/s9_bench_ref.json; cut -c1-160 gpurun_out/s9_bench_ref.json
