@@ -237,6 +237,33 @@ def test_graphed_forward_replays_the_eager_result():
     assert float(runner(ids[0])) == float(eager[0].loss)
 
 
+def test_graphed_forward_llama():
+    """Same for the fused Llama layers (RMSNorm+quantize, RoPE+quantize, attention, SiLU*up+quantize)."""
+    import json
+    import os
+
+    from conftest import GOLD
+    from llm_mixed_q_b200.models.llama_quantized import LlamaQuantizedConfig, LlamaQuantizedForCausalLM
+    from llm_mixed_q_b200.utils.graphs import GraphedForward
+
+    with open(os.path.join(GOLD, "configs.json")) as f:
+        qc = json.load(f)["raw"]["bfp_6bit.toml"]
+    torch.manual_seed(0)
+    cfg = LlamaQuantizedConfig(hidden_size=128, intermediate_size=352, num_hidden_layers=2, num_attention_heads=2, vocab_size=512,
+                               max_position_embeddings=128, quant_config=qc)
+    model = LlamaQuantizedForCausalLM(cfg).eval().cuda()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    ids = [torch.randint(0, 512, (2, 128), device="cuda", generator=g) for _ in range(2)]
+    with torch.no_grad():
+        eager = [model(input_ids=i, labels=i) for i in ids]
+        assert model.model.layers[0]._fused_plan(128) is not None
+    runner = GraphedForward(model, 2, 128)
+    assert runner.graph is not None, runner.error
+    for i, e in zip(ids, eager):
+        loss = runner(i)
+        assert torch.equal(loss, e.loss) and torch.equal(runner.logits, e.logits)
+
+
 def test_fused_layer_falls_back_when_not_eligible():
     model = _opt_model()
     dec = model.model.decoder
