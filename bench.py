@@ -418,7 +418,8 @@ def main():
                        "l2": "per-step working set (2.6 GB bf16 weights + >4 GB activations/layer) >> 126 MB L2; no flush needed",
                        "arithmetic": "operands: exact block-quantised values carried in bf16; fp32 accumulation in TMEM",
                        "instrumentation": "the device-resident timed region carries two CUDA events per kernel launch (per-kernel times for "
-                                          "`roofline`), about 1-2 % of the step; the `e2e` region runs without them",
+                                          "`roofline`), about 2 % of the step (an event between two kernels costs a front-end round trip, whether one or two are "
+                                          "recorded: sharing events between consecutive launches was measured and changed nothing); the `e2e` region runs without them",
                        "loss": loss_val, "layers": Lyr},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * ids_host.element_size(),
