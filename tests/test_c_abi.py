@@ -65,6 +65,33 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert lib.bq_linear(ctypes.byref(f12), 256, 8, 64, 64, 256, 8, None, 256, 8, 256, 1 << 20, None) == 6
     with pytest.raises(NotImplementedError):
         L.check(6, "x")
+    # entry points added later: argument checks run before any CUDA call
+    f6 = L.BqFormat(L.KIND["block_fp"], 6, 8, 127, 0, 1, 16, 0)
+    fl = L.BqFormat(L.KIND["block_log"], 4, 0, 0, 8, 1, 16, 0)
+    q = ctypes.c_void_p
+    # rope + quantise: null pointers, S % 16 != 0, head_dim % 32 != 0, block_log, empty problem
+    assert lib.bq_rope_quantize(None, None, None, None, None, 64, 2, 64, 4, 64, 256, 256, ctypes.byref(f6), ctypes.byref(f6), None, None, None) == 1
+    assert lib.bq_rope_quantize(256, 256, 256, 256, None, 64, 2, 40, 4, 64, 256, 256, ctypes.byref(f6), ctypes.byref(f6), 256, 256, None) == 2
+    assert lib.bq_rope_quantize(256, 256, 256, 256, None, 64, 2, 64, 4, 48, 192, 192, ctypes.byref(f6), ctypes.byref(f6), 256, 256, None) == 2
+    assert lib.bq_rope_quantize(256, 256, 256, 256, None, 64, 2, 64, 4, 64, 256, 256, ctypes.byref(fl), ctypes.byref(f6), 256, 256, None) == 2
+    assert lib.bq_rope_quantize(256, 256, 256, 256, None, 32, 2, 64, 4, 64, 256, 256, ctypes.byref(f6), ctypes.byref(f6), 256, 256, None) == 1  # table shorter than S
+    assert lib.bq_rope_quantize(None, None, None, None, None, 0, 0, 64, 4, 64, 256, 256, ctypes.byref(f6), ctypes.byref(f6), None, None, None) == 0
+    # batched split GEMM: scales are mandatory, K % 8, batch stride smaller than one matrix, empty batch
+    ta = (ctypes.c_int32 * 2)(0, 0)
+    tb = (ctypes.c_int32 * 2)(1, 0)
+    assert lib.bq_bmm_split16_tn(256, 256, 256, None, None, 2, 8, 8, 8, 2, ta, tb, 8, 64, None) == 1
+    assert lib.bq_bmm_split16_tn(256, 256, 256, 256, 256, 2, 8, 8, 12, 2, ta, tb, 8, 64, None) == 1
+    assert lib.bq_bmm_split16_tn(256, 256, 256, 256, 256, 2, 8, 8, 8, 2, ta, tb, 8, 32, None) == 1
+    assert lib.bq_bmm_split16_tn(256, 256, 256, 256, 256, 0, 8, 8, 8, 2, ta, tb, 8, 64, None) == 0
+    # norm + quantize: H % 16, H beyond one block per thread, unsupported kind, more than three outputs
+    fm = (L.BqFormat * 1)(f6)
+    outs = (ctypes.c_void_p * 1)(256)
+    assert lib.bq_norm_quantize(256, 4, 40, 40, 256, None, 1e-5, 1, fm, outs, None) == 2
+    assert lib.bq_norm_quantize(256, 4, 16 * 513, 16 * 513, 256, None, 1e-5, 1, fm, outs, None) == 2
+    assert lib.bq_norm_quantize(256, 4, 64, 64, 256, None, 1e-5, 1, (L.BqFormat * 1)(fl), outs, None) == 2
+    assert lib.bq_norm_quantize(256, 4, 64, 64, 256, None, 1e-5, 4, fm, outs, None) == 1
+    assert lib.bq_norm_quantize(256, 0, 64, 64, 256, None, 1e-5, 1, fm, outs, None) == 0
+    del q
 
 
 def test_no_cpu_fallback():
