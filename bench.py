@@ -255,6 +255,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(L.LIB_PATH):            # fresh checkout (the .so is git-ignored): build the sm_100a library in-tree, once per node
+        if local_rank == 0:
+            subprocess.run(["bash", os.path.join(ROOT, "llm_mixed_q_b200", "csrc", "build.sh")], check=True, stdout=subprocess.DEVNULL)
+        else:
+            t0 = time.time()
+            while not os.path.exists(L.LIB_PATH) and time.time() - t0 < 600:
+                time.sleep(1.0)
+            time.sleep(2.0)                       # let the linker finish writing the file
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU path")
     torch.cuda.set_device(local_rank)
