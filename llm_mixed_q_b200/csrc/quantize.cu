@@ -6,7 +6,10 @@
 // pass at the algorithmic 8 B/element (fp32 in, fp32 out).
 //
 // Kernels
-//   quant_rows_kernel     hot path.  Blocks of b1 in {4..128} consecutive elements of the
+//   quant_stream_kernel   the speed path for dense tensors with blocks of 16 along the last dim (and the element-wise kinds):
+//                         per-warp bulk-copy (1-D TMA) ring, a lane owns whole blocks, in-place quantise, bulk store.
+//   quant_rows_kernel     strided rows / other block widths, and the silu(x) * x2 prologue (Llama down_proj operand).
+//                         Blocks of b1 in {4..128} consecutive elements of the
 //                         unit-stride last dim (every shipped config: [1,16] / [16]).  One thread
 //                         owns 4 consecutive floats (one 16-byte load), a block is b1/4 adjacent
 //                         lanes, the shared exponent comes from a warp-shuffle max over those lanes.
@@ -19,6 +22,10 @@
 //   generic_*             any block shape (2-D blocks, whole-row blocks, odd sizes), any input strides
 //                         (k^T views), optional transposed output.  Two passes over a per-block max
 //                         workspace.  Correctness path, not a speed path.
+//   quant_tile_kernel     k^T views (blocks along a strided dim) through 32x32 shared-memory tiles.
+//   norm_quant_warp_kernel / norm_quant_kernel   LayerNorm / RMSNorm fused with the x-quantizers of the consuming Linears.
+//   rope_quant_q/k_kernel Llama rotary embedding fused with the two operand quantizers of matmul_0.
+//   split3_kernel, split2_f16_rows_kernel        operand planes of the fp32-equivalent split GEMMs.
 #include "bq_internal.h"
 #include "bq_numerics.cuh"
 #include "bq_blockops.cuh"
