@@ -9,10 +9,15 @@
 // block-quantised operands with <= 8 significant bits are exact in bf16 and their products are exact
 // in fp32, so only the accumulation order differs from the reference's fp32 GEMM.
 //
-// Warp roles (256 threads, 1 CTA per SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+// Warp roles (256 threads, or 384 with a fused epilogue; 1 CTA per SM, persistent, static round-robin tile schedule):
 //   warp 0   TMA producer (one elected lane)      warp 1   MMA issuer (one elected lane)
-//   warp 2   TMEM allocator                       warps 4-7 epilogue (TMEM lane quarter = warp % 4)
+//   warp 2   TMEM allocator                       warps 4-7 (4-11) epilogue (TMEM lane quarter = warp % 4)
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty x2 accumulators (MMA <-> epilogue).
+// CG == 2 (the instance every large Linear uses): a cluster of two CTAs shares one 256 x 256 tile through cta_group::2 MMAs —
+// each CTA loads half of A and half of B, the leader issues, commits are multicast to both CTAs' barriers.
+// Tile raster: N-fastest, or M-fastest inside bands of row blocks when B cannot stay in L2 (GemmArgs::band_m).
+// Variants: plain (+bias), fused epilogue (EpiArgs; compile-time specialised instances), split precision (plane pairs accumulated
+// into one TMEM accumulator: the fp32-equivalent lm_head and the batched general-route matmul).
 #include "bq_internal.h"
 #include "bq_blockops.cuh"
 #include "sm100_ptx.cuh"
