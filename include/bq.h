@@ -142,7 +142,9 @@ BQ_API int bq_norm_quantize(const float* x, int64_t rows, int64_t H, int64_t ldx
  *   Qq[b,s,h,:] = Q_fq(q * cos[pos] + rotate_half(q) * sin[pos])   blocks of 16 along head_dim
  *   Kq[b,s,h,e] = Q_fk(k * cos[pos] + rotate_half(k) * sin[pos])   blocks of 16 consecutive positions s at fixed (h, e)  (= blocks of k^T)
  * q, k fp32 [B][S][heads*head_dim] with token strides ldq / ldk; cos / sin tables fp32 [table_rows][head_dim] ALREADY quantised by
- * the rotary table quantizer; position_ids int64 [B][S] or NULL (position = s).  Outputs dense bf16 [B][S][heads*head_dim].
+ * the rotary table quantizer; position_ids int64 [B][S] or NULL (position = s; needs table_rows >= S).  Explicit positions must lie
+ * in [0, table_rows): the kernel clamps to that range (never reads outside the tables); raising the reference's IndexError is the
+ * host binding's job (rotary_positional_encoding.py does).  Outputs dense bf16 [B][S][heads*head_dim].
  * Formats: block_fp / block_minifloat, blocks [1,16]; head_dim % 32 == 0, S % 16 == 0. */
 BQ_API int bq_rope_quantize(const float* q, const float* k, const float* cos_table, const float* sin_table, const int64_t* position_ids,
                             int64_t table_rows, int64_t B, int64_t S, int32_t heads, int32_t head_dim, int64_t ldq, int64_t ldk,

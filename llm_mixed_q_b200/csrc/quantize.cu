@@ -1291,6 +1291,8 @@ struct RopeArgs {
   const float* cs;            // cos table [rows][d]
   const float* sn;            // sin table [rows][d]
   const int64_t* pos;         // [B][S] or nullptr (position = s)
+  int64_t table_rows;         // rows of cs / sn: explicit positions are clamped to [0, table_rows) — never an out-of-bounds read;
+                              // range errors are the host mirror's to raise (IndexError, like the reference's cos[position_ids])
   __nv_bfloat16* Qq;
   __nv_bfloat16* Kq;
   int B, S, heads, d;
@@ -1306,7 +1308,7 @@ __global__ void __launch_bounds__(256) rope_quant_q_kernel(RopeArgs a) {
     const int f0 = (int)(i - tok * bpt) << 4;              // first feature of the block
     const int e0 = f0 % a.d;                               // position inside the head
     const bool lo = e0 < half;
-    const int64_t p = a.pos ? a.pos[tok] : (tok % a.S);
+    const int64_t p = a.pos ? min(max(a.pos[tok], (int64_t)0), a.table_rows - 1) : (tok % a.S);
     const float* x = a.q + tok * a.ldq + f0;
     const float* xp = x + (lo ? half : -half);
     const float* c = a.cs + p * a.d + e0;
@@ -1344,7 +1346,7 @@ __global__ void __launch_bounds__(256) rope_quant_k_kernel(RopeArgs a) {
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
       const int64_t tok = (int64_t)b * a.S + s0 + t;
-      const int64_t p = a.pos ? a.pos[tok] : (int64_t)(s0 + t);
+      const int64_t p = a.pos ? min(max(a.pos[tok], (int64_t)0), a.table_rows - 1) : (int64_t)(s0 + t);
       const float xv = a.k[tok * a.ldk + f], pv = a.k[tok * a.ldk + fp];
       const float cv = __ldg(a.cs + p * a.d + e), sv = __ldg(a.sn + p * a.d + e);
       y[t] = __fadd_rn(__fmul_rn(xv, cv), __fmul_rn(lo ? -pv : pv, sv));
@@ -1362,7 +1364,7 @@ int rope_quantize_impl(const float* q, const float* k, const float* cos_t, const
   if (B == 0 || S == 0) return BQ_OK;
   if (!q || !k || !cos_t || !sin_t || !Qq || !Kq) return BQ_ERR_BAD_ARG;
   if ((d % 32) || (S % 16)) return BQ_ERR_UNSUPPORTED;              // a block of 16 stays inside one half of a head / inside the sequence
-  if (!pos && table_rows < S) return BQ_ERR_BAD_ARG;
+  if (table_rows < 1 || (!pos && table_rows < S)) return BQ_ERR_BAD_ARG;
   const int64_t H = (int64_t)heads * d;
   if (ldq < H || ldk < H || (ldq % 4) || (ldk % 4) || ((uintptr_t)q % 16) || ((uintptr_t)k % 16) || ((uintptr_t)cos_t % 16) ||
       ((uintptr_t)sin_t % 16) || ((uintptr_t)Qq % 16) || ((uintptr_t)Kq % 2))
@@ -1378,7 +1380,7 @@ int rope_quantize_impl(const float* q, const float* k, const float* cos_t, const
     if (rc) return rc;
     (i ? a.fk : a.fq).fold_zero = 0;
   }
-  a.q = q; a.k = k; a.cs = cos_t; a.sn = sin_t; a.pos = pos; a.Qq = (__nv_bfloat16*)Qq; a.Kq = (__nv_bfloat16*)Kq;
+  a.q = q; a.k = k; a.cs = cos_t; a.sn = sin_t; a.pos = pos; a.table_rows = table_rows; a.Qq = (__nv_bfloat16*)Qq; a.Kq = (__nv_bfloat16*)Kq;
   a.B = (int)B; a.S = (int)S; a.heads = heads; a.d = d; a.ldq = ldq; a.ldk = ldk;
   const int64_t nq = B * S * (H / 16), nk = B * (S / 16) * H;
   const int64_t cap = (int64_t)num_sms() * 16;

@@ -152,18 +152,19 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         plan = None
         qc = at.quant_config
         if (seq_len % 16 == 0 and H % 32 == 0 and mlp.gate_proj.out_features % 16 == 0 and mlp.hidden_act == "silu"
-                and _attn_fusable(qc["matmul_0"], qc["matmul_1"], d, seq_len) and output_quantizable(at.o_proj.config, H)):
-            fmts = dict(q_in=linear_input_format(at.q_proj), k_in=linear_input_format(at.k_proj), v_in=linear_input_format(at.v_proj),
-                        o_in=linear_input_format(at.o_proj), gate_in=linear_input_format(mlp.gate_proj),
-                        up_in=linear_input_format(mlp.up_proj), down_in=linear_input_format(mlp.down_proj),
-                        v_out=row_block16_format(qc["matmul_1"], "weight", d))
+                and _attn_fusable(qc["matmul_0"], qc["matmul_1"], d, seq_len) and output_quantizable(at.o_proj.config, H, seq_len)):
+            # every Llama Linear sees the 3-D [B, S, H] activation (reference modeling_llama.py:274-276, :347, :422)
+            lin = lambda m: linear_input_format(m, rows=seq_len)
+            fmts = dict(q_in=lin(at.q_proj), k_in=lin(at.k_proj), v_in=lin(at.v_proj), o_in=lin(at.o_proj),
+                        gate_in=lin(mlp.gate_proj), up_in=lin(mlp.up_proj), down_in=lin(mlp.down_proj),
+                        v_out=row_block16_format(qc["matmul_1"], "weight", d, rows=seq_len))
             if all(v is not None for v in fmts.values()):
                 plan = fmts
         self._plan_cache = (seq_len, plan)
         return plan
 
     @torch.no_grad()
-    def _fused_forward(self, h, position_ids, plan):
+    def _fused_forward(self, h, position_ids, plan, default_positions=False):
         B, S, H = h.shape
         at, mlp = self.self_attn, self.mlp
         n1, n2 = self.input_layernorm, self.post_attention_layernorm
@@ -173,7 +174,8 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         k = at.k_proj.forward_prequantized(xk)
         Vq = at.v_proj.forward_prequantized(xv, out_format=plan["v_out"])        # bmm_1's y-quantizer in the GEMM epilogue
         cos, sin = at.rotary_emb(q, seq_len=S)
-        fusedqk = _rope_token_major_quantized(q.view(B, S, H), k.view(B, S, H), cos, sin, position_ids,
+        # default arange positions: the kernel derives them (no index tensor, no range check, graph-capturable)
+        fusedqk = _rope_token_major_quantized(q.view(B, S, H), k.view(B, S, H), cos, sin, None if default_positions else position_ids,
                                               qc["rotary_positional_encoding"], qc["matmul_0"], at.num_heads) if self.fused_rope else None
         if fusedqk is not None:                                                  # RoPE + both matmul_0 operand quantizers: 2 kernels
             Qq, Kq = fusedqk
@@ -191,12 +193,13 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         h3 = mlp.down_proj.forward_prequantized(a, residual=h2.view(B * S, H))   # residual + down(silu(gate) * up)
         return h3.view(B, S, H)
 
-    def forward(self, hidden_states, attention_mask=None, position_ids=None, output_attentions=False, causal_only=False):
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, output_attentions=False, causal_only=False,
+                default_positions=False):
         if (causal_only and not output_attentions and hidden_states.is_cuda and hidden_states.dtype == torch.float32
                 and not torch.is_grad_enabled() and not self.training and hidden_states.ndim == 3):
             plan = self._fused_plan(hidden_states.shape[1])
             if plan is not None:
-                return self._fused_forward(hidden_states, position_ids, plan), None
+                return self._fused_forward(hidden_states, position_ids, plan, default_positions), None
         residual = hidden_states
         hidden_states = self.input_layernorm(hidden_states)
         hidden_states, attn = self.self_attn(hidden_states, attention_mask=attention_mask, position_ids=position_ids,
@@ -261,7 +264,8 @@ class LlamaQuantizedModel(LlamaQuantizedPreTrainedModel):
         if inputs_embeds is None:
             inputs_embeds = self.embed_tokens(input_ids)
         bsz, q_len = inputs_embeds.shape[:2]
-        if position_ids is None:
+        default_positions = position_ids is None
+        if default_positions:
             position_ids = torch.arange(q_len, dtype=torch.long, device=inputs_embeds.device).unsqueeze(0).view(-1, q_len)
         mask = _causal_mask(attention_mask, bsz, q_len, inputs_embeds.dtype, inputs_embeds.device)
         causal_only = self.fused_glue and (attention_mask is None or bool(attention_mask.all()))
@@ -271,7 +275,8 @@ class LlamaQuantizedModel(LlamaQuantizedPreTrainedModel):
             if output_hidden_states:
                 all_h += (hidden_states,)
             hidden_states, attn = layer(hidden_states, attention_mask=mask, position_ids=position_ids,
-                                        output_attentions=output_attentions, causal_only=causal_only)
+                                        output_attentions=output_attentions, causal_only=causal_only,
+                                        default_positions=default_positions)
             if output_attentions:
                 all_a += (attn,)
         hidden_states = self.norm(hidden_states)

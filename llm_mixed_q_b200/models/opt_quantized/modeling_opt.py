@@ -90,7 +90,7 @@ class OPTQauntizedAttention(nn.Module):      # (sic) class name kept from the re
             q = self.q_proj(hidden_states) * self.scaling
             k = self.k_proj(hidden_states)
             v = self.v_proj(hidden_states)
-            if self.out_proj.accepts_prequantized() and output_quantizable(self.out_proj.config, self.embed_dim):
+            if self.out_proj.accepts_prequantized() and output_quantizable(self.out_proj.config, self.embed_dim, tgt_len):
                 # the x-quantizer of out_proj runs in the attention epilogue; out_proj consumes the bf16 operand directly
                 oq = fused_causal_attention(q, k, v, self.quant_config["bmm_0"], self.quant_config["bmm_1"], self.num_heads,
                                             score_div=1.0, out_cfg=self.out_proj.config)
@@ -162,12 +162,15 @@ class OPTQuantizedDecoderLayer(nn.Module):
               and _attn_fusable(at.quant_config["bmm_0"], at.quant_config["bmm_1"], d, seq_len))
         if ok:
             fmts = dict(
-                q_in=linear_input_format(at.q_proj), k_in=linear_input_format(at.k_proj), v_in=linear_input_format(at.v_proj),
-                o_in=linear_input_format(at.out_proj) if output_quantizable(at.out_proj.config, H) else None,
+                # q/k/v/out_proj see the 3-D [B, S, H] activation (reference modeling_opt.py:206-225, :327), fc1 / fc2 the
+                # 2-D [B*S, H] one (:412); the bmm operands are [B*h, S, d] / [B*h, d, S]
+                q_in=linear_input_format(at.q_proj, rows=seq_len), k_in=linear_input_format(at.k_proj, rows=seq_len),
+                v_in=linear_input_format(at.v_proj, rows=seq_len),
+                o_in=linear_input_format(at.out_proj, rows=seq_len) if output_quantizable(at.out_proj.config, H, seq_len) else None,
                 fc1_in=linear_input_format(self.fc1), fc2_in=linear_input_format(self.fc2),
-                q_out=row_block16_format(at.quant_config["bmm_0"], "data_in", d),
-                k_out=row_block16_format(at.quant_config["bmm_0"], "weight", seq_len),
-                v_out=row_block16_format(at.quant_config["bmm_1"], "weight", d))
+                q_out=row_block16_format(at.quant_config["bmm_0"], "data_in", d, rows=seq_len),
+                k_out=row_block16_format(at.quant_config["bmm_0"], "weight", seq_len, rows=d),
+                v_out=row_block16_format(at.quant_config["bmm_1"], "weight", d, rows=seq_len))
             if all(v is not None for v in fmts.values()):
                 plan = fmts
         self._plan_cache = (key, plan)

@@ -48,8 +48,10 @@ def fusable(cfg0: dict, cfg1: dict, head_dim: int, seq_len: int) -> bool:
         pb[1] == 1 and pb[2] == 16
 
 
-def output_quantizable(out_cfg: dict, hidden: int) -> bool:
-    """Can the x-quantizer of the Linear that consumes the attention output run in the attention epilogue?"""
+def output_quantizable(out_cfg: dict, hidden: int, rows: int = 1) -> bool:
+    """Can the x-quantizer of the Linear that consumes the attention output run in the attention epilogue?
+    `rows` = S: the reference feeds that Linear the 3-D [B, S, H] attention output, so a short block size such as [16]
+    resolves to [1, S, 16] (quantizers/utils.py:42-67) and is NOT a row block."""
     try:
         if out_cfg is None or out_cfg.get("bypass", False) or not out_cfg.get("is_ptq", False):
             return False
@@ -58,7 +60,7 @@ def output_quantizable(out_cfg: dict, hidden: int) -> bool:
         return False
     if ok not in ("block_fp", "block_minifloat") or obs is None or significant_bits(ok, okw) > 8:
         return False
-    ob = resolve_block_shape([1, 1, hidden], obs)
+    ob = resolve_block_shape([1, max(int(rows), 1), hidden], obs)
     return ob[1] == 1 and ob[2] == 16
 
 

@@ -22,9 +22,13 @@ from ..quantizers.utils import canonicalise, make_format, resolve_block_shape
 _EPI_KINDS = ("block_fp", "block_minifloat")
 
 
-def row_block16_format(config: dict, prefix: str, last_dim: int) -> Optional[Tuple[str, dict]]:
+def row_block16_format(config: dict, prefix: str, last_dim: int, rows: int = 1) -> Optional[Tuple[str, dict]]:
     """(kind, kwargs) when `<prefix>_*` of a config node is a block_fp / block_minifloat format that resolves to blocks of
-    16 along a last dim of size `last_dim` and is exact in bf16 — i.e. something an epilogue can apply — else None."""
+    16 along a last dim of size `last_dim` and is exact in bf16 — i.e. something an epilogue can apply — else None.
+    `rows`: second-to-last extent of the operand THE REFERENCE blocks (quantizers/utils.py:42-67 right-aligns the block
+    size and fills missing leading entries with -1 = whole dim): S for a Linear fed a 3-D [B, S, H] activation or a
+    [B*h, S, d] bmm operand, 1 for a Linear fed a 2-D activation (skip_first_dim drops the row dim, utils.py:127-144).  With
+    `block_size = [16]` a 3-D operand resolves to [1, S, 16] — a block spans every token — which no epilogue implements."""
     try:
         if config is None or config.get("bypass", False):
             return None
@@ -33,17 +37,18 @@ def row_block16_format(config: dict, prefix: str, last_dim: int) -> Optional[Tup
         return None
     if kind not in _EPI_KINDS or bs is None or significant_bits(kind, kw) > 8:
         return None
-    b = resolve_block_shape([1, 1, last_dim], bs)
+    b = resolve_block_shape([1, max(int(rows), 1), last_dim], bs)
     if b[1] != 1 or b[2] != 16 or last_dim % 16:
         return None
     return kind, kw
 
 
-def linear_input_format(lin, last_dim: Optional[int] = None) -> Optional[Tuple[str, dict]]:
-    """x-quantizer of a quantized Linear as an epilogue format, if the module can take a pre-quantised bf16 input."""
+def linear_input_format(lin, last_dim: Optional[int] = None, rows: int = 1) -> Optional[Tuple[str, dict]]:
+    """x-quantizer of a quantized Linear as an epilogue format, if the module can take a pre-quantised bf16 input.
+    `rows` = S when the reference feeds the Linear a 3-D [B, S, K] activation, 1 when it feeds a 2-D one."""
     if not isinstance(lin, _LinearBase) or not lin.accepts_prequantized():
         return None
-    return row_block16_format(lin.config, "data_in", lin.in_features if last_dim is None else last_dim)
+    return row_block16_format(lin.config, "data_in", lin.in_features if last_dim is None else last_dim, rows)
 
 
 def _same(a, b) -> bool:

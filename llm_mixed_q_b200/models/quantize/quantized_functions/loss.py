@@ -18,6 +18,11 @@ from .... import _lib as L
 def causal_lm_loss(logits: torch.Tensor, labels: torch.Tensor, shift: bool = True, ignore_index: int = -100) -> torch.Tensor:
     """Mean cross-entropy of logits [B, S, V] (fp32, CUDA) against labels [B, S] (shifted by one when `shift`).
     Returns a 0-dim fp32 tensor, like CrossEntropyLoss()."""
+    if torch.is_grad_enabled() and logits.requires_grad:
+        # the kernel is forward-only: keep the reference's differentiable ops when a graph is being recorded
+        lg, lb = (logits[..., :-1, :], labels[..., 1:]) if shift else (logits, labels)
+        return torch.nn.functional.cross_entropy(lg.reshape(-1, lg.shape[-1]), lb.reshape(-1).to(lg.device),
+                                                 ignore_index=ignore_index)
     L.require_cuda_f32(logits, "logits")
     if logits.dim() == 2:
         logits = logits.unsqueeze(0)

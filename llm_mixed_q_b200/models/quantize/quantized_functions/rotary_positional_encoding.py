@@ -61,7 +61,17 @@ def apply_token_major_quantized(q, k, cos, sin, position_ids, config, matmul0_co
         return None
     pos = None
     if position_ids is not None:
-        pos = position_ids.expand(B, S).contiguous().to(torch.int64)
+        # explicit positions index the [table_rows, d] tables like the reference's cos[position_ids] (:44-45): out-of-range
+        # raises IndexError, negative indices wrap.  One device-to-host look — the model classes pass None for the default
+        # arange, so the captured / steady-state forward never takes it.  (The kernel additionally clamps: no OOB read.)
+        rows = cos_t.shape[0]
+        pos = position_ids.expand(B, S).to(torch.int64)
+        lo, hi = (int(v) for v in torch.stack((pos.min(), pos.max())).tolist())
+        if lo < -rows or hi >= rows:
+            raise IndexError(f"index {hi if hi >= rows else lo} is out of bounds for dimension 0 with size {rows}")
+        if lo < 0:
+            pos = torch.where(pos < 0, pos + rows, pos)
+        pos = pos.contiguous()
     qc, kc = q, k
     if qc.stride(-1) != 1 or qc.stride(0) != S * qc.stride(1):
         qc = qc.contiguous()

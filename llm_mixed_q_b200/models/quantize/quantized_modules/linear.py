@@ -247,9 +247,13 @@ class _LinearBase(nn.Linear):
         if self.bypass:
             return F.linear(x, self.weight, self.bias)
         elif self.is_ptq:
+            # the reference quantises under no_grad but runs F.linear OUTSIDE it (linear.py:63-71): weight / bias receive
+            # gradients when autograd is on.  The fused kernels are forward-only, so they serve only the no-grad case.
+            wants_grad = torch.is_grad_enabled() and (self.weight.requires_grad
+                                                      or (self.bias is not None and self.bias.requires_grad))
             with torch.no_grad():
                 self._ensure_ptq()
-                if self._fusable(x):
+                if not wants_grad and self._fusable(x):
                     return self._fused_forward(x)
                 x = self.x_quantizer(x)
             return F.linear(x, self.weight, self.bias)

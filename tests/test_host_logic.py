@@ -59,3 +59,45 @@ def test_linear_module_surface():
     byp = get_quantized_cls("linear", cfg)(32, 16, config={"name": "block_fp", "bypass": True})
     x = torch.randn(3, 32)
     assert torch.equal(byp(x), torch.nn.functional.linear(x, byp.weight, byp.bias))   # bypass = plain fp32 linear
+
+
+def _tiny_opt_layer(block_size):
+    from llm_mixed_q_b200.models.opt_quantized import OPTQuantizedConfig
+    from llm_mixed_q_b200.models.opt_quantized.modeling_opt import OPTQuantizedDecoderLayer
+
+    d = {"bypass": False, "name": "block_fp", "is_ptq": True}
+    for p in ("data_in", "weight", "bias"):
+        d.update({f"{p}_width": 6, f"{p}_exponent_width": 8, f"{p}_exponent_bias": None,
+                  f"{p}_block_size": [16] if p == "bias" else block_size})
+    cfg = OPTQuantizedConfig(hidden_size=256, num_hidden_layers=1, ffn_dim=512, num_attention_heads=4, vocab_size=128,
+                             max_position_embeddings=64, quant_config={"default": d})
+    return OPTQuantizedDecoderLayer(cfg, 0)
+
+
+def test_fused_plan_resolves_blocks_against_the_real_operand_shape():
+    """reference quantizers/utils.py:42-67: block_size [16] on the 3-D [B, S, H] input of q/k/v/out_proj means [1, S, 16] — a
+    block spans every token — so the 1x16 epilogue quantizers must NOT be selected; [1, 16] is the row-block case they serve."""
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import output_quantizable
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import linear_input_format, row_block16_format
+
+    lyr = _tiny_opt_layer([1, 16])
+    assert lyr._fused_plan(32) is not None
+    lyr16 = _tiny_opt_layer([16])
+    assert lyr16._fused_plan(32) is None
+    at = lyr16.self_attn
+    assert linear_input_format(at.q_proj, rows=32) is None              # 3-D input: [1, 32, 16] blocks
+    assert linear_input_format(lyr16.fc1) is not None                   # 2-D input (reference :412): [1, 16] blocks
+    assert not output_quantizable(at.out_proj.config, 256, 32) and output_quantizable(at.out_proj.config, 256, 1)
+    assert row_block16_format(at.quant_config["bmm_0"], "data_in", 64, rows=32) is None
+    assert row_block16_format(at.quant_config["bmm_0"], "data_in", 64, rows=1) is not None
+
+
+def test_ptq_linear_keeps_autograd_semantics_of_the_reference():
+    """reference linear.py:63-71 runs F.linear outside no_grad: weight / bias get gradients in PTQ mode; the forward-only fused
+    kernels are therefore only eligible when no graph is being recorded (checked before entering no_grad)."""
+    import inspect
+
+    from llm_mixed_q_b200.models.quantize.quantized_modules import linear as lin_mod
+
+    src = inspect.getsource(lin_mod._LinearBase.forward)
+    assert "wants_grad" in src and src.index("wants_grad =") < src.index("with torch.no_grad()")
