@@ -125,8 +125,9 @@ class ClockSampler:
 # CPU path (oracle port of the reference) — cpu_baseline leg and --impl reference
 # ------------------------------------------------------------------------------------------------
 def cpu_layer_sample(steps, warmup):
-    """One OPT-1.3B decoder layer + lm_head share at batch 1, seq 2048 on the host cores with the oracle port of the
-    reference's torch emulation; tokens/s = 2048 / (24 * t_layer + t_head).  Returns (tokens_per_s, per-step ms list)."""
+    """One step = one OPT-1.3B decoder layer + the fp32 lm_head at batch 1, seq 2048 on the host cores with the oracle port of the
+    reference's torch emulation (a bounded sample of the workload); tokens/s = 2048 / (24 * t_layer + t_head) extrapolates it to the
+    24-layer forward.  Returns (tokens_per_s, measured per-step ms list)."""
     from llm_mixed_q_b200.models.opt_quantized import parse_opt_quantized_config
     from oracle import opt_ref
 
@@ -150,33 +151,135 @@ def cpu_layer_sample(steps, warmup):
                                   state)          # populates the one-off PTQ weight quantisation (excluded, like the reference's first call)
         h = torch.randn(1, SEQ, H, generator=g)
         mask = opt_ref.causal_mask(1, SEQ, torch.float32, "cpu")
-        t0 = time.perf_counter()
-        torch.nn.functional.linear(h, head_w)
-        t_head = time.perf_counter() - t0
-        times = []
+        times, heads_t = [], []
         for i in range(warmup + steps):
             t0 = time.perf_counter()
             opt_ref.opt_layer_forward(h, sd, 0, qc, heads, mask, state)
-            dt = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            torch.nn.functional.linear(h, head_w)
+            t2 = time.perf_counter()
             if i >= warmup:
-                times.append(dt)
-    t_layer = statistics.median(times)
-    return SEQ / (L * t_layer + t_head), [1e3 * (L * t + t_head) for t in times]
+                times.append(t1 - t0)
+                heads_t.append(t2 - t1)
+    t_layer, t_head = statistics.median(times), statistics.median(heads_t)
+    # (tokens/s of the extrapolated full forward, MEASURED wall ms of every timed step = one layer + the head)
+    return SEQ / (L * t_layer + t_head), [1e3 * (a + b) for a, b in zip(times, heads_t)]
+
+
+def gpu_port_sample(device, steps=3, warmup=1):
+    """The reference's emulation as it would run after `.to("cuda")` (cli/eval_perplexity.py:64): the oracle port (same ~45 torch
+    ops per quantizer, fp32 cuBLAS GEMMs, S x S scores in HBM) on this GPU — one OPT-1.3B decoder layer at the bench's batch
+    (8 x 2048; batch 1 if that does not fit) + the fp32 lm_head, extrapolated x24.  'What the kernels replace', on the same silicon."""
+    from llm_mixed_q_b200.models.opt_quantized import parse_opt_quantized_config
+    from oracle import opt_ref
+
+    H, F_, heads, Lyr, V = 2048, 8192, 32, 24, 50272
+    g = torch.Generator(device="cpu").manual_seed(0)
+    p = "model.decoder.layers.0."
+    sd = {}
+    for name, shape in [("self_attn.q_proj", (H, H)), ("self_attn.k_proj", (H, H)), ("self_attn.v_proj", (H, H)),
+                        ("self_attn.out_proj", (H, H)), ("fc1", (F_, H)), ("fc2", (H, F_))]:
+        sd[p + name + ".weight"] = (torch.randn(shape, generator=g) * 0.02).to(device)
+        sd[p + name + ".bias"] = torch.zeros(shape[0], device=device)
+    for ln in ("self_attn_layer_norm", "final_layer_norm"):
+        sd[p + ln + ".weight"] = torch.ones(H, device=device)
+        sd[p + ln + ".bias"] = torch.zeros(H, device=device)
+    head_w = (torch.randn(V, H, generator=g) * 0.02).to(device)
+    qc = parse_opt_quantized_config(bfp_config(6), 1)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for batch in (BATCH, 1):
+            try:
+                state = {}
+                with torch.no_grad():
+                    h = torch.randn(batch, SEQ, H, generator=g).to(device)
+                    mask = opt_ref.causal_mask(batch, SEQ, torch.float32, device)
+
+                    def one():
+                        opt_ref.opt_layer_forward(h, sd, 0, qc, heads, mask, state)
+
+                    for _ in range(warmup + 1):                      # + the one-off PTQ weight quantisation
+                        one()
+                    torch.cuda.synchronize()
+                    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    a.record()
+                    for _ in range(steps):
+                        one()
+                    b.record()
+                    torch.nn.functional.linear(h, head_w)
+                    c.record()
+                    torch.cuda.synchronize()
+                t_layer, t_head = a.elapsed_time(b) / steps / 1e3, b.elapsed_time(c) / 1e3
+                return {"value": batch * SEQ / (Lyr * t_layer + t_head), "unit": "tokens/s", "kind": "port on cuda:0",
+                        "layer_ms": 1e3 * t_layer, "lm_head_ms": 1e3 * t_head,
+                        "sample": f"oracle port of the reference's torch emulation run with torch-CUDA fp32 ops (TF32 off) on this GPU: 1 of 24 "
+                                  f"OPT-1.3B decoder layers at batch {batch} x seq 2048 ({steps} timed passes) + fp32 lm_head; "
+                                  f"tokens/s = {batch}*2048/(24*t_layer+t_head)"}
+            except torch.cuda.OutOfMemoryError:
+                torch.cuda.empty_cache()
+        return None
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def lm_head_modes(device, K=3):
+    """The unquantised fp32 lm_head (reference modeling_opt.py:942-944) runs as a split GEMM: default 3 products of row-scaled fp16
+    hi/lo planes (~2^-21 per product); `bf16x3` = 6 products of bf16 planes (2^-24, twice the tensor work).  Both timed at the
+    headline shape, with the logit / loss difference between them and against cuBLAS fp32."""
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fp32_linear import fp32_linear
+    from llm_mixed_q_b200.models.quantize.quantized_functions.loss import causal_lm_loss
+
+    H, V, T = OPT13B["hidden_size"], OPT13B["vocab_size"], BATCH * SEQ
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn(T, H, generator=g).to(device)
+    w = (torch.randn(V, H, generator=g) * 0.02).to(device)
+    labels = torch.randint(0, V, (BATCH, SEQ), generator=g).to(device)
+    out = {}
+    res = {}
+    with torch.no_grad():
+        for mode in ("f16x2", "bf16x3"):
+            for _ in range(2):
+                y = fp32_linear(x, w, None, mode=mode)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(K):
+                y = fp32_linear(x, w, None, mode=mode)
+            b.record()
+            torch.cuda.synchronize()
+            res[mode] = (y, float(causal_lm_loss(y.view(BATCH, SEQ, V), labels)))
+            out[f"{mode}_ms"] = a.elapsed_time(b) / K
+            del y
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref = torch.nn.functional.linear(x[:2048], w)
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        spread = float(ref.std())
+        for mode in res:
+            out[f"{mode}_max_abs_vs_cublas_fp32_over_logit_std"] = float((res[mode][0][:2048] - ref).abs().max()) / spread
+        out["max_abs_dlogit_between_modes_over_logit_std"] = float((res["f16x2"][0] - res["bf16x3"][0]).abs().max()) / spread
+        out["loss_f16x2"], out["loss_bf16x3"] = res["f16x2"][1], res["bf16x3"][1]
+        out["rel_dloss_between_modes"] = abs(res["f16x2"][1] - res["bf16x3"][1]) / abs(res["bf16x3"][1])
+    return out
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)      # honoured as given: one step is ~1.5 s of CPU work (one layer, batch 1)
     tps, ms = cpu_layer_sample(steps, warmup)
     cores = os.cpu_count() or 1
     sample = (f"oracle port of the reference's torch CPU emulation: 1 of 24 OPT-1.3B decoder layers + fp32 lm_head at batch 1, "
-              f"seq 2048, {steps} timed step(s) after {warmup} warm-up (capped to bound the run); tokens/s = 2048/(24*t_layer+t_head)")
+              f"seq 2048, {steps} timed step(s) after {warmup} warm-up; tokens/s = 2048/(24*median t_layer+t_head)")
     line = {"metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": statistics.median(ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "note": "CPU path does not scale with --gpus; one host process"},
+            "config": {"workload": WORKLOAD, "note": "CPU path does not scale with --gpus; one host process",
+                       "step": "one timed step = ONE decoder layer + the lm_head at batch 1 (ms_per_step is that measured time); `value` "
+                               "extrapolates to the 24-layer forward: 2048 / (24 * t_layer + t_head)",
+                       "extrapolated_ms_per_full_forward": 1e3 * SEQ / tps},
             "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -220,10 +323,26 @@ def sub_benchmarks(device, pk):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / iters
 
+    from llm_mixed_q_b200 import _lib as L
+
     for w in (6, 4):
         ms = timed(lambda i: block_fp_quantizer(xs[i % n_buf], w, 8, 127, [1, 16], True), 30)
         out[f"quantizer_bfp_w{w}_GBs"] = 8 * 4096 * 4096 / ms / 1e6
         out[f"quantizer_bfp_w{w}_frac_of_hbm"] = out[f"quantizer_bfp_w{w}_GBs"] / pk["hbm"]
+        # the figure above times the Python API call (allocation + ctypes + launch: ~25 us of host work per 64 MiB tensor); the
+        # kernel's own device time comes from the library's per-launch events (bq_profile_read)
+        L.profile_enable(True)
+        for i in range(30):
+            block_fp_quantizer(xs[i % n_buf], w, 8, 127, [1, 16], True)
+        torch.cuda.synchronize()
+        L.profile_enable(False)
+        kms, kn = 0.0, 0
+        for name, (t, n) in L.profile_read().items():
+            if n and (name.startswith("quant") or name.startswith("generic")):
+                kms, kn = kms + t, kn + n
+        if kn:
+            out[f"quantizer_bfp_w{w}_kernel_only_GBs"] = 8 * 4096 * 4096 * kn / kms / 1e6
+            out[f"quantizer_bfp_w{w}_kernel_only_frac_of_hbm"] = out[f"quantizer_bfp_w{w}_kernel_only_GBs"] / pk["hbm"]
         cfg = bfp_config(w)["default"]
         lin = get_quantized_cls("linear", cfg)(4096, 4096, bias=True, config=cfg).to(device)
         with torch.no_grad():
@@ -413,6 +532,12 @@ def main():
                                                "note": "4 B/elem fp32 read + 2 B/elem bf16 write per launch; HBM-bound"},
                     "quantizer_kernels": {"share_of_step": q_ms / step_ms_local}}}
     gpu_launches = sum(launches1.values()) - sum(launches0.values())
+    from llm_mixed_q_b200.models.quantize.quantized_functions import fp32_linear as fp32_mod
+
+    fp32_mode = fp32_mod.MODE
+    attn_exp_mode = ("libdevice expf numerators (bit-identical to torch's exp(x - max))" if L.load().bq_get_attention_precise_exp()
+                     else "ex2.approx numerators (default; <= ~(3 + 1.44|s - max|) ulp from torch's expf — a probability moves only when it "
+                          "sits on a rounding boundary; both modes are parity-tested)")
 
     if rank != 0:
         if dist is not None:
@@ -420,11 +545,23 @@ def main():
         return
 
     extra = {}
+    gpu_port = None
     if not args.no_sub:
         with torch.no_grad():
             del model
             torch.cuda.empty_cache()
             extra = sub_benchmarks(device, pk)
+            try:
+                extra["lm_head_modes"] = lm_head_modes(device)
+            except Exception as e:                                    # a sub-metric must never cost the headline line
+                extra["lm_head_modes"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+            if world == 1:
+                try:
+                    gpu_port = gpu_port_sample(device)
+                except Exception as e:
+                    gpu_port = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         tps, _ = cpu_layer_sample(steps=1, warmup=0)
@@ -437,11 +574,14 @@ def main():
             "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (independent replicas, no data-path collective)",
                        "l2": "per-step working set (2.6 GB bf16 weights + >4 GB activations/layer) >> 126 MB L2; no flush needed",
                        "arithmetic": "operands: exact block-quantised values carried in bf16; fp32 accumulation in TMEM",
+                       "lm_head": f"unquantised fp32 head as a split GEMM, mode {fp32_mode} (f16x2 = 3 products of row-scaled fp16 hi/lo planes, "
+                                  "~2^-21 per product, 22-bit operands; bf16x3 = 6 products, 2^-24) — sub_metrics.lm_head_modes times both",
+                       "attention_exp": attn_exp_mode,
                        "instrumentation": "`value` and `e2e` are timed without per-kernel events; `roofline` comes from a second pass of the same K "
                                           "steps with two CUDA events per launch (an event between two kernels costs a front-end round trip, ~2 % of "
                                           "the step; sharing events between consecutive launches was measured and changed nothing)",
                        "loss": loss_val, "layers": Lyr},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_port_baseline": gpu_port,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * ids_host.element_size(),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K, "mode": e2e_mode,
                     "capture_error": getattr(runner, "error", None) if runner is not None else None, "clocks": clocks_e2e, "replay_reproduces_eager_loss": replay_ok},

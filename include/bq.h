@@ -13,7 +13,11 @@
  *   - the caller (PyTorch) owns every buffer, including workspaces — nothing here
  *     allocates or frees device memory;
  *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed as
- *     void*) and re-entrant; there is no hidden mutable global state;
+ *     void*) and re-entrant; the only mutable process-wide state is (a) immutable-after-
+ *     first-use caches (TMA descriptors, function attributes), (b) the launch / profile
+ *     counters and (c) the explicitly listed A/B switches (bq_set_* near the end of this
+ *     file: numerator mode of the attention kernel, kernel-variant overrides).  A switch
+ *     is read once per call on the calling thread; change it only between calls;
  *   - return value: 0 on success, otherwise a bq_status (see bq_strerror);
  *   - there is NO CPU fallback: on a machine without a B200 the calls fail with
  *     BQ_ERR_CUDA.
@@ -272,6 +276,7 @@ BQ_API int bq_attention_causal(const bq_format* fp, const void* Qq, const void* 
 /* 1: numerators of the softmax use libdevice expf (bit-identical to torch's exp(x - max)); 0 (default): ex2.approx of a fused
  * multiply-add argument, ~|x - max| * 1.44 ulp less accurate, 30 % fewer instructions per score. */
 BQ_API void bq_set_attention_precise_exp(int on);
+BQ_API int bq_get_attention_precise_exp(void);           /* current mode, so that a benchmark can state which one it timed */
 BQ_API int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq,
                                  void* out_bf16, int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk,
                                  int64_t ldv, int64_t ldo, float score_div, void* stream);

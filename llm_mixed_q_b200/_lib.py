@@ -121,6 +121,8 @@ def load():
                                      POINTER(c_int32), POINTER(c_int32), c_int64, c_void_p]
     lib.bq_set_attention_precise_exp.restype = None
     lib.bq_set_attention_precise_exp.argtypes = [ctypes.c_int]
+    lib.bq_get_attention_precise_exp.restype = ctypes.c_int
+    lib.bq_get_attention_precise_exp.argtypes = []
     lib.bq_rope_quantize.restype = ctypes.c_int
     lib.bq_rope_quantize.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                      c_int64, c_int64, POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_void_p]

@@ -680,6 +680,7 @@ static int attention_impl(const bq_format* fp, const bq_format* fo, const void* 
 }  // namespace bq
 
 extern "C" void bq_set_attention_precise_exp(int on) { bq::g_attn_precise_exp = on != 0; }
+extern "C" int bq_get_attention_precise_exp(void) { return bq::g_attn_precise_exp ? 1 : 0; }
 
 extern "C" int bq_attention_causal(const bq_format* fp, const void* Qq, const void* Kq, const void* Vq, float* out,
                                    int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv,

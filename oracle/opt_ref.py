@@ -26,7 +26,7 @@ def _linear(x, sd, prefix, cfg, state):
             b = O.operand_quantizer(cfg, "bias", False)(b)
         state[prefix] = (w, b)
     w, b = state[prefix]
-    return F.linear(O.operand_quantizer(cfg, "data_in", True)(x), w, b)
+    return O.gemm_linear(O.operand_quantizer(cfg, "data_in", True)(x), w, b)
 
 
 def opt_layer_forward(h, sd, i, qc, num_heads, mask, state, do_layer_norm_before=True, act=F.relu):
@@ -75,8 +75,9 @@ def causal_mask(bsz, tgt, dtype, device):
     return m[None, None].expand(bsz, 1, tgt, tgt)
 
 
-def opt_forward(sd, qc, input_ids, num_layers, num_heads, labels=None, state=None):
-    """Full forward: returns (logits, loss).  `state` caches the PTQ-quantised weights across calls."""
+def opt_forward(sd, qc, input_ids, num_layers, num_heads, labels=None, state=None, collect=None):
+    """Full forward: returns (logits, loss).  `state` caches the PTQ-quantised weights across calls; `collect` (a list)
+    receives the INPUT hidden state of every decoder layer (the reference's output_hidden_states[:-1])."""
     state = {} if state is None else state
     bsz, tgt = input_ids.shape
     emb = sd["model.decoder.embed_tokens.weight"]
@@ -84,11 +85,13 @@ def opt_forward(sd, qc, input_ids, num_layers, num_heads, labels=None, state=Non
     h = F.embedding(input_ids, emb) + pos[torch.arange(tgt, device=input_ids.device) + 2][None]
     mask = causal_mask(bsz, tgt, h.dtype, h.device)
     for i in range(num_layers):
+        if collect is not None:
+            collect.append(h)
         h = opt_layer_forward(h, sd, i, qc, num_heads, mask, state)
     H = h.shape[-1]
     if "model.decoder.final_layer_norm.weight" in sd:
         h = F.layer_norm(h, (H,), sd["model.decoder.final_layer_norm.weight"], sd["model.decoder.final_layer_norm.bias"])
-    logits = F.linear(h, sd.get("lm_head.weight", emb))
+    logits = O.gemm_linear(h, sd.get("lm_head.weight", emb))
     loss = None
     if labels is not None:
         loss = F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1))

@@ -281,6 +281,26 @@ def operand_quantizer(config: dict, prefix: str, skip_first_dim: bool):
     return lambda t: fn(t, **kw)
 
 
+# ---------------------------------------------------------------------------
+# noise-floor control: the same restatement with the contraction run in the opposite order.  Mathematically identical;
+# on a real BLAS the fp32 partial sums round differently, which is the ONLY perturbation — what tests use to measure how far
+# two correct implementations of the quantised forward drift apart (rounding flips seeded by accumulation order).
+# ---------------------------------------------------------------------------
+ACCUMULATION_ORDER = "natural"          # or "reversed"
+
+
+def gemm_linear(x, w, b=None):
+    if ACCUMULATION_ORDER == "reversed":
+        return F.linear(x.flip(-1).contiguous(), w.flip(-1).contiguous(), b)
+    return F.linear(x, w, b)
+
+
+def gemm_mm(mm, x, y):
+    if ACCUMULATION_ORDER == "reversed":
+        return mm(x.flip(-1).contiguous(), y.flip(-2).contiguous())
+    return mm(x, y)
+
+
 def linear_forward(x, weight, bias, config):
     """
     _LinearBase.forward (linear.py:59-76), functional form: returns
@@ -293,7 +313,7 @@ def linear_forward(x, weight, bias, config):
     xq = operand_quantizer(config, "data_in", True)(x)
     wq = operand_quantizer(config, "weight", False)(weight)
     bq = operand_quantizer(config, "bias", False)(bias) if bias is not None else None
-    return F.linear(xq, wq, bq), wq, bq
+    return gemm_linear(xq, wq, bq), wq, bq
 
 
 def matmul_forward(x, y, config, style="matmul"):
@@ -317,7 +337,7 @@ def matmul_forward(x, y, config, style="matmul"):
     else:
         x = operand_quantizer(config, "data_in", False)(x)
         y = operand_quantizer(config, "weight", False)(y)
-    return mm(x, y)
+    return gemm_mm(mm, x, y)
 
 
 def perplexity_from_losses(losses, batch_size, seq_len):
