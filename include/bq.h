@@ -277,6 +277,11 @@ BQ_API int bq_attention_causal(const bq_format* fp, const void* Qq, const void* 
  * multiply-add argument, ~|x - max| * 1.44 ulp less accurate, 30 % fewer instructions per score. */
 BQ_API void bq_set_attention_precise_exp(int on);
 BQ_API int bq_get_attention_precise_exp(void);           /* current mode, so that a benchmark can state which one it timed */
+/* head_dim 64 only.  1 (default): two independent softmax pipelines per CTA with the quantised probabilities written to tensor
+ * memory (tcgen05.st) and PV issued with its A operand read from TMEM; 0: the single-pipeline kernel that stages P through shared
+ * memory (what head_dim 128 uses).  Same arithmetic, same results; A/B measurement switch. */
+BQ_API void bq_set_attention_dual_pipeline(int on);
+BQ_API int bq_get_attention_dual_pipeline(void);
 BQ_API int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq,
                                  void* out_bf16, int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk,
                                  int64_t ldv, int64_t ldo, float score_div, void* stream);

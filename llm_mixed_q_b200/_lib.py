@@ -123,6 +123,10 @@ def load():
     lib.bq_set_attention_precise_exp.argtypes = [ctypes.c_int]
     lib.bq_get_attention_precise_exp.restype = ctypes.c_int
     lib.bq_get_attention_precise_exp.argtypes = []
+    lib.bq_set_attention_dual_pipeline.restype = None
+    lib.bq_set_attention_dual_pipeline.argtypes = [ctypes.c_int]
+    lib.bq_get_attention_dual_pipeline.restype = ctypes.c_int
+    lib.bq_get_attention_dual_pipeline.argtypes = []
     lib.bq_rope_quantize.restype = ctypes.c_int
     lib.bq_rope_quantize.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                      c_int64, c_int64, POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_void_p]

@@ -109,6 +109,17 @@ __device__ __forceinline__ float ex2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// one FMNMX3 each; inline PTX (sm_100 three-input max / min) so that the compiler cannot re-associate the trees below into chains
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -141,43 +152,12 @@ constexpr float kMagicB = 12600064.0f;
 // same class of deviation as the approximate exponential itself.  !SCALED: v holds p_i, inv_l unused.
 // Probabilities are <= 1 mathematically; an approximate exponential may overshoot by an ulp, so the BLOCK MAX is clamped to
 // 1.0 before the shared exponent is derived (an overshooting element then saturates at qmax exactly like the reference's 1.0).
+// Cold tail of quantize_probs16 (a block with a pass-through element, a block whose maximum sits on a log2 cliff or has an extreme
+// exponent, block_minifloat): OUT OF LINE, operands through local memory, so that the hot loop body stays a few hundred contiguous
+// instructions — with two pipelines executing different loops at the same time the inlined cold code (16 KB per copy) pushed the
+// loops out of the 32 KB instruction cache (ncu: no_instruction stalls 1.8 per issue against 0.2 for one pipeline).
 template <int KIND, bool SCALED>
-__device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, const FmtParams& p, uint32_t (&w)[8]) {
-  float mx = v[0], mn = v[0];
-#pragma unroll
-  for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[i]);
-  if (SCALED) mx = __fmul_rn(mx, inv_l);
-  if (mx == 0.f) {                                      // all-zero block -> zeros (pass-through)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = 0u;
-    return;
-  }
-  mx = fminf(mx, 1.0f);
-  const uint32_t mbits = f2u(mx);
-  const FastState fs = fast_state<KIND>(mbits, p);
-  if (KIND == kBlockFP && fs.ok && p.mbits <= 7) {
-#pragma unroll
-    for (int i = 1; i < 16; ++i) mn = fminf(mn, v[i]);
-    if (SCALED) mn = __fmul_rn(mn, inv_l);
-    if (mn > 1e-8f) {
-      // no pass-through element in this block (the common case): rounding in fp32, clamp + de-quantisation packed in bf16
-      const float c0 = __fmul_rn(1e-9f, fs.f0);         // exact: f0 is a power of two
-      const float g0 = SCALED ? __fmul_rn(inv_l, fs.f0) : fs.f0;      // exact (power-of-two factor, |E| <= 100)
-      const uint32_t step2 = pack_bf16_trunc(fs.f1, fs.f1);
-      const float nb = -__fmul_rn(128.0f, fs.f1);
-      const uint32_t base2 = pack_bf16_trunc(nb, nb);
-      const float top = __fadd_rn(128.0f, p.qmax);
-      const uint32_t top2 = pack_bf16_trunc(top, top);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float t0 = __fadd_rn(__fmaf_rn(v[2 * i], g0, c0), kMagicB);            // kMagicB + rint((p + 1e-9f) * 2^(m-E))
-        const float t1 = __fadd_rn(__fmaf_rn(v[2 * i + 1], g0, c0), kMagicB);
-        const uint32_t q2 = bf16x2_min(__byte_perm(f2u(t0), f2u(t1), 0x5410), top2);   // {128 + q0, 128 + q1}, clamped to 128 + qmax
-        w[i] = bf16x2_fma(q2, step2, base2);
-      }
-      return;
-    }
-  }
+__device__ __noinline__ void quantize_probs16_cold(float* v, float inv_l, uint32_t mbits, FastState fs, FmtParams p, uint32_t* w) {
   if (SCALED) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], inv_l);
@@ -206,19 +186,82 @@ __device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, co
   for (int i = 0; i < 8; ++i) w[i] = pack_bf16_trunc(v[2 * i], v[2 * i + 1]);
 }
 
+// Quantise 16 consecutive NON-NEGATIVE values (one reference block of probabilities) and pack them as bf16.
+// SCALED: v holds the UN-normalised exponentials e_i and the probabilities are p_i = rn(e_i * inv_l); the common path never
+// forms p_i: block max / min scale once (rounding is monotonic) and the normalisation rides on the quantiser's scale,
+// t_i = fma(e_i, inv_l * 2^(m-E), c0) — one rounding instead of rn(rn(e_i * inv_l) * 2^(m-E) + c0), i.e. <= 1 ulp of t_i, the
+// same class of deviation as the approximate exponential itself.  !SCALED: v holds p_i, inv_l unused.
+// Probabilities are <= 1 mathematically; an approximate exponential may overshoot by an ulp, so the BLOCK MAX is clamped to
+// 1.0 before the shared exponent is derived (an overshooting element then saturates at qmax exactly like the reference's 1.0).
+template <int KIND, bool SCALED>
+__device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, const FmtParams& p, uint32_t (&w)[8]) {
+  // block max / min as trees of 3-input operations (see max32_tree)
+  float mx = fmaxf(max3f(max3f(v[0], v[1], v[2]), max3f(v[3], v[4], v[5]), max3f(v[6], v[7], v[8])),
+                   max3f(max3f(v[9], v[10], v[11]), max3f(v[12], v[13], v[14]), v[15]));
+  if (SCALED) mx = __fmul_rn(mx, inv_l);
+  if (mx == 0.f) {                                      // all-zero block -> zeros (pass-through)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 0u;
+    return;
+  }
+  mx = fminf(mx, 1.0f);
+  const uint32_t mbits = f2u(mx);
+  const FastState fs = fast_state<KIND>(mbits, p);
+  if (KIND == kBlockFP && fs.ok && p.mbits <= 7) {
+    float mn = fminf(min3f(min3f(v[0], v[1], v[2]), min3f(v[3], v[4], v[5]), min3f(v[6], v[7], v[8])),
+                     min3f(min3f(v[9], v[10], v[11]), min3f(v[12], v[13], v[14]), v[15]));
+    if (SCALED) mn = __fmul_rn(mn, inv_l);
+    if (mn > 1e-8f) {
+      // no pass-through element in this block (the common case): rounding in fp32, clamp + de-quantisation packed in bf16
+      const float c0 = __fmul_rn(1e-9f, fs.f0);         // exact: f0 is a power of two
+      const float g0 = SCALED ? __fmul_rn(inv_l, fs.f0) : fs.f0;      // exact (power-of-two factor, |E| <= 100)
+      const uint32_t step2 = pack_bf16_trunc(fs.f1, fs.f1);
+      const float nb = -__fmul_rn(128.0f, fs.f1);
+      const uint32_t base2 = pack_bf16_trunc(nb, nb);
+      const float top = __fadd_rn(128.0f, p.qmax);
+      const uint32_t top2 = pack_bf16_trunc(top, top);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t0 = __fadd_rn(__fmaf_rn(v[2 * i], g0, c0), kMagicB);            // kMagicB + rint((p + 1e-9f) * 2^(m-E))
+        const float t1 = __fadd_rn(__fmaf_rn(v[2 * i + 1], g0, c0), kMagicB);
+        const uint32_t q2 = bf16x2_min(__byte_perm(f2u(t0), f2u(t1), 0x5410), top2);   // {128 + q0, 128 + q1}, clamped to 128 + qmax
+        w[i] = bf16x2_fma(q2, step2, base2);
+      }
+      return;
+    }
+  }
+  float vc[16];
+  uint32_t wc[8];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) vc[i] = v[i];
+  quantize_probs16_cold<KIND, SCALED>(vc, inv_l, mbits, fs, p, wc);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = wc[i];
+}
+
 // statistics of 32 scores: running max m (with mL = rn(m * log2 e)) and running sum l of 2^(s * log2 e - mL).
 // l is kept in "mL units": the exact exp(s - m) differs from the accumulated term by the factor 2^-(m * log2 e - mL),
 // which is constant per row and applied once in the merge (stat_fixup) — the per-element work is FFMA + EX2 + FADD.
 constexpr float kL2ELo = 1.925963033500011e-08f;     // log2(e) - (float)log2(e)
-template <bool MASK>
-__device__ __forceinline__ void stats32(const uint32_t (&r)[32], int nvalid, float& m, float& mL, float& l) {
-  float tmax = -INFINITY;
+// Scores behind the causal diagonal are pre-set to -inf by the caller (mask_scores32): exp2(-inf) == 0 and max ignores them, so one
+// copy of this code serves full and diagonal slices.
+__device__ __forceinline__ void mask_scores32(uint32_t (&r)[32], int nvalid) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float s = u2f(r[i]);
-    if (MASK) s = (i < nvalid) ? s : -INFINITY;
-    tmax = fmaxf(tmax, s);
-  }
+  for (int i = 0; i < 32; ++i) r[i] = (i < nvalid) ? r[i] : 0xff800000u;
+}
+// maximum of 32 values as a TREE of 3-input maxima (depth 4): the compiler's left-to-right chain of 16 dependent FMNMX3 kept a warp
+// from issuing anything else for ~80 cycles per slice — with every softmax warp of a pipeline in the same phase that showed up as
+// fixed-latency "wait" stalls (ncu: 1.9 warps per issue slot)
+__device__ __forceinline__ float max32_tree(const uint32_t (&r)[32]) {
+  float t[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) t[i] = max3f(u2f(r[3 * i]), u2f(r[3 * i + 1]), u2f(r[3 * i + 2]));
+  t[10] = fmaxf(u2f(r[30]), u2f(r[31]));
+  const float u0 = max3f(t[0], t[1], t[2]), u1 = max3f(t[3], t[4], t[5]), u2 = max3f(t[6], t[7], t[8]), u3 = fmaxf(t[9], t[10]);
+  return fmaxf(fmaxf(u0, u1), fmaxf(u2, u3));
+}
+__device__ __forceinline__ void stats32(const uint32_t (&r)[32], float& m, float& mL, float& l) {
+  const float tmax = max32_tree(r);
   if (tmax > m) {                                        // online rescale of the running sum
     const float mLn = __fmul_rn(tmax, kL2E);
     l = __fmul_rn(l, ex2_fast(__fsub_rn(mL, mLn)));      // first time: mL = -inf -> factor 0 (l is 0 anyway)
@@ -229,20 +272,10 @@ __device__ __forceinline__ void stats32(const uint32_t (&r)[32], int nvalid, flo
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
-    float e0 = ex2_fast(__fmaf_rn(u2f(r[i]), kL2E, nmL));
-    float e1 = ex2_fast(__fmaf_rn(u2f(r[i + 1]), kL2E, nmL));
-    float e2 = ex2_fast(__fmaf_rn(u2f(r[i + 2]), kL2E, nmL));
-    float e3 = ex2_fast(__fmaf_rn(u2f(r[i + 3]), kL2E, nmL));
-    if (MASK) {
-      e0 = (i < nvalid) ? e0 : 0.f;
-      e1 = (i + 1 < nvalid) ? e1 : 0.f;
-      e2 = (i + 2 < nvalid) ? e2 : 0.f;
-      e3 = (i + 3 < nvalid) ? e3 : 0.f;
-    }
-    a0 = __fadd_rn(a0, e0);
-    a1 = __fadd_rn(a1, e1);
-    a2 = __fadd_rn(a2, e2);
-    a3 = __fadd_rn(a3, e3);
+    a0 = __fadd_rn(a0, ex2_fast(__fmaf_rn(u2f(r[i]), kL2E, nmL)));
+    a1 = __fadd_rn(a1, ex2_fast(__fmaf_rn(u2f(r[i + 1]), kL2E, nmL)));
+    a2 = __fadd_rn(a2, ex2_fast(__fmaf_rn(u2f(r[i + 2]), kL2E, nmL)));
+    a3 = __fadd_rn(a3, ex2_fast(__fmaf_rn(u2f(r[i + 3]), kL2E, nmL)));
   }
   l = __fadd_rn(l, __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)));
 }
@@ -258,9 +291,9 @@ __device__ __forceinline__ float stat_fixup(float m, float mL, float l) {
 // instead of libdevice expf's 8 + the subtraction); inv_l already carries the row constant 2^-(m * log2 e - mL).  Relative error
 // of p <= ~(3 + |s - m| * 1.44) ulp instead of <= ~3 ulp; a probability only changes when it sits that close to a rounding
 // boundary.  The largest probability may overshoot 1.0 by an ulp: quantize_probs16 clamps the block max.
-template <int KIND, bool MASK, bool FAST>
-__device__ __forceinline__ void probs32(const uint32_t (&r)[32], int nvalid, float m, float mL, float inv_l, const FmtParams& p,
-                                        uint32_t prow, int chunk0, int sw) {
+template <int KIND, bool FAST>
+__device__ __forceinline__ void probs32_regs(const uint32_t (&r)[32], float m, float mL, float inv_l, const FmtParams& p,
+                                             uint32_t (&w)[16]) {
   const float nmL = -mL;
 #pragma unroll
   for (int blk = 0; blk < 2; ++blk) {
@@ -268,18 +301,28 @@ __device__ __forceinline__ void probs32(const uint32_t (&r)[32], int nvalid, flo
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       if (FAST) {
-        v[i] = ex2_fast(__fmaf_rn(u2f(r[blk * 16 + i]), kL2E, nmL));       // normalised inside quantize_probs16
+        v[i] = ex2_fast(__fmaf_rn(u2f(r[blk * 16 + i]), kL2E, nmL));       // normalised inside quantize_probs16; masked score (-inf) -> 0
       } else {
-        const float e = expf(__fsub_rn(u2f(r[blk * 16 + i]), m));
+        const float e = expf(__fsub_rn(u2f(r[blk * 16 + i]), m));           // expf(-inf) == 0 for masked scores
         v[i] = __fmul_rn(e, inv_l);
       }
-      if (MASK) v[i] = (blk * 16 + i < nvalid) ? v[i] : 0.f;
     }
-    uint32_t w[8];
-    quantize_probs16<KIND, FAST>(v, inv_l, p, w);
+    uint32_t wb[8];
+    quantize_probs16<KIND, FAST>(v, inv_l, p, wb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[blk * 8 + i] = wb[i];
+  }
+}
+template <int KIND, bool FAST>
+__device__ __forceinline__ void probs32(const uint32_t (&r)[32], float m, float mL, float inv_l, const FmtParams& p,
+                                        uint32_t prow, int chunk0, int sw) {
+  uint32_t w[16];
+  probs32_regs<KIND, FAST>(r, m, mL, inv_l, p, w);
+#pragma unroll
+  for (int blk = 0; blk < 2; ++blk) {
     const int chunk = chunk0 + blk * 2;
-    sts_v4(prow + ((chunk ^ sw) << 4), w[0], w[1], w[2], w[3]);
-    sts_v4(prow + (((chunk + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
+    sts_v4(prow + ((chunk ^ sw) << 4), w[blk * 8], w[blk * 8 + 1], w[blk * 8 + 2], w[blk * 8 + 3]);
+    sts_v4(prow + (((chunk + 1) ^ sw) << 4), w[blk * 8 + 4], w[blk * 8 + 5], w[blk * 8 + 6], w[blk * 8 + 7]);
   }
 }
 
@@ -507,21 +550,17 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
               for (int i = 0; i < 32; ++i) r[i] = f2u(__fmul_rn(u2f(r[i]), g.score_mul));
             }
+            if (!skip && diag && diag_partial) mask_scores32(r, nvalid_d);
             if (sweep == 0) {
-              if (!skip) {
-                if (!(diag && diag_partial)) stats32<false>(r, 32, m, mL, l);
-                else stats32<true>(r, nvalid_d, m, mL, l);
-              }
+              if (!skip) stats32(r, m, mL, l);
             } else {
               ptx::mbar_wait(p_empty(pr.idx), pr.phase ^ 1);
               const uint32_t prow = sb + Cfg::kSmemP + (pr.idx * 2 + (cq >> 1)) * kSubTile + r_in * 128;
               if (skip) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) sts_v4(prow + (((chunk0 + c) ^ sw) << 4), 0u, 0u, 0u, 0u);
-              } else if (!(diag && diag_partial)) {
-                probs32<KIND, false, FAST>(r, 32, m, mL, inv_l, g.p, prow, chunk0, sw);
               } else {
-                probs32<KIND, true, FAST>(r, nvalid_d, m, mL, inv_l, g.p, prow, chunk0, sw);
+                probs32<KIND, FAST>(r, m, mL, inv_l, g.p, prow, chunk0, sw);
               }
               ptx::fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the MMA (async proxy)
               __syncwarp();
@@ -604,6 +643,336 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// v4, head_dim 64: TWO independent pipelines ("groups") per CTA and P in tensor memory.
+//
+// Why: the single-pipeline kernel above is ALU-issue bound but only 59 % issue-active (ncu) — all 16 softmax warps walk through the
+// same phases together, so the SM idles whenever they wait together: the hand-over between the two sweeps (row-statistics merge),
+// the wait for the last PV MMA before the epilogue, the first S tile of the next item.  Here the 16 softmax warps form two groups
+// of 8 that work on DIFFERENT work items with their own TMA lane, MMA lane, barriers, shared-memory ring and TMEM columns: one
+// group's bubbles are filled by the other group's math (the two-softmax-warpgroup ping-pong of Blackwell attention kernels).
+// P no longer travels registers -> swizzled smem -> fence.proxy.async -> MMA: a softmax warp writes its 32 x 32 quantised
+// probabilities (bf16 pairs) straight into tensor memory with tcgen05.st and PV runs with the A operand read FROM TMEM
+// (tcgen05.mma [d], [a], b-desc) — no shared-memory store, no generic->async proxy fence on the softmax warps' critical path, and
+// 64 KB of shared memory freed for deeper K / V rings.
+//
+// Key tiles are 64 wide (MMA N = 64) so that one group's accumulators fit 256 TMEM columns:
+//   columns (relative to the group's base): S0 [0,64)  S1 [64,128)  O [128,192)  P0 [192,224)  P1 [224,256)
+// Warp roles (640 threads): warp 0 / 2 TMA of group 0 / 1 (warp 2 also allocates TMEM), warp 1 / 3 MMA of group 0 / 1,
+// warps 4-11 softmax of group 0, 12-19 of group 1; inside a group warp i owns TMEM lane quarter (i & 3) = 32 query rows and key
+// columns [32*cq, 32*cq + 32) of every 64-key tile, cq = i >> 2.  Work items are dealt round-robin to the 2 * gridDim.x groups.
+// ------------------------------------------------------------------------------------------------
+struct At2Cfg {
+  static constexpr int kBN = 64;                                     // keys per tile
+  static constexpr int kQBufs = 2, kKStages = 4, kVStages = 3;
+  static constexpr int kQTile = kAtBM * 64 * 2;                      // 16 KB
+  static constexpr int kKVTile = kBN * 64 * 2;                       //  8 KB
+  static constexpr int kSmemQ = 0;
+  static constexpr int kSmemK = kSmemQ + kQBufs * kQTile;
+  static constexpr int kSmemV = kSmemK + kKStages * kKVTile;
+  static constexpr int kSmemX = kSmemV + kVStages * kKVTile;         // row-stat exchange: 2 parities x (m, l) x 2 column halves x 128 rows
+  static constexpr int kGroupBytes = kSmemX + 2 * 2 * 2 * 128 * 4;
+  static constexpr int kBarsPerGroup = 2 * kQBufs + 2 * kKStages + 2 * kVStages + 4 + 4 + 2;
+  static constexpr int kSmemBar = 2 * kGroupBytes;
+  static constexpr int kSmemBytes = kSmemBar + 2 * kBarsPerGroup * 8 + 16 + 1024;
+  static constexpr uint32_t kTmemGroup = 256, kTmemO = 128, kTmemP = 192;
+  static constexpr int kGroupWarps = 8;
+  static_assert(kGroupBytes % 1024 == 0, "group regions keep the 1024-byte alignment of the swizzle atoms");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                             const __grid_constant__ CUtensorMap tmV, AttnArgs g) {
+  using Cfg = At2Cfg;
+  constexpr int D = 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint32_t sb0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  asm volatile("mov.u32 %0, %0;" : "+r"(sb0));
+  int tid_reg = (int)threadIdx.x;
+  asm volatile("mov.u32 %0, %0;" : "+r"(tid_reg));
+  const int warp = tid_reg >> 5, lane = tid_reg & 31;
+  // group of this warp: control warps 0,1 -> 0; 2,3 -> 1; softmax warps 4-11 -> 0; 12-19 -> 1
+  const int grp = warp < 4 ? (warp >> 1) : ((warp - 4) >> 3);
+  const uint32_t sb = sb0 + (uint32_t)grp * Cfg::kGroupBytes;
+  const uint32_t bar0 = sb0 + Cfg::kSmemBar + (uint32_t)grp * (Cfg::kBarsPerGroup * 8);
+  auto q_full = [&](int s) { return bar0 + 8u * s; };
+  auto q_empty = [&](int s) { return bar0 + 8u * (Cfg::kQBufs + s); };
+  const uint32_t bK = bar0 + 8u * (2 * Cfg::kQBufs);
+  auto k_full = [&](int s) { return bK + 8u * s; };
+  auto k_empty = [&](int s) { return bK + 8u * (Cfg::kKStages + s); };
+  const uint32_t bV = bK + 8u * (2 * Cfg::kKStages);
+  auto v_full = [&](int s) { return bV + 8u * s; };
+  auto v_empty = [&](int s) { return bV + 8u * (Cfg::kVStages + s); };
+  const uint32_t bS = bV + 8u * (2 * Cfg::kVStages);
+  auto s_full = [&](int s) { return bS + 8u * s; };
+  auto s_empty = [&](int s) { return bS + 8u * (2 + s); };
+  auto p_full = [&](int s) { return bS + 8u * (4 + s); };
+  auto p_empty = [&](int s) { return bS + 8u * (6 + s); };
+  const uint32_t o_full = bS + 8u * 8, o_empty = bS + 8u * 9;
+  const uint32_t tmem_slot = sb0 + Cfg::kSmemBar + 2 * Cfg::kBarsPerGroup * 8;
+  const uint32_t xch = sb + Cfg::kSmemX;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+  }
+  if ((warp == 1 || warp == 3) && lane == 0) {                    // each MMA lane initialises its own group's barriers
+    for (int s = 0; s < Cfg::kQBufs; ++s) { ptx::mbar_init(q_full(s), 1); ptx::mbar_init(q_empty(s), 1); }
+    for (int s = 0; s < Cfg::kKStages; ++s) { ptx::mbar_init(k_full(s), 1); ptx::mbar_init(k_empty(s), 1); }
+    for (int s = 0; s < Cfg::kVStages; ++s) { ptx::mbar_init(v_full(s), 1); ptx::mbar_init(v_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(s_full(s), 1);
+      ptx::mbar_init(s_empty(s), Cfg::kGroupWarps);
+      ptx::mbar_init(p_full(s), Cfg::kGroupWarps);
+      ptx::mbar_init(p_empty(s), 1);
+    }
+    ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(o_empty, Cfg::kGroupWarps);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kAtTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+  tmem += (uint32_t)grp * Cfg::kTmemGroup;                        // this group's 256 columns
+
+  const int T = g.q_tiles;
+  const int pairs = (T + 1) >> 1;
+  const int items = g.B * g.H * pairs;
+  const int vb = (int)blockIdx.x * 2 + grp, vgrid = (int)gridDim.x * 2;      // virtual worker index: one per group
+  auto decode = [&](int w, int& b, int& h, int& qt_hi, int& nsub) {
+    const int bh = w / pairs, pr = w - bh * pairs;
+    b = bh / g.H;
+    h = bh - b * g.H;
+    qt_hi = T - 1 - pr;
+    nsub = (qt_hi != pr) ? 2 : 1;
+  };
+
+  if (warp == 0 || warp == 2) {
+    // ------------------------------------------------------------------ TMA producer of this group
+    if (lane == 0) {
+      Ring qr, kr, vr;
+      for (int w = vb; w < items; w += vgrid) {
+        int b, h, qt_hi, nsub;
+        decode(w, b, h, qt_hi, nsub);
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
+          const int n = 2 * (qt + 1);                              // 64-key tiles up to and including the diagonal
+          ptx::mbar_wait(q_empty(qr.idx), qr.phase ^ 1);
+          ptx::mbar_expect_tx(q_full(qr.idx), Cfg::kQTile);
+          tma_load_4d(sb + Cfg::kSmemQ + qr.idx * Cfg::kQTile, &tmQ, q_full(qr.idx), 0, h, qt * kAtBM, b);
+          qr.advance(Cfg::kQBufs);
+          for (int sweep = 0; sweep < 2; ++sweep) {
+            for (int j = 0; j < n; ++j) {
+              ptx::mbar_wait(k_empty(kr.idx), kr.phase ^ 1);
+              ptx::mbar_expect_tx(k_full(kr.idx), Cfg::kKVTile);
+              tma_load_4d(sb + Cfg::kSmemK + kr.idx * Cfg::kKVTile, &tmK, k_full(kr.idx), 0, h, j * Cfg::kBN, b);
+              kr.advance(Cfg::kKStages);
+              if (sweep == 1) {
+                ptx::mbar_wait(v_empty(vr.idx), vr.phase ^ 1);
+                ptx::mbar_expect_tx(v_full(vr.idx), Cfg::kKVTile);
+                tma_load_4d(sb + Cfg::kSmemV + vr.idx * Cfg::kKVTile, &tmV, v_full(vr.idx), 0, h, j * Cfg::kBN, b);
+                vr.advance(Cfg::kVStages);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ------------------------------------------------------------------ MMA issuer of this group
+    if (lane == 0) {
+      constexpr uint32_t idS = ptx::idesc_bf16_f32(kAtBM, Cfg::kBN);
+      constexpr uint32_t idO = idesc_bf16_f32_bmn(kAtBM, D);
+      Ring qr, kr, vr, sr, pr;
+      uint32_t ophase = 0;
+      for (int w = vb; w < items; w += vgrid) {
+        int b, h, qt_hi, nsub;
+        decode(w, b, h, qt_hi, nsub);
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
+          const int n = 2 * (qt + 1);
+          ptx::mbar_wait(q_full(qr.idx), qr.phase);
+          const uint32_t qbase = sb + Cfg::kSmemQ + qr.idx * Cfg::kQTile;
+          auto issue_S = [&]() {
+            ptx::mbar_wait(k_full(kr.idx), kr.phase);
+            ptx::mbar_wait(s_empty(sr.idx), sr.phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t kbase = sb + Cfg::kSmemK + kr.idx * Cfg::kKVTile;
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) {
+              const uint64_t qdesc = ptx::smem_desc_sw128_kmajor(qbase) + (uint64_t)(2 * k);
+              const uint64_t kdesc = ptx::smem_desc_sw128_kmajor(kbase) + (uint64_t)(2 * k);
+              ptx::umma_bf16(tmem + (uint32_t)(sr.idx * Cfg::kBN), qdesc, kdesc, idS, k != 0);
+            }
+            ptx::umma_commit(k_empty(kr.idx));
+            ptx::umma_commit(s_full(sr.idx));
+            kr.advance(Cfg::kKStages);
+            sr.advance(2);
+          };
+          for (int j = 0; j < n; ++j) issue_S();                // statistics sweep
+          issue_S();                                            // S(0) of the final sweep
+          for (int j = 0; j < n; ++j) {
+            if (j + 1 < n) issue_S();                           // keep the softmax warps one tile ahead
+            ptx::mbar_wait(v_full(vr.idx), vr.phase);
+            ptx::mbar_wait(p_full(pr.idx), pr.phase);
+            if (j == 0) { ptx::mbar_wait(o_empty, ophase ^ 1); }
+            ptx::tc_fence_after();
+            const uint32_t vbase = sb + Cfg::kSmemV + vr.idx * Cfg::kKVTile;
+            const uint32_t ptm = tmem + Cfg::kTmemP + (uint32_t)(pr.idx * (Cfg::kBN / 2));
+#pragma unroll
+            for (int k = 0; k < Cfg::kBN / 16; ++k) {
+              // A: 16 keys = 8 TMEM columns of bf16 pairs; B: 16 key rows (128 bytes each) of the V tile, MN-major
+              const uint64_t bdesc = smem_desc_sw128_mnmajor(vbase + k * 16 * 128, Cfg::kKVTile);
+              ptx::umma_bf16_ts(tmem + Cfg::kTmemO, ptm + (uint32_t)(8 * k), bdesc, idO, (j | k) != 0);
+            }
+            ptx::umma_commit(v_empty(vr.idx));
+            ptx::umma_commit(p_empty(pr.idx));
+            vr.advance(Cfg::kVStages);
+            pr.advance(2);
+          }
+          ptx::umma_commit(o_full);
+          ptx::umma_commit(q_empty(qr.idx));
+          qr.advance(Cfg::kQBufs);
+          ophase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / quantise / epilogue
+    const int quarter = warp & 3;                 // TMEM lane quarter (== warp % 4)
+    const int cq = ((warp - 4) & 7) >> 2;         // which 32 key columns of every 64-key tile
+    const int r_in = quarter * 32 + lane;         // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    Ring sr, pr;
+    uint32_t ophase = 0;
+    int xbuf = 0;
+    for (int w = vb; w < items; w += vgrid) {
+      int b, h, qt_hi, nsub;
+      decode(w, b, h, qt_hi, nsub);
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
+        const int n = 2 * (qt + 1);
+        const int row = qt * kAtBM + r_in;
+        const int nvalid_d = lane + 1;
+        const uint32_t xm = xch + xbuf * (2 * 2 * 128 * 4);   // [2][128] partial maxima
+        const uint32_t xl = xm + 2 * 128 * 4;                 // [2][128] partial sums
+        xbuf ^= 1;
+        float m = -INFINITY, mL = -INFINITY, l = 0.f, inv_l = 0.f;
+        for (int sweep = 0; sweep < 2; ++sweep) {
+          for (int j = 0; j < n; ++j) {
+            // the last two 64-key tiles straddle the diagonal: 32-key column group c' = 2 * (j - (n - 2)) + cq of the 128 x 128
+            // diagonal square is fully visible for c' < quarter, fully masked for c' > quarter, per-element for c' == quarter
+            const int cd = (j >= n - 2) ? (2 * (j - (n - 2)) + cq) : -1;
+            const bool skip = cd > quarter;
+            const bool partial = cd == quarter;
+            ptx::mbar_wait(s_full(sr.idx), sr.phase);
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            if (!skip) {
+              ptx::tmem_ld_32x32(tmem + lane_addr + (uint32_t)(sr.idx * Cfg::kBN + cq * 32), r);
+              ptx::tmem_ld_wait();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(s_empty(sr.idx));
+            sr.advance(2);
+            if (!skip && g.scale_mode == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = f2u(__fmul_rn(u2f(r[i]), g.score_mul));
+            }
+            if (partial) mask_scores32(r, nvalid_d);
+            if (sweep == 0) {
+              if (!skip) stats32(r, m, mL, l);
+            } else {
+              uint32_t wq[16];
+              if (skip) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) wq[i] = 0u;
+              } else {
+                probs32_regs<KIND, FAST>(r, m, mL, inv_l, g.p, wq);
+              }
+              ptx::mbar_wait(p_empty(pr.idx), pr.phase ^ 1);   // the PV MMA that read this P buffer two tiles ago has retired
+              ptx::tc_fence_after();
+              ptx::tmem_st_32x16(tmem + lane_addr + Cfg::kTmemP + (uint32_t)(pr.idx * (Cfg::kBN / 2) + cq * 16), wq);
+              ptx::tmem_st_wait();
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(p_full(pr.idx));
+              pr.advance(2);
+            }
+          }
+          if (sweep == 0) {
+            // merge the two column halves of every row (the two warps that share this lane quarter inside the group)
+            sts_f32(xm + (cq * 128 + r_in) * 4, m);
+            sts_f32(xl + (cq * 128 + r_in) * 4, stat_fixup(m, mL, l));
+            named_bar_sync(1 + grp * 4 + quarter, 64);
+            const float m0 = lds_f32(xm + r_in * 4), m1 = lds_f32(xm + (128 + r_in) * 4);
+            const float mm = fmaxf(m0, m1);
+            float ll = __fmul_rn(lds_f32(xl + r_in * 4), expf(__fsub_rn(m0, mm)));
+            ll = __fadd_rn(ll, __fmul_rn(lds_f32(xl + (128 + r_in) * 4), expf(__fsub_rn(m1, mm))));
+            m = mm;
+            l = fmaxf(ll, 1.0f);                                 // see the single-pipeline kernel: the exact sum is >= 1
+            inv_l = __frcp_rn(l);
+            if (FAST) {
+              mL = __fmul_rn(m, kL2E);
+              const float err = __fadd_rn(__fmaf_rn(m, kL2E, -mL), __fmul_rn(m, kL2ELo));
+              inv_l = __fmul_rn(inv_l, ex2_fast(-err));
+            }
+          }
+        }
+        // ---- epilogue: O (128 x 64 fp32 in TMEM) -> global; this warp owns 32 of the 64 columns of its 32 rows
+        ptx::mbar_wait(o_full, ophase);
+        ophase ^= 1;
+        ptx::tc_fence_after();
+        uint32_t ro[2][16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) ptx::tmem_ld_32x16(tmem + lane_addr + Cfg::kTmemO + (uint32_t)(cq * 32 + c * 16), ro[c]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(o_empty);
+        if (row < g.S) {
+          const int64_t off = ((int64_t)b * g.S + row) * g.ldo + (int64_t)h * D + cq * 32;
+          if (g.out_mode == 0) {
+            float* o = reinterpret_cast<float*>(g.out) + off;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(o + c * 16 + i) = make_float4(u2f(ro[c][i]), u2f(ro[c][i + 1]), u2f(ro[c][i + 2]), u2f(ro[c][i + 3]));
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + off;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = u2f(ro[c][i]);
+              quantize_signed16_rt(v, g.po);
+              uint32_t wv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) wv[i] = pack_bf16_rn(v[2 * i], v[2 * i + 1]);
+              *reinterpret_cast<uint4*>(o + c * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+              *reinterpret_cast<uint4*>(o + c * 16 + 8) = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kAtTmemCols>(tmem - (uint32_t)grp * Cfg::kTmemGroup);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 int make_params(const bq_format* f, FmtParams* p);
@@ -611,6 +980,31 @@ int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, i
                       int box_rows);
 
 static bool g_attn_precise_exp = false;       // true: libdevice expf for the numerators (bit-identical to torch's exp(x - max))
+static bool g_attn_dual = true;               // head_dim 64: the two-pipeline / P-in-TMEM kernel (false: the single-pipeline kernel, A/B)
+
+template <int KIND, bool FAST>
+static int launch_attention_dual_f(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
+                                   cudaStream_t st) {
+  static PerDevice<bool> attr_pd;
+  bool& attr = attr_pd.get();
+  if (!attr) {
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_dual_kernel<KIND, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       At2Cfg::kSmemBytes));
+    attr = true;
+  }
+  const int items = g.B * g.H * ((g.q_tiles + 1) / 2);
+  const int grid = std::min((items + 1) / 2, num_sms());
+  {
+    LaunchScope ls(kKernAttention, st);
+    attention_causal_dual_kernel<KIND, FAST><<<grid, kAtThreads, At2Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
+  }
+  BQ_CUDA_CHECK(cudaGetLastError());
+  return BQ_OK;
+}
+template <int KIND>
+static int launch_attention_dual(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g, cudaStream_t st) {
+  return g_attn_precise_exp ? launch_attention_dual_f<KIND, false>(tq, tk, tv, g, st) : launch_attention_dual_f<KIND, true>(tq, tk, tv, g, st);
+}
 
 template <int KIND, int D, bool FAST>
 static int launch_attention_f(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
@@ -669,10 +1063,13 @@ static int attention_impl(const bq_format* fp, const bq_format* fo, const void* 
   g.score_mul = 1.0f / score_div;
   g.scale_mode = (score_div == 1.0f) ? 0 : 1;
   CUtensorMap tq, tk, tv;
+  const bool dual = g_attn_dual && d == 64;
+  const int kv_rows = dual ? At2Cfg::kBN : kAtBN;
   if ((rc = make_tmap_bf16_4d(&tq, Qq, d, S, H, B, ldq, kAtBM))) return rc;
-  if ((rc = make_tmap_bf16_4d(&tk, Kq, d, S, H, B, ldk, kAtBN))) return rc;
-  if ((rc = make_tmap_bf16_4d(&tv, Vq, d, S, H, B, ldv, kAtBN))) return rc;
+  if ((rc = make_tmap_bf16_4d(&tk, Kq, d, S, H, B, ldk, kv_rows))) return rc;
+  if ((rc = make_tmap_bf16_4d(&tv, Vq, d, S, H, B, ldv, kv_rows))) return rc;
   const bool bfp = fp->kind == BQ_KIND_BLOCK_FP;
+  if (dual) return bfp ? launch_attention_dual<kBlockFP>(tq, tk, tv, g, st) : launch_attention_dual<kBlockMinifloat>(tq, tk, tv, g, st);
   if (d == 64) return bfp ? launch_attention<kBlockFP, 64>(tq, tk, tv, g, st) : launch_attention<kBlockMinifloat, 64>(tq, tk, tv, g, st);
   return bfp ? launch_attention<kBlockFP, 128>(tq, tk, tv, g, st) : launch_attention<kBlockMinifloat, 128>(tq, tk, tv, g, st);
 }
@@ -681,6 +1078,8 @@ static int attention_impl(const bq_format* fp, const bq_format* fo, const void* 
 
 extern "C" void bq_set_attention_precise_exp(int on) { bq::g_attn_precise_exp = on != 0; }
 extern "C" int bq_get_attention_precise_exp(void) { return bq::g_attn_precise_exp ? 1 : 0; }
+extern "C" void bq_set_attention_dual_pipeline(int on) { bq::g_attn_dual = on != 0; }
+extern "C" int bq_get_attention_dual_pipeline(void) { return bq::g_attn_dual ? 1 : 0; }
 
 extern "C" int bq_attention_causal(const bq_format* fp, const void* Qq, const void* Kq, const void* Vq, float* out,
                                    int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv,

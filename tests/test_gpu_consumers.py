@@ -237,8 +237,43 @@ def attention_exp_mode(request):
     L.load().bq_set_attention_precise_exp(0)
 
 
-@pytest.mark.parametrize("S", [128, 200, 1024, 2048])
-def test_fused_causal_attention_vs_op_by_op_oracle(S, attention_exp_mode):
+@pytest.fixture(params=[1, 0], ids=["dual_pipeline_p_in_tmem", "single_pipeline_p_in_smem"])
+def attention_pipeline(request):
+    """head_dim 64 runs on the two-pipeline kernel with P in tensor memory by default; the single-pipeline kernel (what head_dim
+    128 uses) stays selectable (bq_set_attention_dual_pipeline) and must give the same answers."""
+    from llm_mixed_q_b200 import _lib as L
+
+    L.load().bq_set_attention_dual_pipeline(request.param)
+    yield request.param
+    L.load().bq_set_attention_dual_pipeline(1)
+
+
+def test_fused_attention_pipelines_agree_bit_for_bit():
+    """Same arithmetic in both kernels (only the tiling of the key axis differs: 64- vs 128-key tiles change the order in which the
+    row sum is accumulated) — the quantised probabilities, and therefore the
+    outputs, must agree almost everywhere; rows whose sums differ in the last ulp may flip single probabilities by one step."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import fused_causal_attention
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, heads, d, S = 2, 4, 64, 1024
+    q = torch.randn(B, S, heads * d, device="cuda", generator=g) * 0.5
+    k = torch.randn(B, S, heads * d, device="cuda", generator=g)
+    v = torch.randn(B, S, heads * d, device="cuda", generator=g)
+    outs = []
+    try:
+        for dual in (1, 0):
+            L.load().bq_set_attention_dual_pipeline(dual)
+            outs.append(fused_causal_attention(q, k, v, CFG_BFP6, CFG_BFP6, heads))
+    finally:
+        L.load().bq_set_attention_dual_pipeline(1)
+    diff = (outs[0] - outs[1]).abs()
+    assert float((diff > 0).float().mean()) <= 2e-2, float((diff > 0).float().mean())
+    assert float(diff.max()) <= (2.0 ** -5) * float(v.abs().max())
+
+
+@pytest.mark.parametrize("S", [64, 128, 200, 1024, 2048])
+def test_fused_causal_attention_vs_op_by_op_oracle(S, attention_exp_mode, attention_pipeline):
     """The fused kernel computes the same function as bmm_0 -> mask -> softmax -> bmm_1.  Scores agree to fp32
     accumulation order; the row sum of the softmax is accumulated in a different order from 2-ulp ex2.approx
     exponentials, so a probability can differ by a few ulp BEFORE quantisation and, when it sits on a rounding boundary,
