@@ -264,6 +264,111 @@ def lm_head_modes(device, K=3):
     return out
 
 
+def column_parallel_block(device, dist, world, rank, pk, tokens_list=(4096, 16384), iters=5):
+    """BASELINE configs[4] on the record (N > 1 only): one OPT-6.7B decoder layer (H 4096, F 16384, 32 heads x 128) under the
+    per-layer mixed-precision block_fp TOML (configs/opt_6.7b_mixed_bfp.toml, section-4.4 search format), tensor-parallel over the
+    ranks of this job — every Linear column-parallel, attention head-parallel, exchanges fused into the producing kernels
+    (llm_mixed_q_b200/dist.py: TensorParallelOPTLayer) — against the same schedule with NCCL all-gathers, both checked BIT-IDENTICAL
+    to the single-GPU fused layer.  Strong scaling: the token count is fixed as N grows.  Times: CUDA events, max over ranks."""
+    from llm_mixed_q_b200.dist import PeerArena, TensorParallelOPTLayer
+    from llm_mixed_q_b200.models.opt_quantized import OPTQuantizedConfig
+    from llm_mixed_q_b200.models.opt_quantized.modeling_opt import OPTQuantizedDecoderLayer
+
+    H, F_, heads, S = 4096, 16384, 32, SEQ
+    toml_path = os.path.join(ROOT, "configs", "opt_6.7b_mixed_bfp.toml")
+    cfg = OPTQuantizedConfig(hidden_size=H, num_hidden_layers=1, ffn_dim=F_, num_attention_heads=heads, vocab_size=512,
+                             max_position_embeddings=SEQ, quant_config=toml_path)
+    torch.manual_seed(1234)                                   # every rank builds the SAME full layer
+    with torch.device(device):
+        layer = OPTQuantizedDecoderLayer(cfg, 0).eval()
+        for lin in (layer.self_attn.q_proj, layer.self_attn.k_proj, layer.self_attn.v_proj, layer.self_attn.out_proj, layer.fc1, layer.fc2):
+            lin.bias.data.normal_(0, 0.02)
+    node = cfg.quant_config["model_layer_0"]
+    widths = {k: [v["data_in_width"], v["weight_width"]] for k, v in
+              [("q_proj", node["self_attn"]["q_proj"]), ("k_proj", node["self_attn"]["k_proj"]), ("v_proj", node["self_attn"]["v_proj"]),
+               ("out_proj", node["self_attn"]["out_proj"]), ("fc1", node["fc1"]), ("fc2", node["fc2"])]}
+    arena = None
+    arena_error = None
+    try:
+        arena = PeerArena(max(tokens_list) * F_ * 2, device, slots=6)
+    except Exception as e:                                    # e.g. CUDA IPC not permitted: the NCCL schedule is still measured
+        arena_error = f"{type(e).__name__}: {e}"
+    tp = TensorParallelOPTLayer(layer, arena=arena)
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def all_true(flag):
+        t = torch.tensor([1.0 if flag else 0.0], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t[0] > 0.5)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        dist.barrier(); torch.cuda.synchronize()
+        return max_over_ranks(a.elapsed_time(b) / iters)
+
+    points = []
+    with torch.no_grad():
+        for M in tokens_list:
+            B = M // S
+            h = torch.randn(B, S, H, device=device, generator=torch.Generator(device=device).manual_seed(7))
+            ref = layer._fused_forward(h, layer._fused_plan(S))
+            t1 = None
+            if M == tokens_list[0]:
+                for _ in range(2):
+                    layer._fused_forward(h, layer._fused_plan(S))
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(iters):
+                    layer._fused_forward(h, layer._fused_plan(S))
+                b.record(); torch.cuda.synchronize()
+                t1 = a.elapsed_time(b) / iters
+            pt = {"tokens": M, "batch": B, "seq_len": S}
+            flops = 2 * M * (4 * H * H + 2 * H * F_) + 2 * 2 * B * heads * S * S * (H // heads)
+            pt["algorithmic_flops"] = flops
+            for mode in (("fused", "nccl") if arena is not None else ("nccl",)):
+                out = tp(h, mode=mode)
+                torch.cuda.synchronize()
+                same = bool(torch.equal(ref.view(torch.int32), out.view(torch.int32)))
+                same = all_true(same and not (arena is not None and arena.timed_out()))
+                ms = timed(lambda: tp(h, mode=mode))
+                ev = []
+                tp(h, mode=mode, events=ev)
+                torch.cuda.synchronize()
+                per_op = {ev[i + 1][0]: round(ev[i][1].elapsed_time(ev[i + 1][1]), 4) for i in range(len(ev) - 1)}
+                pt[mode] = {"layer_ms": ms, "bit_identical_to_1gpu": same, "TFLOPs_job": flops / (ms / 1e3) / 1e12,
+                            "frac_of_n_x_sustained_bf16": flops / (ms / 1e3) / 1e12 / (pk["tf_sustained"] * world),
+                            "per_op_ms_rank0": per_op}
+                del out
+            sent = tp.nvlink_bytes_per_rank(M)
+            pt["nvlink_bytes_sent_per_rank"] = sent
+            pt["nvlink_floor_ms_at_770GBs"] = sent / 770e9 * 1e3
+            pt["gemm_floor_ms_at_sustained_bf16"] = flops / world / (pk["tf_sustained"] * 1e12) * 1e3
+            if t1 is not None:
+                pt["one_gpu_fused_layer_ms"] = t1
+            points.append(pt)
+            del h, ref
+    if arena is not None:
+        arena.close()
+    return {"workload": "OPT-6.7B decoder layer (H 4096, F 16384, 32 heads x 128), per-layer mixed-precision block_fp (configs/opt_6.7b_mixed_bfp.toml, layer 0), "
+                        f"tensor-parallel over {world} GPUs: column-parallel Linears + head-parallel attention; strong scaling (tokens fixed)",
+            "x_w_widths": widths, "exchange": "fused = GEMM / attention epilogues store bf16 (quantised for the consumer) or fp32 (residual stream) slabs "
+                                               "into every rank's buffer over NVLink + one flag barrier per exchange; nccl = all_gather_into_tensor + permute",
+            "bytes_per_token_on_the_wire": 2 * H + 4 * H + 2 * F_ + 4 * H, "bytes_per_token_if_every_linear_gathered_fp32": 4 * (5 * H + F_),
+            "peer_arena_error": arena_error, "points": points}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -364,6 +469,7 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer decoder layers (result is then INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true")
+    ap.add_argument("--no-column-parallel", action="store_true", help="N > 1: skip the tensor-parallel OPT-6.7B layer block")
     ap.add_argument("--eager-e2e", action="store_true", help="end-to-end region through the eager forward instead of graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -539,6 +645,31 @@ def main():
                      else "ex2.approx numerators (default; <= ~(3 + 1.44|s - max|) ulp from torch's expf — a probability moves only when it "
                           "sits on a rounding boundary; both modes are parity-tested)")
 
+    # ---- BASELINE configs[4] (N > 1): tensor-parallel OPT-6.7B layer, the one path with an exchange step ------------------------------
+    column_parallel = None
+    if dist is not None and not args.no_column_parallel:
+        del model, out
+        torch.cuda.empty_cache()
+        box = {}
+
+        def run_cp():
+            try:
+                torch.cuda.set_device(device)                  # the current device is per thread
+                box["r"] = column_parallel_block(device, dist, world, rank, pk)
+            except Exception as e:                             # never lose the headline line to the secondary measurement
+                box["r"] = {"error": f"{type(e).__name__}: {e}"}
+
+        th = threading.Thread(target=run_cp, daemon=True)
+        th.start()
+        th.join(timeout=240)
+        if th.is_alive():                                      # a stalled peer: report what we have and leave without the collective teardown
+            column_parallel = {"error": "column_parallel block exceeded 240 s (stalled peer?); headline numbers above are unaffected"}
+            if rank != 0:
+                os._exit(0)
+        else:
+            column_parallel = box.get("r")
+        model = None
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -548,7 +679,7 @@ def main():
     gpu_port = None
     if not args.no_sub:
         with torch.no_grad():
-            del model
+            model = None
             torch.cuda.empty_cache()
             extra = sub_benchmarks(device, pk)
             try:
@@ -581,7 +712,7 @@ def main():
                                           "steps with two CUDA events per launch (an event between two kernels costs a front-end round trip, ~2 % of "
                                           "the step; sharing events between consecutive launches was measured and changed nothing)",
                        "loss": loss_val, "layers": Lyr},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_port_baseline": gpu_port,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_port_baseline": gpu_port, "column_parallel": column_parallel,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * ids_host.element_size(),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K, "mode": e2e_mode,
                     "capture_error": getattr(runner, "error", None) if runner is not None else None, "clocks": clocks_e2e, "replay_reproduces_eager_loss": replay_ok},
@@ -590,6 +721,8 @@ def main():
     if args.layers:
         line["INVALID"] = "reduced layer count (debug run)"
     print(json.dumps(line), flush=True)
+    if isinstance(column_parallel, dict) and str(column_parallel.get("error", "")).startswith("column_parallel block exceeded"):
+        os._exit(0)
     if dist is not None:
         dist.destroy_process_group()
 

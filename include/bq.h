@@ -344,6 +344,15 @@ BQ_API int bq_ipc_export(const void* dev_ptr, bq_ipc_handle* out);
 BQ_API int bq_ipc_import(const bq_ipc_handle* h, void** base, void** ptr);
 BQ_API int bq_ipc_release(void* base);
 BQ_API int bq_peer_barrier(void* const* signals, int32_t rank, int32_t world, uint32_t epoch, int32_t timeout_ms, void* stream);
+/* Same; a timed-out wait additionally writes 1 to *host_error_flag — a uint32 in MAPPED PINNED HOST memory (device-accessible under
+ * unified addressing), so that the host notices a stalled peer on its next call without synchronising the device. */
+BQ_API int bq_peer_barrier_ex(void* const* signals, int32_t rank, int32_t world, uint32_t epoch, int32_t timeout_ms,
+                              uint32_t* host_error_flag, void* stream);
+/* Copies a strided slab [rows][row_bytes] (16-byte multiples, 16-byte aligned) from local memory to the SAME position of n_dst
+ * (<= BQ_MAX_REPLICAS) peer-mapped buffers: the gather of a slab that no GEMM epilogue produced (this rank's heads of the
+ * attention output in the tensor-parallel decoder layer).  Order visibility with bq_peer_barrier. */
+BQ_API int bq_peer_push(const void* src, void* const* dst, int32_t n_dst, int64_t rows, int64_t row_bytes, int64_t src_stride_bytes,
+                        int64_t dst_stride_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -157,6 +157,10 @@ def load():
     lib.bq_ipc_release.argtypes = [c_void_p]
     lib.bq_peer_barrier.restype = ctypes.c_int
     lib.bq_peer_barrier.argtypes = [POINTER(c_void_p), c_int32, c_int32, ctypes.c_uint32, c_int32, c_void_p]
+    lib.bq_peer_barrier_ex.restype = ctypes.c_int
+    lib.bq_peer_barrier_ex.argtypes = [POINTER(c_void_p), c_int32, c_int32, ctypes.c_uint32, c_int32, c_void_p, c_void_p]
+    lib.bq_peer_push.restype = ctypes.c_int
+    lib.bq_peer_push.argtypes = [c_void_p, POINTER(c_void_p), c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p]
     lib.bq_selftest_log2.restype = ctypes.c_int
     lib.bq_selftest_log2.argtypes = [c_void_p, c_void_p]
     lib.bq_kernel_count.restype = ctypes.c_int

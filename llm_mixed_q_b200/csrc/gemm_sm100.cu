@@ -255,6 +255,36 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     if (e.q.kind == kBlockFP) quant_rowblocks32<kBlockFP>(v, e.q, scratch, lane);
     else quant_rowblocks32<kBlockMinifloat>(v, e.q, scratch, lane);
   }
+  if (out_bf16 && n_rep > 0) {
+    // fused all-gather of a quantised bf16 operand (tensor-parallel layer: fc1's output in fc2's format, dist.py): the warp's
+    // 32 rows x 64 bytes are transposed through its scratch so that one store instruction covers 8 rows x 64 contiguous bytes
+    // (lane-per-row 16-byte packets crossed NVLink at a fifth of the link rate); the local copy and the peers' copies use the
+    // same registers.  All 32 lanes take part (rows beyond M are skipped at the store).
+    uint4* sc = reinterpret_cast<uint4*>(scratch);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sc[lane * 4 + (j ^ (lane & 3))] = make_uint4(pack_bf16_rn(v[8 * j], v[8 * j + 1]), pack_bf16_rn(v[8 * j + 2], v[8 * j + 3]),
+                                                   pack_bf16_rn(v[8 * j + 4], v[8 * j + 5]), pack_bf16_rn(v[8 * j + 6], v[8 * j + 7]));
+    __syncwarp();
+    const int rsub = lane >> 2, c = lane & 3, wrow0 = row - lane;
+    uint4 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + rsub;
+      o[i] = sc[r * 4 + (c ^ (r & 3))];
+    }
+    __syncwarp();                                                // scratch is reused by the next chunk
+#pragma unroll 1
+    for (int p = -1; p < n_rep; ++p) {                           // -1: this rank's C, then the peers' copies
+      __nv_bfloat16* cp = (p < 0 ? reinterpret_cast<__nv_bfloat16*>(g.C) : reinterpret_cast<__nv_bfloat16*>(e.rep[p])) + col0 + c * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = wrow0 + i * 8 + rsub;
+        if (rr < g.M) *reinterpret_cast<uint4*>(cp + (int64_t)rr * g.ldc) = o[i];
+      }
+    }
+    return;
+  }
   if (!row_ok) return;
   const int64_t off = (int64_t)row * g.ldc + col0;
   if (out_bf16) {
@@ -263,15 +293,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     for (int j = 0; j < 4; ++j)
       o[j] = make_uint4(pack_bf16_rn(v[8 * j], v[8 * j + 1]), pack_bf16_rn(v[8 * j + 2], v[8 * j + 3]),
                         pack_bf16_rn(v[8 * j + 4], v[8 * j + 5]), pack_bf16_rn(v[8 * j + 6], v[8 * j + 7]));
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(g.C) + off;
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(g.C) + off;      // (replicas of a bf16 result took the coalesced path above)
 #pragma unroll
     for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(c)[j] = o[j];
-#pragma unroll 1
-    for (int p = 0; p < n_rep; ++p) {                          // peers' copies of the gathered output
-      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(e.rep[p]) + off;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(cp)[j] = o[j];
-    }
   } else {
     float* c = g.C + off;
 #pragma unroll

@@ -11,7 +11,8 @@ emulation on one device, or lets `accelerate` place layers (`cli/eval_lm.py`), w
 2. Column-parallel quantized Linear (config 5): `W[N, K]` is blocked [1,16] along K and the bias [16] along
    N (reference quantized_modules/linear.py:113-143), so a split along N at multiples of 16 keeps every block
    inside one shard.  Rank r holds rows [r*N/g, (r+1)*N/g) of the weight (quantised locally — identical
-   values to quantising the full matrix, because no block crosses the cut), computes its column slab
+   values to quantising the full matrix, because no block crosses the cut; block_log, whose all-zero blocks take a
+   tensor-global minimum, is quantised on the full matrix before it is cut), computes its column slab
    of y from the replicated x, and the slabs are all-gathered.  The K-reduction of every output element is
    done by the same kernel in the same order as on one GPU, so the result is bit-identical to 1 GPU.
    `ColumnParallelLinear`.  Two exchange implementations behind the same module:
@@ -201,12 +202,16 @@ class PeerArena:
         self._signals = (ctypes.c_void_p * self.world)(*self.ptrs)
         self.epoch = 0
         self._next = 0
+        # sticky error word in mapped pinned host memory: a barrier that gives up waiting writes 1 here (bq_peer_barrier_ex), and the
+        # next take() / barrier() on the host raises instead of handing out a partially filled result
+        self._host_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
         # nobody signals into a flag block before its owner zeroed it
         if self.world > 1:
             dist.barrier(group=group)
 
     def take(self, shape, dtype=torch.float32):
         """Next slot as a local tensor of `shape`, and the address of the same slot on every rank."""
+        self._raise_if_timed_out()
         n = 1
         for d in shape:
             n *= int(d)
@@ -218,18 +223,41 @@ class PeerArena:
         local = self.buf[off:off + nbytes].view(dtype).view(*shape)
         return local, [p + off for p in self.ptrs]
 
+    def _raise_if_timed_out(self):
+        if int(self._host_flag[0]) != 0:
+            raise RuntimeError(f"PeerArena: a peer barrier on rank {self.rank} timed out after {self.TIMEOUT_MS} ms — a peer is stalled or "
+                               "gone; results gathered since then are incomplete")
+
     def barrier(self):
-        """Stream-ordered flag barrier over peer memory (one tiny kernel; no NCCL)."""
+        """Stream-ordered flag barrier over peer memory (one tiny kernel; no NCCL).  The epoch is a HOST counter passed by value:
+        a captured CUDA graph would replay a stale epoch and every replayed barrier would pass at once, so capture is refused."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("PeerArena.barrier() cannot be captured in a CUDA graph (host-side epoch); run the tensor-parallel "
+                               "path eagerly")
+        self._raise_if_timed_out()
         self.epoch += 1
         if self.world == 1:
             return
         L = self._L
-        L.check(self.lib.bq_peer_barrier(self._signals, self.rank, self.world, self.epoch & 0xFFFFFFFF, self.TIMEOUT_MS,
-                                         L.stream_ptr(self.device)), "bq_peer_barrier")
+        L.check(self.lib.bq_peer_barrier_ex(self._signals, self.rank, self.world, self.epoch & 0xFFFFFFFF, self.TIMEOUT_MS,
+                                            self._host_flag.data_ptr(), L.stream_ptr(self.device)), "bq_peer_barrier_ex")
+
+    def push(self, local: torch.Tensor, bases, col_offset_bytes: int):
+        """Copy the strided 2-D slab `local` (a column range of the tensor take() returned) to the same place in every peer's slot."""
+        if self.world == 1:
+            return
+        L = self._L
+        rows, cols = local.shape
+        row_bytes = cols * local.element_size()
+        dst = [b + col_offset_bytes for r, b in enumerate(bases) if r != self.rank]
+        arr = (ctypes.c_void_p * len(dst))(*dst)
+        stride = local.stride(0) * local.element_size()
+        L.check(self.lib.bq_peer_push(local.data_ptr(), arr, len(dst), rows, row_bytes, stride, stride, L.stream_ptr(self.device)),
+                "bq_peer_push")
 
     def timed_out(self) -> bool:
         """True if any barrier on this rank gave up waiting (synchronises the device)."""
-        return bool(self.buf[:self._flag_bytes].view(torch.int32)[32].item())
+        return bool(self.buf[:self._flag_bytes].view(torch.int32)[32].item()) or int(self._host_flag[0]) != 0
 
     def close(self):
         for key in self._bases:
@@ -279,6 +307,12 @@ class ColumnParallelLinear(nn.Module):
         else:
             local = kind(linear.in_features, hi - lo, bias=has_bias)
         local = local.to(linear.weight.device)
+        # block_log replaces the maximum of all-zero blocks by the TENSOR-global minimum non-zero block maximum (reference
+        # block_log.py:50-53): a per-shard minimum would differ, so such a module is quantised on the full tensor first and the
+        # quantised values are sharded (block_fp / block_minifloat need no such care: no block crosses the cut)
+        if (getattr(linear, "weight_requires_quantisation", False) and config is not None
+                and config.get("name") in ("block_log", "log") and hasattr(linear, "_ensure_ptq") and linear.weight.is_cuda):
+            linear._ensure_ptq()
         with torch.no_grad():
             local.weight.copy_(linear.weight[lo:hi])
             if has_bias:
@@ -323,6 +357,128 @@ class ColumnParallelLinear(nn.Module):
         world, rank = _world(self.group)
         how = "peer-store epilogue" if self.arena is not None else "nccl all-gather"
         return f"in_features={self.in_features}, out_features={self.out_features}, shard={rank}/{world}, gather={how}"
+
+
+class TensorParallelOPTLayer(nn.Module):
+    """
+    One quantized OPT decoder layer with every Linear column-parallel over the ranks of `group` and the exchange fused into the
+    producing kernels (BASELINE configs[4]: OPT-6.7B per-layer mixed-precision block_fp, column-parallel at 2 / 4 / 8 B200).
+
+    Column-parallel only — the K-reduction of every output element stays on one rank in the single-GPU order, so the layer output
+    is BIT-IDENTICAL to `OPTQuantizedDecoderLayer._fused_forward` on one GPU (row-parallel would regroup fp32 partial sums).  What
+    crosses NVLink is decided by the CONSUMER of each tensor, not by the Linear that produced it:
+
+        LN1 + x-quantizers            replicated (every rank holds h)
+        q / k / v_proj                N = H/g columns = h/g whole heads per rank; epilogue applies bmm_0 / bmm_1's operand
+                                      quantizers -> bf16, LOCAL only: attention is head-parallel, nothing is exchanged
+        attention                     this rank's heads; epilogue applies out_proj's x-quantizer -> bf16 slab of [M, H],
+                                      pushed to every peer (bq_peer_push)                                 2 B/elem on the wire
+        out_proj (+ residual)         fp32 slab of h2 [M, H], stored to all ranks by the GEMM epilogue    4 B/elem (residual stream)
+        LN2 + x-quantizer             replicated
+        fc1 (+ ReLU + fc2's x-quantizer)  bf16 slab of [M, F], stored to all ranks by the GEMM epilogue   2 B/elem instead of 4
+        fc2 (+ residual)              fp32 slab of h3 [M, H], stored to all ranks by the GEMM epilogue
+
+    i.e. 2H + 4H + 2F + 4H = 72 KB per token for OPT-6.7B against 147 KB when each of the six Linears gathers an fp32 result.  One
+    flag barrier (bq_peer_barrier) after each of the four exchanges.  `mode="nccl"` runs the same schedule with
+    `all_gather_into_tensor` + permute in place of the peer stores (the library baseline).
+    """
+
+    def __init__(self, layer: nn.Module, arena: Optional[PeerArena] = None, group=None):
+        super().__init__()
+        world, rank = _world(group)
+        at = layer.self_attn
+        H, F_, heads, d = layer.embed_dim, layer.fc1.out_features, at.num_heads, at.head_dim
+        if heads % world or (H // world) % 32 or (F_ // world) % 32:
+            raise ValueError(f"cannot split {heads} heads / H={H} / F={F_} over {world} ranks in whole heads and multiples of 32 columns")
+        self.group, self.world, self.rank, self.arena = group, world, rank, arena
+        self.H, self.F, self.heads_local, self.head_dim = H, F_, heads // world, d
+        self.scaling = at.scaling
+        self.qc = at.quant_config
+        self.plan_of = layer._fused_plan                      # format resolution stays the full layer's (same TOML node)
+        self.ln1, self.ln2 = layer.self_attn_layer_norm, layer.final_layer_norm
+        cut = lambda lin: ColumnParallelLinear.from_linear(lin, group=group, gather_output=False, world=world, rank=rank).local
+        self.q_proj, self.k_proj, self.v_proj, self.out_proj = cut(at.q_proj), cut(at.k_proj), cut(at.v_proj), cut(at.out_proj)
+        self.fc1, self.fc2 = cut(layer.fc1), cut(layer.fc2)
+
+    def nvlink_bytes_per_rank(self, tokens: int, mode: str = "fused") -> int:
+        """Bytes one rank SENDS per layer call."""
+        per_tok = (2 * self.H + 4 * self.H + 2 * self.F + 4 * self.H) // self.world
+        return tokens * per_tok * (self.world - 1)
+
+    @torch.no_grad()
+    def forward(self, h: torch.Tensor, mode: str = "fused", events: Optional[list] = None) -> torch.Tensor:
+        from .models.quantize.quantized_functions.attention import fused_causal_attention_q
+        from .models.quantize.quantized_functions.fused_glue import norm_quantize
+
+        B, S, H = h.shape
+        M, g, r = B * S, self.world, self.rank
+        Hl, Fl = H // g, self.F // g
+        c0, f0 = r * Hl, r * Fl
+        plan = self.plan_of(S)
+        if plan is None:
+            raise NotImplementedError("TensorParallelOPTLayer needs a layer the fused path serves (PTQ block_fp / block_minifloat, "
+                                      "[1,16] blocks, <= 8 significant bits)")
+        fused = mode == "fused" and self.arena is not None and g > 1
+        arena = self.arena
+        ln1, ln2 = self.ln1, self.ln2
+        h2d = h.reshape(M, H)
+
+        def mark(name):
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append((name, e))
+
+        mark("start")
+        xq_q, xq_k, xq_v = norm_quantize(h, ln1.weight, ln1.bias, ln1.eps, [plan["q_in"], plan["k_in"], plan["v_in"]])
+        mark("ln1")
+        Qq = self.q_proj.forward_prequantized(xq_q, scale=self.scaling, out_format=plan["q_out"])
+        Kq = self.k_proj.forward_prequantized(xq_k, out_format=plan["k_out"], out_blocks_along_rows=True)
+        Vq = self.v_proj.forward_prequantized(xq_v, out_format=plan["v_out"])
+        mark("qkv")
+        # attention on this rank's heads; the bf16 result (already in out_proj's x-format) lands in the gathered [M, H] buffer
+        if fused:
+            attn_full, bases = arena.take((M, H), torch.bfloat16)
+            slab = attn_full[:, c0:c0 + Hl]
+            fused_causal_attention_q(Qq, Kq, Vq, self.qc["bmm_1"], self.heads_local, B, S, 1.0, out_cfg=self.out_proj.config, out=slab)
+            mark("attention")
+            arena.push(slab, bases, c0 * 2)
+            arena.barrier()
+        else:
+            o_l = fused_causal_attention_q(Qq, Kq, Vq, self.qc["bmm_1"], self.heads_local, B, S, 1.0, out_cfg=self.out_proj.config)
+            mark("attention")
+            attn_full = all_gather_columns(o_l.view(M, Hl), self.group)
+        mark("gather_attn")
+        if fused:
+            h2_full, bases = arena.take((M, H), torch.float32)
+            self.out_proj.forward_prequantized(attn_full, residual=h2d[:, c0:c0 + Hl], out=h2_full[:, c0:c0 + Hl],
+                                               peer_out_ptrs=[b + c0 * 4 for i, b in enumerate(bases) if i != r])
+            arena.barrier()
+        else:
+            h2_l = self.out_proj.forward_prequantized(attn_full, residual=h2d[:, c0:c0 + Hl])
+            h2_full = all_gather_columns(h2_l, self.group)
+        mark("out_proj")
+        (x1,) = norm_quantize(h2_full, ln2.weight, ln2.bias, ln2.eps, [plan["fc1_in"]])
+        mark("ln2")
+        if fused:
+            a_full, bases = arena.take((M, self.F), torch.bfloat16)
+            self.fc1.forward_prequantized(x1, relu=True, out_format=plan["fc2_in"], out=a_full[:, f0:f0 + Fl],
+                                          peer_out_ptrs=[b + f0 * 2 for i, b in enumerate(bases) if i != r])
+            arena.barrier()
+        else:
+            a_l = self.fc1.forward_prequantized(x1, relu=True, out_format=plan["fc2_in"])
+            a_full = all_gather_columns(a_l, self.group)
+        mark("fc1")
+        if fused:
+            h3_full, bases = arena.take((M, H), torch.float32)
+            self.fc2.forward_prequantized(a_full, residual=h2_full[:, c0:c0 + Hl], out=h3_full[:, c0:c0 + Hl],
+                                          peer_out_ptrs=[b + c0 * 4 for i, b in enumerate(bases) if i != r])
+            arena.barrier()
+        else:
+            h3_l = self.fc2.forward_prequantized(a_full, residual=h2_full[:, c0:c0 + Hl])
+            h3_full = all_gather_columns(h3_l, self.group)
+        mark("fc2")
+        return h3_full.view(B, S, H)
 
 
 def column_parallelize(model: nn.Module, names: Iterable[str], group=None) -> List[str]:

@@ -82,9 +82,11 @@ def quantize_qkv(q, k, v, cfg0: dict, cfg1: dict, num_heads: int):
 
 
 def fused_causal_attention_q(Qq: torch.Tensor, Kq: torch.Tensor, Vq: torch.Tensor, cfg1: dict, num_heads: int, B: int, S: int,
-                             score_div: float = 1.0, out_cfg: dict = None) -> torch.Tensor:
+                             score_div: float = 1.0, out_cfg: dict = None, out: torch.Tensor = None) -> torch.Tensor:
     """Kernel call on already-quantised bf16 operands ([B*S, H] or [B, S, H], unit stride along H).
-    Returns fp32 [B, S, H], or — with `out_cfg` (config of the Linear consuming the result) — its bf16 x-quantised form."""
+    Returns fp32 [B, S, H], or — with `out_cfg` (config of the Linear consuming the result) — its bf16 x-quantised form.
+    `out` (with `out_cfg`): preallocated bf16 [B*S, H] destination with unit column stride and any row stride — e.g. this rank's
+    column slab of a gathered [B*S, H_total] buffer (tensor-parallel layer, dist.py)."""
     lib = L.load()
     H = Qq.shape[-1]
     d = H // num_heads
@@ -100,9 +102,15 @@ def fused_causal_attention_q(Qq: torch.Tensor, Kq: torch.Tensor, Vq: torch.Tenso
         return out
     ok, okw, _ = operand_format(out_cfg, "data_in")
     fo = make_format(ok, b0=1, b1=16, **okw)
-    out = torch.empty((B, S, H), dtype=torch.bfloat16, device=dev)
+    ldo = H
+    if out is None:
+        out = torch.empty((B, S, H), dtype=torch.bfloat16, device=dev)
+    else:
+        if out.dtype != torch.bfloat16 or out.device != dev or out.shape[-1] != H or out.stride(-1) != 1 or out.numel() != B * S * H:
+            raise ValueError(f"out must be a bf16 [{B * S}, {H}] tensor with unit column stride on {dev}")
+        ldo = out.stride(-2)
     rc = lib.bq_attention_causal_q(ctypes.byref(fp), ctypes.byref(fo), Qq.data_ptr(), Kq.data_ptr(), Vq.data_ptr(), out.data_ptr(),
-                                   B, num_heads, S, d, ld(Qq), ld(Kq), ld(Vq), H, float(score_div), L.stream_ptr(dev))
+                                   B, num_heads, S, d, ld(Qq), ld(Kq), ld(Vq), ldo, float(score_div), L.stream_ptr(dev))
     L.check(rc, "bq_attention_causal_q")
     return out
 

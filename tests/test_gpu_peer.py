@@ -138,3 +138,99 @@ def test_fused_column_parallel_two_ranks_bit_identical():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), 512, 1024, 384, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# tensor-parallel decoder layer (BASELINE configs[4]): every Linear column-parallel, exchanges fused into the producing kernels
+# ------------------------------------------------------------------------------------------------------------------------------
+def _tiny_layer(dev, widths=(6, 6)):
+    from llm_mixed_q_b200.models.opt_quantized import OPTQuantizedConfig
+    from llm_mixed_q_b200.models.opt_quantized.modeling_opt import OPTQuantizedDecoderLayer
+
+    d = dict(CFG)
+    d["data_in_width"], d["weight_width"] = widths
+    cfg = OPTQuantizedConfig(hidden_size=256, num_hidden_layers=1, ffn_dim=512, num_attention_heads=4, vocab_size=128,
+                             max_position_embeddings=256, quant_config={"default": d})
+    torch.manual_seed(21)
+    with torch.device(dev):
+        layer = OPTQuantizedDecoderLayer(cfg, 0).eval()
+        for lin in (layer.self_attn.q_proj, layer.self_attn.k_proj, layer.self_attn.v_proj, layer.self_attn.out_proj, layer.fc1, layer.fc2):
+            lin.weight.data.normal_(0, 0.05)
+            lin.bias.data.normal_(0, 0.02)
+    return layer
+
+
+def _tp_worker(rank, world, port, backend, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    ndev = torch.cuda.device_count()
+    dev = torch.device("cuda", rank % ndev)
+    torch.cuda.set_device(dev)
+    dist.init_process_group(backend, rank=rank, world_size=world, **({"device_id": dev} if backend == "nccl" else {}))
+    try:
+        from llm_mixed_q_b200.dist import PeerArena, TensorParallelOPTLayer
+
+        layer = _tiny_layer(dev)                                   # same seed on every rank: identical full layer
+        B, S, H = 2, 128, 256
+        arena = PeerArena(B * S * 512 * 4, dev, slots=6)
+        tp = TensorParallelOPTLayer(layer, arena=arena)            # shards BEFORE any PTQ overwrite
+        ok = True
+        with torch.no_grad():
+            for it in range(3):                                    # 12 takes over 6 slots: exercises slot reuse
+                h = torch.randn(B, S, H, device=dev, generator=torch.Generator(device=dev).manual_seed(300 + it))
+                ref = layer._fused_forward(h, layer._fused_plan(S))
+                out = tp(h, mode="fused").clone()
+                torch.cuda.synchronize()
+                ok = ok and bool(torch.equal(ref.view(torch.int32), out.view(torch.int32)))
+                if backend == "nccl":
+                    out2 = tp(h, mode="nccl")
+                    ok = ok and bool(torch.equal(ref.view(torch.int32), out2.view(torch.int32)))
+        ok = ok and not arena.timed_out()
+        ret[rank] = ok
+        dist.barrier()
+        arena.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_tensor_parallel_layer_two_ranks_bit_identical_shared_device():
+    """2 ranks: head-parallel attention + column-parallel Linears with bf16 / fp32 peer stores from the producing kernels; the layer
+    output on every rank is bit-identical to the single-GPU fused layer.  (Both ranks share cuda:0 on a one-GPU box.)"""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_tp_worker, args=(world, _free_port(), "gloo", ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+def test_tensor_parallel_layer_two_ranks_distinct_devices_nccl():
+    """Same on two REAL devices over NVLink, one rank per GPU, NCCL rendezvous; also checks the NCCL-gather baseline schedule."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_tp_worker, args=(world, _free_port(), "nccl", ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+def test_fused_column_parallel_two_ranks_distinct_devices():
+    """test_fused_column_parallel_two_ranks_bit_identical with one rank per GPU (the worker places rank r on cuda:r when it exists)."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), 512, 1024, 384, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_peer_push_copies_strided_slab():
+    from llm_mixed_q_b200 import _lib as L
+
+    lib = L.load()
+    src = torch.arange(64 * 96, dtype=torch.float32, device="cuda:0").view(64, 96)
+    dsts = [torch.full((64, 96), -1.0, device="cuda:0") for _ in range(3)]
+    arr = (ctypes.c_void_p * 3)(*[d.data_ptr() + 32 * 4 for d in dsts])
+    L.check(lib.bq_peer_push(src.data_ptr() + 32 * 4, arr, 3, 64, 32 * 4, 96 * 4, 96 * 4, L.stream_ptr(src.device)), "push")
+    torch.cuda.synchronize()
+    for d in dsts:
+        assert torch.equal(d[:, 32:64], src[:, 32:64]) and bool((d[:, :32] == -1).all()) and bool((d[:, 64:] == -1).all())
+    assert lib.bq_peer_push(src.data_ptr() + 4, arr, 3, 64, 32 * 4, 96 * 4, 96 * 4, None) != 0      # misaligned source
