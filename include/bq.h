@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BQ_ABI_VERSION 2
+#define BQ_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define BQ_API __attribute__((visibility("default")))
@@ -240,6 +240,29 @@ BQ_API int bq_gemm_split_tn(const void* A_planes, const void* B_planes, float* C
 BQ_API size_t bq_linear_workspace_bytes(const bq_format* fx, int64_t M, int64_t K);
 BQ_API int bq_linear(const bq_format* fx, const float* x, int64_t M, int64_t K, int64_t ldx, const void* Wq_bf16, int64_t N,
               const float* bias_q, float* y, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
+/* Same contract in ONE launch: the x-quantizer runs in the GEMM PROLOGUE — raw fp32 A tiles arrive by TMA, transform warps
+ * quantise them in shared memory (same arithmetic as bq_quantize) and hand tcgen05.mma a bf16 K-major tile; no bf16 copy of x
+ * in HBM, no workspace.  Each N-tile of a row block re-quantises the same A tile, which is why bq_linear (two launches) stays
+ * the default for wide N (measured A/B: DESIGN.md §3).  fx: block_fp / block_minifloat, blocks [1,16]; K % 64 == 0, N % 32 == 0. */
+BQ_API int bq_linear_fused(const bq_format* fx, const float* x, int64_t M, int64_t K, int64_t ldx, const void* Wq_bf16, int64_t N,
+                           const float* bias_q, float* y, int64_t ldy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed weight cache.  The reference's PTQ state is the quantised weight (quantized_modules/linear.py:66-70) and its cost model
+ * charges `width` bits per element plus one shared exponent per block (quantized_layer_profiler.py:18-27): w + 0.5 bits/element
+ * for block_fp, blocks of 16.  bq_pack_weight stores exactly that: per row, per group of 256 K-elements, 32*w bytes of fields
+ * (16 per block, w bits each: sign in the top bit, magnitude below, little-endian bit order) followed by 16 exponent bytes
+ * (E + exponent_bias, one per block; value = (-1)^sign * magnitude * 2^(E - (w-1))).  Wq: fp32 [N][ldw] ALREADY on the block_fp
+ * grid (after the PTQ overwrite); *mismatches (device) counts elements the packed form does not reproduce bit for bit — the
+ * reference's pass-through elements (|x| <= 1e-8 left unquantised, block_fp.py:93-94), rounded to the grid here.
+ * bq_gemm_packed_tn: y = A_bf16[M][K] @ unpack(packed)[N][K]^T (+ bias), weights decoded to bf16 inside the mainloop (exact:
+ * <= 7 magnitude bits x a power of two).  K % 256 == 0, N % 32 == 0, block_fp with 2 <= width <= 8.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API size_t bq_packed_weight_bytes(const bq_format* fw, int64_t N, int64_t K);
+BQ_API int bq_pack_weight(const bq_format* fw, const float* Wq, int64_t N, int64_t K, int64_t ldw, void* packed,
+                          unsigned long long* mismatches, void* stream);
+BQ_API int bq_gemm_packed_tn(const void* A_bf16, const void* packed, const bq_format* fw, float* y, const float* bias, int64_t M,
+                             int64_t N, int64_t K, int64_t lda, int64_t ldy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Quantized bmm / matmul.  Replaces generic_matmul_block_fp / _block_minifloat / _block_log /

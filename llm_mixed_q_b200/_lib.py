@@ -105,6 +105,16 @@ def load():
     lib.bq_linear.restype = ctypes.c_int
     lib.bq_linear.argtypes = [POINTER(BqFormat), c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                               c_void_p, c_int64, c_void_p, c_size_t, c_void_p]
+    lib.bq_linear_fused.restype = ctypes.c_int
+    lib.bq_linear_fused.argtypes = [POINTER(BqFormat), c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_int64, c_void_p]
+    lib.bq_packed_weight_bytes.restype = c_size_t
+    lib.bq_packed_weight_bytes.argtypes = [POINTER(BqFormat), c_int64, c_int64]
+    lib.bq_pack_weight.restype = ctypes.c_int
+    lib.bq_pack_weight.argtypes = [POINTER(BqFormat), c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.bq_gemm_packed_tn.restype = ctypes.c_int
+    lib.bq_gemm_packed_tn.argtypes = [c_void_p, c_void_p, POINTER(BqFormat), c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                      c_int64, c_void_p]
     lib.bq_bmm_workspace_bytes.restype = c_size_t
     lib.bq_bmm_workspace_bytes.argtypes = [POINTER(BqFormat), POINTER(BqFormat), c_int64, c_int64, c_int64, c_int64]
     lib.bq_bmm.restype = ctypes.c_int

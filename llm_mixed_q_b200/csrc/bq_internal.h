@@ -26,7 +26,7 @@ template <typename T> struct PerDevice {
   T& get() { return v[current_device()]; }
 };
 enum KernelId { kKernQuantRows = 0, kKernBlockLogFixup, kKernQuantTile, kKernGenericMax, kKernGenericMin, kKernGenericQuant,
-                kKernGemm, kKernAttention, kKernSplit3, kKernGemmEpi, kKernGemmSplit, kKernLnQuant, kKernQuantStream, kKernSiluMulQuant, kKernTokenCe, kKernTokenCeMean, kKernPeerBarrier, kKernRopeQuant, kKernPeerPush, kKernCount };
+                kKernGemm, kKernAttention, kKernSplit3, kKernGemmEpi, kKernGemmSplit, kKernLnQuant, kKernQuantStream, kKernSiluMulQuant, kKernTokenCe, kKernTokenCeMean, kKernPeerBarrier, kKernRopeQuant, kKernPeerPush, kKernGemmXformA, kKernGemmXformB, kKernPackWeight, kKernCount };
 // RAII launch bracket: counts the launch; records start/stop events on `st` when profiling is enabled.
 struct LaunchScope {
   LaunchScope(int id, cudaStream_t st);

@@ -23,7 +23,8 @@ static const char* kKernelNames[kKernCount] = {"quant_rows_kernel", "blocklog_fi
                                                "generic_blockmax_kernel", "generic_gmin_kernel", "generic_quant_kernel",
                                                "gemm_bf16_tn_kernel", "attention_causal_kernel", "split3_kernel",
                                                "gemm_bf16_tn_kernel<epilogue>", "gemm_bf16_tn_kernel<split>", "layernorm_quant_kernel", "quant_stream_kernel",
-                                               "silu_mul_quant_kernel", "ce_rows_kernel", "ce_mean_kernel", "peer_barrier_kernel", "rope_quant_kernel", "peer_push_kernel"};
+                                               "silu_mul_quant_kernel", "ce_rows_kernel", "ce_mean_kernel", "peer_barrier_kernel", "rope_quant_kernel", "peer_push_kernel", "gemm_xform_kernel<quantize A>", "gemm_xform_kernel<packed B>",
+                                               "pack_weight_kernel"};
 static std::atomic<int64_t> g_launches[kKernCount];
 static std::atomic<int> g_profiling{0};
 struct EventPair { int id; cudaEvent_t a, b; };

@@ -584,6 +584,29 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* base, int64_t K, int64_t 
   return BQ_OK;
 }
 
+// plain 2-D map over 32-bit elements [rows][inner] (fp32: dtype_code 0, uint32: 1), box {box_inner, box_rows}, optional 128B swizzle
+// (box_inner * 4 == 128 then) — the raw operands of gemm_xform_sm100.cu: fp32 activation tiles, packed weight groups
+int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype_code, int64_t inner, int64_t rows, int64_t row_stride_bytes, int box_inner,
+                 int box_rows, int swizzle128) {
+  int rc = load_encode();
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, dtype_code == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base),
+                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(2d) failed with CUresult %d", (int)r);
+    set_last_cuda_error(msg, __FILE__, __LINE__);
+    return BQ_ERR_CUDA;
+  }
+  return BQ_OK;
+}
+
 // bf16 [B][S][H][d] (token stride ld_tok elements) as a 4-D map ordered {d, H, S, B} (strides ascending),
 // box {64, 1, box_rows, 1}: one head's [box_rows tokens x 64] tile lands as 128-byte rows, 128B-swizzled.
 int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, int64_t H, int64_t B, int64_t ld_tok,
