@@ -28,17 +28,18 @@ namespace bq {
 constexpr int kXBM = 128, kXBK = 64;
 constexpr int kXformWarps = 8;
 constexpr int kXThreads = 512;
-enum { XF_QUANT_A = 1, XF_PACKED_B = 2 };
+enum { XF_QUANT_A = 1, XF_PACKED_B = 2, XF_PACKED_A = 3 };
 
 template <int BN, int XF> struct XCfg {
   static constexpr int kStageA = kXBM * kXBK * 2;                  // 16 KB
   static constexpr int kStageB = BN * kXBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = XF == XF_QUANT_A ? 3 : (BN <= 32 ? 4 : 4);
+  static constexpr int kStages = XF == XF_QUANT_A ? 3 : (XF == XF_PACKED_B && BN <= 32 ? 8 : 4);
   // raw stage: XF_QUANT_A: one 64-wide K tile of fp32 A = two {32 floats x 128 rows} swizzled boxes; XF_PACKED_B: one 256-element K
   // group of BN packed rows, sized for the widest format (w = 8: 272 bytes per row)
-  static constexpr int kRawStage = XF == XF_QUANT_A ? kXBM * kXBK * 4 : ((BN * 272 + 1023) / 1024) * 1024;
-  static constexpr int kRawStages = XF == XF_QUANT_A ? 2 : (BN <= 32 ? 12 : 2);     // a packed raw stage feeds four MMA stages
+  static constexpr int kRawRows = XF == XF_PACKED_A ? kXBM : BN;      // packed rows per raw stage
+  static constexpr int kRawStage = XF == XF_QUANT_A ? kXBM * kXBK * 4 : ((kRawRows * 272 + 1023) / 1024) * 1024;
+  static constexpr int kRawStages = XF == XF_QUANT_A ? 2 : (XF == XF_PACKED_B && BN <= 32 ? 6 : (XF == XF_PACKED_A && BN <= 32 ? 4 : 2));   // a packed raw stage feeds four MMA stages
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int kOffRaw = kStages * kStage;
   static constexpr int kOffBar = kOffRaw + kRawStages * kRawStage;
@@ -160,7 +161,7 @@ gemm_xform_kernel(const __grid_constant__ CUtensorMap tmDirect, const __grid_con
   const int total_tiles = g.tiles_m * g.tiles_n;
   auto decode = [&](int tile, int& row0, int& nb) {
     const int mb = tile / g.tiles_n;                   // n fastest: the CTAs of a wave share A rows through L2
-    nb = tile - mb * g.tiles_n;
+    nb = tile - mb * g.tiles_n;                        // XF_PACKED_A: tiles_m == 1, nb counts 128-row blocks of the weight
     row0 = mb * kXBM;
   };
 
@@ -178,6 +179,9 @@ gemm_xform_kernel(const __grid_constant__ CUtensorMap tmDirect, const __grid_con
           if (XF == XF_QUANT_A) {
             ptx::mbar_expect_tx(op_full(stage), Cfg::kStageB);
             ptx::tma_load_3d(sa + Cfg::kStageA, &tmDirect, op_full(stage), kb * kXBK, nb * BN, 0);
+          } else if (XF == XF_PACKED_A) {                        // swapped roles: the activation (<= BN rows) is the B operand
+            ptx::mbar_expect_tx(op_full(stage), Cfg::kStageB);
+            ptx::tma_load_3d(sa + Cfg::kStageA, &tmDirect, op_full(stage), kb * kXBK, 0, 0);
           } else {
             ptx::mbar_expect_tx(op_full(stage), Cfg::kStageA);
             ptx::tma_load_3d(sa, &tmDirect, op_full(stage), kb * kXBK, row0, 0);
@@ -203,8 +207,8 @@ gemm_xform_kernel(const __grid_constant__ CUtensorMap tmDirect, const __grid_con
             tma_load_2d(dst, &tmRaw, raw_full(rs), i * kXBK, row0);                    // k [0,32) of the tile: 128 rows x 128 bytes
             tma_load_2d(dst + kXBM * 128, &tmRaw, raw_full(rs), i * kXBK + 32, row0);  // k [32,64)
           } else {
-            ptx::mbar_expect_tx(raw_full(rs), (uint32_t)(BN * g.row_bytes));
-            tma_load_2d(dst, &tmRaw, raw_full(rs), i * (g.row_bytes / 4), nb * BN);    // one 256-element group of BN packed rows
+            ptx::mbar_expect_tx(raw_full(rs), (uint32_t)(Cfg::kRawRows * g.row_bytes));
+            tma_load_2d(dst, &tmRaw, raw_full(rs), i * (g.row_bytes / 4), nb * Cfg::kRawRows);    // one 256-element group of packed rows
           }
           if (++rs == Cfg::kRawStages) { rs = 0; rphase ^= 1; }
         }
@@ -255,6 +259,11 @@ gemm_xform_kernel(const __grid_constant__ CUtensorMap tmDirect, const __grid_con
             float* d = c < 4 ? &v0[4 * c] : &v1[4 * (c - 4)];
             d[0] = u2f(q4.x); d[1] = u2f(q4.y); d[2] = u2f(q4.z); d[3] = u2f(q4.w);
           }
+          // Cross-proxy write-after-read: the slot is about to be refilled by TMA (async proxy) while it was read through the generic
+          // proxy.  Without a proxy fence between the reads and the release, ~1e-4 of the row blocks saw the NEXT K tile's data
+          // (measured: non-deterministic outputs, gone with this fence and only with it; a fence after the full-barrier wait is not
+          // needed).  The mbarrier arrive alone orders the reads within the generic proxy only.
+          ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(raw_empty(rs));            // the raw tile is in registers
           if (++rs == Cfg::kRawStages) { rs = 0; rphase ^= 1; }
@@ -272,10 +281,106 @@ gemm_xform_kernel(const __grid_constant__ CUtensorMap tmDirect, const __grid_con
           if (lane == 0) ptx::mbar_arrive(op_full(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-      } else {
-        // thread -> (row, 32-element unit of the 64-wide K tile); BN = 32: only threads 0..63 hold a unit
+      } else if (XF == XF_PACKED_B && BN == 32) {
+        // decode regime (M <= 128, the weight stream is the bound): the 256 threads take ONE 256-element group of the 32 packed rows
+        // at a time — thread -> (row, unit of 32 elements) — and fill FOUR MMA stages per step, so the per-stage hand-over latency
+        // (wait empty -> store -> proxy fence -> arrive) is paid once per 256 K-elements instead of once per 64
+        static_assert(BN != 32 || XF != XF_PACKED_B || Cfg::kStages % 4 == 0, "four MMA stages are filled per packed group");
+        const int row = t >> 3, unit = t & 7, sub = unit >> 1, u01 = unit & 1, sw = row & 7;
+        const int m = g.w - 1;
+        for (int grp = 0; grp < num_kb / 4; ++grp) {
+          ptx::mbar_wait(raw_full(rs), rphase);
+          const uint32_t rbase = smem_base + Cfg::kOffRaw + rs * Cfg::kRawStage + row * g.row_bytes;
+          uint32_t words[8], outw[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) words[i] = i < g.w ? lds_u32(rbase + unit * 4 * g.w + 4 * i) : 0u;
+          const uint32_t eb = lds_u32(rbase + 32 * g.w + (unit >> 1) * 4);
+          const int sh = (unit & 1) * 16;
+          const uint32_t s0 = scale_bf16x2((int)((eb >> sh) & 0xffu), g.exp_bias, m);
+          const uint32_t s1 = scale_bf16x2((int)((eb >> (sh + 8)) & 0xffu), g.exp_bias, m);
+          switch (g.w) {
+            case 2: decode_unit<2>(words, s0, s1, outw); break;
+            case 3: decode_unit<3>(words, s0, s1, outw); break;
+            case 4: decode_unit<4>(words, s0, s1, outw); break;
+            case 5: decode_unit<5>(words, s0, s1, outw); break;
+            case 6: decode_unit<6>(words, s0, s1, outw); break;
+            case 7: decode_unit<7>(words, s0, s1, outw); break;
+            default: decode_unit<8>(words, s0, s1, outw); break;
+          }
+          // stages stage .. stage + 3 (kStages % 4 == 0: no wrap inside a step); every warp holds all eight units of four rows, so it
+          // contributes to — and arrives on — each of the four stages
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ptx::mbar_wait(op_empty(stage + j), phase ^ 1);
+          const uint32_t dst = smem_base + (stage + sub) * Cfg::kStage + Cfg::kStageA + row * 128;
+          const int c0 = u01 * 4;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sts_v4u(dst + (((c0 + c) ^ sw) << 4), outw[4 * c], outw[4 * c + 1], outw[4 * c + 2], outw[4 * c + 3]);
+          ptx::fence_proxy_async_smem();                 // also orders this thread's raw-slot reads before the slot's release
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ptx::mbar_arrive(op_full(stage + j));
+            ptx::mbar_arrive(raw_empty(rs));
+          }
+          stage += 4;
+          if (stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++rs == Cfg::kRawStages) { rs = 0; rphase ^= 1; }
+        }
+      } else if (XF == XF_PACKED_A) {
+        // decode regime with swapped roles: thread -> (weight row, left / right 32-element unit) of each of the four 64-wide K tiles
+        // of a 256-element group.  All four units are decoded into registers FIRST (ALU work that overlaps the MMAs still reading the
+        // four stages), then the stages are claimed, filled and handed over with ONE proxy fence per group — the per-stage hand-over
+        // (wait -> store -> fence -> arrive, ~0.7 us) had made the kernel latency-bound at 1.2 TB/s of packed bytes.
+        static_assert(XF != XF_PACKED_A || Cfg::kStages == 4, "one packed group fills the whole MMA ring");
         const int row = t >> 1, u01 = t & 1, sw = row & 7;
-        const bool active = row < BN;
+        const int m = g.w - 1;
+        for (int grp = 0; grp < num_kb / 4; ++grp) {
+          ptx::mbar_wait(raw_full(rs), rphase);
+          const uint32_t rbase = smem_base + Cfg::kOffRaw + rs * Cfg::kRawStage + row * g.row_bytes;
+          // the four stages of the ring are claimed up front (the MMAs of the previous group are short: 16 instructions), then one
+          // SMALL loop body decodes and stores a unit per trip — unrolling it four times over seven field widths put 200 KB of code
+          // in front of a 32 KB instruction cache and the kernel ran at a third of this speed
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub) ptx::mbar_wait(op_empty(sub), phase ^ 1);
+          const int c0 = u01 * 4;
+#pragma unroll 1
+          for (int sub = 0; sub < 4; ++sub) {
+            const int unit = sub * 2 + u01;
+            uint32_t words[8], outw[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) words[i] = i < g.w ? lds_u32(rbase + unit * 4 * g.w + 4 * i) : 0u;
+            const uint32_t eb = lds_u32(rbase + 32 * g.w + (unit >> 1) * 4);
+            const int sh = (unit & 1) * 16;
+            const uint32_t s0 = scale_bf16x2((int)((eb >> sh) & 0xffu), g.exp_bias, m);
+            const uint32_t s1 = scale_bf16x2((int)((eb >> (sh + 8)) & 0xffu), g.exp_bias, m);
+            switch (g.w) {
+              case 2: decode_unit<2>(words, s0, s1, outw); break;
+              case 3: decode_unit<3>(words, s0, s1, outw); break;
+              case 4: decode_unit<4>(words, s0, s1, outw); break;
+              case 5: decode_unit<5>(words, s0, s1, outw); break;
+              case 6: decode_unit<6>(words, s0, s1, outw); break;
+              case 7: decode_unit<7>(words, s0, s1, outw); break;
+              default: decode_unit<8>(words, s0, s1, outw); break;
+            }
+            const uint32_t dst = smem_base + sub * Cfg::kStage + row * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sts_v4u(dst + (((c0 + c) ^ sw) << 4), outw[4 * c], outw[4 * c + 1], outw[4 * c + 2], outw[4 * c + 3]);
+          }
+          ptx::fence_proxy_async_smem();                 // also orders this thread's raw-slot reads before the slot's release
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) ptx::mbar_arrive(op_full(sub));
+            ptx::mbar_arrive(raw_empty(rs));
+          }
+          phase ^= 1;
+          if (++rs == Cfg::kRawStages) { rs = 0; rphase ^= 1; }
+        }
+      } else {
+        // thread -> (row, 32-element unit of the 64-wide K tile)
+        const int row = t >> 1, u01 = t & 1, sw = row & 7;
+        const bool active = row < Cfg::kRawRows;
+        constexpr int kDstOff = Cfg::kStageA;
         const int m = g.w - 1;
         for (int grp = 0; grp < num_kb / 4; ++grp) {
           ptx::mbar_wait(raw_full(rs), rphase);
@@ -304,7 +409,7 @@ gemm_xform_kernel(const __grid_constant__ CUtensorMap tmDirect, const __grid_con
             }
             ptx::mbar_wait(op_empty(stage), phase ^ 1);
             if (active) {
-              const uint32_t dst = smem_base + stage * Cfg::kStage + Cfg::kStageA + row * 128;
+              const uint32_t dst = smem_base + stage * Cfg::kStage + kDstOff + row * 128;
               const int c0 = u01 * 4;
 #pragma unroll
               for (int c = 0; c < 4; ++c)
@@ -315,6 +420,7 @@ gemm_xform_kernel(const __grid_constant__ CUtensorMap tmDirect, const __grid_con
             if (lane == 0) ptx::mbar_arrive(op_full(stage));
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
+          // (the generic-proxy reads of this group are already behind the proxy fence of the last sub-tile's op_full hand-over)
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(raw_empty(rs));
           if (++rs == Cfg::kRawStages) { rs = 0; rphase ^= 1; }
@@ -338,6 +444,18 @@ gemm_xform_kernel(const __grid_constant__ CUtensorMap tmDirect, const __grid_con
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
         ptx::tmem_ld_wait();
+        if (XF == XF_PACKED_A) {
+          // accumulator lane = weight row n, column = activation row m: y[m][n] — for a fixed m the 32 lanes of the warp write 32
+          // consecutive n (one 128-byte segment)
+          const int n = nb * kXBM + q * 32 + lane;
+          const float bv = (g.bias && n < g.N) ? g.bias[n] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int mrow = c * 32 + j;
+            if (mrow < g.M && n < g.N) g.C[(int64_t)mrow * g.ldc + n] = __fadd_rn(u2f(r[j]), bv);
+          }
+          continue;
+        }
         const int col0 = nb * BN + c * 32;
         if (row < g.M && col0 < g.N) {                             // N % 32 == 0, ldc % 4 == 0, pointers 16-byte aligned: host-checked
 #pragma unroll
@@ -396,15 +514,15 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(PackArgs a) {
     int E = a.e_lo;
     if (mx >= 0x00800000u) E = (int)(mx >> 23) - 127 + 1;           // floor(log2 max) + 1: max < 2^E
     E = min(max(E, a.e_lo), a.e_hi);
-    const float inv_step = exp2f((float)(m - E)), step = exp2f((float)(E - m));
     const float qcap = (float)((1 << m) - 1);
     uint64_t lo = 0, hi = 0;                                         // 16 fields x w bits <= 128 bits
     unsigned bad = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float mag = fminf(rintf(fabsf(v[j]) * inv_step), qcap);
+      // scalbnf: |v| * 2^(m-E) without forming 2^(m-E) (it overflows for the smallest exponents)
+      const float mag = mx ? fminf(rintf(scalbnf(fabsf(v[j]), m - E)), qcap) : 0.f;
       const uint32_t sgn = (__float_as_uint(v[j]) >> 31) & (mag != 0.f ? 1u : 0u);
-      const float back = (sgn ? -mag : mag) * step;
+      const float back = scalbnf(sgn ? -mag : mag, E - m);
       bad += (back != v[j]) ? 1u : 0u;
       const uint64_t f = (uint64_t)(((uint32_t)mag) | (sgn << m));
       const int bit = j * a.w;
@@ -442,8 +560,8 @@ static int launch_xform(const CUtensorMap& tmD, const CUtensorMap& tmR, XArgs g,
     BQ_CUDA_CHECK(cudaFuncSetAttribute(gemm_xform_kernel<BN, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr = true;
   }
-  g.tiles_m = (g.M + kXBM - 1) / kXBM;
-  g.tiles_n = (g.N + BN - 1) / BN;
+  g.tiles_m = XF == XF_PACKED_A ? 1 : (g.M + kXBM - 1) / kXBM;
+  g.tiles_n = XF == XF_PACKED_A ? (g.N + kXBM - 1) / kXBM : (g.N + BN - 1) / BN;
   const int64_t total = (int64_t)g.tiles_m * g.tiles_n;
   if (total > 0x7fffffffll) return BQ_ERR_UNSUPPORTED;
   const int grid = (int)std::min<int64_t>(total, num_sms());
@@ -532,12 +650,22 @@ int bq_gemm_packed_tn(const void* A_bf16, const void* packed, const bq_format* f
   memset(&g, 0, sizeof(g));
   g.w = fw->width; g.exp_bias = fw->exponent_bias; g.row_bytes = 32 * fw->width + 16;
   g.C = y; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.ldc = ldy;
-  const bool small_m = M <= 128 || (N % 128);
-  const int BN = small_m ? 32 : 128;
   CUtensorMap tmA, tmR;
   int rc;
-  if ((rc = make_tmap_bf16_kmajor(&tmA, A_bf16, K, M, 1, lda, 0, kXBM))) return rc;
   const int64_t row_bytes_total = packed_row_bytes(fw->width, K);
+  if (M <= 128 && (N % 128) == 0) {
+    // decode regime: the weight stream is the bound.  Roles swapped — 128 packed weight rows are the M operand, the (few) activation
+    // rows the N operand — so that the weights are decoded and read exactly once and the activation re-read is (N/128) * M * K * 2 B
+    const int BNx = M <= 32 ? 32 : 128;
+    if ((rc = make_tmap_bf16_kmajor(&tmA, A_bf16, K, M, 1, lda, 0, BNx))) return rc;
+    if ((rc = make_tmap_2d(&tmR, packed, /*u32*/ 1, row_bytes_total / 4, N, row_bytes_total, g.row_bytes / 4, kXBM, 0))) return rc;
+    g.tiles_m = 1;
+    if (BNx == 32) return launch_xform<32, XF_PACKED_A>(tmA, tmR, g, (cudaStream_t)stream, kKernGemmXformB);
+    return launch_xform<128, XF_PACKED_A>(tmA, tmR, g, (cudaStream_t)stream, kKernGemmXformB);
+  }
+  const bool small_m = M <= 128 || (N % 128);
+  const int BN = small_m ? 32 : 128;
+  if ((rc = make_tmap_bf16_kmajor(&tmA, A_bf16, K, M, 1, lda, 0, kXBM))) return rc;
   if ((rc = make_tmap_2d(&tmR, packed, /*u32*/ 1, row_bytes_total / 4, N, row_bytes_total, g.row_bytes / 4, BN, 0))) return rc;
   if (BN == 32) return launch_xform<32, XF_PACKED_B>(tmA, tmR, g, (cudaStream_t)stream, kKernGemmXformB);
   return launch_xform<128, XF_PACKED_B>(tmA, tmR, g, (cudaStream_t)stream, kKernGemmXformB);

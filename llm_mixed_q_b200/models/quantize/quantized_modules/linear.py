@@ -76,6 +76,53 @@ def quantize_operand_bf16(x: torch.Tensor, kind, kw, block_size, skip_first_dim,
     return launch_quantize(xd, fmt, canon, out_dtype=torch.bfloat16, transpose_out=transpose_out)
 
 
+# A/B switches for the two north-star variants of the operator-API call (measured against the default two-launch path in
+# DESIGN.md §3; both give bit-identical results to it):
+#   FUSED_PROLOGUE   x-quantizer inside the GEMM prologue (bq_linear_fused): one launch, no bf16 copy of x in HBM
+#   PACKED_WEIGHTS   weights held as w + 0.5 bits / element (sign+magnitude fields + one exponent byte per block of 16) and decoded to
+#                    bf16 in the GEMM mainloop (bq_pack_weight / bq_gemm_packed_tn) instead of the 16-bit bf16 cache
+FUSED_PROLOGUE = False
+PACKED_WEIGHTS = False
+
+
+def pack_weight(wq: torch.Tensor, width: int, exponent_width: int, exponent_bias: int):
+    """Quantised fp32 weight [N, K] (on the block_fp grid, K % 256 == 0) -> (packed uint8 [N, K/256 * (32*width + 16)], number of
+    elements the packed form does not reproduce bit for bit — the reference's pass-through elements)."""
+    lib = L.load()
+    L.require_cuda_f32(wq, "weight")
+    N, K = wq.shape
+    fmt = make_format("block_fp", width=width, exponent_width=exponent_width, exponent_bias=exponent_bias, b0=1, b1=16)
+    nbytes = lib.bq_packed_weight_bytes(ctypes.byref(fmt), N, K)
+    if nbytes == 0:
+        raise NotImplementedError(f"packed weights need block_fp with 2 <= width <= 8 and K % 256 == 0 (width={width}, K={K})")
+    w2 = wq.detach()
+    if w2.stride(-1) != 1 or w2.stride(0) % 4:
+        w2 = w2.contiguous()
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=wq.device)
+    bad = torch.zeros(1, dtype=torch.int64, device=wq.device)
+    L.check(lib.bq_pack_weight(ctypes.byref(fmt), w2.data_ptr(), N, K, w2.stride(0), packed.data_ptr(), bad.data_ptr(),
+                               L.stream_ptr(wq.device)), "bq_pack_weight")
+    return packed.view(N, -1), int(bad.item())
+
+
+def gemm_packed(xq: torch.Tensor, packed: torch.Tensor, width: int, exponent_width: int, exponent_bias: int, N: int,
+                bias: torch.Tensor = None) -> torch.Tensor:
+    """y = xq @ unpack(packed)^T (+ bias): bf16 [M, K] activation operand against packed block_fp weights, decoded in the mainloop."""
+    lib = L.load()
+    K = xq.shape[-1]
+    x2 = xq.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8):
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    fmt = make_format("block_fp", width=width, exponent_width=exponent_width, exponent_bias=exponent_bias, b0=1, b1=16)
+    y = torch.empty((M, N), dtype=torch.float32, device=xq.device)
+    if M:
+        L.check(lib.bq_gemm_packed_tn(x2.data_ptr(), packed.data_ptr(), ctypes.byref(fmt), y.data_ptr(),
+                                      bias.data_ptr() if bias is not None else None, M, N, K, x2.stride(0) if M > 1 else K, N,
+                                      L.stream_ptr(xq.device)), "bq_gemm_packed_tn")
+    return y.reshape(*xq.shape[:-1], N)
+
+
 class _LinearBase(nn.Linear):
     def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None,
                  config: dict = None) -> None:
@@ -89,6 +136,7 @@ class _LinearBase(nn.Linear):
         self.b_quantizer = None
         self._wq_bf16 = None          # derived bf16 cache of the quantised weight [N, K]
         self._wq_key = None
+        self._wq_packed = None        # derived packed cache (PACKED_WEIGHTS): (key, packed uint8 [N, row_bytes], mismatching elements)
         if not self.bypass:
             self._setup_quantizers(config)
 
@@ -119,6 +167,35 @@ class _LinearBase(nn.Linear):
             self._wq_key = key
         return self._wq_bf16
 
+    def _packable(self):
+        try:
+            wkind, wkw, wbs = operand_format(self.config, "weight")
+        except KeyError:
+            return None
+        if wkind != "block_fp" or not (2 <= wkw["width"] <= 8) or self.in_features % 256 or self.out_features % 32 or wbs is None:
+            return None
+        from ..quantizers.utils import resolve_block_shape
+
+        if resolve_block_shape([self.out_features, self.in_features], wbs) != [1, 16]:
+            return None
+        return wkw
+
+    def _packed_cache(self):
+        """(packed weight, format kwargs) — w + 0.5 bits per element — or None when the weight format is not packable."""
+        wkw = self._packable()
+        if wkw is None:
+            return None
+        w = self.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if self._wq_packed is None or self._wq_packed[0] != key:
+            packed, bad = pack_weight(w.detach(), wkw["width"], wkw["exponent_width"], wkw["exponent_bias"])
+            self._wq_packed = (key, packed, bad)
+        return self._wq_packed[1], wkw
+
+    def packed_bits_per_element(self):
+        c = self._packed_cache()
+        return None if c is None else 8.0 * c[0].numel() / (self.in_features * self.out_features)
+
     def _fused_forward(self, x):
         lib = L.load()
         kind, kw, block_size = operand_format(self.config, "data_in")
@@ -127,14 +204,28 @@ class _LinearBase(nn.Linear):
         if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 4 != 0):
             x2 = x2.contiguous()
         M = x2.shape[0]
-        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        wq = self._weight_cache()
-        bias = self.bias.detach() if self.bias is not None else None
         blocked = block_size is not None
         b0, b1 = 1, 1
         if blocked:
             cn = canonicalise(x.detach(), block_size, True, blocked=True)
             b0, b1 = cn.b0, cn.b1
+        bias = self.bias.detach() if self.bias is not None else None
+        if PACKED_WEIGHTS and M > 0 and b0 == 1:
+            pc = self._packed_cache()
+            if pc is not None:
+                # x-quantizer (streaming kernel, bf16 out) -> GEMM that decodes the packed weights in its mainloop
+                xq = quantize_operand_bf16(x2, kind, kw, [1, b1] if blocked else None, True)
+                return gemm_packed(xq, pc[0], pc[1]["width"], pc[1]["exponent_width"], pc[1]["exponent_bias"], N, bias).reshape(
+                    *x.shape[:-1], N)
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        wq = self._weight_cache()
+        if (FUSED_PROLOGUE and M > 0 and N > 0 and b0 == 1 and b1 == 16 and kind in ("block_fp", "block_minifloat")
+                and K % 64 == 0 and N % 32 == 0):
+            fmt = make_format(kind, b0=1, b1=16, fold=False, **kw)
+            rc = lib.bq_linear_fused(ctypes.byref(fmt), x2.data_ptr(), M, K, x2.stride(0) if M > 1 else K, wq.data_ptr(), N,
+                                     bias.data_ptr() if bias is not None else None, y.data_ptr(), N, L.stream_ptr(x.device))
+            L.check(rc, "bq_linear_fused")
+            return y.reshape(*x.shape[:-1], N)
         if M > 0 and N > 0:
             if b0 == 1:
                 fmt = make_format(kind, b0=1, b1=b1, fold=False, **kw)
@@ -163,6 +254,7 @@ class _LinearBase(nn.Linear):
                     self.bias.copy_(self.b_quantizer(self.bias.data))
             self.weight_requires_quantisation = False
             self._wq_bf16 = None
+            self._wq_packed = None
 
     def accepts_prequantized(self) -> bool:
         """True when `forward_prequantized` may be used: PTQ mode and a weight format that is exact in bf16."""
