@@ -182,6 +182,11 @@ def load():
     lib.bq_profile_enable.argtypes = [ctypes.c_int]
     lib.bq_profile_read.restype = ctypes.c_int
     lib.bq_profile_read.argtypes = [ctypes.c_int, POINTER(ctypes.c_double), POINTER(c_int64)]
+    # A/B switches from the environment (measurement only; the defaults are the shipped configuration)
+    if os.environ.get("BQ_ATTENTION_DUAL_PIPELINE") in ("0", "1"):
+        lib.bq_set_attention_dual_pipeline(int(os.environ["BQ_ATTENTION_DUAL_PIPELINE"]))
+    if os.environ.get("BQ_ATTENTION_PRECISE_EXP") in ("0", "1"):
+        lib.bq_set_attention_precise_exp(int(os.environ["BQ_ATTENTION_PRECISE_EXP"]))
     _lib = lib
     return lib
 
