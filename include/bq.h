@@ -305,6 +305,15 @@ BQ_API int bq_get_attention_precise_exp(void);           /* current mode, so tha
  * memory (what head_dim 128 uses).  Same arithmetic, same results; A/B measurement switch. */
 BQ_API void bq_set_attention_dual_pipeline(int on);
 BQ_API int bq_get_attention_dual_pipeline(void);
+/* General form: causal != 0 -> decoder mask (keys above the diagonal excluded); causal == 0 -> bidirectional (BERT,
+ * bert_quantized/modeling_bert.py:366-435).  key_mask: optional bitmap [B][key_mask_words] (bit i of word w set = key 32*w + i
+ * takes part; the reference adds finfo.min to the other scores — opt_quantized/modeling_opt.py:520-548 — whose probabilities are
+ * exactly 0).  key_mask_words >= 4 * ceil(S / 128), bits of keys >= S clear; REQUIRED when causal == 0.  Every query row must keep at
+ * least one key (the reference's all-masked rows degenerate to a uniform distribution over ALL keys; callers route such batches to
+ * the op-by-op path).  fo NULL: fp32 output (out = float*), else bf16 output quantised for the consuming Linear. */
+BQ_API int bq_attention_masked(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq, void* out,
+                               int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                               float score_div, int32_t causal, const uint32_t* key_mask, int64_t key_mask_words, void* stream);
 BQ_API int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq,
                                  void* out_bf16, int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk,
                                  int64_t ldv, int64_t ldo, float score_div, void* stream);

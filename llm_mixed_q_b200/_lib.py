@@ -124,6 +124,9 @@ def load():
     lib.bq_attention_causal.argtypes = [POINTER(BqFormat), c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 8 + [ctypes.c_float, c_void_p]
     lib.bq_attention_causal_q.restype = ctypes.c_int
     lib.bq_attention_causal_q.argtypes = [POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 8 + [ctypes.c_float, c_void_p]
+    lib.bq_attention_masked.restype = ctypes.c_int
+    lib.bq_attention_masked.argtypes = [POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 8 + [
+        ctypes.c_float, c_int32, c_void_p, c_int64, c_void_p]
     lib.bq_split3_bf16.restype = ctypes.c_int
     lib.bq_split3_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.bq_gemm_split_tn.restype = ctypes.c_int

@@ -83,6 +83,9 @@ struct AttnArgs {
   int out_mode;         // 0: fp32 unquantised; 1: bf16, block-quantised with `po` (blocks of 16 along d)
   FmtParams p;          // format of P (data_in of bmm_1 / matmul_1)
   FmtParams po;         // format of the output (data_in of the following Linear), out_mode 1
+  int causal;           // 1: keys above the diagonal are masked (decoder); 0: bidirectional (BERT, modeling_bert.py:366-435)
+  const uint32_t* kmask;   // key-validity bitmap [B][kmask_words], bit i of word w = key 32 * w + i takes part; nullptr: all keys < S
+  int kmask_words;      // words per batch row (covers whole 128-key tiles; keys >= S are 0)
 };
 
 // MN-major SWIZZLE_128B operand: rows of 128 bytes run along MN (64 bf16), 8 such rows (8 K indices) per
@@ -260,8 +263,17 @@ __device__ __forceinline__ float max32_tree(const uint32_t (&r)[32]) {
   const float u0 = max3f(t[0], t[1], t[2]), u1 = max3f(t[3], t[4], t[5]), u2 = max3f(t[6], t[7], t[8]), u3 = fmaxf(t[9], t[10]);
   return fmaxf(fmaxf(u0, u1), fmaxf(u2, u3));
 }
+// key-padding mask: bit i of mw clear -> key i of the slice does not take part (the reference adds finfo.min to its score,
+// opt_quantized/modeling_opt.py:520-548, bert_quantized/modeling_bert.py:366-370: exp(finfo.min - max) == 0 exactly like -inf here)
+__device__ __forceinline__ void mask_scores32_bits(uint32_t (&r)[32], uint32_t mw) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = ((mw >> i) & 1u) ? r[i] : 0xff800000u;
+}
 __device__ __forceinline__ void stats32(const uint32_t (&r)[32], float& m, float& mL, float& l) {
   const float tmax = max32_tree(r);
+  // a row whose 32 keys of this slice are all masked (key-padding holes) before it has met a valid key: nothing to add, and
+  // (-inf) * log2 e - (-inf) below would be NaN
+  if (tmax == -INFINITY) return;
   if (tmax > m) {                                        // online rescale of the running sum
     const float mLn = __fmul_rn(tmax, kL2E);
     l = __fmul_rn(l, ex2_fast(__fsub_rn(mL, mLn)));      // first time: mL = -inf -> factor 0 (l is 0 anyway)
@@ -396,15 +408,15 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
   const int T = g.q_tiles;
-  const int pairs = (T + 1) >> 1;
+  const int pairs = g.causal ? (T + 1) >> 1 : T;          // bidirectional: every query tile sees every key tile, no pairing needed
   const int items = g.B * g.H * pairs;
   // item -> (b, h, first query tile, number of query tiles); second query tile = T - 1 - first
   auto decode = [&](int w, int& b, int& h, int& qt_hi, int& nsub) {
     const int bh = w / pairs, pr = w - bh * pairs;
     b = bh / g.H;
     h = bh - b * g.H;
-    qt_hi = T - 1 - pr;
-    nsub = (qt_hi != pr) ? 2 : 1;
+    qt_hi = g.causal ? T - 1 - pr : pr;
+    nsub = (g.causal && qt_hi != pr) ? 2 : 1;
   };
 
   if (warp == 0) {
@@ -416,7 +428,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         decode(w, b, h, qt_hi, nsub);
         for (int sub = 0; sub < nsub; ++sub) {
           const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-          const int n = qt + 1;
+          const int n = g.causal ? qt + 1 : T;
           ptx::mbar_wait(q_empty(qr.idx), qr.phase ^ 1);
           ptx::mbar_expect_tx(q_full(qr.idx), Cfg::kTile);
 #pragma unroll
@@ -456,7 +468,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         decode(w, b, h, qt_hi, nsub);
         for (int sub = 0; sub < nsub; ++sub) {
           const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-          const int n = qt + 1;
+          const int n = g.causal ? qt + 1 : T;
           ptx::mbar_wait(q_full(qr.idx), qr.phase);
           const uint32_t qbase = sb + Cfg::kSmemQ + qr.idx * Cfg::kTile;
           auto issue_S = [&]() {
@@ -523,7 +535,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       decode(w, b, h, qt_hi, nsub);
       for (int sub = 0; sub < nsub; ++sub) {
         const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-        const int n = qt + 1;
+        const int n = g.causal ? qt + 1 : T;
         const int row = qt * kAtBM + r_in;
         const int nvalid_d = lane + 1;            // cq == quarter: keys [32*cq, 32*cq + lane] of the diagonal tile
         const uint32_t xm = xch + xbuf * (2 * 4 * 128 * 4);   // [4][128] partial maxima
@@ -532,8 +544,10 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         float m = -INFINITY, mL = -INFINITY, l = 0.f, inv_l = 0.f;
         for (int sweep = 0; sweep < 2; ++sweep) {
           for (int j = 0; j < n; ++j) {
-            const bool diag = (j == n - 1);
-            const bool skip = diag && diag_masked;
+            const bool diag = g.causal && (j == n - 1);
+            uint32_t mw = 0xffffffffu;                           // key-padding bits of this warp's 32 keys
+            if (g.kmask) mw = __ldg(g.kmask + (int64_t)b * g.kmask_words + j * 4 + cq);
+            const bool skip = (diag && diag_masked) || mw == 0u;
             ptx::mbar_wait(s_full(sr.idx), sr.phase);
             ptx::tc_fence_after();
             uint32_t r[32];
@@ -551,6 +565,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               for (int i = 0; i < 32; ++i) r[i] = f2u(__fmul_rn(u2f(r[i]), g.score_mul));
             }
             if (!skip && diag && diag_partial) mask_scores32(r, nvalid_d);
+            if (!skip && mw != 0xffffffffu) mask_scores32_bits(r, mw);
             if (sweep == 0) {
               if (!skip) stats32(r, m, mL, l);
             } else {
@@ -741,15 +756,16 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   tmem += (uint32_t)grp * Cfg::kTmemGroup;                        // this group's 256 columns
 
   const int T = g.q_tiles;
-  const int pairs = (T + 1) >> 1;
+  const int pairs = g.causal ? (T + 1) >> 1 : T;
   const int items = g.B * g.H * pairs;
   const int vb = (int)blockIdx.x * 2 + grp, vgrid = (int)gridDim.x * 2;      // virtual worker index: one per group
+  const int kt_all = (g.S + Cfg::kBN - 1) / Cfg::kBN;                        // key tiles of a bidirectional row block
   auto decode = [&](int w, int& b, int& h, int& qt_hi, int& nsub) {
     const int bh = w / pairs, pr = w - bh * pairs;
     b = bh / g.H;
     h = bh - b * g.H;
-    qt_hi = T - 1 - pr;
-    nsub = (qt_hi != pr) ? 2 : 1;
+    qt_hi = g.causal ? T - 1 - pr : pr;
+    nsub = (g.causal && qt_hi != pr) ? 2 : 1;
   };
 
   if (warp == 0 || warp == 2) {
@@ -761,7 +777,7 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         decode(w, b, h, qt_hi, nsub);
         for (int sub = 0; sub < nsub; ++sub) {
           const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-          const int n = 2 * (qt + 1);                              // 64-key tiles up to and including the diagonal
+          const int n = g.causal ? 2 * (qt + 1) : kt_all;                              // 64-key tiles up to and including the diagonal
           ptx::mbar_wait(q_empty(qr.idx), qr.phase ^ 1);
           ptx::mbar_expect_tx(q_full(qr.idx), Cfg::kQTile);
           tma_load_4d(sb + Cfg::kSmemQ + qr.idx * Cfg::kQTile, &tmQ, q_full(qr.idx), 0, h, qt * kAtBM, b);
@@ -795,7 +811,7 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         decode(w, b, h, qt_hi, nsub);
         for (int sub = 0; sub < nsub; ++sub) {
           const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-          const int n = 2 * (qt + 1);
+          const int n = g.causal ? 2 * (qt + 1) : kt_all;
           ptx::mbar_wait(q_full(qr.idx), qr.phase);
           const uint32_t qbase = sb + Cfg::kSmemQ + qr.idx * Cfg::kQTile;
           auto issue_S = [&]() {
@@ -856,7 +872,7 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       decode(w, b, h, qt_hi, nsub);
       for (int sub = 0; sub < nsub; ++sub) {
         const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-        const int n = 2 * (qt + 1);
+        const int n = g.causal ? 2 * (qt + 1) : kt_all;
         const int row = qt * kAtBM + r_in;
         const int nvalid_d = lane + 1;
         const uint32_t xm = xch + xbuf * (2 * 2 * 128 * 4);   // [2][128] partial maxima
@@ -867,8 +883,10 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
           for (int j = 0; j < n; ++j) {
             // the last two 64-key tiles straddle the diagonal: 32-key column group c' = 2 * (j - (n - 2)) + cq of the 128 x 128
             // diagonal square is fully visible for c' < quarter, fully masked for c' > quarter, per-element for c' == quarter
-            const int cd = (j >= n - 2) ? (2 * (j - (n - 2)) + cq) : -1;
-            const bool skip = cd > quarter;
+            const int cd = (g.causal && j >= n - 2) ? (2 * (j - (n - 2)) + cq) : -1;
+            uint32_t mw = 0xffffffffu;                           // key-padding bits of this warp's 32 keys
+            if (g.kmask) mw = __ldg(g.kmask + (int64_t)b * g.kmask_words + j * 2 + cq);
+            const bool skip = cd > quarter || mw == 0u;
             const bool partial = cd == quarter;
             ptx::mbar_wait(s_full(sr.idx), sr.phase);
             ptx::tc_fence_after();
@@ -885,7 +903,8 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
 #pragma unroll
               for (int i = 0; i < 32; ++i) r[i] = f2u(__fmul_rn(u2f(r[i]), g.score_mul));
             }
-            if (partial) mask_scores32(r, nvalid_d);
+            if (partial && !skip) mask_scores32(r, nvalid_d);
+            if (!skip && mw != 0xffffffffu) mask_scores32_bits(r, mw);
             if (sweep == 0) {
               if (!skip) stats32(r, m, mL, l);
             } else {
@@ -992,7 +1011,7 @@ static int launch_attention_dual_f(const CUtensorMap& tq, const CUtensorMap& tk,
                                        At2Cfg::kSmemBytes));
     attr = true;
   }
-  const int items = g.B * g.H * ((g.q_tiles + 1) / 2);
+  const int items = g.B * g.H * (g.causal ? (g.q_tiles + 1) / 2 : g.q_tiles);
   const int grid = std::min((items + 1) / 2, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
@@ -1017,7 +1036,7 @@ static int launch_attention_f(const CUtensorMap& tq, const CUtensorMap& tk, cons
                                        Cfg::kSmemBytes));
     attr = true;
   }
-  const int items = g.B * g.H * ((g.q_tiles + 1) / 2);
+  const int items = g.B * g.H * (g.causal ? (g.q_tiles + 1) / 2 : g.q_tiles);
   const int grid = std::min(items, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
@@ -1034,7 +1053,7 @@ static int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const 
 
 static int attention_impl(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq, void* out,
                           int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                          float score_div, cudaStream_t st) {
+                          float score_div, cudaStream_t st, int causal = 1, const uint32_t* key_mask = nullptr, int64_t key_mask_words = 0) {
   if (!fp || B < 0 || H < 0 || S < 0) return BQ_ERR_BAD_ARG;
   if (B == 0 || H == 0 || S == 0) return BQ_OK;
   if (!Qq || !Kq || !Vq || !out) return BQ_ERR_BAD_ARG;
@@ -1060,6 +1079,15 @@ static int attention_impl(const bq_format* fp, const bq_format* fo, const void* 
   }
   g.out = out; g.B = (int)B; g.H = (int)H; g.S = (int)S; g.ldo = ldo;
   g.q_tiles = (int)((S + kAtBM - 1) / kAtBM);
+  g.causal = causal ? 1 : 0;
+  // every 128-key tile must be covered by the bitmap (keys >= S cleared by the caller); bidirectional attention NEEDS one (nothing
+  // else masks the zero-filled keys beyond S), causal attention takes it only for padded batches
+  if (key_mask) {
+    if (key_mask_words < 4 * (int64_t)g.q_tiles || ((uintptr_t)key_mask % 4)) return BQ_ERR_BAD_ARG;
+    g.kmask = key_mask; g.kmask_words = (int)key_mask_words;
+  } else if (!causal) {
+    return BQ_ERR_BAD_ARG;
+  }
   g.score_mul = 1.0f / score_div;
   g.scale_mode = (score_div == 1.0f) ? 0 : 1;
   CUtensorMap tq, tk, tv;
@@ -1085,6 +1113,13 @@ extern "C" int bq_attention_causal(const bq_format* fp, const void* Qq, const vo
                                    int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv,
                                    int64_t ldo, float score_div, void* stream) {
   return bq::attention_impl(fp, nullptr, Qq, Kq, Vq, out, B, H, S, d, ldq, ldk, ldv, ldo, score_div, (cudaStream_t)stream);
+}
+
+extern "C" int bq_attention_masked(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq, void* out,
+                                   int64_t B, int64_t H, int64_t S, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                   float score_div, int32_t causal, const uint32_t* key_mask, int64_t key_mask_words, void* stream) {
+  return bq::attention_impl(fp, fo, Qq, Kq, Vq, out, B, H, S, d, ldq, ldk, ldv, ldo, score_div, (cudaStream_t)stream, causal, key_mask,
+                            key_mask_words);
 }
 
 extern "C" int bq_attention_causal_q(const bq_format* fp, const bq_format* fo, const void* Qq, const void* Kq, const void* Vq,

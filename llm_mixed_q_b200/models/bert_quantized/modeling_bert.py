@@ -21,6 +21,7 @@ from transformers.modeling_outputs import (BaseModelOutputWithPoolingAndCrossAtt
 from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
+from ..quantize.quantized_functions.attention import fusable as _attn_fusable, fused_causal_attention, key_mask_bits, output_quantizable
 from .configuration_bert import BertQuantizedConfig
 
 
@@ -74,7 +75,24 @@ class BertQuantizedSelfAttention(nn.Module):
     def transpose_for_scores(self, x: torch.Tensor) -> torch.Tensor:
         return x.view(x.size()[:-1] + (self.num_attention_heads, self.attention_head_size)).permute(0, 2, 1, 3)
 
-    def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False):
+    def fused_eligible(self, hidden_states, key_mask, head_mask, output_attentions) -> bool:
+        """matmul_0 -> /sqrt(d) -> +mask -> softmax -> matmul_1 (:366-435) as ONE kernel (bq_attention_masked, bidirectional with
+        the key-padding bitmap): scores and probabilities never reach HBM."""
+        return (key_mask is not None and head_mask is None and not output_attentions and hidden_states.is_cuda
+                and hidden_states.dtype == torch.float32 and hidden_states.ndim == 3 and not torch.is_grad_enabled()
+                and not (self.training and self.dropout.p > 0)
+                and _attn_fusable(self.quant_config["matmul_0"], self.quant_config["matmul_1"], self.attention_head_size,
+                                  hidden_states.shape[1]))
+
+    def fused_forward(self, hidden_states, key_mask, out_cfg=None):
+        """fp32 context [B, S, H], or with `out_cfg` (config of attention.output.dense) its bf16 x-quantised form."""
+        return fused_causal_attention(self.query(hidden_states), self.key(hidden_states), self.value(hidden_states),
+                                      self.quant_config["matmul_0"], self.quant_config["matmul_1"], self.num_attention_heads,
+                                      score_div=math.sqrt(self.attention_head_size), out_cfg=out_cfg, causal=False, key_mask=key_mask)
+
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False, key_mask=None):
+        if self.fused_eligible(hidden_states, key_mask, head_mask, output_attentions):
+            return (self.fused_forward(hidden_states, key_mask),)
         query_layer = self.transpose_for_scores(self.query(hidden_states))
         key_layer = self.transpose_for_scores(self.key(hidden_states))
         value_layer = self.transpose_for_scores(self.value(hidden_states))
@@ -111,8 +129,15 @@ class BertQuantizedAttention(nn.Module):
         self.self = BertQuantizedSelfAttention(config, position_embedding_type=position_embedding_type, quant_config=quant_config)
         self.output = BertQuantizedSelfOutput(config, quant_config=quant_config["output"])
 
-    def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False):
-        self_outputs = self.self(hidden_states, attention_mask, head_mask, output_attentions)
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False, key_mask=None):
+        dense = self.output.dense
+        if (self.self.fused_eligible(hidden_states, key_mask, head_mask, output_attentions) and dense.accepts_prequantized()
+                and output_quantizable(dense.config, hidden_states.shape[-1], hidden_states.shape[1])):
+            # the x-quantizer of attention.output.dense runs in the attention epilogue; dense reads the bf16 operand
+            oq = self.self.fused_forward(hidden_states, key_mask, out_cfg=dense.config)
+            out = dense.forward_prequantized(oq).view(hidden_states.shape)
+            return (self.output.LayerNorm(self.output.dropout(out) + hidden_states),)
+        self_outputs = self.self(hidden_states, attention_mask, head_mask, output_attentions, key_mask=key_mask)
         return (self.output(self_outputs[0], hidden_states),) + self_outputs[1:]
 
 
@@ -151,8 +176,8 @@ class BertQuantizedLayer(nn.Module):
         self.intermediate = BertQuantizedIntermediate(config, quant_config=qc["intermediate"])
         self.output = BertQuantizedOutput(config, quant_config=qc["output"])
 
-    def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False):
-        attn = self.attention(hidden_states, attention_mask, head_mask, output_attentions)
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False, key_mask=None):
+        attn = self.attention(hidden_states, attention_mask, head_mask, output_attentions, key_mask=key_mask)
         attention_output = attn[0]
         layer_output = self.output(self.intermediate(attention_output), attention_output)
         return (layer_output,) + attn[1:]
@@ -164,12 +189,14 @@ class BertQuantizedEncoder(nn.Module):
         self.config = config
         self.layer = nn.ModuleList([BertQuantizedLayer(config, i) for i in range(config.num_hidden_layers)])
 
-    def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False, output_hidden_states=False):
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, output_attentions=False, output_hidden_states=False,
+                key_mask=None):
         all_h, all_a = (), ()
         for i, layer in enumerate(self.layer):
             if output_hidden_states:
                 all_h += (hidden_states,)
-            out = layer(hidden_states, attention_mask, head_mask[i] if head_mask is not None else None, output_attentions)
+            out = layer(hidden_states, attention_mask, head_mask[i] if head_mask is not None else None, output_attentions,
+                        key_mask=key_mask)
             hidden_states = out[0]
             if output_attentions:
                 all_a += (out[1],)
@@ -271,6 +298,7 @@ class BertQuantizedModel(BertQuantizedPreTrainedModel):
         self.embeddings = BertEmbeddings(config)
         self.encoder = BertQuantizedEncoder(config)
         self.pooler = BertPooler(config) if add_pooling_layer else None
+        self.fused_attention = True      # set False to force the op-by-op attention path (QUANTIZED_FUNC_MAP matmul functions)
         self.post_init()
 
     def get_input_embeddings(self):
@@ -299,9 +327,17 @@ class BertQuantizedModel(BertQuantizedPreTrainedModel):
                 head_mask = head_mask[:, None, :, None, None]
         emb = self.embeddings(input_ids=input_ids, token_type_ids=token_type_ids, position_ids=position_ids,
                               inputs_embeds=inputs_embeds)
+        # fused attention (bq_attention_masked) takes the 2-D 0/1 padding mask as a bitmap; every sequence must keep one key
+        # (an all-masked row is a uniform distribution over the padding in the reference — op-by-op path)
+        key_mask = None
+        if self.fused_attention and emb.is_cuda and attention_mask.ndim == 2 and not torch.is_grad_enabled():
+            valid = attention_mask != 0
+            binary = bool(((attention_mask == 0) | (attention_mask == 1)).all())
+            if binary and bool(valid.any(dim=1).all()):
+                key_mask = key_mask_bits(valid)
         seq_out, all_h, all_a = self.encoder(emb, attention_mask=ext, head_mask=head_mask,
                                              output_attentions=bool(output_attentions),
-                                             output_hidden_states=bool(output_hidden_states))
+                                             output_hidden_states=bool(output_hidden_states), key_mask=key_mask)
         pooled = self.pooler(seq_out) if self.pooler is not None else None
         if return_dict is False:
             return (seq_out, pooled) + tuple(v for v in (all_h, all_a) if v is not None)

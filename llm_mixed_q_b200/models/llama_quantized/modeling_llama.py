@@ -19,8 +19,8 @@ from transformers.modeling_outputs import CausalLMOutputWithPast, SequenceClassi
 from transformers.modeling_utils import PreTrainedModel
 
 from ..quantize import get_quantized_cls, get_quantized_func
-from ..quantize.quantized_functions.attention import (fusable as _attn_fusable, fused_causal_attention_q, output_quantizable,
-                                                       quantize_qkv)
+from ..quantize.quantized_functions.attention import (causal_key_mask, fusable as _attn_fusable, fused_causal_attention_q,
+                                                       output_quantizable, quantize_qkv)
 from ..quantize.quantized_functions.fp32_linear import fp32_linear
 from ..quantize.quantized_functions.loss import causal_lm_loss
 from ..quantize.quantized_functions.fused_glue import (linear_input_format, norm_quantize, row_block16_format,
@@ -164,7 +164,7 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         return plan
 
     @torch.no_grad()
-    def _fused_forward(self, h, position_ids, plan, default_positions=False):
+    def _fused_forward(self, h, position_ids, plan, default_positions=False, key_mask=None):
         B, S, H = h.shape
         at, mlp = self.self_attn, self.mlp
         n1, n2 = self.input_layernorm, self.post_attention_layernorm
@@ -184,7 +184,7 @@ class LlamaQuantizedDecoderLayer(nn.Module):
                                        position_ids, qc["rotary_positional_encoding"])
             Qq, Kq, _ = quantize_qkv(q4.view(B, S, H), k4.view(B, S, H), None, qc["matmul_0"], qc["matmul_1"], at.num_heads)
         oq = fused_causal_attention_q(Qq, Kq, Vq, qc["matmul_1"], at.num_heads, B, S, math.sqrt(at.head_dim),
-                                      out_cfg=at.o_proj.config)
+                                      out_cfg=at.o_proj.config, key_mask=key_mask)
         h2 = at.o_proj.forward_prequantized(oq, residual=h)                      # residual + o_proj(attn)
         xg, xu = norm_quantize(h2, n2.weight, None, n2.variance_epsilon, [plan["gate_in"], plan["up_in"]])
         g = mlp.gate_proj.forward_prequantized(xg)
@@ -194,12 +194,12 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         return h3.view(B, S, H)
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, output_attentions=False, causal_only=False,
-                default_positions=False):
+                default_positions=False, key_mask=None):
         if (causal_only and not output_attentions and hidden_states.is_cuda and hidden_states.dtype == torch.float32
                 and not torch.is_grad_enabled() and not self.training and hidden_states.ndim == 3):
             plan = self._fused_plan(hidden_states.shape[1])
             if plan is not None:
-                return self._fused_forward(hidden_states, position_ids, plan, default_positions), None
+                return self._fused_forward(hidden_states, position_ids, plan, default_positions, key_mask), None
         residual = hidden_states
         hidden_states = self.input_layernorm(hidden_states)
         hidden_states, attn = self.self_attn(hidden_states, attention_mask=attention_mask, position_ids=position_ids,
@@ -268,7 +268,13 @@ class LlamaQuantizedModel(LlamaQuantizedPreTrainedModel):
         if default_positions:
             position_ids = torch.arange(q_len, dtype=torch.long, device=inputs_embeds.device).unsqueeze(0).view(-1, q_len)
         mask = _causal_mask(attention_mask, bsz, q_len, inputs_embeds.dtype, inputs_embeds.device)
-        causal_only = self.fused_glue and (attention_mask is None or bool(attention_mask.all()))
+        no_padding = attention_mask is None or bool(attention_mask.all())
+        # right-padded batches keep the fused layers: the attention kernel takes the key-padding bitmap (every causal row keeps
+        # key 0); left padding has fully masked rows -> op-by-op path (see attention.causal_key_mask)
+        key_mask = None
+        if self.fused_glue and not no_padding and inputs_embeds.is_cuda:
+            key_mask = causal_key_mask(attention_mask)
+        causal_only = self.fused_glue and (no_padding or key_mask is not None)
         hidden_states = inputs_embeds
         all_h, all_a = (), ()
         for layer in self.layers:
@@ -276,7 +282,7 @@ class LlamaQuantizedModel(LlamaQuantizedPreTrainedModel):
                 all_h += (hidden_states,)
             hidden_states, attn = layer(hidden_states, attention_mask=mask, position_ids=position_ids,
                                         output_attentions=output_attentions, causal_only=causal_only,
-                                        default_positions=default_positions)
+                                        default_positions=default_positions, key_mask=key_mask)
             if output_attentions:
                 all_a += (attn,)
         hidden_states = self.norm(hidden_states)

@@ -22,7 +22,7 @@ from transformers.modeling_utils import PreTrainedModel
 from ..quantize import get_quantized_cls, get_quantized_func
 from ..quantize.quantized_functions.fp32_linear import fp32_linear
 from ..quantize.quantized_functions.loss import causal_lm_loss
-from ..quantize.quantized_functions.attention import (fusable as _attn_fusable, fused_causal_attention,
+from ..quantize.quantized_functions.attention import (causal_key_mask, fusable as _attn_fusable, fused_causal_attention,
                                                       fused_causal_attention_q, output_quantizable)
 from ..quantize.quantized_functions.fused_glue import linear_input_format, norm_quantize, row_block16_format
 from .configuration_opt import OPTQuantizedConfig
@@ -81,7 +81,9 @@ class OPTQauntizedAttention(nn.Module):      # (sic) class name kept from the re
         return tensor.view(bsz, seq_len, self.num_heads, self.head_dim).transpose(1, 2).contiguous()
 
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-                output_attentions: bool = False, causal_only: bool = False):
+                output_attentions: bool = False, causal_only: bool = False, key_mask: Optional[torch.Tensor] = None):
+        """`causal_only`: the additive mask is the causal one, plus — when `key_mask` (attention.key_mask_bits) is given — key
+        padding that leaves every query row at least one key; the fused kernel then applies both itself."""
         bsz, tgt_len, _ = hidden_states.size()
         if (causal_only and not output_attentions and hidden_states.is_cuda and not torch.is_grad_enabled()
                 and not (self.training and self.dropout > 0)
@@ -93,10 +95,10 @@ class OPTQauntizedAttention(nn.Module):      # (sic) class name kept from the re
             if self.out_proj.accepts_prequantized() and output_quantizable(self.out_proj.config, self.embed_dim, tgt_len):
                 # the x-quantizer of out_proj runs in the attention epilogue; out_proj consumes the bf16 operand directly
                 oq = fused_causal_attention(q, k, v, self.quant_config["bmm_0"], self.quant_config["bmm_1"], self.num_heads,
-                                            score_div=1.0, out_cfg=self.out_proj.config)
+                                            score_div=1.0, out_cfg=self.out_proj.config, key_mask=key_mask)
                 return self.out_proj.forward_prequantized(oq), None
             attn_output = fused_causal_attention(q, k, v, self.quant_config["bmm_0"], self.quant_config["bmm_1"],
-                                                 self.num_heads, score_div=1.0)
+                                                 self.num_heads, score_div=1.0, key_mask=key_mask)
             return self.out_proj(attn_output), None
         query_states = self.q_proj(hidden_states) * self.scaling
         key_states = self._shape(self.k_proj(hidden_states), -1, bsz)
@@ -177,7 +179,7 @@ class OPTQuantizedDecoderLayer(nn.Module):
         return plan
 
     @torch.no_grad()
-    def _fused_forward(self, h, plan):
+    def _fused_forward(self, h, plan, key_mask=None):
         B, S, H = h.shape
         at = self.self_attn
         ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm
@@ -185,24 +187,26 @@ class OPTQuantizedDecoderLayer(nn.Module):
         Qq = at.q_proj.forward_prequantized(xq_q, scale=at.scaling, out_format=plan["q_out"])
         Kq = at.k_proj.forward_prequantized(xq_k, out_format=plan["k_out"], out_blocks_along_rows=True)
         Vq = at.v_proj.forward_prequantized(xq_v, out_format=plan["v_out"])
-        oq = fused_causal_attention_q(Qq, Kq, Vq, at.quant_config["bmm_1"], at.num_heads, B, S, 1.0, out_cfg=at.out_proj.config)
+        oq = fused_causal_attention_q(Qq, Kq, Vq, at.quant_config["bmm_1"], at.num_heads, B, S, 1.0, out_cfg=at.out_proj.config,
+                                      key_mask=key_mask)
         h2 = at.out_proj.forward_prequantized(oq, residual=h)                         # residual + out_proj(attn)
         (x1,) = norm_quantize(h2, ln2.weight, ln2.bias, ln2.eps, [plan["fc1_in"]])
         a = self.fc1.forward_prequantized(x1.view(B * S, H), relu=True, out_format=plan["fc2_in"])
         h3 = self.fc2.forward_prequantized(a, residual=h2.view(B * S, H))             # residual + fc2(relu(fc1(x)))
         return h3.view(B, S, H)
 
-    def forward(self, hidden_states, attention_mask=None, output_attentions=False, causal_only=False, fused_glue=False):
+    def forward(self, hidden_states, attention_mask=None, output_attentions=False, causal_only=False, fused_glue=False,
+                key_mask=None):
         if (fused_glue and causal_only and not output_attentions and hidden_states.is_cuda and hidden_states.dtype == torch.float32
                 and not torch.is_grad_enabled() and not self.training and hidden_states.ndim == 3):
             plan = self._fused_plan(hidden_states.shape[1])
             if plan is not None:
-                return self._fused_forward(hidden_states, plan), None
+                return self._fused_forward(hidden_states, plan, key_mask), None
         residual = hidden_states
         if self.do_layer_norm_before:
             hidden_states = self.self_attn_layer_norm(hidden_states)
         hidden_states, attn = self.self_attn(hidden_states, attention_mask=attention_mask, output_attentions=output_attentions,
-                                             causal_only=causal_only)
+                                             causal_only=causal_only, key_mask=key_mask)
         hidden_states = nn.functional.dropout(hidden_states, p=self.dropout, training=self.training)
         hidden_states = residual + hidden_states
         if not self.do_layer_norm_before:
@@ -285,7 +289,13 @@ class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
         no_padding = attention_mask is None or bool(attention_mask.all())
         if attention_mask is None:
             attention_mask = torch.ones(bsz, seq_len, dtype=torch.bool, device=inputs_embeds.device)
-        causal_only = no_padding and self.fused_attention
+        # padded batches stay on the fused kernels when every causal row keeps a key (key 0 valid: right padding) — the kernel
+        # takes the key-padding bitmap; left padding has fully masked rows, which the reference turns into a uniform
+        # distribution over ALL keys (:520-548 + the max(finfo.min) clamp): op-by-op path
+        key_mask = None
+        if self.fused_attention and not no_padding and inputs_embeds.is_cuda:
+            key_mask = causal_key_mask(attention_mask)
+        causal_only = self.fused_attention and (no_padding or key_mask is not None)
         causal = _causal_additive_mask(attention_mask, bsz, seq_len, inputs_embeds.dtype, inputs_embeds.device, all_ones=no_padding)
         pos_embeds = self.embed_positions(attention_mask, 0)
         if self.project_in is not None:
@@ -297,7 +307,7 @@ class OPTQuantizedDecoder(OPTQuantizedPreTrainedModel):
             if output_hidden_states:
                 all_h += (hidden_states,)
             hidden_states, attn = layer(hidden_states, attention_mask=causal, output_attentions=output_attentions,
-                                        causal_only=causal_only, fused_glue=self.fused_glue and causal_only)
+                                        causal_only=causal_only, fused_glue=self.fused_glue and causal_only, key_mask=key_mask)
             if output_attentions:
                 all_a += (attn,)
         if self.final_layer_norm is not None:

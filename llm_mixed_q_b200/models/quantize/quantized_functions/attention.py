@@ -81,8 +81,33 @@ def quantize_qkv(q, k, v, cfg0: dict, cfg1: dict, num_heads: int):
     return Qq, Kq, Vq
 
 
+def key_mask_bits(valid: torch.Tensor) -> torch.Tensor:
+    """[B, S] boolean / 0-1 key-validity mask -> int32 bitmap [B, 4 * ceil(S / 128)] for bq_attention_masked: bit i of word w set
+    = key 32 * w + i takes part; keys >= S are cleared (the kernel's key tiles are zero-filled there)."""
+    B, S = valid.shape
+    words = 4 * ((S + 127) // 128)
+    v = torch.zeros((B, words * 32), dtype=torch.int64, device=valid.device)
+    v[:, :S] = valid.to(torch.int64)
+    w = (v.view(B, words, 32) << torch.arange(32, device=valid.device, dtype=torch.int64)).sum(-1)      # < 2^32
+    return (w & 0xFFFFFFFF).to(torch.int64).where(w < 2 ** 31, w - 2 ** 32).to(torch.int32).contiguous()
+
+
+def causal_key_mask(attention_mask: torch.Tensor):
+    """Key-padding bitmap for a decoder batch, or None when the fused kernel must not be used: with the causal mask every query
+    row needs one visible key, which holds for every row iff key 0 of every sequence is valid (right padding).  Fully masked rows
+    (left padding) are a uniform distribution over ALL keys in the reference (finfo.min everywhere after the clamp,
+    opt_quantized/modeling_opt.py:520-548, :266-270) — the op-by-op path reproduces that.  One device-to-host look."""
+    if attention_mask is None or attention_mask.ndim != 2:
+        return None
+    valid = attention_mask != 0
+    if not bool(valid[:, 0].all()):
+        return None
+    return key_mask_bits(valid)
+
+
 def fused_causal_attention_q(Qq: torch.Tensor, Kq: torch.Tensor, Vq: torch.Tensor, cfg1: dict, num_heads: int, B: int, S: int,
-                             score_div: float = 1.0, out_cfg: dict = None, out: torch.Tensor = None) -> torch.Tensor:
+                             score_div: float = 1.0, out_cfg: dict = None, out: torch.Tensor = None, causal: bool = True,
+                             key_mask: torch.Tensor = None) -> torch.Tensor:
     """Kernel call on already-quantised bf16 operands ([B*S, H] or [B, S, H], unit stride along H).
     Returns fp32 [B, S, H], or — with `out_cfg` (config of the Linear consuming the result) — its bf16 x-quantised form.
     `out` (with `out_cfg`): preallocated bf16 [B*S, H] destination with unit column stride and any row stride — e.g. this rank's
@@ -94,6 +119,26 @@ def fused_causal_attention_q(Qq: torch.Tensor, Kq: torch.Tensor, Vq: torch.Tenso
     fp = make_format(pk, b0=1, b1=16, **pkw)
     dev = Qq.device
     ld = lambda t: t.stride(-2)
+    if not causal or key_mask is not None:
+        # bidirectional (BERT) and / or key-padding mask: `key_mask` = key_mask_bits(valid keys); built here when absent
+        if key_mask is None:
+            key_mask = key_mask_bits(torch.ones((B, S), dtype=torch.bool, device=dev))
+        if key_mask.dtype != torch.int32 or key_mask.device != dev or not key_mask.is_contiguous() or key_mask.shape[0] != B:
+            raise ValueError("key_mask must be the int32 [B, words] bitmap of key_mask_bits() on the operands' device")
+        fo = None
+        if out_cfg is not None:
+            ok, okw, _ = operand_format(out_cfg, "data_in")
+            fo = make_format(ok, b0=1, b1=16, **okw)
+        ldo = H
+        if out is None:
+            out = torch.empty((B, S, H), dtype=torch.float32 if fo is None else torch.bfloat16, device=dev)
+        else:
+            ldo = out.stride(-2)
+        rc = lib.bq_attention_masked(ctypes.byref(fp), ctypes.byref(fo) if fo is not None else None, Qq.data_ptr(), Kq.data_ptr(),
+                                     Vq.data_ptr(), out.data_ptr(), B, num_heads, S, d, ld(Qq), ld(Kq), ld(Vq), ldo, float(score_div),
+                                     1 if causal else 0, key_mask.data_ptr(), key_mask.shape[1], L.stream_ptr(dev))
+        L.check(rc, "bq_attention_masked")
+        return out
     if out_cfg is None:
         out = torch.empty((B, S, H), dtype=torch.float32, device=dev)
         rc = lib.bq_attention_causal(ctypes.byref(fp), Qq.data_ptr(), Kq.data_ptr(), Vq.data_ptr(), out.data_ptr(), B, num_heads,
@@ -116,7 +161,8 @@ def fused_causal_attention_q(Qq: torch.Tensor, Kq: torch.Tensor, Vq: torch.Tenso
 
 
 def fused_causal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cfg0: dict, cfg1: dict, num_heads: int,
-                           score_div: float = 1.0, out_cfg: dict = None) -> torch.Tensor:
+                           score_div: float = 1.0, out_cfg: dict = None, causal: bool = True,
+                           key_mask: torch.Tensor = None) -> torch.Tensor:
     """
     q, k, v: fp32 [B, S, H] projections (q already scaled where the model scales before bmm_0, as OPT does).
     Returns fp32 [B, S, H] = concat over heads of  Q(softmax(Q(q) Q(k)^T / score_div, causal)) @ Q(v)
@@ -124,4 +170,4 @@ def fused_causal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cf
     """
     B, S, H = q.shape
     Qq, Kq, Vq = quantize_qkv(q, k, v, cfg0, cfg1, num_heads)
-    return fused_causal_attention_q(Qq, Kq, Vq, cfg1, num_heads, B, S, score_div, out_cfg)
+    return fused_causal_attention_q(Qq, Kq, Vq, cfg1, num_heads, B, S, score_div, out_cfg, causal=causal, key_mask=key_mask)

@@ -302,6 +302,90 @@ def test_fused_causal_attention_vs_op_by_op_oracle(S, attention_exp_mode, attent
     assert torch.equal(out[:, 0, :], exp0)
 
 
+def _oracle_attention_masked(q, k, v, cfg, heads, valid, causal, score_div=1.0):
+    """op-by-op reference composition with an additive key-padding mask: decoder (causal + padding, clamped at finfo.min —
+    opt_quantized/modeling_opt.py:520-548, :266-270) or encoder (padding only, no clamp — bert_quantized/modeling_bert.py:366-435)."""
+    B, S, H = q.shape
+    d = H // heads
+    neg = torch.finfo(torch.float32).min
+
+    def shape(t):
+        return t.view(B, S, heads, d).transpose(1, 2).contiguous().view(B * heads, S, d)
+
+    q3, k3, v3 = shape(q), shape(k), shape(v)
+    s = (O.matmul_forward(q3, k3.transpose(1, 2), cfg, style="bmm") / score_div).view(B, heads, S, S)
+    pad = torch.zeros(B, 1, 1, S, device=q.device).masked_fill(~valid[:, None, None, :], neg)
+    if causal:
+        mask = (torch.triu(torch.full((S, S), neg, device=q.device), diagonal=1)[None, None] + pad).clamp(min=neg)
+        s = torch.max(s + mask, torch.tensor(neg, device=q.device))
+    else:
+        s = s + pad
+    p = torch.softmax(s, dim=-1).view(B * heads, S, S)
+    o = O.matmul_forward(p, v3, cfg, style="bmm")
+    return o.view(B, heads, S, d).transpose(1, 2).reshape(B, S, H)
+
+
+@pytest.mark.parametrize("S,d,causal,pattern", [(200, 64, True, "right"), (1024, 64, True, "right"), (640, 128, True, "right"),
+                                                (384, 64, True, "holes"), (80, 64, False, "right"), (512, 64, False, "right"),
+                                                (333, 64, False, "holes"), (384, 128, False, "right"), (512, 64, False, "none")])
+def test_fused_attention_with_key_padding_and_bidirectional_masks(S, d, causal, pattern, attention_pipeline):
+    """bq_attention_masked: the key-padding bitmap (padded OPT / Llama batches) and the bidirectional mode (BERT) against the
+    op-by-op composition; same stated tolerance as the causal test.  "holes": arbitrary key subsets (key 0 kept, so every causal
+    row has a key) — some rows meet 32-key slices with no visible key before their first valid one."""
+    import math
+
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import fused_causal_attention, key_mask_bits
+
+    g = torch.Generator(device="cuda").manual_seed(S + d + (7 if causal else 0))
+    B, heads = 3, 2
+    H = heads * d
+    q = torch.randn(B, S, H, device="cuda", generator=g) * 0.5
+    k = torch.randn(B, S, H, device="cuda", generator=g)
+    v = torch.randn(B, S, H, device="cuda", generator=g)
+    valid = torch.ones(B, S, dtype=torch.bool, device="cuda")
+    if pattern == "right":
+        valid[1, S // 2 + 5:] = False
+        valid[2, 33:] = False
+    elif pattern == "holes":
+        valid[1] = torch.rand(S, device="cuda", generator=g) > 0.6
+        valid[2, 1:130] = False
+        valid[:, 0] = True
+    sd = math.sqrt(d) if not causal else 1.0
+    out = fused_causal_attention(q, k, v, CFG_BFP6, CFG_BFP6, heads, score_div=sd, causal=causal, key_mask=key_mask_bits(valid))
+    ref = _oracle_attention_masked(q, k, v, CFG_BFP6, heads, valid, causal, score_div=sd)
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs()
+    vmax = float(v.abs().max())
+    assert float(err.max()) <= (2.0 ** -5) * vmax, float(err.max())
+    assert float((err > 0.01 * vmax).float().mean()) <= 1e-4
+    assert float(err.mean()) <= 2e-4, float(err.mean())
+    # the x-quantised output form agrees with the quantizer applied to the fp32 form
+    from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer
+    oq = fused_causal_attention(q, k, v, CFG_BFP6, CFG_BFP6, heads, score_div=sd, causal=causal, key_mask=key_mask_bits(valid),
+                                out_cfg=CFG_BFP6)
+    want = block_fp_quantizer(out, 6, 8, 127, [1, 16], True)
+    big = out.abs() > 1e-8
+    assert torch.equal(oq.float()[big], want[big])
+
+
+def test_key_mask_bits_layout_and_argument_checks():
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import fused_causal_attention, key_mask_bits
+
+    valid = torch.zeros(2, 200, dtype=torch.bool, device="cuda")
+    valid[0, [0, 31, 32, 199]] = True
+    valid[1, :] = True
+    bits = key_mask_bits(valid)
+    assert bits.shape == (2, 8) and bits.dtype == torch.int32
+    w = bits.cpu().numpy().astype("int64") & 0xFFFFFFFF
+    assert w[0, 0] == (1 | (1 << 31)) and w[0, 1] == 1 and w[0, 6] == (1 << 7) and w[0, 7] == 0
+    assert w[1, 6] == 0xFF and w[1, 5] == 0xFFFFFFFF and w[1, 7] == 0          # keys >= S cleared
+    q = torch.randn(2, 200, 128, device="cuda")
+    with pytest.raises(ValueError):
+        fused_causal_attention(q, q, q, CFG_BFP6, CFG_BFP6, 2, causal=False, key_mask=bits[:, :4].contiguous().to(torch.int64))
+    with pytest.raises(ValueError):                         # bitmap shorter than the key tiles (BQ_ERR_BAD_ARG)
+        fused_causal_attention(q, q, q, CFG_BFP6, CFG_BFP6, 2, causal=False, key_mask=bits[:, :4].contiguous())
+
+
 def test_fused_causal_attention_head_dim_128_and_score_div(attention_exp_mode):
     """Llama-7B geometry: d = 128, scores divided by sqrt(d) after matmul_0 (modeling_llama.py:309-314).  torch-CUDA
     evaluates `tensor / python_float` as a multiplication by the fp32 reciprocal; the kernel does the same."""
