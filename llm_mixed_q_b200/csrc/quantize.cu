@@ -273,6 +273,12 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
@@ -1052,28 +1058,36 @@ __global__ void __maxnreg__(80) norm_quant_kernel(LnArgs a) {
 // shuffle trees, the row slot is handed back to the bulk-copy engine as soon as the row is in registers (the next row lands
 // while this one is processed), gamma / beta are read from one shared copy per CTA.  ~16 instructions per element against 33
 // for v5 (whose per-row CTA barriers, partial-sum exchange and thread-0 bookkeeping are per-row costs paid by 4 warps).
-constexpr int kLwWarps = 8;
-// FULL: the row has exactly NB * 32 blocks (H = 512 * NB), no per-block predicate anywhere
-template <int KIND, int NB, bool FULL>
-__global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArgs a) {
+constexpr int kLwWarps = 8;              // rows in flight per CTA
+// FULL: the row has exactly NB * 32 * G blocks (H = 512 * NB * G), no per-block predicate anywhere.
+// G: warps per row.  G = 1 serves H <= 2048 (a lane holds up to 4 blocks = 64 values); G = 2 serves H <= 4096 (OPT-6.7B, Llama-7B: the
+// row-per-CTA kernel ran those at 3.7 TB/s) with the same 64 values per lane: warp gw of a row's pair owns blocks (j * G + gw) * 32 + lane,
+// the two statistics are exchanged through 8 bytes of shared memory per warp and one 64-thread named barrier each, and the pair's
+// first lane drives the row slot's bulk copies.
+template <int KIND, int NB, bool FULL, int G>
+__global__ void __launch_bounds__(kLwWarps * G * 32, G == 1 ? 2 : 1) norm_quant_warp_kernel(LnArgs a) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = warp / G, gw = warp % G;                // row slot of this warp, position inside the row's warp group
   const uint32_t row_bytes = (uint32_t)a.H * 4u, out_bytes = (uint32_t)a.H * 2u;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ln_smem);
   const uint32_t gam0 = sbase, bet0 = sbase + row_bytes;
-  const uint32_t in0 = sbase + 2u * row_bytes + (uint32_t)warp * (row_bytes + out_bytes);
+  const uint32_t in0 = sbase + 2u * row_bytes + (uint32_t)rg * (row_bytes + out_bytes);
   const uint32_t outb = in0 + row_bytes;
-  const uint32_t bar = sbase + 2u * row_bytes + (uint32_t)kLwWarps * (row_bytes + out_bytes) + 8u * (uint32_t)warp;
+  const uint32_t bars = sbase + 2u * row_bytes + (uint32_t)kLwWarps * (row_bytes + out_bytes);
+  const uint32_t bar = bars + 8u * (uint32_t)rg;
+  const uint32_t xch = bars + 8u * (uint32_t)kLwWarps + (uint32_t)rg * (2u * G * 4u);      // [2 statistics][G warps] partial sums
   const bool ln = a.beta != nullptr;
+  const bool leader = lane == 0 && gw == 0;
   const int nblk = a.H >> 4;
   const int stride = gridDim.x * kLwWarps;
-  int row = blockIdx.x * kLwWarps + warp;
-  if (lane == 0) {
+  int row = blockIdx.x * kLwWarps + rg;
+  if (leader) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (row < a.rows) bulk_load_row(in0, a.x + (int64_t)row * a.ldx, row_bytes, bar);
   }
-  for (int i = threadIdx.x; i < (a.H >> 2); i += kLwWarps * 32) {
+  for (int i = threadIdx.x; i < (a.H >> 2); i += kLwWarps * G * 32) {
     sts128(gam0 + 16u * i, __ldg(reinterpret_cast<const float4*>(a.gamma) + i));
     if (ln) sts128(bet0 + 16u * i, __ldg(reinterpret_cast<const float4*>(a.beta) + i));
   }
@@ -1081,13 +1095,31 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
   const uint32_t rot = (uint32_t)((lane >> 1) + (lane >> 3)) & 3u;
   const float invH = 1.0f / (float)a.H;
   uint32_t parity = 0;
+  auto group_bar = [&]() {
+    if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + rg), "r"(32 * G) : "memory");
+    else __syncwarp();
+  };
+  // sum over the row's G warps of a per-warp total; every warp adds the partials in the same order, so all agree bit for bit
+  auto group_sum = [&](float v, int which) {
+    v = warp_sum(v);
+    if (G == 1) return v;
+    if (lane == 0) sts_f32(xch + (uint32_t)(which * G + gw) * 4u, v);
+    group_bar();
+    float t = lds_f32(xch + (uint32_t)(which * G) * 4u);
+#pragma unroll
+    for (int w = 1; w < G; ++w) t = __fadd_rn(t, lds_f32(xch + (uint32_t)(which * G + w) * 4u));
+    return t;
+  };
   for (; row < a.rows; row += stride) {
+    // (G > 1) the previous row's store must have left the output slot before ANY warp of the group rewrites it: the leader waits
+    // here, ahead of the first group barrier of this row
+    if (G > 1 && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     st_mbar_wait(bar, parity);
     parity ^= 1u;
     float v[NB][16];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      const int blk = j * 32 + lane;
+      const int blk = (j * G + gw) * 32 + lane;
       const uint32_t base = in0 + (uint32_t)blk * 64u;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -1095,11 +1127,17 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
         v[j][4 * c] = t.x; v[j][4 * c + 1] = t.y; v[j][4 * c + 2] = t.z; v[j][4 * c + 3] = t.w;
       }
     }
-    __syncwarp();                                        // the row is in registers: refill the slot while it is processed
-    if (lane == 0) {
-      const int64_t next = (int64_t)row + stride;
-      if (next < a.rows) bulk_load_row(in0, a.x + next * a.ldx, row_bytes, bar);
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous row's store has left the output slot
+    // the row is in registers once the group has passed its next barrier: refill the slot while the row is processed
+    auto refill = [&]() {
+      if (leader) {
+        const int64_t next = (int64_t)row + stride;
+        if (next < a.rows) bulk_load_row(in0, a.x + next * a.ldx, row_bytes, bar);
+        if (G == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous row's store has left the output slot
+      }
+    };
+    if (G == 1) {
+      __syncwarp();
+      refill();
     }
     float mean = 0.f;
     if (ln) {
@@ -1111,7 +1149,8 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
         for (int c = 0; c < 4; ++c) t[c] = __fadd_rn(__fadd_rn(v[j][4 * c], v[j][4 * c + 1]), __fadd_rn(v[j][4 * c + 2], v[j][4 * c + 3]));
         s = __fadd_rn(s, __fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])));
       }
-      mean = __fmul_rn(warp_sum(s), invH);
+      mean = __fmul_rn(group_sum(s, 0), invH);
+      if (G > 1) refill();
     }
     float q = 0.f;
 #pragma unroll
@@ -1122,20 +1161,21 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
         v[j][i] = __fsub_rn(v[j][i], mean);
         t[i & 3] = __fmaf_rn(v[j][i], v[j][i], t[i & 3]);
       }
-      if (FULL || j * 32 + lane < nblk) q = __fadd_rn(q, __fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])));
+      if (FULL || (j * G + gw) * 32 + lane < nblk) q = __fadd_rn(q, __fadd_rn(__fadd_rn(t[0], t[1]), __fadd_rn(t[2], t[3])));
     }
-    const float rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(q), invH), a.eps));     // (warp_sum's shuffles also order lane 0's wait above)
+    const float rstd = rsqrtf(__fadd_rn(__fmul_rn(group_sum(q, 1), invH), a.eps));     // (G = 1: warp_sum's shuffles also order lane 0's wait above)
+    if (G > 1 && !ln) refill();
 #pragma unroll 1
     for (int k = 0; k < a.n_out; ++k) {
       const FmtParams& p = (k == 0) ? a.f[0] : ((k == 1) ? a.f[1] : a.f[2]);
       __nv_bfloat16* outp = ((k == 0) ? a.out[0] : ((k == 1) ? a.out[1] : a.out[2])) + (int64_t)row * a.H;
       if (k > 0) {
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        group_bar();
       }
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        const int blk = j * 32 + lane;
+        const int blk = (j * G + gw) * 32 + lane;
         if (FULL || blk < nblk) {
           float y[16];
 #pragma unroll
@@ -1165,20 +1205,20 @@ __global__ void __launch_bounds__(kLwWarps * 32, 2) norm_quant_warp_kernel(LnArg
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) st_bulk_store(outp, outb, out_bytes);
+      group_bar();
+      if (leader) st_bulk_store(outp, outb, out_bytes);
     }
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int KIND, int NB, bool FULL>
+template <int KIND, int NB, bool FULL, int G>
 static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)2 * a.H * 4 + (size_t)kLwWarps * ((size_t)a.H * 6) + kLwWarps * 8;
+  const size_t smem = (size_t)2 * a.H * 4 + (size_t)kLwWarps * ((size_t)a.H * 6) + kLwWarps * 8 + kLwWarps * 2 * G * 4;
   static PerDevice<size_t> smem_attr_pd;
   size_t& smem_attr = smem_attr_pd.get();
   if (smem > smem_attr) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_warp_kernel<KIND, NB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(norm_quant_warp_kernel<KIND, NB, FULL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
   static PerDevice<int> occ_h_pd, occ_pd;
@@ -1186,7 +1226,7 @@ static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
   int& occ = occ_pd.get();
   if (occ_h != a.H) {
     int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_warp_kernel<KIND, NB, FULL>, kLwWarps * 32, smem) != cudaSuccess || o < 1) o = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, norm_quant_warp_kernel<KIND, NB, FULL, G>, kLwWarps * G * 32, smem) != cudaSuccess || o < 1) o = 1;
     occ = o;
     occ_h = a.H;
   }
@@ -1194,7 +1234,7 @@ static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
   const int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * occ);
   {
     LaunchScope ls(kKernLnQuant, st);
-    norm_quant_warp_kernel<KIND, NB, FULL><<<grid, kLwWarps * 32, smem, st>>>(a);
+    norm_quant_warp_kernel<KIND, NB, FULL, G><<<grid, kLwWarps * G * 32, smem, st>>>(a);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
@@ -1202,11 +1242,13 @@ static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
 template <int KIND>
 static int launch_norm_quant_warp_nb(const LnArgs& a, cudaStream_t st) {
   const int nblk = a.H / 16;
-  if (nblk == 128) return launch_norm_quant_warp<KIND, 4, true>(a, st);
-  if (nblk == 64) return launch_norm_quant_warp<KIND, 2, true>(a, st);
-  if (nblk <= 32) return launch_norm_quant_warp<KIND, 1, false>(a, st);
-  if (nblk <= 64) return launch_norm_quant_warp<KIND, 2, false>(a, st);
-  return launch_norm_quant_warp<KIND, 4, false>(a, st);
+  if (nblk == 256) return launch_norm_quant_warp<KIND, 4, true, 2>(a, st);
+  if (nblk > 128) return launch_norm_quant_warp<KIND, 4, false, 2>(a, st);
+  if (nblk == 128) return launch_norm_quant_warp<KIND, 4, true, 1>(a, st);
+  if (nblk == 64) return launch_norm_quant_warp<KIND, 2, true, 1>(a, st);
+  if (nblk <= 32) return launch_norm_quant_warp<KIND, 1, false, 1>(a, st);
+  if (nblk <= 64) return launch_norm_quant_warp<KIND, 2, false, 1>(a, st);
+  return launch_norm_quant_warp<KIND, 4, false, 1>(a, st);
 }
 static bool g_ln_warp_rows = true;
 void set_ln_warp_rows(int on) { g_ln_warp_rows = on != 0; }
@@ -1231,7 +1273,7 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
     a.out[k] = (__nv_bfloat16*)outs[k];
   }
   a.rows = (int)rows;
-  if (g_ln_warp_rows && H <= 2048) {
+  if (g_ln_warp_rows && H <= 4096) {
     bool same = true;
     for (int k = 1; k < n_out; ++k) same = same && fmts[k].kind == fmts[0].kind;
     if (same) {

@@ -124,9 +124,11 @@ def test_gemm_epilogue_row_blocks_rare_path_with_nonfinite_values():
 
 
 @pytest.mark.parametrize("warp_rows", [1, 0])
-@pytest.mark.parametrize("H,rows", [(2048, 512), (768, 300), (4096, 64), (64, 1000), (1024, 1), (2048, 8 * 148 * 2 + 3)])
+@pytest.mark.parametrize("H,rows", [(2048, 512), (768, 300), (4096, 64), (64, 1000), (1024, 1), (2048, 8 * 148 * 2 + 3),
+                                    (4096, 8 * 148 + 5), (3072, 129), (2304, 50), (5120, 40)])
 def test_layernorm_quantize_vs_torch_layernorm_then_quantizer(H, rows, warp_rows):
-    """Both norm+quantize kernels: row-per-warp (H <= 2048, default) and row-per-CTA (any H; forced by the A/B switch)."""
+    """Both norm+quantize kernels: row-per-warp / row-per-warp-pair (H <= 2048 / <= 4096, default) and row-per-CTA (any H; forced by
+    the A/B switch)."""
     from llm_mixed_q_b200 import _lib as L
     from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import norm_quantize
     from llm_mixed_q_b200.models.quantize.quantizers import block_fp_quantizer
