@@ -153,6 +153,52 @@ BQ_API int bq_norm_quantize(const float* x, int64_t rows, int64_t H, int64_t ldx
 BQ_API int bq_rope_quantize(const float* q, const float* k, const float* cos_table, const float* sin_table, const int64_t* position_ids,
                             int64_t table_rows, int64_t B, int64_t S, int32_t heads, int32_t head_dim, int64_t ldq, int64_t ldk,
                             const bq_format* fq, const bq_format* fk, void* Qq_bf16, void* Kq_bf16, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Attention of the formats whose matmuls keep an UNQUANTISED fp32 operand — block_log: generic_matmul_block_log quantises x only,
+ * quantized_functions/matmul.py:286-297 — and of every geometry the one-kernel attention below rejects.  The S x S scores go through
+ * HBM once in fp32 and once as bf16 probabilities instead of the reference's ~10 fp32 passes + two ~45-kernel quantizer calls:
+ *
+ *   bq_rope_quantize_split     Llama RoPE (as bq_rope_quantize) of q followed by matmul_0's x-quantizer -> Qq bf16 HEAD-major
+ *                              [B][heads][S][head_dim]; RoPE of k followed by the error-free split of the fp32 result into three bf16
+ *                              planes, k = k0 + k1 + k2 -> [B][3][heads][S][head_dim].  fq: block_fp / block_minifloat / block_log, [1,16].
+ *                              cos_table == sin_table == NULL: no rotation (attention without rotary embedding).
+ *   bq_split3_bf16_transposed  v fp32 [B][S][heads*head_dim] (token stride ldv) -> planes of v^T, [B][3][heads][head_dim][S] bf16
+ *                              (keys contiguous: the K-major B operand of P @ V).  S % 2 == 0, heads*head_dim % 32 == 0.
+ *   bq_bmm_split_tn            batched form of bq_gemm_split_tn for bf16 planes laid out [plane][batch][rows][K]:
+ *                              C[b][m][n] = sum_t A_plane[term_a[t]][b][m][:] . B_plane[term_b[t]][b][n][:]; C row stride ldc, batch
+ *                              stride sc — batch-major (sc >= M*ldc) or interleaved in the rows (sc >= N, ldc >= batch*sc: the heads of
+ *                              one sequence written into the token-major activation).  With a power-of-two (block_log) or otherwise
+ *                              bf16-exact x as the single A plane and the three planes of y, every product is exact: the result is the
+ *                              reference's fp32 matmul up to accumulation order.
+ *                              causal: 0 none; 1 (M == N, QK^T) output tiles wholly above the diagonal are neither computed nor
+ *                              stored — their contents are undefined and bq_softmax_quantize(causal) never reads them; 2 (M == K,
+ *                              P @ V) the K loop of a row tile stops at the last key its rows can see (P is zero beyond it).
+ *   bq_softmax_quantize        P = Q_fp(softmax(max(scores / score_div + mask, finfo.min)))  in bf16 — the reference's chain
+ *                              models/llama_quantized/modeling_llama.py:314-337, models/opt_quantized/modeling_opt.py:262-312,
+ *                              bert_quantized/modeling_bert.py:370-435 ending in the x-quantizer of matmul_1 / bmm_1 (blocks of 16 keys).
+ *                              scores fp32 [batch][Sq][lds] (batch stride ss), P bf16 [batch][Sq][ldp] (batch stride sp); batch = B*heads;
+ *                              causal != 0: key j > query i masked (Sq == Sk); key_mask: optional bitmap [B][key_mask_words] (bit i of
+ *                              word w = key 32w+i takes part).  causal == 2: as 1, and probabilities beyond the 256-key boundary
+ *                              that follows the query are not written (the causal == 2 bq_bmm_split_tn never reads them; a fully
+ *                              masked row is still written in full).  Masked scores are finfo.min exactly like the reference's additive masks
+ *                              leave them, so a fully masked row comes out uniform over ALL keys as it does there.  expf / IEEE division
+ *                              like torch's softmax; the row sum is accumulated in a different order.  Sk % 16 == 0.
+ *                              fp: block_fp / block_minifloat / block_log, blocks [1,16].
+ * block_log in a 16-bit carrier (this function, bq_rope_quantize_split, bq_norm_quantize, the GEMM epilogue quantizer): block-local
+ * "carrier rule" — an all-zero block stays 0 (the reference fills it with 2^(ceil(log2 g) - 127), g = the tensor's smallest non-zero
+ * block maximum) and outputs the reference puts below 2^-126 are 0 or 2^-126; every other output is bit-identical.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API int bq_rope_quantize_split(const float* q, const float* k, const float* cos_table, const float* sin_table,
+                                  const int64_t* position_ids, int64_t table_rows, int64_t B, int64_t S, int32_t heads, int32_t head_dim,
+                                  int64_t ldq, int64_t ldk, const bq_format* fq, void* Qq_bf16, void* K_planes_bf16, void* stream);
+BQ_API int bq_split3_bf16_transposed(const float* v, void* planes_bf16, int64_t B, int64_t S, int32_t heads, int32_t head_dim, int64_t ldv,
+                                     void* stream);
+BQ_API int bq_bmm_split_tn(const void* A_planes, const void* B_planes, float* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                           int32_t planes_a, int32_t planes_b, int32_t n_terms, const int32_t* term_a, const int32_t* term_b,
+                           int64_t ldc, int64_t sc, int32_t causal, void* stream);
+BQ_API int bq_softmax_quantize(const bq_format* fp, const float* scores, void* P_bf16, int64_t batch, int64_t heads, int64_t Sq, int64_t Sk,
+                               int64_t lds, int64_t ss, int64_t ldp, int64_t sp, float score_div, int32_t causal, const uint32_t* key_mask,
+                               int64_t key_mask_words, void* stream);
 BQ_API int bq_selftest_log2(unsigned long long* mismatches_dev3, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

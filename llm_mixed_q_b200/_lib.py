@@ -140,6 +140,17 @@ def load():
     lib.bq_set_attention_dual_pipeline.argtypes = [ctypes.c_int]
     lib.bq_get_attention_dual_pipeline.restype = ctypes.c_int
     lib.bq_get_attention_dual_pipeline.argtypes = []
+    lib.bq_rope_quantize_split.restype = ctypes.c_int
+    lib.bq_rope_quantize_split.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
+                                           c_int64, c_int64, POINTER(BqFormat), c_void_p, c_void_p, c_void_p]
+    lib.bq_split3_bf16_transposed.restype = ctypes.c_int
+    lib.bq_split3_bf16_transposed.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int64, c_void_p]
+    lib.bq_bmm_split_tn.restype = ctypes.c_int
+    lib.bq_bmm_split_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                    POINTER(c_int32), POINTER(c_int32), c_int64, c_int64, c_int32, c_void_p]
+    lib.bq_softmax_quantize.restype = ctypes.c_int
+    lib.bq_softmax_quantize.argtypes = [POINTER(BqFormat), c_void_p, c_void_p] + [c_int64] * 8 + [ctypes.c_float, c_int32, c_void_p,
+                                                                                                 c_int64, c_void_p]
     lib.bq_rope_quantize.restype = ctypes.c_int
     lib.bq_rope_quantize.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                      c_int64, c_int64, POINTER(BqFormat), POINTER(BqFormat), c_void_p, c_void_p, c_void_p]

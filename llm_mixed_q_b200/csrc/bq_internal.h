@@ -18,6 +18,8 @@ size_t quantize_ws_bytes(const bq_format* fmt, const bq_tensor3* t);
 int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t batch, int64_t M, int64_t N,
                       int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc,
                       cudaStream_t st);
+struct FmtParams;
+int make_params(const bq_format* f, FmtParams* p);
 // Per-device slot for lazily initialised launch state (function attributes and occupancy are per-device properties: a process
 // that drives more than one GPU must not reuse device 0's answers).
 int current_device();
@@ -26,7 +28,7 @@ template <typename T> struct PerDevice {
   T& get() { return v[current_device()]; }
 };
 enum KernelId { kKernQuantRows = 0, kKernBlockLogFixup, kKernQuantTile, kKernGenericMax, kKernGenericMin, kKernGenericQuant,
-                kKernGemm, kKernAttention, kKernSplit3, kKernGemmEpi, kKernGemmSplit, kKernLnQuant, kKernQuantStream, kKernSiluMulQuant, kKernTokenCe, kKernTokenCeMean, kKernPeerBarrier, kKernRopeQuant, kKernPeerPush, kKernGemmXformA, kKernGemmXformB, kKernPackWeight, kKernCount };
+                kKernGemm, kKernAttention, kKernSplit3, kKernGemmEpi, kKernGemmSplit, kKernLnQuant, kKernQuantStream, kKernSiluMulQuant, kKernTokenCe, kKernTokenCeMean, kKernPeerBarrier, kKernRopeQuant, kKernPeerPush, kKernGemmXformA, kKernGemmXformB, kKernPackWeight, kKernSoftmaxQuant, kKernRopeSplit, kKernSplit3T, kKernCount };
 // RAII launch bracket: counts the launch; records start/stop events on `st` when profiling is enabled.
 struct LaunchScope {
   LaunchScope(int id, cudaStream_t st);

@@ -24,7 +24,7 @@ static const char* kKernelNames[kKernCount] = {"quant_rows_kernel", "blocklog_fi
                                                "gemm_bf16_tn_kernel", "attention_causal_kernel", "split3_kernel",
                                                "gemm_bf16_tn_kernel<epilogue>", "gemm_bf16_tn_kernel<split>", "layernorm_quant_kernel", "quant_stream_kernel",
                                                "silu_mul_quant_kernel", "ce_rows_kernel", "ce_mean_kernel", "peer_barrier_kernel", "rope_quant_kernel", "peer_push_kernel", "gemm_xform_kernel<quantize A>", "gemm_xform_kernel<packed B>",
-                                               "pack_weight_kernel"};
+                                               "pack_weight_kernel", "softmax_quant_kernel", "rope_split_kernel", "split3_transposed_kernel"};
 static std::atomic<int64_t> g_launches[kKernCount];
 static std::atomic<int> g_profiling{0};
 struct EventPair { int id; cudaEvent_t a, b; };

@@ -83,6 +83,10 @@ struct GemmArgs {
   int n_terms;
   int8_t term_a[8], term_b[8];
   int fp16;                    // operands are fp16 (kind::f16 with F16 inputs) instead of bf16
+  // causal structure of attention matmuls (square per-batch problems, rows = queries): 1 = output tiles that lie wholly above the
+  // diagonal are neither computed nor stored (QK^T: the consumer never reads them); 2 = the K loop stops at the last key a tile's
+  // rows can see (P @ V: P is zero behind the diagonal)
+  int causal;
   const float* row_scale;      // optional exact power-of-two output scales: C = acc * row_scale[m] * col_scale[n] (+ bias)
   const float* col_scale;
   EpiArgs epi;
@@ -377,6 +381,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     row0 = (mb * CG + rank) * kBM;
   };
 
+  // causal modes: first row past this tile (of the CTA pair's 256 rows when CG == 2) decides what is skipped
+  auto tile_skipped = [&](int row0, int nb) { return g.causal == 1 && nb * BN >= (row0 - rank * kBM) + CG * kBM; };
+  auto tile_kb_per_term = [&](int row0) {
+    return g.causal == 2 ? min(kb_per_term, ((row0 - rank * kBM) + CG * kBM + kBK - 1) / kBK) : kb_per_term;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
@@ -384,13 +394,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = worker; tile < total_tiles; tile += num_workers) {
         int b, row0, nb;
         decode(tile, b, row0, nb);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        if (tile_skipped(row0, nb)) continue;
+        const int kpt = tile_kb_per_term(row0), nkb = kpt * (g.n_terms > 0 ? g.n_terms : 1);
+        for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStage;
           int ca = b, cb = g.b_broadcast ? 0 : b, kk = kb;
           if (g.n_terms > 0) {
-            const int t = kb / kb_per_term;
-            kk = kb - t * kb_per_term;
+            const int t = kb / kpt;
+            kk = kb - t * kpt;
             ca = g.term_a[t] * g.batch + b;                       // planes are stacked outside the batch: [plane][batch][rows][K]
             cb = g.term_b[t] * (g.b_broadcast ? 1 : g.batch) + (g.b_broadcast ? 0 : b);
           }
@@ -416,10 +428,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = worker; tile < total_tiles; tile += num_workers) {
+        int nkb = num_kb;
+        if (g.causal) {
+          int b, row0, nb;
+          decode(tile, b, row0, nb);
+          if (tile_skipped(row0, nb)) continue;
+          nkb = tile_kb_per_term(row0) * (g.n_terms > 0 ? g.n_terms : 1);
+        }
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStage;
@@ -450,6 +469,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = worker; tile < total_tiles; tile += num_workers) {
       int b, row0, nb;
       decode(tile, b, row0, nb);
+      if (tile_skipped(row0, nb)) continue;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const int row = row0 + q * 32 + lane;
@@ -723,7 +743,7 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
   g.C = C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = (int)batch;
   g.ldc = ldc; g.sc = sc; g.tiles_m = g.tiles_n = 0; g.b_broadcast = bcast ? 1 : 0;
   g.n_terms = 0;
-  g.fp16 = 0; g.row_scale = g.col_scale = nullptr;
+  g.fp16 = 0; g.row_scale = g.col_scale = nullptr; g.causal = 0;
   memset(&g.epi, 0, sizeof(g.epi));
   return launch_gemm_any<false>(BN, pair, tmA, tmB, g, st, kKernGemm);
 }
@@ -753,9 +773,10 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
   g.epi.out_bf16 = out_bf16 ? 1 : 0;
   if (ep->qfmt) {
     const bq_format* f = ep->qfmt;
-    if (f->kind != BQ_KIND_BLOCK_FP && f->kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
+    if (f->kind != BQ_KIND_BLOCK_FP && f->kind != BQ_KIND_BLOCK_MINIFLOAT && f->kind != BQ_KIND_BLOCK_LOG) return BQ_ERR_UNSUPPORTED;
     if (f->block_rows != 1 || f->block_cols != 16) return BQ_ERR_UNSUPPORTED;     // block of 16 along the chosen direction
     if (ep->qdir != 0 && ep->qdir != 1) return BQ_ERR_BAD_ARG;
+    if (f->kind == BQ_KIND_BLOCK_LOG && ep->qdir != 0) return BQ_ERR_UNSUPPORTED;   // (block_log matmuls leave the k^T operand unquantised)
     if (ep->qdir == 1 && (M % 16)) return BQ_ERR_UNSUPPORTED;
     int rc = make_params(f, &g.epi.q);
     if (rc) return rc;
@@ -786,14 +807,20 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
 int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias, int64_t M, int64_t N, int64_t K,
                        int planes_a, int planes_b, int n_terms, const int* ta, const int* tb, int64_t ldc, cudaStream_t st,
                        int fp16 = 0, const float* row_scale = nullptr, const float* col_scale = nullptr, int64_t batch = 1,
-                       int64_t sc = 0) {
+                       int64_t sc = 0, int causal = 0) {
   if (M < 0 || N < 0 || K <= 0 || n_terms < 1 || n_terms > 8 || !ta || !tb || batch < 0) return BQ_ERR_BAD_ARG;
   if (M == 0 || N == 0 || batch == 0) return BQ_OK;
-  if (batch > 1 && (sc < M * ldc || planes_a * batch > 0x7fffffff || planes_b * batch > 0x7fffffff)) return BQ_ERR_BAD_ARG;
+  // C of batch z starts at z * sc: batch-major (sc >= M * ldc) or interleaved inside the rows (ldc >= batch * sc, sc >= N — e.g. the
+  // heads of one sequence written straight into the token-major [S][heads * d] activation)
+  if (batch > 1 && (!(sc >= M * ldc || (sc >= N && ldc >= batch * sc)) || planes_a * batch > 0x7fffffff || planes_b * batch > 0x7fffffff))
+    return BQ_ERR_BAD_ARG;
   if (!A || !B || !C) return BQ_ERR_BAD_ARG;
   if ((K % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)C % 4) || ldc < N) return BQ_ERR_BAD_ARG;
   if ((row_scale == nullptr) != (col_scale == nullptr)) return BQ_ERR_BAD_ARG;
   if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  for (int i = 0; i < n_terms; ++i)
+    if (ta[i] < 0 || ta[i] >= planes_a || tb[i] < 0 || tb[i] >= planes_b) return BQ_ERR_BAD_ARG;
+  if (causal < 0 || causal > 2 || (causal == 1 && M != N) || (causal == 2 && M != K)) return BQ_ERR_BAD_ARG;
   const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, planes_a * batch, K, M * K, kBM);     // 16-bit elements: the map only moves bytes
@@ -807,6 +834,7 @@ int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias
   g.ldc = ldc; g.sc = batch > 1 ? sc : 0; g.tiles_m = g.tiles_n = 0; g.b_broadcast = batch > 1 ? 0 : 1;
   g.n_terms = n_terms;
   g.fp16 = fp16; g.row_scale = row_scale; g.col_scale = col_scale;
+  g.causal = causal;
   for (int i = 0; i < n_terms; ++i) {
     if (ta[i] < 0 || ta[i] >= planes_a || tb[i] < 0 || tb[i] >= planes_b) return BQ_ERR_BAD_ARG;
     g.term_a[i] = (int8_t)ta[i];
@@ -834,6 +862,13 @@ extern "C" int bq_bmm_split16_tn(const void* A_planes_f16, const void* B_planes_
   if (!a_inv_scale || !b_inv_scale) return BQ_ERR_BAD_ARG;
   return bq::gemm_split_tn_impl(A_planes_f16, B_planes_f16, C, nullptr, M, N, K, 2, 2, n_terms, term_a, term_b, ldc,
                                 (cudaStream_t)stream, 1, a_inv_scale, b_inv_scale, batch, sc);
+}
+
+extern "C" int bq_bmm_split_tn(const void* A_planes, const void* B_planes, float* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                               int32_t planes_a, int32_t planes_b, int32_t n_terms, const int32_t* term_a, const int32_t* term_b,
+                               int64_t ldc, int64_t sc, int32_t causal, void* stream) {
+  return bq::gemm_split_tn_impl(A_planes, B_planes, C, nullptr, M, N, K, planes_a, planes_b, n_terms, term_a, term_b, ldc,
+                                (cudaStream_t)stream, 0, nullptr, nullptr, batch, sc, causal);
 }
 
 extern "C" int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_gemm_epilogue* ep, int64_t M, int64_t N,

@@ -1265,7 +1265,7 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
   a.x = x; a.ldx = ldx; a.gamma = gamma; a.beta = beta; a.eps = eps; a.H = (int)H; a.n_out = n_out;
   for (int k = 0; k < n_out; ++k) {
     if (!outs[k] || ((uintptr_t)outs[k] % 16)) return BQ_ERR_BAD_ARG;
-    if (fmts[k].kind != BQ_KIND_BLOCK_FP && fmts[k].kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
+    if (fmts[k].kind != BQ_KIND_BLOCK_FP && fmts[k].kind != BQ_KIND_BLOCK_MINIFLOAT && fmts[k].kind != BQ_KIND_BLOCK_LOG) return BQ_ERR_UNSUPPORTED;
     if (fmts[k].block_rows != 1 || fmts[k].block_cols != 16) return BQ_ERR_UNSUPPORTED;
     int rc = make_params(&fmts[k], &a.f[k]);
     if (rc) return rc;
@@ -1278,6 +1278,7 @@ int norm_quantize_impl(const float* x, int64_t rows, int64_t H, int64_t ldx, con
     for (int k = 1; k < n_out; ++k) same = same && fmts[k].kind == fmts[0].kind;
     if (same) {
       a.stages = 1;
+      if (fmts[0].kind == BQ_KIND_BLOCK_LOG) return launch_norm_quant_warp_nb<kBlockLog>(a, st);
       return fmts[0].kind == BQ_KIND_BLOCK_FP ? launch_norm_quant_warp_nb<kBlockFP>(a, st) : launch_norm_quant_warp_nb<kBlockMinifloat>(a, st);
     }
   }

@@ -23,8 +23,9 @@ from ..quantize.quantized_functions.attention import (causal_key_mask, fusable a
                                                        output_quantizable, quantize_qkv)
 from ..quantize.quantized_functions.fp32_linear import fp32_linear
 from ..quantize.quantized_functions.loss import causal_lm_loss
-from ..quantize.quantized_functions.fused_glue import (linear_input_format, norm_quantize, row_block16_format,
+from ..quantize.quantized_functions.fused_glue import (_NORM_KINDS, linear_input_format, norm_quantize, row_block16_format,
                                                         silu_mul_quantize)
+from ..quantize.quantized_functions.split_attention import rope_quantize_split, split_attention, splittable as _attn_splittable
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major as _rope_token_major
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major_quantized as _rope_token_major_quantized
 from ..quantize.quantized_modules.linear import operand_format, quantize_operand_bf16
@@ -160,11 +161,48 @@ class LlamaQuantizedDecoderLayer(nn.Module):
                         v_out=row_block16_format(qc["matmul_1"], "weight", d, rows=seq_len))
             if all(v is not None for v in fmts.values()):
                 plan = fmts
+        if (plan is None and seq_len % 16 == 0 and H % 32 == 0 and mlp.gate_proj.out_features % 16 == 0 and mlp.hidden_act == "silu"
+                and _attn_splittable(qc["matmul_0"], qc["matmul_1"], d, seq_len)):
+            # block_log: matmul_0 / matmul_1 keep k / v in fp32 (reference matmul.py:286-297) -> the three-kernel attention of
+            # split_attention.py; the Linears' x-quantizers still run inside RMSNorm / SiLU*up (block-local carrier rule, bq.h)
+            lin = lambda m: linear_input_format(m, rows=seq_len, kinds=_NORM_KINDS)
+            fmts = dict(mode="split", q_in=lin(at.q_proj), k_in=lin(at.k_proj), v_in=lin(at.v_proj), o_in=lin(at.o_proj),
+                        gate_in=lin(mlp.gate_proj), up_in=lin(mlp.up_proj), down_in=lin(mlp.down_proj))
+            if all(v is not None for v in fmts.values()):
+                plan = fmts
         self._plan_cache = (seq_len, plan)
         return plan
 
     @torch.no_grad()
+    def _split_forward(self, h, position_ids, plan, default_positions=False, key_mask=None):
+        """Layer forward for configs whose matmuls keep an fp32 operand (block_log): same fused glue, attention through
+        rope_quantize_split / split_attention (scores cross HBM once as fp32 and once as quantised bf16 probabilities)."""
+        B, S, H = h.shape
+        at, mlp = self.self_attn, self.mlp
+        n1, n2 = self.input_layernorm, self.post_attention_layernorm
+        qc = at.quant_config
+        xq, xk, xv = norm_quantize(h, n1.weight, None, n1.variance_epsilon, [plan["q_in"], plan["k_in"], plan["v_in"]])
+        q = at.q_proj.forward_prequantized(xq)
+        k = at.k_proj.forward_prequantized(xk)
+        v = at.v_proj.forward_prequantized(xv)
+        cos, sin = at.rotary_emb(q, seq_len=S)
+        Qq, Kp = rope_quantize_split(q.view(B, S, H), k.view(B, S, H), cos, sin, None if default_positions else position_ids,
+                                     qc["rotary_positional_encoding"], qc["matmul_0"], at.num_heads)
+        o = split_attention(Qq, Kp, v.view(B, S, H), qc["matmul_1"], at.num_heads, math.sqrt(at.head_dim), causal=True, key_mask=key_mask)
+        okind, okw = plan["o_in"]
+        oq = quantize_operand_bf16(o.view(B * S, H), okind, okw, [1, 16], True)      # o_proj's x-quantizer (exact, incl. the global-min rule)
+        h2 = at.o_proj.forward_prequantized(oq, residual=h)
+        xg, xu = norm_quantize(h2, n2.weight, None, n2.variance_epsilon, [plan["gate_in"], plan["up_in"]])
+        g = mlp.gate_proj.forward_prequantized(xg)
+        u = mlp.up_proj.forward_prequantized(xu)
+        a = silu_mul_quantize(g.view(B * S, -1), u.view(B * S, -1), plan["down_in"])
+        h3 = mlp.down_proj.forward_prequantized(a, residual=h2.view(B * S, H))
+        return h3.view(B, S, H)
+
+    @torch.no_grad()
     def _fused_forward(self, h, position_ids, plan, default_positions=False, key_mask=None):
+        if plan.get("mode") == "split":
+            return self._split_forward(h, position_ids, plan, default_positions, key_mask)
         B, S, H = h.shape
         at, mlp = self.self_attn, self.mlp
         n1, n2 = self.input_layernorm, self.post_attention_layernorm

@@ -22,7 +22,10 @@ from ..quantizers.utils import canonicalise, make_format, resolve_block_shape
 _EPI_KINDS = ("block_fp", "block_minifloat")
 
 
-def row_block16_format(config: dict, prefix: str, last_dim: int, rows: int = 1) -> Optional[Tuple[str, dict]]:
+_NORM_KINDS = ("block_fp", "block_minifloat", "block_log")    # block_log: carrier rule of include/bq.h (block-local, bf16)
+
+
+def row_block16_format(config: dict, prefix: str, last_dim: int, rows: int = 1, kinds=_EPI_KINDS) -> Optional[Tuple[str, dict]]:
     """(kind, kwargs) when `<prefix>_*` of a config node is a block_fp / block_minifloat format that resolves to blocks of
     16 along a last dim of size `last_dim` and is exact in bf16 — i.e. something an epilogue can apply — else None.
     `rows`: second-to-last extent of the operand THE REFERENCE blocks (quantizers/utils.py:42-67 right-aligns the block
@@ -35,7 +38,7 @@ def row_block16_format(config: dict, prefix: str, last_dim: int, rows: int = 1) 
         kind, kw, bs = operand_format(config, prefix)
     except KeyError:
         return None
-    if kind not in _EPI_KINDS or bs is None or significant_bits(kind, kw) > 8:
+    if kind not in kinds or bs is None or significant_bits(kind, kw) > 8:
         return None
     b = resolve_block_shape([1, max(int(rows), 1), last_dim], bs)
     if b[1] != 1 or b[2] != 16 or last_dim % 16:
@@ -43,12 +46,12 @@ def row_block16_format(config: dict, prefix: str, last_dim: int, rows: int = 1) 
     return kind, kw
 
 
-def linear_input_format(lin, last_dim: Optional[int] = None, rows: int = 1) -> Optional[Tuple[str, dict]]:
+def linear_input_format(lin, last_dim: Optional[int] = None, rows: int = 1, kinds=_EPI_KINDS) -> Optional[Tuple[str, dict]]:
     """x-quantizer of a quantized Linear as an epilogue format, if the module can take a pre-quantised bf16 input.
     `rows` = S when the reference feeds the Linear a 3-D [B, S, K] activation, 1 when it feeds a 2-D one."""
     if not isinstance(lin, _LinearBase) or not lin.accepts_prequantized():
         return None
-    return row_block16_format(lin.config, "data_in", lin.in_features if last_dim is None else last_dim, rows)
+    return row_block16_format(lin.config, "data_in", lin.in_features if last_dim is None else last_dim, rows, kinds)
 
 
 def _same(a, b) -> bool:

@@ -88,7 +88,28 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     outs = (ctypes.c_void_p * 1)(256)
     assert lib.bq_norm_quantize(256, 4, 40, 40, 256, None, 1e-5, 1, fm, outs, None) == 2
     assert lib.bq_norm_quantize(256, 4, 16 * 513, 16 * 513, 256, None, 1e-5, 1, fm, outs, None) == 2
-    assert lib.bq_norm_quantize(256, 4, 64, 64, 256, None, 1e-5, 1, (L.BqFormat * 1)(fl), outs, None) == 2
+    fd = L.BqFormat(L.KIND["minifloat_denorm"], 8, 4, 7, 0, 1, 16, 0)
+    assert lib.bq_norm_quantize(256, 4, 64, 64, 256, None, 1e-5, 1, (L.BqFormat * 1)(fd), outs, None) == 2
+    # split-attention entry points (block_log path): format, geometry and pointer checks precede any CUDA call
+    assert lib.bq_softmax_quantize(ctypes.byref(fd), 256, 256, 4, 2, 64, 64, 64, 4096, 64, 4096, 1.0, 1, None, 0, None) == 2
+    assert lib.bq_softmax_quantize(ctypes.byref(fl), 256, 256, 4, 2, 64, 40, 40, 2560, 40, 2560, 1.0, 0, None, 0, None) == 2     # Sk % 16
+    assert lib.bq_softmax_quantize(ctypes.byref(fl), 256, 256, 4, 2, 64, 128, 128, 8192, 128, 8192, 1.0, 1, None, 0, None) == 2  # causal needs Sq == Sk
+    assert lib.bq_softmax_quantize(ctypes.byref(fl), 256, 256, 3, 2, 64, 64, 64, 4096, 64, 4096, 1.0, 1, None, 0, None) == 1     # batch % heads
+    assert lib.bq_softmax_quantize(ctypes.byref(fl), 256, 256, 4, 2, 64, 64, 64, 4096, 64, 4096, 0.0, 1, None, 0, None) == 1     # score_div
+    assert lib.bq_softmax_quantize(ctypes.byref(fl), 256, 256, 4, 2, 64, 64, 64, 4096, 64, 4096, 1.0, 1, 256, 1, None) == 1      # bitmap too short
+    assert lib.bq_softmax_quantize(ctypes.byref(fl), None, None, 0, 2, 64, 64, 64, 4096, 64, 4096, 1.0, 1, None, 0, None) == 0
+    assert lib.bq_rope_quantize_split(256, 256, 256, None, None, 64, 2, 64, 4, 64, 256, 256, ctypes.byref(fl), 256, 256, None) == 1   # one table only
+    assert lib.bq_rope_quantize_split(256, 256, 256, 256, None, 64, 2, 64, 4, 48, 192, 192, ctypes.byref(fl), 256, 256, None) == 2  # head_dim % 32
+    assert lib.bq_rope_quantize_split(256, 256, 256, 256, None, 32, 2, 64, 4, 64, 256, 256, ctypes.byref(fl), 256, 256, None) == 1  # table shorter than S
+    assert lib.bq_rope_quantize_split(256, 256, None, None, None, 0, 2, 64, 4, 64, 256, 256, ctypes.byref(fd), 256, 256, None) == 2 # format
+    assert lib.bq_split3_bf16_transposed(256, 256, 2, 63, 4, 64, 256, None) == 2
+    assert lib.bq_split3_bf16_transposed(256, 256, 2, 64, 4, 64, 128, None) == 1
+    t3a = (ctypes.c_int32 * 3)(0, 0, 0)
+    t3b = (ctypes.c_int32 * 3)(2, 1, 0)
+    assert lib.bq_bmm_split_tn(256, 256, 256, 4, 64, 64, 64, 1, 3, 3, t3a, t3b, 64, 32, 0, None) == 1        # C batches would overlap
+    assert lib.bq_bmm_split_tn(256, 256, 256, 4, 64, 64, 64, 1, 2, 3, t3a, t3b, 64, 4096, 0, None) == 1      # term names a missing plane
+    assert lib.bq_bmm_split_tn(256, 256, 256, 4, 64, 128, 64, 1, 3, 3, t3a, t3b, 128, 8192, 1, None) == 1   # causal 1 needs M == N
+    assert lib.bq_bmm_split_tn(256, 256, 256, 0, 64, 64, 64, 1, 3, 3, t3a, t3b, 64, 4096, 0, None) == 0
     assert lib.bq_norm_quantize(256, 4, 64, 64, 256, None, 1e-5, 4, fm, outs, None) == 1
     assert lib.bq_norm_quantize(256, 0, 64, 64, 256, None, 1e-5, 1, fm, outs, None) == 0
     del q

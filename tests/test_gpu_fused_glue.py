@@ -387,7 +387,7 @@ def test_silu_mul_quantize_is_bit_identical_to_torch_silu_mul_then_quantizer(kin
         L.load().bq_set_stream_quantizer(1)
 
 
-def test_fused_llama_not_eligible_for_block_log():
+def test_fused_llama_block_log_takes_the_split_attention_plan():
     import json
     import os
 
@@ -399,4 +399,9 @@ def test_fused_llama_not_eligible_for_block_log():
     cfg = LlamaQuantizedConfig(hidden_size=128, intermediate_size=352, num_hidden_layers=1, num_attention_heads=2, vocab_size=512,
                                max_position_embeddings=128, quant_config=qc)
     model = LlamaQuantizedForCausalLM(cfg).eval().cuda()
-    assert model.model.layers[0]._fused_plan(128) is None      # tensor-global zero-block rule: stays op by op
+    plan = model.model.layers[0]._fused_plan(128)
+    # matmul_0 / matmul_1 keep k / v in fp32 (reference matmul.py:286-297): three-kernel attention, fused glue around it
+    assert plan is not None and plan["mode"] == "split" and plan["q_in"][0] == "block_log"
+    cfg2 = LlamaQuantizedConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=4, vocab_size=512,
+                                max_position_embeddings=128, quant_config=qc)
+    assert LlamaQuantizedForCausalLM(cfg2).eval().cuda().model.layers[0]._fused_plan(128) is None       # head_dim 16: op by op

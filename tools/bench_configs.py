@@ -105,6 +105,28 @@ def config4(args, world, rank, dev):
             barrier(world)
         ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / K
         launches = sum(L.launch_counts().values()) - l0
+        # the same forward replayed from a CUDA graph (llm_mixed_q_b200/utils/graphs.py): ~700 launches per step issued from Python
+        # make the eager number follow the host's speed
+        graph_ms, graph_err = None, None
+        if args.graph:
+            from llm_mixed_q_b200.utils.graphs import GraphedForward
+            runner = GraphedForward(model, args.batch, SEQ, device=dev)
+            graph_err = runner.error
+            if runner.graph is not None:
+                for _ in range(2):
+                    runner(ids)
+                barrier(world)
+                e0.record()
+                for _ in range(K):
+                    runner(ids)
+                e1.record()
+                barrier(world)
+                graph_ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / K
+                assert abs(float(runner.loss) - float(out.loss)) <= 1e-6 * abs(float(out.loss)), (float(runner.loss), float(out.loss))
+            del runner
+        eager_ms = ms
+        if graph_ms is not None:
+            ms = graph_ms
         tokens = args.batch * SEQ * world
         # algorithmic FLOPs per token: 7 Linears + 2 matmuls per layer + lm_head
         H, I, Lyr, V, h, d = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.vocab_size, 32, 128
@@ -116,7 +138,8 @@ def config4(args, world, rank, dev):
                          "toml": os.path.relpath(toml_path, ROOT), "layers": Lyr, "init_std": init,
                          "parallelism": f"dp{world} (independent replicas)", "loss": float(out.loss)},
               "algorithmic_TFLOPs": flops * world / (ms / 1e3) / 1e12, "frac_of_bf16_sustained": flops / (ms / 1e3) / 1e12 / sus,
-              "peak_source": src, "gpu_launches_per_step": launches // K, "build_s": round(time.time() - t0, 1)}, rank)
+              "peak_source": src, "gpu_launches_per_step": launches // K, "build_s": round(time.time() - t0, 1),
+              "eager_ms_per_step": eager_ms, "graph_replay_ms_per_step": graph_ms, "graph_error": graph_err}, rank)
         del model, out
         torch.cuda.empty_cache()
 
@@ -218,6 +241,7 @@ def main():
     ap.add_argument("--layer", type=int, default=0)
     ap.add_argument("--no-peer", action="store_true", help="config 5: skip the fused peer-store path (NCCL all-gather only)")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--graph", action="store_true", help="config 4: also time the forward replayed from a CUDA graph (reported value)")
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
     world, rank, dev = setup()
