@@ -196,6 +196,8 @@ BQ_API int bq_split3_bf16_transposed(const float* v, void* planes_bf16, int64_t 
 BQ_API int bq_bmm_split_tn(const void* A_planes, const void* B_planes, float* C, int64_t batch, int64_t M, int64_t N, int64_t K,
                            int32_t planes_a, int32_t planes_b, int32_t n_terms, const int32_t* term_a, const int32_t* term_b,
                            int64_t ldc, int64_t sc, int32_t causal, void* stream);
+/* A/B switch of bq_softmax_quantize: 1 (default) = row staged in shared memory, rolled loops; 0 = row held in registers (v1).  Same results. */
+BQ_API void bq_set_softmax_smem_rows(int on);
 BQ_API int bq_softmax_quantize(const bq_format* fp, const float* scores, void* P_bf16, int64_t batch, int64_t heads, int64_t Sq, int64_t Sk,
                                int64_t lds, int64_t ss, int64_t ldp, int64_t sp, float score_div, int32_t causal, const uint32_t* key_mask,
                                int64_t key_mask_words, void* stream);

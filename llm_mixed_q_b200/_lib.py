@@ -148,6 +148,8 @@ def load():
     lib.bq_bmm_split_tn.restype = ctypes.c_int
     lib.bq_bmm_split_tn.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32,
                                     POINTER(c_int32), POINTER(c_int32), c_int64, c_int64, c_int32, c_void_p]
+    lib.bq_set_softmax_smem_rows.restype = None
+    lib.bq_set_softmax_smem_rows.argtypes = [ctypes.c_int]
     lib.bq_softmax_quantize.restype = ctypes.c_int
     lib.bq_softmax_quantize.argtypes = [POINTER(BqFormat), c_void_p, c_void_p] + [c_int64] * 8 + [ctypes.c_float, c_int32, c_void_p,
                                                                                                  c_int64, c_void_p]

@@ -160,7 +160,8 @@ constexpr float kMagicB = 12600064.0f;
 // instructions — with two pipelines executing different loops at the same time the inlined cold code (16 KB per copy) pushed the
 // loops out of the 32 KB instruction cache (ncu: no_instruction stalls 1.8 per issue against 0.2 for one pipeline).
 template <int KIND, bool SCALED>
-__device__ __noinline__ void quantize_probs16_cold(float* v, float inv_l, uint32_t mbits, FastState fs, FmtParams p, uint32_t* w) {
+__device__ __forceinline__ void quantize_probs16_general(float* v, float inv_l, uint32_t mbits, const FastState& fs, const FmtParams& p,
+                                                         uint32_t* w) {
   if (SCALED) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], inv_l);
@@ -187,6 +188,10 @@ __device__ __noinline__ void quantize_probs16_cold(float* v, float inv_l, uint32
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) w[i] = pack_bf16_trunc(v[2 * i], v[2 * i + 1]);
+}
+template <int KIND, bool SCALED>
+__device__ __noinline__ void quantize_probs16_cold(float* v, float inv_l, uint32_t mbits, FastState fs, FmtParams p, uint32_t* w) {
+  quantize_probs16_general<KIND, SCALED>(v, inv_l, mbits, fs, p, w);
 }
 
 // Quantise 16 consecutive NON-NEGATIVE values (one reference block of probabilities) and pack them as bf16.
@@ -233,6 +238,21 @@ __device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, co
       return;
     }
   }
+  if (KIND == kBlockMinifloat) {
+    // block_minifloat has no packed path above: this IS its hot path — keep it in registers (out of line it cost the Llama-7B W4A4
+    // attention 0.37 -> 0.58 ms per layer: every block went through local memory and a call)
+    if (fs.ok) {
+      if (SCALED) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], inv_l);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = quant_elem_fast<KIND>(v[i], fs, p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = pack_bf16_trunc(v[2 * i], v[2 * i + 1]);
+      return;
+    }
+  }
   float vc[16];
   uint32_t wc[8];
 #pragma unroll
@@ -269,11 +289,12 @@ __device__ __forceinline__ void mask_scores32_bits(uint32_t (&r)[32], uint32_t m
 #pragma unroll
   for (int i = 0; i < 32; ++i) r[i] = ((mw >> i) & 1u) ? r[i] : 0xff800000u;
 }
+template <bool MASKED>
 __device__ __forceinline__ void stats32(const uint32_t (&r)[32], float& m, float& mL, float& l) {
   const float tmax = max32_tree(r);
   // a row whose 32 keys of this slice are all masked (key-padding holes) before it has met a valid key: nothing to add, and
   // (-inf) * log2 e - (-inf) below would be NaN
-  if (tmax == -INFINITY) return;
+  if (MASKED && tmax == -INFINITY) return;
   if (tmax > m) {                                        // online rescale of the running sum
     const float mLn = __fmul_rn(tmax, kL2E);
     l = __fmul_rn(l, ex2_fast(__fsub_rn(mL, mLn)));      // first time: mL = -inf -> factor 0 (l is 0 anyway)
@@ -346,11 +367,15 @@ struct Ring {
   }
 };
 
-template <int KIND, int D, bool FAST>
+// MASKED = false: purely causal, no key-padding bitmap — the instance the benchmarked decoder path runs; the mask arithmetic of the
+// general instance (bidirectional mode, bitmap loads, per-bit selects) is compiled out of it
+template <int KIND, int D, bool FAST, bool MASKED>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, AttnArgs g) {
   using Cfg = AtCfg<D>;
+  const bool causal_m = MASKED ? (g.causal != 0) : true;
+  const uint32_t* const kmask_m = MASKED ? g.kmask : nullptr;
   constexpr int kSub = D / 64;                     // 64-wide sub-tiles along d
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // all shared-memory traffic of this kernel uses 32-bit shared-space addresses (no generic pointers: their window base is
@@ -408,15 +433,15 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
 
   const int T = g.q_tiles;
-  const int pairs = g.causal ? (T + 1) >> 1 : T;          // bidirectional: every query tile sees every key tile, no pairing needed
+  const int pairs = causal_m ? (T + 1) >> 1 : T;          // bidirectional: every query tile sees every key tile, no pairing needed
   const int items = g.B * g.H * pairs;
   // item -> (b, h, first query tile, number of query tiles); second query tile = T - 1 - first
   auto decode = [&](int w, int& b, int& h, int& qt_hi, int& nsub) {
     const int bh = w / pairs, pr = w - bh * pairs;
     b = bh / g.H;
     h = bh - b * g.H;
-    qt_hi = g.causal ? T - 1 - pr : pr;
-    nsub = (g.causal && qt_hi != pr) ? 2 : 1;
+    qt_hi = causal_m ? T - 1 - pr : pr;
+    nsub = (causal_m && qt_hi != pr) ? 2 : 1;
   };
 
   if (warp == 0) {
@@ -428,7 +453,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         decode(w, b, h, qt_hi, nsub);
         for (int sub = 0; sub < nsub; ++sub) {
           const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-          const int n = g.causal ? qt + 1 : T;
+          const int n = causal_m ? qt + 1 : T;
           ptx::mbar_wait(q_empty(qr.idx), qr.phase ^ 1);
           ptx::mbar_expect_tx(q_full(qr.idx), Cfg::kTile);
 #pragma unroll
@@ -468,7 +493,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         decode(w, b, h, qt_hi, nsub);
         for (int sub = 0; sub < nsub; ++sub) {
           const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-          const int n = g.causal ? qt + 1 : T;
+          const int n = causal_m ? qt + 1 : T;
           ptx::mbar_wait(q_full(qr.idx), qr.phase);
           const uint32_t qbase = sb + Cfg::kSmemQ + qr.idx * Cfg::kTile;
           auto issue_S = [&]() {
@@ -535,7 +560,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       decode(w, b, h, qt_hi, nsub);
       for (int sub = 0; sub < nsub; ++sub) {
         const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-        const int n = g.causal ? qt + 1 : T;
+        const int n = causal_m ? qt + 1 : T;
         const int row = qt * kAtBM + r_in;
         const int nvalid_d = lane + 1;            // cq == quarter: keys [32*cq, 32*cq + lane] of the diagonal tile
         const uint32_t xm = xch + xbuf * (2 * 4 * 128 * 4);   // [4][128] partial maxima
@@ -544,9 +569,9 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         float m = -INFINITY, mL = -INFINITY, l = 0.f, inv_l = 0.f;
         for (int sweep = 0; sweep < 2; ++sweep) {
           for (int j = 0; j < n; ++j) {
-            const bool diag = g.causal && (j == n - 1);
+            const bool diag = causal_m && (j == n - 1);
             uint32_t mw = 0xffffffffu;                           // key-padding bits of this warp's 32 keys
-            if (g.kmask) mw = __ldg(g.kmask + (int64_t)b * g.kmask_words + j * 4 + cq);
+            if (kmask_m) mw = __ldg(kmask_m + (int64_t)b * g.kmask_words + j * 4 + cq);
             const bool skip = (diag && diag_masked) || mw == 0u;
             ptx::mbar_wait(s_full(sr.idx), sr.phase);
             ptx::tc_fence_after();
@@ -567,7 +592,7 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             if (!skip && diag && diag_partial) mask_scores32(r, nvalid_d);
             if (!skip && mw != 0xffffffffu) mask_scores32_bits(r, mw);
             if (sweep == 0) {
-              if (!skip) stats32(r, m, mL, l);
+              if (!skip) stats32<MASKED>(r, m, mL, l);
             } else {
               ptx::mbar_wait(p_empty(pr.idx), pr.phase ^ 1);
               const uint32_t prow = sb + Cfg::kSmemP + (pr.idx * 2 + (cq >> 1)) * kSubTile + r_in * 128;
@@ -695,11 +720,13 @@ struct At2Cfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int KIND, bool FAST>
+template <int KIND, bool FAST, bool MASKED>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                              const __grid_constant__ CUtensorMap tmV, AttnArgs g) {
   using Cfg = At2Cfg;
+  const bool causal_m = MASKED ? (g.causal != 0) : true;
+  const uint32_t* const kmask_m = MASKED ? g.kmask : nullptr;
   constexpr int D = 64;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint32_t sb0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -756,7 +783,7 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   tmem += (uint32_t)grp * Cfg::kTmemGroup;                        // this group's 256 columns
 
   const int T = g.q_tiles;
-  const int pairs = g.causal ? (T + 1) >> 1 : T;
+  const int pairs = causal_m ? (T + 1) >> 1 : T;
   const int items = g.B * g.H * pairs;
   const int vb = (int)blockIdx.x * 2 + grp, vgrid = (int)gridDim.x * 2;      // virtual worker index: one per group
   const int kt_all = (g.S + Cfg::kBN - 1) / Cfg::kBN;                        // key tiles of a bidirectional row block
@@ -764,8 +791,8 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     const int bh = w / pairs, pr = w - bh * pairs;
     b = bh / g.H;
     h = bh - b * g.H;
-    qt_hi = g.causal ? T - 1 - pr : pr;
-    nsub = (g.causal && qt_hi != pr) ? 2 : 1;
+    qt_hi = causal_m ? T - 1 - pr : pr;
+    nsub = (causal_m && qt_hi != pr) ? 2 : 1;
   };
 
   if (warp == 0 || warp == 2) {
@@ -777,7 +804,7 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         decode(w, b, h, qt_hi, nsub);
         for (int sub = 0; sub < nsub; ++sub) {
           const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-          const int n = g.causal ? 2 * (qt + 1) : kt_all;                              // 64-key tiles up to and including the diagonal
+          const int n = causal_m ? 2 * (qt + 1) : kt_all;                              // 64-key tiles up to and including the diagonal
           ptx::mbar_wait(q_empty(qr.idx), qr.phase ^ 1);
           ptx::mbar_expect_tx(q_full(qr.idx), Cfg::kQTile);
           tma_load_4d(sb + Cfg::kSmemQ + qr.idx * Cfg::kQTile, &tmQ, q_full(qr.idx), 0, h, qt * kAtBM, b);
@@ -811,7 +838,7 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         decode(w, b, h, qt_hi, nsub);
         for (int sub = 0; sub < nsub; ++sub) {
           const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-          const int n = g.causal ? 2 * (qt + 1) : kt_all;
+          const int n = causal_m ? 2 * (qt + 1) : kt_all;
           ptx::mbar_wait(q_full(qr.idx), qr.phase);
           const uint32_t qbase = sb + Cfg::kSmemQ + qr.idx * Cfg::kQTile;
           auto issue_S = [&]() {
@@ -872,7 +899,7 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       decode(w, b, h, qt_hi, nsub);
       for (int sub = 0; sub < nsub; ++sub) {
         const int qt = sub ? (T - 1 - qt_hi) : qt_hi;
-        const int n = g.causal ? 2 * (qt + 1) : kt_all;
+        const int n = causal_m ? 2 * (qt + 1) : kt_all;
         const int row = qt * kAtBM + r_in;
         const int nvalid_d = lane + 1;
         const uint32_t xm = xch + xbuf * (2 * 2 * 128 * 4);   // [2][128] partial maxima
@@ -883,9 +910,9 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
           for (int j = 0; j < n; ++j) {
             // the last two 64-key tiles straddle the diagonal: 32-key column group c' = 2 * (j - (n - 2)) + cq of the 128 x 128
             // diagonal square is fully visible for c' < quarter, fully masked for c' > quarter, per-element for c' == quarter
-            const int cd = (g.causal && j >= n - 2) ? (2 * (j - (n - 2)) + cq) : -1;
+            const int cd = (causal_m && j >= n - 2) ? (2 * (j - (n - 2)) + cq) : -1;
             uint32_t mw = 0xffffffffu;                           // key-padding bits of this warp's 32 keys
-            if (g.kmask) mw = __ldg(g.kmask + (int64_t)b * g.kmask_words + j * 2 + cq);
+            if (kmask_m) mw = __ldg(kmask_m + (int64_t)b * g.kmask_words + j * 2 + cq);
             const bool skip = cd > quarter || mw == 0u;
             const bool partial = cd == quarter;
             ptx::mbar_wait(s_full(sr.idx), sr.phase);
@@ -906,7 +933,7 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
             if (partial && !skip) mask_scores32(r, nvalid_d);
             if (!skip && mw != 0xffffffffu) mask_scores32_bits(r, mw);
             if (sweep == 0) {
-              if (!skip) stats32(r, m, mL, l);
+              if (!skip) stats32<MASKED>(r, m, mL, l);
             } else {
               uint32_t wq[16];
               if (skip) {
@@ -1001,13 +1028,13 @@ int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, int64_t d, int64_t S, i
 static bool g_attn_precise_exp = false;       // true: libdevice expf for the numerators (bit-identical to torch's exp(x - max))
 static bool g_attn_dual = true;               // head_dim 64: the two-pipeline / P-in-TMEM kernel (false: the single-pipeline kernel, A/B)
 
-template <int KIND, bool FAST>
-static int launch_attention_dual_f(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
-                                   cudaStream_t st) {
+template <int KIND, bool FAST, bool MASKED>
+static int launch_attention_dual_fm(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
+                                    cudaStream_t st) {
   static PerDevice<bool> attr_pd;
   bool& attr = attr_pd.get();
   if (!attr) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_dual_kernel<KIND, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_dual_kernel<KIND, FAST, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        At2Cfg::kSmemBytes));
     attr = true;
   }
@@ -1015,24 +1042,30 @@ static int launch_attention_dual_f(const CUtensorMap& tq, const CUtensorMap& tk,
   const int grid = std::min((items + 1) / 2, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
-    attention_causal_dual_kernel<KIND, FAST><<<grid, kAtThreads, At2Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
+    attention_causal_dual_kernel<KIND, FAST, MASKED><<<grid, kAtThreads, At2Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
+}
+template <int KIND, bool FAST>
+static int launch_attention_dual_f(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
+                                   cudaStream_t st) {
+  return (g.causal && !g.kmask) ? launch_attention_dual_fm<KIND, FAST, false>(tq, tk, tv, g, st)
+                                : launch_attention_dual_fm<KIND, FAST, true>(tq, tk, tv, g, st);
 }
 template <int KIND>
 static int launch_attention_dual(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g, cudaStream_t st) {
   return g_attn_precise_exp ? launch_attention_dual_f<KIND, false>(tq, tk, tv, g, st) : launch_attention_dual_f<KIND, true>(tq, tk, tv, g, st);
 }
 
-template <int KIND, int D, bool FAST>
-static int launch_attention_f(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
-                              cudaStream_t st) {
+template <int KIND, int D, bool FAST, bool MASKED>
+static int launch_attention_fm(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
+                               cudaStream_t st) {
   using Cfg = AtCfg<D>;
   static PerDevice<bool> attr_pd;
   bool& attr = attr_pd.get();
   if (!attr) {
-    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_kernel<KIND, D, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BQ_CUDA_CHECK(cudaFuncSetAttribute(attention_causal_kernel<KIND, D, FAST, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr = true;
   }
@@ -1040,10 +1073,16 @@ static int launch_attention_f(const CUtensorMap& tq, const CUtensorMap& tk, cons
   const int grid = std::min(items, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
-    attention_causal_kernel<KIND, D, FAST><<<grid, kAtThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
+    attention_causal_kernel<KIND, D, FAST, MASKED><<<grid, kAtThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
+}
+template <int KIND, int D, bool FAST>
+static int launch_attention_f(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnArgs& g,
+                              cudaStream_t st) {
+  return (g.causal && !g.kmask) ? launch_attention_fm<KIND, D, FAST, false>(tq, tk, tv, g, st)
+                                : launch_attention_fm<KIND, D, FAST, true>(tq, tk, tv, g, st);
 }
 
 template <int KIND, int D>

@@ -219,11 +219,136 @@ __global__ void __launch_bounds__(256) softmax_quant_kernel(SmqArgs a) {
   }
 }
 
+// ---- v2 (rows of up to 8192 keys): the row lives in SHARED memory, loops are rolled.
+// v1 above keeps a 2048-key row in 64 registers per lane and unrolls everything: 118 registers (16 warps per SM), 6700 static
+// instructions (107 KB of code: 2 of every 10 issue slots lost to instruction fetch) and ~11 divergence-capable branches per chunk from
+// the inlined checked quantizer — 60 executed instructions per visible score, 0.69 ms per Llama-7B layer (profiles/r02_ncu_softmax_quant_v1.json).
+// Here: the visible part of the row arrives by cp.async (no registers), three short rolled passes (max / exp + sum / normalise +
+// quantise) read and write it in place, the block_log quantiser of a PROBABILITY (>= 0: no sign handling) is branch-free — rint(log2)
+// from the exponent field with the distance to the sqrt(2) cliff min-accumulated and tested once per chunk.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// 4 probabilities of one block (maximum bits m, shared by the block's 4 lanes) -> quantised values
+template <int KIND>
+__device__ __forceinline__ float4 quant4_probs(float4 p, uint32_t m, const FmtParams& f) {
+  if (KIND != kBlockLog) return quant4_block<KIND>(p, m, f);
+  if (m == 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!(f.fast_fmt && m < 0x7f800000u && m >= 0x00800000u)) return quant4_block<KIND>(p, m, f);
+  int b = f.eb_top_i - ceil_log2_i(__uint_as_float(m));
+  b = min(max(b, 0), f.bias_hi_i);
+  const int i0 = -b, i1 = f.eb_top_i - b;
+  if (i1 > 127 || i1 < -125) return quant4_block<KIND>(p, m, f);
+  // delta = 0.1 * 2^emin (log.py:49-52): 2^emin is a normal number, a denormal (emin >= -149) or 0
+  const uint32_t p2 = i0 >= -126 ? (uint32_t)(i0 + 127) << 23 : (i0 >= -149 ? 1u << (i0 + 149) : 0u);
+  const float delta = __fmul_rn(__uint_as_float(p2), 0.1f);
+  const int lo = max(i0 + 127, 0), hi = i1 + 127;          // biased exponents; 0 = "below 2^-126": flushed (carrier rule)
+  uint32_t zacc = 0xffffffffu;
+  const int e0 = min(max(rint_log2_biased_f<true>(__fadd_rn(p.x, delta), zacc), lo), hi);
+  const int e1 = min(max(rint_log2_biased_f<true>(__fadd_rn(p.y, delta), zacc), lo), hi);
+  const int e2 = min(max(rint_log2_biased_f<true>(__fadd_rn(p.z, delta), zacc), lo), hi);
+  const int e3 = min(max(rint_log2_biased_f<true>(__fadd_rn(p.w, delta), zacc), lo), hi);
+  if (zone_hit<kBlockLog>(zacc)) return quant4_block<KIND>(p, m, f);          // an element within 2^-13 of the sqrt(2) cliff: checked path
+  return make_float4(__int_as_float(e0 << 23), __int_as_float(e1 << 23), __int_as_float(e2 << 23), __int_as_float(e3 << 23));
+}
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__(256) softmax_quant_smem_kernel(SmqArgs a, int warps_per_cta) {
+  extern __shared__ __align__(16) uint8_t smq_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t rowb = (uint32_t)__cvta_generic_to_shared(smq_smem) + (uint32_t)warp * (uint32_t)a.Sk * 4u;
+  const int64_t nw = (int64_t)gridDim.x * warps_per_cta;
+  const int64_t rows = (int64_t)a.batch * a.Sq;
+  const int nchunk = a.Sk >> 2;
+  for (int64_t row = (int64_t)blockIdx.x * warps_per_cta + warp; row < rows; row += nw) {
+    const int bi = (int)(row / a.Sq), qi = (int)(row - (int64_t)bi * a.Sq);
+    const float* sr = a.s + (int64_t)bi * a.ss + (int64_t)qi * a.lds;
+    __nv_bfloat16* pr = a.p + (int64_t)bi * a.sp + (int64_t)qi * a.ldp;
+    const uint32_t* km = a.kmask ? a.kmask + (int64_t)(bi / a.heads) * a.kwords : nullptr;
+    const int kvis = a.causal ? qi + 1 : a.Sk;
+    const int zchunk = a.causal == 2 ? min(nchunk, ((qi >> 8) + 1) << 6) : nchunk;
+    const int vchunk = min(nchunk, (kvis + 3) >> 2);              // chunks that hold a visible key
+    for (int c = lane; c < vchunk; c += 32) cp_async16(rowb + 16u * c, sr + 4 * c);
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // pass 1: scale, mask (only chunks that need it), row maximum; the masked / scaled scores go back to the row
+    float m = kNegMax;
+    for (int c = lane; c < vchunk; c += 32) {
+      float4 v = lds4(rowb + 16u * c);
+      const int k0 = c << 2;
+      if (a.scale) { v.x = __fmul_rn(v.x, a.mul); v.y = __fmul_rn(v.y, a.mul); v.z = __fmul_rn(v.z, a.mul); v.w = __fmul_rn(v.w, a.mul); }
+      if (km || k0 + 3 >= kvis) {
+        uint32_t bits = 0xfu;
+        if (km) bits = (km[k0 >> 5] >> (k0 & 31)) & 0xfu;
+        if (k0 + 3 >= kvis) bits &= (1u << (kvis - k0)) - 1u;
+        v.x = (bits & 1u) ? fmaxf(v.x, kNegMax) : kNegMax; v.y = (bits & 2u) ? fmaxf(v.y, kNegMax) : kNegMax;
+        v.z = (bits & 4u) ? fmaxf(v.z, kNegMax) : kNegMax; v.w = (bits & 8u) ? fmaxf(v.w, kNegMax) : kNegMax;
+      }
+      if (a.scale || km || k0 + 3 >= kvis) sts4(rowb + 16u * c, v);
+      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    m = warp_max(fmaxf(m, kNegMax));
+    // a fully masked row (every score finfo.min) is uniform over ALL keys like the reference's: fill the rest of the row and take it along
+    int echunk = vchunk;
+    if (m == kNegMax) {
+      for (int c = vchunk + lane; c < nchunk; c += 32) sts4(rowb + 16u * c, make_float4(kNegMax, kNegMax, kNegMax, kNegMax));
+      echunk = nchunk;
+    }
+    // pass 2: numerators and their sum
+    float l = 0.f;
+    for (int c = lane; c < echunk; c += 32) {
+      float4 v = lds4(rowb + 16u * c);
+      v.x = exp_sm<FAST>(v.x, m); v.y = exp_sm<FAST>(v.y, m); v.z = exp_sm<FAST>(v.z, m); v.w = exp_sm<FAST>(v.w, m);
+      sts4(rowb + 16u * c, v);
+      l = __fadd_rn(l, __fadd_rn(__fadd_rn(v.x, v.y), __fadd_rn(v.z, v.w)));
+    }
+    const float inv_l = __frcp_rn(warp_add(l));
+    // pass 3: normalise, quantise inside the block of 16 (4 lanes), store; whole warps take part in the shuffles
+    const int e32 = (echunk + 31) & ~31;
+    for (int c = lane; c < e32; c += 32) {
+      float4 e = c < echunk ? lds4(rowb + 16u * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 p = make_float4(__fmul_rn(e.x, inv_l), __fmul_rn(e.y, inv_l), __fmul_rn(e.z, inv_l), __fmul_rn(e.w, inv_l));
+      uint32_t mb = max(max(f2u(p.x), f2u(p.y)), max(f2u(p.z), f2u(p.w)));
+      mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+      mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+      if (c < nchunk) {
+        const float4 q = quant4_probs<KIND>(p, mb, a.f);
+        st_stream2(pr + (c << 2), pack_bf16_rn(q.x, q.y), pack_bf16_rn(q.z, q.w));
+      }
+    }
+    for (int c = e32 + lane; c < zchunk; c += 32) st_stream2(pr + (c << 2), 0u, 0u);       // behind the diagonal: exact zeros
+    __syncwarp();                                            // the row slot is rewritten by the next row's cp.async
+  }
+}
+
+bool g_smq_smem_rows = true;          // false: the register-resident v1 kernel (A/B measurement, tests)
+
 template <int KIND, bool FAST>
 int launch_smq2(const SmqArgs& a, cudaStream_t st) {
   const int64_t rows = (int64_t)a.batch * a.Sq;
   const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)num_sms() * 8);
   LaunchScope ls(kKernSoftmaxQuant, st);
+  if (g_smq_smem_rows && a.Sk <= 8192) {
+    const int wpc = a.Sk <= 2048 ? 8 : (a.Sk <= 4096 ? 4 : 2);
+    const size_t smem = (size_t)wpc * a.Sk * 4;
+    static PerDevice<size_t> attr_pd;
+    size_t& attr = attr_pd.get();
+    if (smem > attr) {
+      BQ_CUDA_CHECK(cudaFuncSetAttribute(softmax_quant_smem_kernel<KIND, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      attr = 65536;
+    }
+    const int g2 = (int)std::min<int64_t>((rows + wpc - 1) / wpc, (int64_t)num_sms() * 8);
+    softmax_quant_smem_kernel<KIND, FAST><<<g2, wpc * 32, smem, st>>>(a, wpc);
+    return BQ_OK;
+  }
   if (a.Sk <= 512) softmax_quant_kernel<KIND, 4, FAST><<<grid, 256, 0, st>>>(a);
   else if (a.Sk <= 1024) softmax_quant_kernel<KIND, 8, FAST><<<grid, 256, 0, st>>>(a);
   else if (a.Sk <= 2048) softmax_quant_kernel<KIND, 16, FAST><<<grid, 256, 0, st>>>(a);
@@ -360,6 +485,8 @@ __global__ void __launch_bounds__(256) split3_transposed_kernel(const float* __r
 }  // namespace bq
 
 extern "C" {
+
+void bq_set_softmax_smem_rows(int on) { bq::g_smq_smem_rows = on != 0; }
 
 int bq_softmax_quantize(const bq_format* fp, const float* scores, void* P_bf16, int64_t batch, int64_t heads, int64_t Sq, int64_t Sk,
                         int64_t lds, int64_t ss, int64_t ldp, int64_t sp, float score_div, int32_t causal, const uint32_t* key_mask,

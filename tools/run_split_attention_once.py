@@ -21,6 +21,8 @@ def run():
 for _ in range(2):
     run()
 torch.cuda.synchronize()
+if len(sys.argv) > 3:
+    lib.bq_set_softmax_smem_rows(int(sys.argv[3]))
 if len(sys.argv) > 2:
     L.profile_enable(True)
     for _ in range(5):
