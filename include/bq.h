@@ -392,6 +392,8 @@ BQ_API int bq_token_ce_mean(const float* logits, int64_t n_seq, int64_t seq_len,
 BQ_API void bq_set_stream_quantizer(int on);           /* 0: force the per-slot quant_rows_kernel instead of the bulk-copy streaming kernel (A/B measurement) */
 BQ_API void bq_set_norm_warp_rows(int on);             /* 0: force the row-per-CTA norm_quant_kernel for H <= 2048 too (A/B measurement, tests) */
 BQ_API void bq_set_cta_pairs(int on);                  /* 0: force cta_group::1 GEMM tiles (A/B measurement) */
+BQ_API void bq_set_small_tiles(int on);                /* 0: always the largest GEMM tile the shape admits; 1 (default): 128 x 128 tiles when the
+                                                          problem would not fill the chip with larger ones (A/B measurement) */
 BQ_API int bq_kernel_count(void);
 BQ_API const char* bq_kernel_name(int kernel_id);
 BQ_API int64_t bq_launch_count(int kernel_id);          /* launches since load (kernel_id < 0: all kernels) */

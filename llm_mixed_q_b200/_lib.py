@@ -162,6 +162,8 @@ def load():
     lib.bq_set_stream_quantizer.argtypes = [ctypes.c_int]
     lib.bq_set_cta_pairs.restype = None
     lib.bq_set_cta_pairs.argtypes = [ctypes.c_int]
+    lib.bq_set_small_tiles.restype = None
+    lib.bq_set_small_tiles.argtypes = [ctypes.c_int]
     lib.bq_split2_f16_rows.restype = ctypes.c_int
     lib.bq_split2_f16_rows.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.bq_gemm_split16_tn.restype = ctypes.c_int

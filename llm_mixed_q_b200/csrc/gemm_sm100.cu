@@ -699,6 +699,25 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmAr
 // is built, because its box holds BN / CG rows.
 static bool g_pairs_enabled = true;
 static bool use_pairs(int64_t batch, int64_t M, int64_t N) { return g_pairs_enabled && batch == 1 && N > 128 && M > 128; }
+// Tile shape for a problem: {BN, pair}.  Large problems take the 256 x 256 CTA-pair tile (best operand reuse).  A problem whose
+// pair tiles do not even fill the 74 pairs once — the per-rank GEMMs of the tensor-parallel layer at 8 GPUs (M 4096, N 512: 32 pair
+// tiles, each a 28 us mainloop at K 4096 with 57 % of the chip idle) — is latency-bound by ONE tile's duration: 128 x 128 tiles on
+// single CTAs put every SM to work for half as long.  Cost model in units of per-SM tile work, waves x tile area x a measured
+// inefficiency factor of the narrower tiles (less operand reuse per shared-memory byte).
+static bool g_small_tiles = true;
+static void choose_tile(int64_t batch, int64_t M, int64_t N, int* BN, bool* pair) {
+  *BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  *pair = use_pairs(batch, M, N);
+  if (!g_small_tiles || N <= 128 || M <= 128) return;
+  const int64_t sms = num_sms();
+  auto waves = [](int64_t tiles, int64_t workers) { return (tiles + workers - 1) / workers; };
+  const int64_t t_pair = ((M + 255) / 256) * ((N + 255) / 256) * batch, t_256 = ((M + 127) / 128) * ((N + 255) / 256) * batch,
+                t_128 = ((M + 127) / 128) * ((N + 127) / 128) * batch;
+  const double c_pair = *pair ? (double)waves(t_pair, sms / 2) * 32768.0 : 1e30;
+  const double c_256 = (double)waves(t_256, sms) * 32768.0 * 1.05, c_128 = (double)waves(t_128, sms) * 16384.0 * 1.25;
+  if (c_128 < c_pair && c_128 < c_256) { *BN = 128; *pair = false; }
+  else if (c_256 < c_pair) { *BN = 256; *pair = false; }
+}
 
 template <bool EPI>
 static int launch_gemm_any(int BN, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st,
@@ -731,12 +750,13 @@ int gemm_bf16_tn_impl(const void* A, const void* B, float* C, const float* bias,
   if (batch > 1 && ((sa % 8) || (sb % 8))) return BQ_ERR_BAD_ARG;
   if (lda < K || ldb < K || ldc < N) return BQ_ERR_BAD_ARG;
   if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff || batch > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
-  const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  int BN;
+  bool pair;
+  choose_tile(batch, M, N, &BN, &pair);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, batch, lda, sa, kBM);
   if (rc) return rc;
   const bool bcast = (sb == 0) || batch == 1;
-  const bool pair = use_pairs(batch, M, N);
   rc = make_tmap_bf16_kmajor(&tmB, B, K, N, bcast ? 1 : batch, ldb, sb, pair ? 128 : BN);
   if (rc) return rc;
   GemmArgs g;
@@ -789,11 +809,12 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
     if (!ep->replicas[i] || ((uintptr_t)ep->replicas[i] % 16)) return BQ_ERR_BAD_ARG;
     g.epi.rep[i] = ep->replicas[i];
   }
-  const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  int BN;
+  bool pair;
+  choose_tile(1, M, N, &BN, &pair);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, 1, lda, 0, kBM);
   if (rc) return rc;
-  const bool pair = use_pairs(1, M, N);
   rc = make_tmap_bf16_kmajor(&tmB, B, K, N, 1, ldb, 0, pair ? 128 : BN);
   if (rc) return rc;
   g.C = (float*)C; g.bias = ep->bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = 1;
@@ -821,11 +842,12 @@ int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias
   for (int i = 0; i < n_terms; ++i)
     if (ta[i] < 0 || ta[i] >= planes_a || tb[i] < 0 || tb[i] >= planes_b) return BQ_ERR_BAD_ARG;
   if (causal < 0 || causal > 2 || (causal == 1 && M != N) || (causal == 2 && M != K)) return BQ_ERR_BAD_ARG;
-  const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  int BN;
+  bool pair;
+  choose_tile(batch, M, N, &BN, &pair);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, planes_a * batch, K, M * K, kBM);     // 16-bit elements: the map only moves bytes
   if (rc) return rc;
-  const bool pair = use_pairs(batch, M, N);
   rc = make_tmap_bf16_kmajor(&tmB, B, K, N, planes_b * batch, K, N * K, pair ? 128 : BN);
   if (rc) return rc;
   GemmArgs g;
@@ -847,6 +869,8 @@ int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias
 
 // debugging / measurement switch: 0 forces cta_group::1 tiles everywhere
 extern "C" void bq_set_cta_pairs(int on) { bq::g_pairs_enabled = on != 0; }
+// A/B switch: 0 = always the largest tile the shape admits (round-1 behaviour), 1 (default) = cost model of choose_tile
+extern "C" void bq_set_small_tiles(int on) { bq::g_small_tiles = on != 0; }
 
 extern "C" int bq_gemm_split16_tn(const void* A_planes_f16, const void* B_planes_f16, float* C, const float* bias,
                                   const float* a_inv_scale, const float* b_inv_scale, int64_t M, int64_t N, int64_t K,

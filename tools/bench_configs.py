@@ -145,6 +145,51 @@ def config4(args, world, rank, dev):
 
 
 # ---------------------------------------------------------------------------------------------------
+def config_bert(args, world, rank, dev):
+    """BERT-base shape (12 layers, H 768, 12 heads x 64, I 3072) W6A6 block_fp sequence classification, seq 512: the bidirectional /
+    key-padded fused attention (bq_attention_masked) against the op-by-op attention of this package (S x S scores through HBM).
+    One third of the sequences is right-padded to 384 tokens."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.bert_quantized import BertQuantizedConfig, BertQuantizedForSequenceClassification
+
+    S, B = 512, args.batch
+    toml_path = os.path.join(ROOT, "configs", "bfp_w6a6.toml")
+    cfg = BertQuantizedConfig(quant_config=toml_path, num_labels=2)
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = BertQuantizedForSequenceClassification(cfg).eval()
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    ids = torch.randint(1000, cfg.vocab_size, (B, S), generator=g).to(dev)
+    am = torch.ones(B, S, dtype=torch.long, device=dev)
+    am[::3, 384:] = 0
+    K, W = args.steps, max(args.warmup, 2)
+    res = {}
+    for fused in (True, False):
+        model.bert.fused_attention = fused
+        with torch.no_grad():
+            for _ in range(W):
+                out = model(input_ids=ids, attention_mask=am)
+            barrier(world)
+            n0 = L.launch_counts()["attention_causal_kernel"]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                out = model(input_ids=ids, attention_mask=am)
+            e1.record()
+            barrier(world)
+        res[fused] = (max_over_ranks(e0.elapsed_time(e1), world, dev) / K, (L.launch_counts()["attention_causal_kernel"] - n0) // K,
+                      out.logits.float().cpu())
+    ms = res[True][0]
+    emit({"metric": "W6A6-BFP fwd tokens/s (BERT-base, seq 512)", "value": B * S * world / (ms / 1e3), "unit": "tokens/s", "n_gpus": world,
+          "steps": K, "warmup": W, "ms_per_step": ms, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+          "config": {"workload": f"BERT-base shape W6A6 block_fp sequence classification, seq 512, batch {B} per GPU, 1/3 of the rows "
+                                 "right-padded to 384 tokens (key-padding mask)", "toml": os.path.relpath(toml_path, ROOT)},
+          "fused_attention_launches_per_step": res[True][1], "op_by_op_attention_ms_per_step": res[False][0],
+          "op_by_op_tokens_per_s": B * S * world / (res[False][0] / 1e3),
+          "max_abs_dlogit_fused_vs_op_by_op": float((res[True][2] - res[False][2]).abs().max())}, rank)
+
+
+# ---------------------------------------------------------------------------------------------------
 def config5(args, world, rank, dev):
     from llm_mixed_q_b200 import _lib as L
     from llm_mixed_q_b200.dist import ColumnParallelLinear, PeerArena
@@ -233,7 +278,7 @@ def config5(args, world, rank, dev):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[4, 5])
+    ap.add_argument("--config", type=int, required=True, choices=[4, 5, 0], help="4 / 5: BASELINE configs[3] / [4]; 0: BERT-base")
     ap.add_argument("--format", default="both", choices=["block_minifloat", "block_log", "both"])
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers")
@@ -248,7 +293,7 @@ def main():
     from llm_mixed_q_b200 import _lib as L
 
     L.load()
-    (config4 if args.config == 4 else config5)(args, world, rank, dev)
+    {4: config4, 5: config5, 0: config_bert}[args.config](args, world, rank, dev)
     if world > 1:
         dist.destroy_process_group()
 
