@@ -351,6 +351,30 @@ def column_parallel_block(device, dist, world, rank, pk, tokens_list=(4096, 1638
                             "frac_of_n_x_sustained_bf16": flops / (ms / 1e3) / 1e12 / (pk["tf_sustained"] * world),
                             "per_op_ms_rank0": per_op}
                 del out
+                if mode == "fused":
+                    # the same layer call replayed from a CUDA graph (the peer barrier keeps its count on the device, so it can be
+                    # captured): ~20 launches of 20-200 us each are issued from Python in the eager number above
+                    try:
+                        side = torch.cuda.Stream(device)
+                        side.wait_stream(torch.cuda.current_stream(device))
+                        with torch.cuda.stream(side):
+                            for _ in range(2):
+                                tp(h, mode=mode)
+                        torch.cuda.current_stream(device).wait_stream(side)
+                        dist.barrier(); torch.cuda.synchronize()
+                        gr = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr):
+                            gout = tp(h, mode=mode)
+                        gms = timed(gr.replay)
+                        torch.cuda.synchronize()
+                        gsame = all_true(bool(torch.equal(ref.view(torch.int32), gout.view(torch.int32))) and not arena.timed_out())
+                        pt[mode].update({"graph_replay_layer_ms": gms, "graph_replay_bit_identical_to_1gpu": gsame,
+                                         "graph_replay_TFLOPs_job": flops / (gms / 1e3) / 1e12,
+                                         "graph_replay_frac_of_n_x_sustained_bf16": flops / (gms / 1e3) / 1e12 / (pk["tf_sustained"] * world)})
+                        del gr, gout
+                    except Exception as e:
+                        pt[mode]["graph_replay_error"] = f"{type(e).__name__}: {e}"
+                        torch.cuda.synchronize()
             sent = tp.nvlink_bytes_per_rank(M)
             pt["nvlink_bytes_sent_per_rank"] = sent
             pt["nvlink_floor_ms_at_770GBs"] = sent / 770e9 * 1e3

@@ -414,6 +414,8 @@ BQ_API int bq_profile_read(int kernel_id, double* total_ms, int64_t* launches);
  *                   caller identically on all ranks).  All writes issued by earlier work on `stream` (including
  *                   epilogue stores into peers) are visible to the peers' later work.  A wait longer than
  *                   timeout_ms sets word [BQ_PEER_FLAG_TIMEOUT] of the own block and returns (never hangs the GPU).
+ *                   epoch == 0: device-resident count (word [BQ_PEER_FLAG_EPOCH] of the own block, advanced by the kernel) — no
+ *                   per-call host state, so the launch can be captured in a CUDA graph and replayed.  Use one mode per flag block.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct bq_ipc_handle {
   unsigned char reserved[64];   /* cudaIpcMemHandle_t */
@@ -422,6 +424,7 @@ typedef struct bq_ipc_handle {
 } bq_ipc_handle;
 #define BQ_PEER_FLAG_WORDS 64
 #define BQ_PEER_FLAG_TIMEOUT 32
+#define BQ_PEER_FLAG_EPOCH 33      /* epoch == 0 passed to bq_peer_barrier[_ex]: the barrier count is kept (and advanced) here on the device */
 BQ_API int bq_ipc_export(const void* dev_ptr, bq_ipc_handle* out);
 BQ_API int bq_ipc_import(const bq_ipc_handle* h, void** base, void** ptr);
 BQ_API int bq_ipc_release(void* base);

@@ -44,8 +44,20 @@ struct PeerSignals { uint32_t* blk[8]; };
 // write this GPU issued before the barrier (kernel boundary + the release) is visible to p once p observes the count;
 // (2) acquire-wait for word [p] of the own block to reach `epoch`.  Counters only grow, so there is no reset race; the
 // comparison is on the signed difference (wrap-safe).
+// epoch == 0: the count lives in word [BQ_PEER_FLAG_EPOCH] of the own block and is advanced by the kernel — the launch carries no
+// per-call host state, so it can be captured in a CUDA graph and replayed (a host-side epoch would be frozen at capture time and
+// every replayed barrier would pass at once).
 __global__ void peer_barrier_kernel(PeerSignals s, int rank, int world, uint32_t epoch, uint64_t timeout_ns, uint32_t* host_flag) {
   const int p = threadIdx.x;
+  const bool dev_epoch = epoch == 0u;
+  if (dev_epoch) {
+    __shared__ uint32_t e;
+    if (p == 0) e = s.blk[rank][BQ_PEER_FLAG_EPOCH] + 1u;
+    __syncthreads();
+    epoch = e;
+    __syncthreads();
+    if (p == 0) s.blk[rank][BQ_PEER_FLAG_EPOCH] = epoch;          // only this rank's barrier kernels (stream-ordered) touch the word
+  }
   if (p < world && p != rank) {
     __threadfence_system();
     red_release_sys_add(s.blk[p] + rank, 1u);

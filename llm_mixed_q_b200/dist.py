@@ -229,17 +229,16 @@ class PeerArena:
                                "gone; results gathered since then are incomplete")
 
     def barrier(self):
-        """Stream-ordered flag barrier over peer memory (one tiny kernel; no NCCL).  The epoch is a HOST counter passed by value:
-        a captured CUDA graph would replay a stale epoch and every replayed barrier would pass at once, so capture is refused."""
-        if torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("PeerArena.barrier() cannot be captured in a CUDA graph (host-side epoch); run the tensor-parallel "
-                               "path eagerly")
+        """Stream-ordered flag barrier over peer memory (one tiny kernel; no NCCL).  The barrier count lives on the device (epoch 0 of
+        bq_peer_barrier_ex: word BQ_PEER_FLAG_EPOCH of the own flag block, advanced by the kernel), so the launch carries no per-call
+        host state and a forward that contains barriers can be captured in a CUDA graph and replayed — every rank must then replay
+        the same number of barriers."""
         self._raise_if_timed_out()
-        self.epoch += 1
+        self.epoch += 1                      # informational (number of barriers issued from the host)
         if self.world == 1:
             return
         L = self._L
-        L.check(self.lib.bq_peer_barrier_ex(self._signals, self.rank, self.world, self.epoch & 0xFFFFFFFF, self.TIMEOUT_MS,
+        L.check(self.lib.bq_peer_barrier_ex(self._signals, self.rank, self.world, 0, self.TIMEOUT_MS,
                                             self._host_flag.data_ptr(), L.stream_ptr(self.device)), "bq_peer_barrier_ex")
 
     def push(self, local: torch.Tensor, bases, col_offset_bytes: int):
