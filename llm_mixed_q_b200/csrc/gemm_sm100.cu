@@ -179,7 +179,7 @@ __device__ __forceinline__ void chunk_to_coalesced(const float (&v)[32], float4 
 // one 32-column chunk of one accumulator row through the fused epilogue
 template <int EM>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], const float4 (&res)[8], int row, int col0,
-                                               bool row_ok, uint32_t* scratch, int lane) {
+                                               bool row_ok, uint32_t* scratch, int lane, float* Cb) {
   const EpiArgs& e = g.epi;
   const int qmode = (EM == 1) ? e.qmode : (EM == 2 ? 0 : (EM == 3 ? 1 : 2));
   const bool out_bf16 = (EM == 1) ? (e.out_bf16 != 0) : (EM != 2);
@@ -228,7 +228,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     }
 #pragma unroll 1
     for (int p = -1; p < n_rep; ++p) {                           // -1: this rank's C, then the peers' copies of the gathered output
-      float* cp = (p < 0 ? g.C : reinterpret_cast<float*>(e.rep[p])) + col0 + c4;
+      float* cp = (p < 0 ? Cb : reinterpret_cast<float*>(e.rep[p])) + col0 + c4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = wrow0 + i * 4 + rsub;
@@ -280,7 +280,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     __syncwarp();                                                // scratch is reused by the next chunk
 #pragma unroll 1
     for (int p = -1; p < n_rep; ++p) {                           // -1: this rank's C, then the peers' copies
-      __nv_bfloat16* cp = (p < 0 ? reinterpret_cast<__nv_bfloat16*>(g.C) : reinterpret_cast<__nv_bfloat16*>(e.rep[p])) + col0 + c * 8;
+      __nv_bfloat16* cp = (p < 0 ? reinterpret_cast<__nv_bfloat16*>(Cb) : reinterpret_cast<__nv_bfloat16*>(e.rep[p])) + col0 + c * 8;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int rr = wrow0 + i * 8 + rsub;
@@ -297,11 +297,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     for (int j = 0; j < 4; ++j)
       o[j] = make_uint4(pack_bf16_rn(v[8 * j], v[8 * j + 1]), pack_bf16_rn(v[8 * j + 2], v[8 * j + 3]),
                         pack_bf16_rn(v[8 * j + 4], v[8 * j + 5]), pack_bf16_rn(v[8 * j + 6], v[8 * j + 7]));
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(g.C) + off;      // (replicas of a bf16 result took the coalesced path above)
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(Cb) + off;      // (replicas of a bf16 result took the coalesced path above)
 #pragma unroll
     for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(c)[j] = o[j];
   } else {
-    float* c = g.C + off;
+    float* c = Cb + off;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
 #pragma unroll 1
@@ -501,7 +501,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(rrow + (c + c_step) * 32 + 4 * j);
           }
           ptx::tmem_ld_wait();
-          epilogue_chunk<EPI>(g, r, res, row, col0, row_ok, scratch, lane);
+          epilogue_chunk<EPI>(g, r, res, row, col0, row_ok, scratch, lane, g.C + (int64_t)b * g.sc);      // batch b of a batched problem
         }
       } else {
         float* crow = g.C + (int64_t)b * g.sc + (int64_t)row * g.ldc;
@@ -861,6 +861,14 @@ int gemm_split_tn_impl(const void* A, const void* B, float* C, const float* bias
     if (ta[i] < 0 || ta[i] >= planes_a || tb[i] < 0 || tb[i] >= planes_b) return BQ_ERR_BAD_ARG;
     g.term_a[i] = (int8_t)ta[i];
     g.term_b[i] = (int8_t)tb[i];
+  }
+  // fp32 results of the bf16-plane products leave through the coalesced epilogue (32 x 32 chunk transposed in shared memory: full
+  // 128-byte row segments per store instruction) when the layout allows; the lane-per-row 16-byte stores of the plain epilogue
+  // bound the S x S score writes of the split attention (1 GB per Llama-7B layer)
+  if (!fp16 && !row_scale && (N % 32) == 0 && (ldc % 4) == 0 && ((uintptr_t)C % 16) == 0 && (batch == 1 || (sc % 4) == 0) &&
+      (!bias || ((uintptr_t)bias % 16) == 0)) {
+    g.epi.scale = 1.0f;
+    return launch_gemm_any<true>(BN, pair, tmA, tmB, g, st, kKernGemmSplit);
   }
   return launch_gemm_any<false>(BN, pair, tmA, tmB, g, st, kKernGemmSplit);
 }
