@@ -54,6 +54,11 @@ for w in (6, 4):
                     same = bool(torch.equal(y.view(torch.int32), ref.view(torch.int32)))
                     ms = timeit(lambda i: lin(xs[i % nbuf]), 20 if M >= 4096 else 50)
                     res[mode] = {"ms": round(ms, 5), "TFLOPs": round(flops / ms / 1e9, 1), "bit_identical_to_two_launch": same}
+                    if mode == "packed":
+                        # the packed form cannot hold the reference's pass-through weights (|w| <= 1e-8 stay UNQUANTISED fp32 values,
+                        # block_fp.py:93-94): bq_pack_weight counts them; with N(0, 0.02) weights that is ~4e-7 of the elements
+                        res[mode]["pass_through_weight_elements"] = int(lin._wq_packed[2]) if lin._wq_packed else None
+                        res[mode]["max_abs_diff_vs_two_launch"] = float((y - ref).abs().max())
                 finally:
                     lin_mod.FUSED_PROLOGUE = lin_mod.PACKED_WEIGHTS = False
             bits = lin.packed_bits_per_element()
