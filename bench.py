@@ -58,7 +58,9 @@ def gemm_traffic_from_profile():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, averaged over the six
     quantized-Linear launches of one OPT-1.3B layer in the committed `ncu --set full` capture (tools/ncu_layer.py, same shapes
     as this bench).  Returns (bytes_per_launch or None, source)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_layer_s9.json")
+    path = os.path.join(ROOT, "profiles", "r02_ncu_layer.json")        # latest committed capture (tools/gpu_call_r02.sh)
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_ncu_layer_s9.json")
     try:
         d = json.load(open(path))
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
