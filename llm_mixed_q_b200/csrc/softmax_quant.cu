@@ -299,7 +299,9 @@ __global__ void __launch_bounds__(256) softmax_quant_smem_kernel(SmqArgs a, int 
     // a fully masked row (every score finfo.min) is uniform over ALL keys like the reference's: fill the rest of the row and take it along
     int echunk = vchunk;
     if (m == kNegMax) {
-      for (int c = vchunk + lane; c < nchunk; c += 32) sts4(rowb + 16u * c, make_float4(kNegMax, kNegMax, kNegMax, kNegMax));
+      // (same chunk -> lane mapping as the passes below: a lane only ever touches chunks c = lane mod 32 of the row slot)
+      for (int c = lane; c < nchunk; c += 32)
+        if (c >= vchunk) sts4(rowb + 16u * c, make_float4(kNegMax, kNegMax, kNegMax, kNegMax));
       echunk = nchunk;
     }
     // pass 2: numerators and their sum

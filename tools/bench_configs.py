@@ -145,6 +145,40 @@ def config4(args, world, rank, dev):
 
 
 # ---------------------------------------------------------------------------------------------------
+def config1(args, world, rank, dev):
+    """BASELINE configs[0]: OPT-125M shape (the config class defaults), random init, W6A6 block_fp, 1 x 2048 tokens — the case the
+    reference itself runs on a CPU (oracle/gen_golden_opt125m.py: 44.7 s on 8 cores = 46 tokens/s) — and the same model at batch 8.
+    Parity of this model against the reference's own forward: tests/test_gpu_models.py::test_opt125m_config1_*."""
+    from llm_mixed_q_b200.models.opt_quantized import OPTQuantizedConfig, OPTQuantizedForCausalLM
+    from llm_mixed_q_b200.utils.graphs import GraphedForward
+
+    cfg = OPTQuantizedConfig(quant_config=os.path.join(ROOT, "configs", "bfp_w6a6.toml"), tie_word_embeddings=False)
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = OPTQuantizedForCausalLM(cfg).eval()
+    K, W = args.steps, max(args.warmup, 2)
+    for B in (1, 8):
+        g = torch.Generator(device="cpu").manual_seed(rank)
+        ids = torch.randint(0, cfg.vocab_size, (B, SEQ), generator=g).to(dev)
+        runner = GraphedForward(model, B, SEQ, device=dev)
+        for _ in range(W):
+            runner(ids)
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            runner(ids)
+        e1.record()
+        barrier(world)
+        ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / K
+        emit({"metric": "W6A6-BFP fwd tokens/s (OPT-125M)", "value": B * SEQ * world / (ms / 1e3), "unit": "tokens/s", "n_gpus": world,
+              "steps": K, "warmup": W, "ms_per_step": ms, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+              "config": {"workload": f"OPT-125M shape W6A6 block_fp full forward + loss, seq 2048, batch {B} per GPU", "mode":
+                         "cuda-graph replay" if runner.graph is not None else "eager", "loss": float(runner.loss)}}, rank)
+        del runner
+
+
+# ---------------------------------------------------------------------------------------------------
 def config_bert(args, world, rank, dev):
     """BERT-base shape (12 layers, H 768, 12 heads x 64, I 3072) W6A6 block_fp sequence classification, seq 512: the bidirectional /
     key-padded fused attention (bq_attention_masked) against the op-by-op attention of this package (S x S scores through HBM).
@@ -278,7 +312,7 @@ def config5(args, world, rank, dev):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[4, 5, 0], help="4 / 5: BASELINE configs[3] / [4]; 0: BERT-base")
+    ap.add_argument("--config", type=int, required=True, choices=[4, 5, 0, 1], help="1 / 4 / 5: BASELINE configs[0] / [3] / [4]; 0: BERT-base")
     ap.add_argument("--format", default="both", choices=["block_minifloat", "block_log", "both"])
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers")
@@ -293,7 +327,7 @@ def main():
     from llm_mixed_q_b200 import _lib as L
 
     L.load()
-    {4: config4, 5: config5, 0: config_bert}[args.config](args, world, rank, dev)
+    {4: config4, 5: config5, 0: config_bert, 1: config1}[args.config](args, world, rank, dev)
     if world > 1:
         dist.destroy_process_group()
 
