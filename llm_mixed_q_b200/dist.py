@@ -414,7 +414,7 @@ class TensorParallelOPTLayer(nn.Module):
         Hl, Fl = H // g, self.F // g
         c0, f0 = r * Hl, r * Fl
         plan = self.plan_of(S)
-        if plan is None:
+        if plan is None or plan.get("mode") == "split":
             raise NotImplementedError("TensorParallelOPTLayer needs a layer the fused path serves (PTQ block_fp / block_minifloat, "
                                       "[1,16] blocks, <= 8 significant bits)")
         fused = mode == "fused" and self.arena is not None and g > 1

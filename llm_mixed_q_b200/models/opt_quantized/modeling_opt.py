@@ -24,7 +24,9 @@ from ..quantize.quantized_functions.fp32_linear import fp32_linear
 from ..quantize.quantized_functions.loss import causal_lm_loss
 from ..quantize.quantized_functions.attention import (causal_key_mask, fusable as _attn_fusable, fused_causal_attention,
                                                       fused_causal_attention_q, output_quantizable)
-from ..quantize.quantized_functions.fused_glue import linear_input_format, norm_quantize, row_block16_format
+from ..quantize.quantized_functions.fused_glue import _NORM_KINDS, linear_input_format, norm_quantize, row_block16_format
+from ..quantize.quantized_functions.split_attention import rope_quantize_split, split_attention, splittable as _attn_splittable
+from ..quantize.quantized_modules.linear import quantize_operand_bf16
 from .configuration_opt import OPTQuantizedConfig
 
 
@@ -158,10 +160,18 @@ class OPTQuantizedDecoderLayer(nn.Module):
         at = self.self_attn
         plan = None
         H, d = self.embed_dim, at.head_dim
-        ok = (self.do_layer_norm_before and getattr(self, "activation_name", None) == "relu" and seq_len % 16 == 0
-              and H % 32 == 0 and self.fc1.out_features % 32 == 0
-              and self.self_attn_layer_norm.elementwise_affine and self.final_layer_norm.elementwise_affine
-              and _attn_fusable(at.quant_config["bmm_0"], at.quant_config["bmm_1"], d, seq_len))
+        common = (self.do_layer_norm_before and getattr(self, "activation_name", None) == "relu" and seq_len % 16 == 0
+                  and H % 32 == 0 and self.fc1.out_features % 32 == 0
+                  and self.self_attn_layer_norm.elementwise_affine and self.final_layer_norm.elementwise_affine)
+        ok = common and _attn_fusable(at.quant_config["bmm_0"], at.quant_config["bmm_1"], d, seq_len)
+        if common and not ok and _attn_splittable(at.quant_config["bmm_0"], at.quant_config["bmm_1"], d, seq_len):
+            # block_log: bmm_0 / bmm_1 keep k / v in fp32 (reference matmul.py:286-297) -> three-kernel attention
+            # (split_attention.py); the Linears' x-quantizers run inside LayerNorm / the fc1 epilogue (carrier rule, bq.h)
+            lin = lambda m, rows: linear_input_format(m, rows=rows, kinds=_NORM_KINDS)
+            fmts = dict(mode="split", q_in=lin(at.q_proj, seq_len), k_in=lin(at.k_proj, seq_len), v_in=lin(at.v_proj, seq_len),
+                        o_in=lin(at.out_proj, seq_len), fc1_in=lin(self.fc1, 1), fc2_in=lin(self.fc2, 1))
+            if all(v is not None for v in fmts.values()):
+                plan = fmts
         if ok:
             fmts = dict(
                 # q/k/v/out_proj see the 3-D [B, S, H] activation (reference modeling_opt.py:206-225, :327), fc1 / fc2 the
@@ -179,7 +189,29 @@ class OPTQuantizedDecoderLayer(nn.Module):
         return plan
 
     @torch.no_grad()
+    def _split_forward(self, h, plan, key_mask=None):
+        """Layer forward for configs whose bmms keep an fp32 operand (block_log): fused glue around the three-kernel attention."""
+        B, S, H = h.shape
+        at = self.self_attn
+        ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm
+        xq_q, xq_k, xq_v = norm_quantize(h, ln1.weight, ln1.bias, ln1.eps, [plan["q_in"], plan["k_in"], plan["v_in"]])
+        q = at.q_proj.forward_prequantized(xq_q, scale=at.scaling)                    # q_proj(x) * scaling, then bmm_0's x-quantizer
+        k = at.k_proj.forward_prequantized(xq_k)
+        v = at.v_proj.forward_prequantized(xq_v)
+        Qq, Kp = rope_quantize_split(q.view(B, S, H), k.view(B, S, H), None, None, None, None, at.quant_config["bmm_0"], at.num_heads)
+        o = split_attention(Qq, Kp, v.view(B, S, H), at.quant_config["bmm_1"], at.num_heads, 1.0, causal=True, key_mask=key_mask)
+        okind, okw = plan["o_in"]
+        oq = quantize_operand_bf16(o.view(B * S, H), okind, okw, [1, 16], True)       # out_proj's x-quantizer (exact)
+        h2 = at.out_proj.forward_prequantized(oq, residual=h)
+        (x1,) = norm_quantize(h2, ln2.weight, ln2.bias, ln2.eps, [plan["fc1_in"]])
+        a = self.fc1.forward_prequantized(x1.view(B * S, H), relu=True, out_format=plan["fc2_in"])
+        h3 = self.fc2.forward_prequantized(a, residual=h2.view(B * S, H))
+        return h3.view(B, S, H)
+
+    @torch.no_grad()
     def _fused_forward(self, h, plan, key_mask=None):
+        if plan.get("mode") == "split":
+            return self._split_forward(h, plan, key_mask)
         B, S, H = h.shape
         at = self.self_attn
         ln1, ln2 = self.self_attn_layer_norm, self.final_layer_norm

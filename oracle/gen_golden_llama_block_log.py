@@ -5,6 +5,7 @@ ORACLE — TEST INFRASTRUCTURE ONLY.  Golden for the block_log attention path (s
                                      batch of 3 x 96 tokens, one sequence right-padded: matmul_0 / matmul_1 quantise x only and keep
                                      k / v in fp32 (reference quantized_functions/matmul.py:286-297), causal + key-padding mask
                                      (models/llama_quantized/modeling_llama.py:309-337)
+  tests/golden/opt_small_bl8.npz     OPTQuantizedForCausalLM under block_log.toml, head_dim 64, same token batch (right-padded row)
 
 Usage (authoring container only):  python oracle/gen_golden_llama_block_log.py
 """
@@ -48,6 +49,23 @@ def main():
                 loss=np.array(float(o.loss)), logits_unpadded_row0=o2.logits.numpy().copy(), loss_unpadded_row0=np.array(float(o2.loss)))
     np.savez_compressed(os.path.join(GOLD, "llama_small_bl8.npz"), **arrs)
     print("llama_small_bl8", float(o.loss), float(o2.loss))
+
+    # OPT under block_log.toml, head_dim 64: bmm_0 / bmm_1 quantise x only (q is scaled before bmm_0, modeling_opt.py:206-246)
+    torch.manual_seed(0)
+    ocfg = m.opt_cfg.OPTQuantizedConfig(hidden_size=128, num_hidden_layers=2, ffn_dim=256, num_attention_heads=2, vocab_size=512,
+                                        max_position_embeddings=128, quant_config=deepcopy(qc), pad_token_id=1, init_std=0.05)
+    omodel = m.opt.OPTQuantizedForCausalLM(ocfg).eval()
+    arrs = {"sd::" + k: v.detach().cpu().numpy().copy() for k, v in omodel.state_dict().items()}
+    oids = ids.clone()
+    oids[am == 0] = 1
+    olabels = oids.clone()
+    olabels[am == 0] = -100
+    with torch.no_grad():
+        o = omodel(input_ids=oids, attention_mask=am, labels=olabels)
+    arrs.update(input_ids=oids.numpy(), attention_mask=am.numpy(), labels=olabels.numpy(), logits=o.logits.numpy().copy(),
+                loss=np.array(float(o.loss)))
+    np.savez_compressed(os.path.join(GOLD, "opt_small_bl8.npz"), **arrs)
+    print("opt_small_bl8", float(o.loss))
 
 
 if __name__ == "__main__":

@@ -261,6 +261,45 @@ def test_llama_block_log_runs_the_split_path_and_matches_reference_forward():
     assert res[(True, "")] <= 1.5 * res[(False, "")] + 1e-3, res
 
 
+def test_opt_block_log_runs_the_split_path_and_matches_reference_forward():
+    """OPT under block_log.toml (q scaled before bmm_0, LayerNorm, ReLU -> fc2's x-quantizer in the fc1 epilogue: all-zero blocks after
+    the ReLU exercise the carrier rule).  Golden = the unmodified reference's forward of a right-padded batch."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.opt_quantized import OPTQuantizedConfig, OPTQuantizedForCausalLM
+
+    with open(os.path.join(GOLD, "configs.json")) as f:
+        qc = json.load(f)["raw"]["block_log.toml"]
+    z = np.load(os.path.join(GOLD, "opt_small_bl8.npz"))
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    ids, am, labels = (torch.from_numpy(z[k]).cuda() for k in ("input_ids", "attention_mask", "labels"))
+    valid = am.bool().cpu()
+    ref_logits, ref_loss = torch.from_numpy(z["logits"]), float(z["loss"])
+    res = {}
+    for fused in (True, False):
+        cfg = OPTQuantizedConfig(hidden_size=128, num_hidden_layers=2, ffn_dim=256, num_attention_heads=2, vocab_size=512,
+                                 max_position_embeddings=128, quant_config=json.loads(json.dumps(qc)), pad_token_id=1, init_std=0.05,
+                                 tie_word_embeddings=False)
+        model = OPTQuantizedForCausalLM(cfg).eval()
+        missing, _ = model.load_state_dict(sd, strict=False)
+        assert not missing, missing
+        model = model.cuda()
+        model.model.decoder.fused_attention = fused
+        model.model.decoder.fused_glue = fused
+        if fused:
+            plan = model.model.decoder.layers[0]._fused_plan(ids.shape[1])
+            assert plan is not None and plan["mode"] == "split" and plan["fc2_in"][0] == "block_log"
+        n0 = L.launch_counts()["softmax_quant_kernel"]
+        with torch.no_grad():
+            out = model(input_ids=ids, attention_mask=am, labels=labels)
+        assert L.launch_counts()["softmax_quant_kernel"] - n0 == (2 if fused else 0)
+        assert abs(float(out.loss) - ref_loss) <= 5e-3 * abs(ref_loss), (fused, float(out.loss), ref_loss)
+        err = (out.logits.cpu() - ref_logits).abs()[valid]
+        spread = float(ref_logits[valid].std())
+        res[fused] = float(err.mean()) / spread
+        assert float(err.mean()) <= 0.05 * spread, (fused, float(err.mean()), float(err.max()), spread)
+    assert res[True] <= 1.5 * res[False] + 1e-3, res
+
+
 def test_norm_quantize_block_log_carrier_rule():
     from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import norm_quantize
 
