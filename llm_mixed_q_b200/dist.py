@@ -398,6 +398,7 @@ class TensorParallelOPTLayer(nn.Module):
         cut = lambda lin: ColumnParallelLinear.from_linear(lin, group=group, gather_output=False, world=world, rank=rank).local
         self.q_proj, self.k_proj, self.v_proj, self.out_proj = cut(at.q_proj), cut(at.k_proj), cut(at.v_proj), cut(at.out_proj)
         self.fc1, self.fc2 = cut(layer.fc1), cut(layer.fc2)
+        self.fc1_exchange = "push"             # or "epilogue": remote stores from the fc1 GEMM epilogue (A/B)
 
     def nvlink_bytes_per_rank(self, tokens: int, mode: str = "fused") -> int:
         """Bytes one rank SENDS per layer call."""
@@ -461,8 +462,16 @@ class TensorParallelOPTLayer(nn.Module):
         mark("ln2")
         if fused:
             a_full, bases = arena.take((M, self.F), torch.bfloat16)
-            self.fc1.forward_prequantized(x1, relu=True, out_format=plan["fc2_in"], out=a_full[:, f0:f0 + Fl],
-                                          peer_out_ptrs=[b + f0 * 2 for i, b in enumerate(bases) if i != r])
+            if self.fc1_exchange == "epilogue":
+                self.fc1.forward_prequantized(x1, relu=True, out_format=plan["fc2_in"], out=a_full[:, f0:f0 + Fl],
+                                              peer_out_ptrs=[b + f0 * 2 for i, b in enumerate(bases) if i != r])
+            else:
+                # bf16 slab: the epilogue's remote stores are 64-byte row segments (32 columns x 2 bytes per warp row) and sustain
+                # ~400 GB/s; the push kernel's 512-byte warp stores reach 560-650 GB/s (profiles/r02_peer_exchange_n8.json) — store
+                # locally, then push: fc1 0.34 -> 0.26 ms at 4096 tokens on 8 GPUs
+                slab = a_full[:, f0:f0 + Fl]
+                self.fc1.forward_prequantized(x1, relu=True, out_format=plan["fc2_in"], out=slab)
+                arena.push(slab, bases, f0 * 2)
             arena.barrier()
         else:
             a_l = self.fc1.forward_prequantized(x1, relu=True, out_format=plan["fc2_in"])
