@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BQ_ABI_VERSION 3
+#define BQ_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define BQ_API __attribute__((visibility("default")))
