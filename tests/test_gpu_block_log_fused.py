@@ -300,6 +300,92 @@ def test_opt_block_log_runs_the_split_path_and_matches_reference_forward():
     assert res[True] <= 1.5 * res[False] + 1e-3, res
 
 
+@pytest.mark.parametrize("toml", ["llama_w4a4_block_log.toml", "block_log.toml"])
+def test_llama_7b_shape_block_log_layer_split_path_vs_op_by_op_stage_by_stage(toml):
+    """BASELINE configs[3] geometry (H 4096, 32 heads x 128, I 11008, 2048 tokens), one decoder layer: the split path (fused glue +
+    three-kernel attention) against this package's op-by-op path — itself held to the unmodified reference at head_dim 64 above — on
+    the same weights, STAGE BY STAGE on identical stage inputs.  A power-of-two format has no mantissa: a rounding-boundary flip is a
+    factor of 2 on that element and the layer amplifies a seed of 1e-7 (two ulps on the input) to 1e-3 of its update and a seed of
+    1e-4 to a few per cent (measured below), so only the per-stage comparison can tell an error from that noise: a wrong scale, mask
+    or block orientation would show as >= 1e-2 at its own stage."""
+    from llm_mixed_q_b200.models.llama_quantized import LlamaQuantizedConfig, LlamaQuantizedForCausalLM
+    from llm_mixed_q_b200.models.quantize import get_quantized_func
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import norm_quantize, silu_mul_quantize
+    from llm_mixed_q_b200.models.quantize.quantized_functions.split_attention import rope_quantize_split, split_attention
+    from llm_mixed_q_b200.models.quantize.quantized_modules.linear import quantize_operand_bf16
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if toml == "block_log.toml":
+        with open(os.path.join(GOLD, "configs.json")) as f:
+            qc = json.load(f)["raw"]["block_log.toml"]
+    else:
+        qc = os.path.join(root, "configs", toml)
+    cfg = LlamaQuantizedConfig(quant_config=qc, num_hidden_layers=1, vocab_size=1024)
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        model = LlamaQuantizedForCausalLM(cfg).eval()
+    layer = model.model.layers[0]
+    at, mlp, qcfg = layer.self_attn, layer.mlp, layer.self_attn.quant_config
+    g = torch.Generator(device="cuda").manual_seed(1)
+    h = torch.randn(1, 2048, 4096, device="cuda", generator=g)
+    B, S, H = h.shape
+    nh, d = at.num_heads, at.head_dim
+    pos = torch.arange(S, device="cuda")[None]
+    plan = layer._fused_plan(S)
+    assert plan is not None and plan["mode"] == "split"
+    rms = lambda t: float(t.double().pow(2).mean().sqrt())
+    rel = lambda a, b: rms(a.float() - b.float()) / (rms(b.float()) + 1e-30)
+    neg = torch.finfo(torch.float32).min
+    with torch.no_grad():
+        # 1. RMSNorm + x-quantizers + q / k / v projections
+        n1 = layer.input_layernorm
+        x = n1(h)
+        q_o, k_o, v_o = at.q_proj(x), at.k_proj(x), at.v_proj(x)
+        xq, xk, xv = norm_quantize(h, n1.weight, None, n1.variance_epsilon, [plan["q_in"], plan["k_in"], plan["v_in"]])
+        for f_, o_ in ((at.q_proj.forward_prequantized(xq), q_o), (at.k_proj.forward_prequantized(xk), k_o),
+                       (at.v_proj.forward_prequantized(xv), v_o)):
+            assert rel(f_.view_as(o_), o_) <= 1e-3                      # statistics summed in another order: a handful of flips
+        # 2. attention on the SAME q, k, v
+        qs, ks, vs = (t.view(B, S, nh, d).transpose(1, 2) for t in (q_o, k_o, v_o))
+        cos, sin = at.rotary_emb(vs, seq_len=S)
+        rope_cfg = qcfg["rotary_positional_encoding"]
+        qr, kr = get_quantized_func("rotary_positional_encoding", rope_cfg)(qs, ks, cos, sin, pos, rope_cfg)
+        sc = get_quantized_func("matmul", qcfg["matmul_0"])(qr, kr.transpose(2, 3), config=qcfg["matmul_0"]) / math.sqrt(d)
+        mask = torch.triu(torch.full((S, S), neg, device="cuda"), diagonal=1)[None, None]
+        p = torch.softmax(torch.max(sc + mask, torch.tensor(neg, device="cuda")), dim=-1, dtype=torch.float32)
+        o_o = get_quantized_func("matmul", qcfg["matmul_1"])(p, vs, config=qcfg["matmul_1"]).transpose(1, 2).reshape(B, S, H)
+        del sc, p
+        Qq, Kp = rope_quantize_split(q_o.view(B, S, H), k_o.view(B, S, H), cos, sin, None, rope_cfg, qcfg["matmul_0"], nh)
+        o_s = split_attention(Qq, Kp, v_o.view(B, S, H), qcfg["matmul_1"], nh, math.sqrt(d), causal=True)
+        r_att = rel(o_s, o_o)
+        assert r_att <= 2e-4, r_att                                      # flips of single probabilities (row sum order, exp mode)
+        assert abs(float((o_s - o_o).mean())) <= 1e-5 * rms(o_o)
+        # 3. everything after the attention is bit-identical on identical inputs
+        h2_o = h + at.o_proj(o_o)
+        okind, okw = plan["o_in"]
+        h2_f = at.o_proj.forward_prequantized(quantize_operand_bf16(o_o.reshape(B * S, H), okind, okw, [1, 16], True), residual=h).view(B, S, H)
+        assert torch.equal(h2_f, h2_o)
+        n2 = layer.post_attention_layernorm
+        x2 = n2(h2_o)
+        g_o, u_o = mlp.gate_proj(x2), mlp.up_proj(x2)
+        xg, xu = norm_quantize(h2_o, n2.weight, None, n2.variance_epsilon, [plan["gate_in"], plan["up_in"]])
+        g_f, u_f = mlp.gate_proj.forward_prequantized(xg), mlp.up_proj.forward_prequantized(xu)
+        assert rel(g_f.view_as(g_o), g_o) <= 1e-3 and rel(u_f.view_as(u_o), u_o) <= 1e-3
+        d_o = mlp.down_proj(mlp.act_fn(g_o) * u_o)
+        d_f = mlp.down_proj.forward_prequantized(silu_mul_quantize(g_o.view(B * S, -1), u_o.view(B * S, -1), plan["down_in"])).view(B, S, H)
+        assert torch.equal(d_f, d_o)
+        # 4. the whole layer, with the amplification control (op-by-op against itself on an input moved by ~2 ulp)
+        mask4 = mask.expand(B, 1, S, S)
+        ref, _ = layer(h, attention_mask=mask4, position_ids=pos, causal_only=False)
+        got = layer._fused_forward(h, pos, plan, default_positions=True)
+        ctl, _ = layer(h * (1.0 + 2.0 ** -22), attention_mask=mask4, position_ids=pos, causal_only=False)
+    upd = ref - h
+    r_layer, r_ctl = rms(got - ref) / rms(upd), rms(ctl - ref - h * 2.0 ** -22) / rms(upd)
+    print(f"[{toml}] attention stage {r_att:.2e}; layer update: split vs op-by-op {r_layer:.4f}, op-by-op vs itself (+2 ulp on the input) {r_ctl:.4f}")
+    assert torch.isfinite(got).all() and r_layer <= 0.10, r_layer
+    assert abs(float((got - ref).mean())) <= 0.01 * rms(upd)            # no systematic offset
+
+
 def test_norm_quantize_block_log_carrier_rule():
     from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import norm_quantize
 
