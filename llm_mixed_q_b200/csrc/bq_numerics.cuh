@@ -216,6 +216,16 @@ template <bool NC> __device__ __forceinline__ int rint_log2_biased_f(float x, ui
   else if (key < 2 * kZone) return (b >> 23) ? rint_log2_slow(x) + 127 : 0;
   return (int)((b + (0x7fffffu - kSqrt2Mant)) >> 23);
 }
+// rint(log2f(x)) + 127 for ANY finite x >= 0 of a block whose maximum is below 2^100, denormals included: the argument is scaled by
+// 2^24 (exact), which turns every denormal into a normal number with the same significand; the shortcut then reads the exponent field
+// and the sqrt(2) comparison as before.  Near the cliff (NC = false) libdevice's log2f is evaluated on the ORIGINAL value, like the
+// reference does.  x == 0 returns -24 + 0 (callers clamp from below and select on the sign word).
+template <bool NC> __device__ __forceinline__ int rint_log2_biased_deep(float x, uint32_t& zacc) {
+  const uint32_t b = __float_as_uint(__fmul_rn(x, 16777216.0f)), key = (b & 0x7fffffu) - kSqrt2Mant + kZone;
+  if (NC) zacc = min(zacc, key);
+  else if (key < 2 * kZone) return rint_log2_slow(x) + 127;
+  return (int)((b + (0x7fffffu - kSqrt2Mant)) >> 23) - 24;
+}
 __device__ __forceinline__ float pow2_i(int e) { return __int_as_float((e + 127) << 23); }   // e in [-126, 127]
 // rintf(t) for |t| < 2^22 as two full-rate FADDs (FRND runs on the quarter-rate conversion pipe): adding 1.5 * 2^23 moves t into
 // a binade whose ulp is 1, the addition itself rounds to nearest-even, the subtraction is exact.
@@ -224,6 +234,7 @@ __device__ __forceinline__ float rint_small(float t) { return __fsub_rn(__fadd_r
 
 struct FastState {
   bool ok;
+  bool deep;      // block_log: emin < -126 — outputs and the log2 argument reach into the denormal range (block maxima <= 1 at width 8)
   float f0, f1;   // block_fp: scale 2^(m-E), step 2^(E-m)            block_log: delta, 2^emin
   int i0, i1, i2; // block_log: emin, emax (integers); minifloat: biased step-exponent clamp [i0, i1], normal threshold i2
   float c0, c1, hi;   // block_fp: 1e-9f * f0, -kRintMagic * f1, kRintMagic + qmax  (all exact)
@@ -234,6 +245,7 @@ template <int KIND>
 __device__ __forceinline__ FastState fast_state(uint32_t mbits, const FmtParams& p) {
   FastState s;
   s.ok = false;
+  s.deep = false;
   s.f0 = s.f1 = 0.f;
   s.i0 = s.i1 = s.i2 = 0;
   s.c0 = s.c1 = s.hi = 0.f;
@@ -273,8 +285,12 @@ __device__ __forceinline__ FastState fast_state(uint32_t mbits, const FmtParams&
     b = min(max(b, 0), p.bias_hi_i);
     s.i0 = -b;
     s.i1 = p.eb_top_i - b;
-    s.ok = (s.i0 >= -126 && s.i1 <= 127 && s.i1 >= s.i0);
-    s.f1 = pow2_i(s.i0 < -126 ? -126 : s.i0);
+    // deep: 2^emin is a denormal (or 0 below 2^-149) and so may be |x| + delta and the output; handled by scaling the log2 argument
+    // by 2^24 (exact; needs the block maximum below 2^100) and building denormal results from integers — softmax probabilities
+    // (block maxima < 1) used to take the literal path here: 1.98 TB/s against 4.7 for maxima above 1
+    s.deep = s.i0 < -126;
+    s.ok = (s.i1 <= 127 && s.i1 >= s.i0 && (!s.deep || (s.i0 >= -400 && mbits < ((100u + 127u) << 23))));
+    s.f1 = s.deep ? pow2_t((float)s.i0) : pow2_i(s.i0);
     s.f0 = __fmul_rn(s.f1, 0.1f);
   } else if (KIND == kMinifloatDenorm) {
     s.i0 = p.emin_i + 127;                                    // format-level range check: FmtParams::fast_fmt
@@ -317,8 +333,15 @@ __device__ __forceinline__ float quant_elem_fast_impl(float x, const FastState& 
     const float v = __fadd_rn(ax, s.f0);
     // v is finite (block max is) and every v below 2^emin — zeros (v = delta), denormals — clamps to emin whatever the shortcut
     // returns for it (its biased result is <= 1 there), so neither an exponent-range test nor a v < 2^emin select is needed.
-    const int eb = min(max(rint_log2_biased_f<NC>(v, zacc), s.i0 + 127), s.i1 + 127);
-    out = (w == 0.f) ? 0.f : copysignf(__int_as_float(eb << 23), w);
+    if (!s.deep) {
+      const int eb = min(max(rint_log2_biased_f<NC>(v, zacc), s.i0 + 127), s.i1 + 127);
+      out = (w == 0.f) ? 0.f : copysignf(__int_as_float(eb << 23), w);
+    } else {
+      const int eb = min(max(rint_log2_biased_deep<NC>(v, zacc), s.i0 + 127), s.i1 + 127);      // biased exponent, may be <= 0
+      // 2^(eb - 127): normal for eb >= 1, the denormal 1 << (eb + 22) down to eb = -22 (2^-149), 0 below (torch: pow(2, e) underflows)
+      const uint32_t bits = eb >= 1 ? (uint32_t)eb << 23 : (eb >= -22 ? 1u << (eb + 22) : 0u);
+      out = (w == 0.f) ? 0.f : copysignf(__uint_as_float(bits), w);
+    }
   } else if (KIND == kMinifloatDenorm) {
     // minifloat.py:60-80 with e = clamp(ceil(log2(|x|+1e-9)), emin, emax):  y = 2^(e-M) * min(rint(|x| * 2^(M-e)), 2^M - 1)
     const int eb = min(max(ceil_log2_biased_nf<NC>(__fadd_rn(ax, 1e-9f), zacc), s.i0), s.i1);

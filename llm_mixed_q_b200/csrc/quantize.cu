@@ -1516,6 +1516,13 @@ __global__ void selftest_log2_kernel(unsigned long long* mism) {
     } else {
       bad2 += (rint_log2_biased_f<false>(x, zu) > 1) + (rint_log2_biased_f<true>(x, z2) > 1);   // denormals: anything <= 1
     }
+    // the scaled ("deep") variant of the block_log fast path: every pattern below 2^100, denormals included
+    if (i < ((100ull + 127ull) << 23)) {
+      uint32_t z3 = 0xffffffffu;
+      bad2 += (rint_log2_biased_deep<false>(x, zu) != r + 127);
+      const int rd = rint_log2_biased_deep<true>(x, z3);
+      bad2 += (!zone_hit<kBlockLog>(z3) && rd != r + 127);
+    }
   }
   if (bad0) atomicAdd(&mism[0], bad0);
   if (bad1) atomicAdd(&mism[1], bad1);
