@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BQ_ABI_VERSION 4
+#define BQ_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define BQ_API __attribute__((visibility("default")))
@@ -227,13 +227,18 @@ BQ_API int bq_gemm_bf16_tn(const void* A, const void* B, float* C, const float* 
  * data_in of a following Linear, q and v of the attention bmms), qdir 1: along M (16 consecutive tokens at one feature:
  * the k^T operand of bmm_0, modeling_opt.py:246; needs M % 16 == 0).  With qfmt the natural out_dtype is BQ_BF16 (exact
  * carrier); fp32 output of quantised values is also allowed.  N % 32 == 0; bias / residual / C 16-byte aligned.
+ * act 2 — gated SiLU, the Llama MLP's `down_proj(act_fn(gate_proj(x)) * up_proj(x))` (models/llama_quantized/modeling_llama.py:84)
+ * in one launch: B holds BOTH quantised weights interleaved in groups of 16 rows ([gate f..f+16), [up f..f+16), ...; N = 2 * features,
+ * bias — if any — interleaved the same way), the epilogue forms silu(gate) * up = gate / (1 + expf(-gate)) * up (torch-CUDA's op
+ * order), applies qfmt (required; qdir 0 — the x-quantizer of down_proj, block_fp / block_minifloat / block_log carrier rule) and
+ * stores bf16 C[M][N / 2] (ldc >= N / 2).  No residual, scale 1, no replicas.  Same bits as two GEMMs + bq_silu_mul_quantize.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct bq_gemm_epilogue {
   const float* bias;       /* [N] or NULL                                   */
   const float* residual;   /* fp32 [M][ldr] or NULL                         */
   int64_t ldr;
   float scale;             /* 1.0f = none                                   */
-  int32_t act;             /* 0 none, 1 ReLU                                */
+  int32_t act;             /* 0 none, 1 ReLU, 2 gated SiLU (see above)      */
   int32_t out_dtype;       /* bq_dtype of C                                 */
   const bq_format* qfmt;   /* NULL = no quantisation                        */
   int32_t qdir;            /* 0: blocks along N, 1: blocks along M          */

@@ -238,6 +238,33 @@ __device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, co
       return;
     }
   }
+  if (KIND == kBlockFP && fs.ok) {
+    // Blocks that hold pass-through probabilities (p <= 1e-8, which the reference returns unquantised: block_fp.py's isclose(x, 0)
+    // blend) — the common case of a PEAKED softmax, i.e. of trained checkpoints.  Two in-line tiers with the arithmetic of the
+    // out-of-line general path (bit-identical to it), so that such rows no longer pay a call and a round trip through local
+    // memory per block (1.08 ms against 0.578 ms at B8 h32 S2048 when most blocks were of this kind):
+    if (mx <= 1e-8f) {
+      // (a) the whole block is below the threshold: every element passes through, truncated to bf16
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        w[i] = SCALED ? pack_bf16_trunc(__fmul_rn(v[2 * i], inv_l), __fmul_rn(v[2 * i + 1], inv_l)) : pack_bf16_trunc(v[2 * i], v[2 * i + 1]);
+      return;
+    }
+    // (b) mixed block: quantise in fp32 and select per element
+    const float c0 = __fmul_rn(1e-9f, fs.f0);
+    const float hi = __fadd_rn(kMagic, p.qmax);
+    const float c1 = -__fmul_rn(kMagic, fs.f1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float pi = SCALED ? __fmul_rn(v[i], inv_l) : v[i];
+      const float tm = fminf(__fadd_rn(__fmaf_rn(pi, fs.f0, c0), kMagic), hi);
+      const float y = __fmaf_rn(tm, fs.f1, c1);
+      v[i] = (pi <= 1e-8f) ? pi : y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pack_bf16_trunc(v[2 * i], v[2 * i + 1]);
+    return;
+  }
   if (KIND == kBlockMinifloat) {
     // block_minifloat has no packed path above: this IS its hot path — keep it in registers (out of line it cost the Llama-7B W4A4
     // attention 0.37 -> 0.58 ms per layer: every block went through local memory and a call)

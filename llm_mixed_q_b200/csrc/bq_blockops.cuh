@@ -108,6 +108,13 @@ __device__ __forceinline__ void quantize_signed16_blocklog(float (&v)[16], const
 template <>
 __device__ __forceinline__ void quantize_signed16<kBlockLog>(float (&v)[16], const FmtParams& p) { quantize_signed16_blocklog(v, p); }
 
+// silu(g) * u (Llama MLP: act_fn(gate_proj(h)) * up_proj(h), reference modeling_llama.py:246) in torch-CUDA's op order:
+// silu(g) = g / (1 + expf(-g)) (ActivationSiluKernel.cu), then one multiply.  Shared by the streaming silu*mul quantizer
+// (quantize.cu) and the gated GEMM epilogue (gemm_sm100.cu) so that both give the same bits.
+__device__ __forceinline__ float silu_mul1(float g, float u) {
+  return __fmul_rn(__fdiv_rn(g, __fadd_rn(1.0f, expf(-g))), u);
+}
+
 // runtime-kind wrapper for the block formats of the fused kernels (block_log: carrier rule above)
 __device__ __forceinline__ void quantize_signed16_rt(float (&v)[16], const FmtParams& p) {
   if (p.kind == kBlockFP) quantize_signed16<kBlockFP>(v, p);

@@ -33,7 +33,7 @@ constexpr int kEpiWarpWords = 32 * 33 + 64 * 4;      // per epilogue warp: 32x33
 // EPI: 0 none; 1 generic (every EpiArgs combination, runtime dispatch); specialised instances of the same code with the mode
 // fixed at compile time (each path gets its own register allocation — in the generic instance the fp32 / row-block paths cost the
 // bf16 column-block path 7 %): 2 = fp32 out, no quantiser (coalesced store / residual / replicas); 3 = blocks along N, bf16 out;
-// 4 = blocks along M, bf16 out (3, 4: no residual, no replicas).
+// 4 = blocks along M, bf16 out (3, 4: no residual, no replicas); 5 = gated SiLU over interleaved gate / up column groups (EpiArgs::act 2).
 // With CG == 2 a CTA pair computes a 256 x 256 tile: each CTA owns 128 rows of A and of the accumulator and HALF of the B tile,
 // which the pair's MMA reads from both shared memories — 2/3 of the smem fill traffic and operand reads per FLOP of CG == 1.
 template <int BN, int EPI = 0, int CG = 1> struct GemmCfg {
@@ -61,7 +61,8 @@ struct EpiArgs {
   const float* residual;   // fp32 [M][ldr] or nullptr
   int64_t ldr;
   float scale;             // 1.0f: skipped
-  int act;                 // 0 none, 1 ReLU
+  int act;                 // 0 none, 1 ReLU, 2 gated SiLU: B's rows come in groups of 32 = 16 gate rows + the 16 up rows of the same
+                           // features; the epilogue forms silu(gate) * up, block-quantises the 16 results and stores bf16 [M][N / 2]
   int out_bf16;            // 0: fp32 store, 1: bf16 store
   int qmode;               // 0 none; 1: blocks of 16 along N (one thread's registers); 2: blocks of 16 along M (16 lanes)
   FmtParams q;
@@ -195,6 +196,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       v[j] = __fadd_rn(v[j], bv.x); v[j + 1] = __fadd_rn(v[j + 1], bv.y);
       v[j + 2] = __fadd_rn(v[j + 2], bv.z); v[j + 3] = __fadd_rn(v[j + 3], bv.w);
     }
+  }
+  if (EM == 5) {
+    // Gated SiLU (Llama MLP, reference models/llama_quantized/modeling_llama.py:84 down_proj(act_fn(gate_proj(x)) * up_proj(x))): this
+    // 32-column chunk holds gate[f .. f+16) and up[f .. f+16) of the same 16 features (weights interleaved by the host), i.e. exactly one
+    // block of down_proj's x-quantizer in this thread's registers.  Replaces two fp32 GEMM outputs (8 B/elem written, 8 read back) and
+    // the silu*mul+quantise kernel by one 2 B/elem store; same silu_mul1 / quantize_signed16 as that kernel, so the same bits.
+    if (!row_ok) return;
+    float t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = silu_mul1(v[i], v[16 + i]);
+    quantize_signed16_rt(t, e.q);
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(Cb) + (int64_t)row * g.ldc + (col0 >> 1);
+    reinterpret_cast<uint4*>(c)[0] = make_uint4(pack_bf16_rn(t[0], t[1]), pack_bf16_rn(t[2], t[3]), pack_bf16_rn(t[4], t[5]), pack_bf16_rn(t[6], t[7]));
+    reinterpret_cast<uint4*>(c)[1] = make_uint4(pack_bf16_rn(t[8], t[9]), pack_bf16_rn(t[10], t[11]), pack_bf16_rn(t[12], t[13]), pack_bf16_rn(t[14], t[15]));
+    return;
   }
   if (e.scale != 1.0f) {
 #pragma unroll
@@ -722,6 +738,12 @@ static void choose_tile(int64_t batch, int64_t M, int64_t N, int* BN, bool* pair
 template <bool EPI>
 static int launch_gemm_any(int BN, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st,
                            int kern_id) {
+  if (EPI && g.epi.act == 2) {                                   // gated SiLU: its own instances (N = 2 * features >= 128)
+    if (pair) return launch_gemm_cg<256, 5, 2>(tmA, tmB, g, st, kern_id);
+    if (BN == 128) return launch_gemm_cg<128, 5, 1>(tmA, tmB, g, st, kern_id);
+    if (BN == 256) return launch_gemm_cg<256, 5, 1>(tmA, tmB, g, st, kern_id);
+    return BQ_ERR_UNSUPPORTED;
+  }
   if (pair) {
     if (!EPI) return launch_gemm_cg<256, 0, 2>(tmA, tmB, g, st, kern_id);
     const EpiArgs& e = g.epi;
@@ -778,7 +800,7 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
   if (!A || !B || !C) return BQ_ERR_BAD_ARG;
   if (K == 0) return BQ_ERR_UNSUPPORTED;
   if ((lda % 8) || (ldb % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)C % 16)) return BQ_ERR_BAD_ARG;
-  if (lda < K || ldb < K || ldc < N) return BQ_ERR_BAD_ARG;
+  if (lda < K || ldb < K || ldc < (ep->act == 2 ? N / 2 : N)) return BQ_ERR_BAD_ARG;
   if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
   if (N % 32) return BQ_ERR_UNSUPPORTED;
   const bool out_bf16 = ep->out_dtype == BQ_BF16;
@@ -786,7 +808,12 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
   if (ldc % (out_bf16 ? 8 : 4)) return BQ_ERR_BAD_ARG;
   if (ep->bias && ((uintptr_t)ep->bias % 16)) return BQ_ERR_BAD_ARG;
   if (ep->residual && (((uintptr_t)ep->residual % 16) || (ep->ldr % 4) || ep->ldr < N)) return BQ_ERR_BAD_ARG;
-  if (ep->act != 0 && ep->act != 1) return BQ_ERR_UNSUPPORTED;
+  if (ep->act != 0 && ep->act != 1 && ep->act != 2) return BQ_ERR_UNSUPPORTED;
+  if (ep->act == 2) {
+    // gated SiLU: N counts the interleaved gate / up columns, C is bf16 [M][N / 2] in the format of the consuming Linear
+    if (!ep->qfmt || ep->qdir != 0 || !out_bf16 || ep->residual || ep->n_replicas != 0 || ep->scale != 1.0f) return BQ_ERR_UNSUPPORTED;
+    if (N < 128 || ldc < N / 2) return BQ_ERR_BAD_ARG;
+  }
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.epi.residual = ep->residual; g.epi.ldr = ep->ldr; g.epi.scale = ep->scale; g.epi.act = ep->act;

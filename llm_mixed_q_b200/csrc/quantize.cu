@@ -135,11 +135,7 @@ __device__ __forceinline__ float4 quant4(float4 v, uint32_t mbits, const FmtPara
 }
 
 // gstate[0]: min over non-zero block maxima (uint bits, init 0xffffffff); gstate[1]: 0xffffffff until a zero block is seen
-// PRE: the element fed to the quantizer is silu(x) * x2 (Llama MLP: act_fn(gate_proj(h)) * up_proj(h), reference
-// modeling_llama.py:246) in torch-CUDA's op order: silu(g) = g / (1 + expf(-g)) (ActivationSiluKernel.cu), then one multiply.
-__device__ __forceinline__ float silu_mul1(float g, float u) {
-  return __fmul_rn(__fdiv_rn(g, __fadd_rn(1.0f, expf(-g))), u);
-}
+// PRE: the element fed to the quantizer is silu(x) * x2 (silu_mul1, bq_blockops.cuh)
 template <int KIND, typename OutT, bool FLAT, bool PRE = false>
 __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const float* __restrict__ x, OutT* __restrict__ y, RowsGeom g,
                                                                FmtParams p, uint32_t* __restrict__ gstate,

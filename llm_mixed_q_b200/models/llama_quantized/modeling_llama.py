@@ -28,7 +28,7 @@ from ..quantize.quantized_functions.fused_glue import (_NORM_KINDS, linear_input
 from ..quantize.quantized_functions.split_attention import rope_quantize_split, split_attention, splittable as _attn_splittable
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major as _rope_token_major
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major_quantized as _rope_token_major_quantized
-from ..quantize.quantized_modules.linear import operand_format, quantize_operand_bf16
+from ..quantize.quantized_modules.linear import gated_silu_fusable, gated_silu_prequantized, operand_format, quantize_operand_bf16
 from .configuration_llama import LlamaQuantizedConfig
 
 
@@ -173,6 +173,17 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         self._plan_cache = (seq_len, plan)
         return plan
 
+    def _gated_mlp_operand(self, xg, xu, plan, rows):
+        """Q_down(silu(gate_proj(x)) * up_proj(x)) as bf16 [rows, I] (reference modeling_llama.py:84).  gate_proj and up_proj with the
+        same x-quantizer read ONE operand: both GEMMs run as one launch over the interleaved weights and the SiLU, the product and
+        down_proj's x-quantizer sit in its epilogue (gated_silu_prequantized).  Otherwise: two GEMMs + the silu*mul quantizer kernel."""
+        mlp = self.mlp
+        if xg.data_ptr() == xu.data_ptr() and gated_silu_fusable(mlp.gate_proj, mlp.up_proj):
+            return gated_silu_prequantized(mlp.gate_proj, mlp.up_proj, xg.view(rows, -1), plan["down_in"])
+        g = mlp.gate_proj.forward_prequantized(xg)
+        u = mlp.up_proj.forward_prequantized(xu)
+        return silu_mul_quantize(g.view(rows, -1), u.view(rows, -1), plan["down_in"])
+
     @torch.no_grad()
     def _split_forward(self, h, position_ids, plan, default_positions=False, key_mask=None):
         """Layer forward for configs whose matmuls keep an fp32 operand (block_log): same fused glue, attention through
@@ -193,9 +204,7 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         oq = quantize_operand_bf16(o.view(B * S, H), okind, okw, [1, 16], True)      # o_proj's x-quantizer (exact, incl. the global-min rule)
         h2 = at.o_proj.forward_prequantized(oq, residual=h)
         xg, xu = norm_quantize(h2, n2.weight, None, n2.variance_epsilon, [plan["gate_in"], plan["up_in"]])
-        g = mlp.gate_proj.forward_prequantized(xg)
-        u = mlp.up_proj.forward_prequantized(xu)
-        a = silu_mul_quantize(g.view(B * S, -1), u.view(B * S, -1), plan["down_in"])
+        a = self._gated_mlp_operand(xg, xu, plan, B * S)
         h3 = mlp.down_proj.forward_prequantized(a, residual=h2.view(B * S, H))
         return h3.view(B, S, H)
 
@@ -225,9 +234,7 @@ class LlamaQuantizedDecoderLayer(nn.Module):
                                       out_cfg=at.o_proj.config, key_mask=key_mask)
         h2 = at.o_proj.forward_prequantized(oq, residual=h)                      # residual + o_proj(attn)
         xg, xu = norm_quantize(h2, n2.weight, None, n2.variance_epsilon, [plan["gate_in"], plan["up_in"]])
-        g = mlp.gate_proj.forward_prequantized(xg)
-        u = mlp.up_proj.forward_prequantized(xu)
-        a = silu_mul_quantize(g.view(B * S, -1), u.view(B * S, -1), plan["down_in"])   # Q_down(silu(gate) * up), one kernel
+        a = self._gated_mlp_operand(xg, xu, plan, B * S)                         # Q_down(silu(gate) * up)
         h3 = mlp.down_proj.forward_prequantized(a, residual=h2.view(B * S, H))   # residual + down(silu(gate) * up)
         return h3.view(B, S, H)
 

@@ -370,6 +370,57 @@ class _LinearBase(nn.Linear):
             self.config.get("data_in_width", "NA"), self.config.get("weight_width", "NA"), self.config.get("bias_width", "NA"))
 
 
+GATED_EPILOGUE = True     # False: gate / up GEMMs + the silu*mul quantizer kernel (A/B, tests)
+
+
+def gated_silu_fusable(gate: "_LinearBase", up: "_LinearBase") -> bool:
+    """Whether `gated_silu_prequantized` can serve this gate / up pair: both PTQ with bf16-exact weights, no bias, the same shape,
+    whole blocks of 16 features."""
+    return (GATED_EPILOGUE and gate.accepts_prequantized() and up.accepts_prequantized() and gate.bias is None and up.bias is None
+            and gate.in_features == up.in_features and gate.out_features == up.out_features and gate.out_features % 16 == 0
+            and gate.out_features >= 64)
+
+
+@torch.no_grad()
+def gated_silu_prequantized(gate: "_LinearBase", up: "_LinearBase", xq: torch.Tensor, out_format) -> torch.Tensor:
+    """Q_out(silu(gate(xq)) * up(xq)) in ONE GEMM launch — the operand of Llama's down_proj (reference
+    models/llama_quantized/modeling_llama.py:84 `down_proj(act_fn(gate_proj(x)) * up_proj(x))`, x-quantizer of
+    quantized_modules/linear.py:63-71) for an input that already went through the (identical) x-quantizers of gate_proj and up_proj.
+    The two quantised weights are interleaved in groups of 16 rows ([gate f..f+16), [up f..f+16), ...) so that a 32-column chunk of
+    the accumulator holds one block of the consumer's x-quantizer; the epilogue (bq_gemm_bf16_tn_ex, act = 2) applies silu * up and
+    the quantizer and stores bf16 [M, F].  Bit-identical to gate GEMM + up GEMM + silu_mul_quantize (same accumulation order per
+    output column, same element-wise code), without the 16 B/element fp32 round trip between them."""
+    assert xq.dtype == torch.bfloat16 and xq.is_cuda and xq.shape[-1] == gate.in_features
+    gate._ensure_ptq()
+    up._ensure_ptq()
+    lib = L.load()
+    K, Fo = gate.in_features, gate.out_features
+    key = (gate.weight.data_ptr(), gate.weight._version, up.weight.data_ptr(), up.weight._version, gate.weight.device)
+    cache = getattr(gate, "_gu_cache", None)
+    if cache is None or cache[0] != key:
+        wg, wu = gate._weight_cache(), up._weight_cache()
+        wgu = torch.stack((wg.view(Fo // 16, 16, K), wu.view(Fo // 16, 16, K)), dim=1).reshape(2 * Fo, K).contiguous()
+        gate._gu_cache = cache = (key, wgu)
+        gate._wq_bf16 = up._wq_bf16 = None      # the separate bf16 copies are rebuilt on demand (op-by-op path); no need to hold both
+    wgu = cache[1]
+    x2 = xq.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0):
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    y = torch.empty((M, Fo), dtype=torch.bfloat16, device=xq.device)
+    if M > 0:
+        kind, kw = out_format
+        fmt = make_format(kind, b0=1, b1=16, **kw)
+        ep = L.BqGemmEpilogue()
+        ep.scale, ep.act, ep.out_dtype = 1.0, 2, L.BQ_BF16
+        ep.qfmt = ctypes.pointer(fmt)
+        ep.qdir = 0
+        rc = lib.bq_gemm_bf16_tn_ex(x2.data_ptr(), wgu.data_ptr(), y.data_ptr(), ctypes.byref(ep), M, 2 * Fo, K,
+                                    x2.stride(0) if M > 1 else K, K, Fo, L.stream_ptr(xq.device))
+        L.check(rc, "bq_gemm_bf16_tn_ex(gated silu)")
+    return y.reshape(*xq.shape[:-1], Fo)
+
+
 def _bind(self, quantizer, keys, config, with_blocks):
     """Bind x / w / b quantizers from `<prefix>_<key>` entries (x: skip_first_dim=True, w/b: False)."""
     def one(prefix, skip):

@@ -302,6 +302,36 @@ def test_fused_causal_attention_vs_op_by_op_oracle(S, attention_exp_mode, attent
     assert torch.equal(out[:, 0, :], exp0)
 
 
+@pytest.mark.parametrize("q_scale", [1.0, 2.5])
+def test_fused_attention_peaked_softmax_pass_through_tiers(q_scale, attention_exp_mode, attention_pipeline):
+    """Peaked softmax rows (what trained checkpoints produce): most probabilities are <= 1e-8, which the reference returns
+    UNQUANTISED (block_fp.py:93-94).  The kernel serves such blocks from two in-line tiers — the whole block below the threshold
+    (truncated to the bf16 carrier) and mixed blocks (fp32 quantise + per-element select) — and must still be the op-by-op
+    composition within the tolerance of test_fused_causal_attention_vs_op_by_op_oracle."""
+    from llm_mixed_q_b200.models.quantize.quantized_functions.attention import fused_causal_attention
+
+    g = torch.Generator(device="cuda").manual_seed(77)
+    B, heads, d, S = 2, 4, 64, 1024
+    H = heads * d
+    q = torch.randn(B, S, H, device="cuda", generator=g) * q_scale
+    k = torch.randn(B, S, H, device="cuda", generator=g)
+    v = torch.randn(B, S, H, device="cuda", generator=g)
+    out = fused_causal_attention(q, k, v, CFG_BFP6, CFG_BFP6, heads)
+    ref, p = _oracle_attention(q, k, v, CFG_BFP6, heads)
+    visible = torch.tril(torch.ones(S, S, dtype=torch.bool, device="cuda"))
+    tiny = (p <= 1e-8) & visible
+    blocks = (p * visible).view(B * heads, S, S // 16, 16)
+    all_tiny = ((blocks <= 1e-8).all(-1) & (blocks > 0).any(-1)).float().mean()
+    mixed = ((blocks <= 1e-8).any(-1) & (blocks > 1e-8).any(-1)).float().mean()
+    assert float(tiny.float().sum() / visible.sum() / (B * heads)) > 0.5          # the tiers ARE what this input exercises
+    assert float(all_tiny) > 0.02 and float(mixed) > 0.05, (float(all_tiny), float(mixed))     # shares of ALL S x S / 16 blocks, half of them masked
+    err = (out - ref).abs()
+    vmax = float(v.abs().max())
+    assert float(err.max()) <= (2.0 ** -5) * vmax, float(err.max())
+    assert float((err > 0.01 * vmax).float().mean()) <= 1e-4
+    assert float(err.mean()) <= 2e-4, float(err.mean())
+
+
 def _oracle_attention_masked(q, k, v, cfg, heads, valid, causal, score_div=1.0):
     """op-by-op reference composition with an additive key-padding mask: decoder (causal + padding, clamped at finfo.min —
     opt_quantized/modeling_opt.py:520-548, :266-270) or encoder (padding only, no clamp — bert_quantized/modeling_bert.py:366-435)."""

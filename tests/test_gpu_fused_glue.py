@@ -387,6 +387,105 @@ def test_silu_mul_quantize_is_bit_identical_to_torch_silu_mul_then_quantizer(kin
         L.load().bq_set_stream_quantizer(1)
 
 
+@pytest.mark.parametrize("kind", ["block_fp", "block_minifloat", "block_log"])
+def test_gated_silu_gemm_epilogue_is_bit_identical_to_two_gemms_and_the_silu_mul_quantizer(kind):
+    """gated_silu_prequantized (one GEMM over the interleaved gate / up weights, silu * up and down_proj's x-quantizer in the
+    epilogue: bq_gemm_bf16_tn_ex act = 2) against gate GEMM + up GEMM + silu_mul_quantize — the reference's
+    down_proj(act_fn(gate_proj(x)) * up_proj(x)) operand (modeling_llama.py:84).  Pair tiles, single-CTA tiles, ragged rows."""
+    import copy
+
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.quantize import get_quantized_cls
+    from llm_mixed_q_b200.models.quantize.quantized_functions.fused_glue import silu_mul_quantize
+    from llm_mixed_q_b200.models.quantize.quantized_modules import linear as QL
+
+    if kind == "block_fp":
+        fmt = ("block_fp", dict(width=6, exponent_width=8, exponent_bias=127))
+    elif kind == "block_minifloat":
+        fmt = ("block_minifloat", dict(width=8, exponent_width=4, exponent_bias_width=8))
+    else:
+        fmt = ("block_log", dict(width=8, exponent_bias_width=8))
+    cfg = bfp_cfg(6)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n0 = L.launch_counts().get("gemm_bf16_tn_kernel<epilogue>", 0)
+    for rows, K, I in [(300, 256, 352), (4096, 512, 1408), (64, 128, 64), (130, 64, 11008)]:
+        gate = get_quantized_cls("linear", cfg)(K, I, bias=False, config=copy.deepcopy(cfg)).cuda()
+        up = get_quantized_cls("linear", cfg)(K, I, bias=False, config=copy.deepcopy(cfg)).cuda()
+        with torch.no_grad():
+            gate.weight.mul_(20.0)                      # gate pre-activations of a few units: both tails of the SiLU
+            up.weight[:16].zero_()                      # an all-zero block of products
+        assert QL.gated_silu_fusable(gate, up)
+        x = torch.randn(rows, K, device="cuda", generator=g)
+        xq = QL.quantize_operand_bf16(x, "block_fp", dict(width=6, exponent_width=8, exponent_bias=127), [1, 16], True)
+        gv, uv = gate.forward_prequantized(xq), up.forward_prequantized(xq)
+        want = silu_mul_quantize(gv, uv, fmt)
+        got = QL.gated_silu_prequantized(gate, up, xq, fmt)
+        assert got.shape == want.shape and got.dtype == torch.bfloat16
+        if kind != "block_log":
+            assert torch.equal(got.view(torch.int16), want.view(torch.int16)), (kind, rows, K, I)
+        else:
+            # block_log in a 16-bit carrier (include/bq.h, "carrier rule"): bit-identical to the exact fp32 quantizer output wherever
+            # that is >= 2^-126 in magnitude; an all-zero block stays 0 and smaller outputs come out as 0 or 2^-126
+            want32 = silu_mul_quantize(gv, uv, fmt, out_dtype=torch.float32)
+            prod = torch.nn.functional.silu(gv) * uv
+            zero_blocks = (prod.view(rows, I // 16, 16) == 0).all(-1, keepdim=True).expand(rows, I // 16, 16).reshape(rows, I)
+            want32 = torch.where(zero_blocks, torch.zeros_like(want32), want32)
+            tiny = 2.0 ** -126
+            big = want32.abs() >= tiny
+            assert torch.equal(got.float()[big], want32[big]), (kind, rows, K, I)
+            small = got.float()[~big].abs()
+            assert bool(((small == 0) | (small == tiny)).all())
+    assert L.launch_counts().get("gemm_bf16_tn_kernel<epilogue>", 0) - n0 >= 4
+    # argument contract of act = 2 (include/bq.h)
+    lib = L.load()
+    from llm_mixed_q_b200.models.quantize.quantizers.utils import make_format
+
+    A = torch.zeros(32, 64, device="cuda", dtype=torch.bfloat16)
+    B = torch.zeros(256, 64, device="cuda", dtype=torch.bfloat16)
+    C = torch.zeros(32, 128, device="cuda", dtype=torch.bfloat16)
+    f = make_format("block_fp", b0=1, b1=16, width=6, exponent_width=8, exponent_bias=127)
+    ep = L.BqGemmEpilogue()
+    ep.scale, ep.act, ep.out_dtype = 1.0, 2, L.BQ_BF16
+    assert lib.bq_gemm_bf16_tn_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), ctypes.byref(ep), 32, 256, 64, 64, 64, 128, L.stream_ptr()) == 2
+    ep.qfmt = ctypes.pointer(f)
+    assert lib.bq_gemm_bf16_tn_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), ctypes.byref(ep), 32, 256, 64, 64, 64, 64, L.stream_ptr()) == 1
+    ep.out_dtype = L.BQ_F32
+    assert lib.bq_gemm_bf16_tn_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), ctypes.byref(ep), 32, 256, 64, 64, 64, 128, L.stream_ptr()) == 2
+
+
+def test_llama_layer_with_gated_epilogue_equals_three_launch_mlp():
+    """The fused Llama layer with the gated GEMM epilogue is bit-identical to the same layer with gate GEMM + up GEMM + silu*mul
+    quantizer (QL.GATED_EPILOGUE = False), block_minifloat W4A4-style config and block_log (split plan)."""
+    import json
+    import os
+
+    from conftest import GOLD
+    from llm_mixed_q_b200.models.llama_quantized import LlamaQuantizedConfig, LlamaQuantizedForCausalLM
+    from llm_mixed_q_b200.models.quantize.quantized_modules import linear as QL
+
+    with open(os.path.join(GOLD, "configs.json")) as f:
+        raw = json.load(f)["raw"]
+    for name in ("block_minifloat.toml", "block_log.toml", "bfp_6bit.toml"):
+        if name not in raw:
+            continue
+        cfg = LlamaQuantizedConfig(hidden_size=128, intermediate_size=352, num_hidden_layers=2, num_attention_heads=2, vocab_size=512,
+                                   max_position_embeddings=128, quant_config=raw[name])
+        torch.manual_seed(0)
+        model = LlamaQuantizedForCausalLM(cfg).eval().cuda()
+        ids = torch.randint(0, 512, (2, 128), device="cuda")
+        assert model.model.layers[0]._fused_plan(128) is not None
+        outs = []
+        try:
+            for on in (True, False):
+                QL.GATED_EPILOGUE = on
+                with torch.no_grad():
+                    outs.append(model(ids).logits)
+        finally:
+            QL.GATED_EPILOGUE = True
+        assert torch.equal(outs[0], outs[1]), name
+        assert getattr(model.model.layers[0].mlp.gate_proj, "_gu_cache", None) is not None
+
+
 def test_fused_llama_block_log_takes_the_split_attention_plan():
     import json
     import os
