@@ -497,6 +497,7 @@ def main():
     ap.add_argument("--no-sub", action="store_true")
     ap.add_argument("--no-column-parallel", action="store_true", help="N > 1: skip the tensor-parallel OPT-6.7B layer block")
     ap.add_argument("--eager-e2e", action="store_true", help="end-to-end region through the eager forward instead of graph replay")
+    ap.add_argument("--pdl", action="store_true", help="A/B: programmatic dependent launch between our kernels (bq_set_pdl(1); default off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -525,6 +526,8 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=device)
     L.load()
+    if args.pdl:
+        L.load().bq_set_pdl(1)
     pk = peaks()
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
@@ -734,6 +737,9 @@ def main():
                        "lm_head": f"unquantised fp32 head as a split GEMM, mode {fp32_mode} (f16x2 = 3 products of row-scaled fp16 hi/lo planes, "
                                   "~2^-21 per product, 22-bit operands; bf16x3 = 6 products, 2^-24) — sub_metrics.lm_head_modes times both",
                        "attention_exp": attn_exp_mode,
+                       "launch": ("programmatic dependent launch between the GEMM / attention / norm+quantize kernels (set-up overlaps the "
+                                  "predecessor's tail; griddepcontrol.wait before any global access)" if L.load().bq_get_pdl()
+                                  else "plain stream order (programmatic dependent launch measured 0.7 % slower on this power-capped step: --pdl)"),
                        "instrumentation": "`value` and `e2e` are timed without per-kernel events; `roofline` comes from a second pass of the same K "
                                           "steps with two CUDA events per launch (an event between two kernels costs a front-end round trip, ~2 % of "
                                           "the step; sharing events between consecutive launches was measured and changed nothing)",

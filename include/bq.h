@@ -399,6 +399,12 @@ BQ_API void bq_set_norm_warp_rows(int on);             /* 0: force the row-per-C
 BQ_API void bq_set_cta_pairs(int on);                  /* 0: force cta_group::1 GEMM tiles (A/B measurement) */
 BQ_API void bq_set_small_tiles(int on);                /* 0: always the largest GEMM tile the shape admits; 1 (default): 128 x 128 tiles when the
                                                           problem would not fill the chip with larger ones (A/B measurement) */
+BQ_API void bq_set_pdl(int on);                        /* 1: the tcgen05 GEMM, attention and norm+quantize kernels are launched with
+                                                          programmatic stream serialization — a kernel's set-up (barriers, TMEM, descriptors)
+                                                          overlaps the tail of its predecessor, every global access waits for the predecessor's
+                                                          completion (griddepcontrol.wait); 0 (default — measured 0.7 % slower with it on the
+                                                          power-capped headline step): plain stream order */
+BQ_API int bq_get_pdl(void);
 BQ_API int bq_kernel_count(void);
 BQ_API const char* bq_kernel_name(int kernel_id);
 BQ_API int64_t bq_launch_count(int kernel_id);          /* launches since load (kernel_id < 0: all kernels) */

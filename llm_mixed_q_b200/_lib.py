@@ -162,6 +162,10 @@ def load():
     lib.bq_set_stream_quantizer.argtypes = [ctypes.c_int]
     lib.bq_set_cta_pairs.restype = None
     lib.bq_set_cta_pairs.argtypes = [ctypes.c_int]
+    lib.bq_set_pdl.restype = None
+    lib.bq_set_pdl.argtypes = [ctypes.c_int]
+    lib.bq_get_pdl.restype = ctypes.c_int
+    lib.bq_get_pdl.argtypes = []
     lib.bq_set_small_tiles.restype = None
     lib.bq_set_small_tiles.argtypes = [ctypes.c_int]
     lib.bq_split2_f16_rows.restype = ctypes.c_int

@@ -458,6 +458,8 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   ptx::tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+  ptx::griddep_launch();                                  // programmatic dependent launch: see gemm_sm100.cu
+  ptx::griddep_wait();
 
   const int T = g.q_tiles;
   const int pairs = causal_m ? (T + 1) >> 1 : T;          // bidirectional: every query tile sees every key tile, no pairing needed
@@ -808,6 +810,8 @@ attention_causal_dual_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
   tmem += (uint32_t)grp * Cfg::kTmemGroup;                        // this group's 256 columns
+  ptx::griddep_launch();                                          // programmatic dependent launch: see gemm_sm100.cu
+  ptx::griddep_wait();
 
   const int T = g.q_tiles;
   const int pairs = causal_m ? (T + 1) >> 1 : T;
@@ -1069,7 +1073,7 @@ static int launch_attention_dual_fm(const CUtensorMap& tq, const CUtensorMap& tk
   const int grid = std::min((items + 1) / 2, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
-    attention_causal_dual_kernel<KIND, FAST, MASKED><<<grid, kAtThreads, At2Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
+    BQ_CUDA_CHECK(launch_ex(attention_causal_dual_kernel<KIND, FAST, MASKED>, grid, kAtThreads, At2Cfg::kSmemBytes, st, 1, tq, tk, tv, g));
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
@@ -1100,7 +1104,7 @@ static int launch_attention_fm(const CUtensorMap& tq, const CUtensorMap& tk, con
   const int grid = std::min(items, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
-    attention_causal_kernel<KIND, D, FAST, MASKED><<<grid, kAtThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, g);
+    BQ_CUDA_CHECK(launch_ex(attention_causal_kernel<KIND, D, FAST, MASKED>, grid, kAtThreads, Cfg::kSmemBytes, st, 1, tq, tk, tv, g));
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;

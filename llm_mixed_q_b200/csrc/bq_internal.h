@@ -37,6 +37,34 @@ struct LaunchScope {
   cudaStream_t st_;
   cudaEvent_t stop_;
 };
+// Kernel launch through cudaLaunchKernelEx with the optional attributes our kernels use: thread-block cluster width and
+// programmatic dependent launch (see ptx::griddep_wait; on when pdl_enabled()).  Also valid during stream capture (the dependency
+// becomes a programmatic edge of the CUDA graph).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 }  // namespace bq
 
 #define BQ_CUDA_CHECK(expr)                                                  \

@@ -46,6 +46,11 @@ LaunchScope::LaunchScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(null
 LaunchScope::~LaunchScope() {
   if (stop_) cudaEventRecord(stop_, st_);
 }
+// programmatic dependent launch between consecutive kernels of this library (bq_set_pdl).  Default OFF: measured on the headline
+// step (OPT-1.3B, 232 launches, CUDA-graph replay, power-capped B200) 56.87 / 56.67 ms with it against 56.41 / 56.36 ms without
+// (profiles/r02_bench_pdl_ab.json) — the step is energy-limited, the launch gaps it removes were not costing time.
+static std::atomic<int> g_pdl{0};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 }  // namespace bq
 
 extern "C" {
@@ -93,6 +98,8 @@ const char* bq_strerror(int status) {
     default: return "unknown status";
   }
 }
+void bq_set_pdl(int on) { bq::g_pdl.store(on ? 1 : 0); }
+int bq_get_pdl(void) { return bq::g_pdl.load(); }
 int bq_abi_version(void) { return BQ_ABI_VERSION; }
 const char* bq_last_cuda_error(void) { return bq::g_last_err; }
 }

@@ -371,6 +371,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();     // the peer's barriers exist before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // programmatic dependent launch: everything above ran while the previous kernel of the stream was draining; from here on
+  // global memory is read and written, which needs that kernel COMPLETE.  The next kernel may start its own set-up as soon as
+  // SMs free up (it blocks in the same wait until this grid has finished).
+  ptx::griddep_launch();
+  ptx::griddep_wait();
 
   const int kb_per_term = (g.K + kBK - 1) / kBK;
   const int num_kb = kb_per_term * (g.n_terms > 0 ? g.n_terms : 1);
@@ -690,22 +695,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmAr
   const int grid = CG * (int)std::min<int64_t>(total, num_sms() / CG);
   {
     LaunchScope ls(kern_id, st);
-    if (CG == 1) {
-      gemm_bf16_tn_kernel<BN, EPI, CG><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, g);
-    } else {
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(grid, 1, 1);
-      cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
-      cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      BQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, EPI, CG>, tmA, tmB, g));
-    }
+    BQ_CUDA_CHECK(launch_ex(gemm_bf16_tn_kernel<BN, EPI, CG>, grid, Cfg::kThreads, Cfg::kSmemBytes, st, CG, tmA, tmB, g));
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;

@@ -1081,12 +1081,17 @@ __global__ void __launch_bounds__(kLwWarps * G * 32, G == 1 ? 2 : 1) norm_quant_
   if (leader) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (row < a.rows) bulk_load_row(in0, a.x + (int64_t)row * a.ldx, row_bytes, bar);
   }
+  // programmatic dependent launch (see sm100_ptx.cuh: griddep_wait): the barrier set-up and the copy of gamma / beta — model
+  // parameters, never written by a kernel of the forward — overlap the tail of the previous kernel; the activation rows are read
+  // and the outputs written only after that kernel has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int i = threadIdx.x; i < (a.H >> 2); i += kLwWarps * G * 32) {
     sts128(gam0 + 16u * i, __ldg(reinterpret_cast<const float4*>(a.gamma) + i));
     if (ln) sts128(bet0 + 16u * i, __ldg(reinterpret_cast<const float4*>(a.beta) + i));
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (leader && row < a.rows) bulk_load_row(in0, a.x + (int64_t)row * a.ldx, row_bytes, bar);
   __syncthreads();
   const uint32_t rot = (uint32_t)((lane >> 1) + (lane >> 3)) & 3u;
   const float invH = 1.0f / (float)a.H;
@@ -1230,7 +1235,7 @@ static int launch_norm_quant_warp(const LnArgs& a, cudaStream_t st) {
   const int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * occ);
   {
     LaunchScope ls(kKernLnQuant, st);
-    norm_quant_warp_kernel<KIND, NB, FULL, G><<<grid, kLwWarps * G * 32, smem, st>>>(a);
+    BQ_CUDA_CHECK(launch_ex(norm_quant_warp_kernel<KIND, NB, FULL, G>, grid, kLwWarps * G * 32, smem, st, 1, a));
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;

@@ -239,6 +239,37 @@ def test_graphed_forward_replays_the_eager_result():
     assert float(runner(ids[0])) == float(eager[0].loss)
 
 
+def test_programmatic_dependent_launch_does_not_change_results():
+    """bq_set_pdl: the GEMM / attention / norm+quantize kernels start their set-up under the tail of the previous kernel and wait
+    (griddepcontrol.wait) before touching global memory.  Results must be bit-identical with the switch off, eagerly and from a
+    captured graph, and stable over repeated back-to-back forwards (a kernel reading its predecessor's output too early would
+    show up as run-to-run differences)."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.utils.graphs import GraphedForward
+
+    lib = L.load()
+    before = lib.bq_get_pdl()
+    model = _opt_model()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    ids = torch.randint(0, 512, (3, 128), device="cuda", generator=g)
+    try:
+        lib.bq_set_pdl(0)
+        with torch.no_grad():
+            want = model(input_ids=ids, labels=ids)
+        lib.bq_set_pdl(1)
+        with torch.no_grad():
+            for _ in range(20):
+                got = model(input_ids=ids, labels=ids)
+                assert torch.equal(got.logits, want.logits) and torch.equal(got.loss, want.loss)
+        runner = GraphedForward(model, 3, 128)
+        assert runner.graph is not None, runner.error
+        for _ in range(20):
+            loss = runner(ids)
+            assert torch.equal(loss, want.loss) and torch.equal(runner.logits, want.logits)
+    finally:
+        lib.bq_set_pdl(before)
+
+
 def test_graphed_forward_llama():
     """Same for the fused Llama layers (RMSNorm+quantize, RoPE+quantize, attention, SiLU*up+quantize)."""
     import json
