@@ -254,6 +254,21 @@ BQ_API int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_ge
                               int64_t lda, int64_t ldb, int64_t ldc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * q_proj / k_proj of a Llama layer with the rotary position embedding AND matmul_0's operand quantizer in the GEMM epilogue:
+ *   y = A @ B^T (+ bias);  y = rope(y, cos[pos], sin[pos]) per head of head_dim features;  C = Q_qfmt(y) as bf16 [M][ldc]
+ * replacing (models/llama_quantized/modeling_llama.py:274-276, :309-314; quantized_functions/rotary_positional_encoding.py:27-36;
+ * quantized_functions/matmul.py:165-193) an fp32 GEMM output, ~12 element-wise kernels and a quantizer call.  Tables: fp32
+ * [table_rows][head_dim], already quantised by the caller exactly as the reference quantises them; position of row m =
+ * position_ids[m] (clamped into the table) or m % S when position_ids is NULL.  qdir 0: blocks of 16 along the features (q, the x
+ * operand of matmul_0); qdir 1: blocks of 16 consecutive tokens at one feature (k^T, its y operand; M % 16 == 0, S % 16 == 0).
+ * head_dim 64 or 128, N % head_dim == 0; block_fp / block_minifloat.  Same arithmetic and order as bq_rope_quantize: same bits.
+ * ---------------------------------------------------------------------------------------------- */
+BQ_API int bq_gemm_bf16_tn_rope(const void* A, const void* B, void* C_bf16, const float* bias, const bq_format* qfmt, int32_t qdir,
+                                const float* cos_table, const float* sin_table, const int64_t* position_ids, int64_t table_rows,
+                                int64_t S, int64_t head_dim, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                                void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fp32-equivalent GEMM on the bf16 tensor cores, for the matmuls the reference leaves UNQUANTISED in fp32
  * (lm_head: models/opt_quantized/modeling_opt.py:942-944, models/llama_quantized/modeling_llama.py:772; bypass
  * layers: quantized_modules/linear.py:60-62; the y operand of block_log matmuls: quantized_functions/matmul.py:293-296).

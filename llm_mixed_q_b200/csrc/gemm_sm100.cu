@@ -33,7 +33,8 @@ constexpr int kEpiWarpWords = 32 * 33 + 64 * 4;      // per epilogue warp: 32x33
 // EPI: 0 none; 1 generic (every EpiArgs combination, runtime dispatch); specialised instances of the same code with the mode
 // fixed at compile time (each path gets its own register allocation — in the generic instance the fp32 / row-block paths cost the
 // bf16 column-block path 7 %): 2 = fp32 out, no quantiser (coalesced store / residual / replicas); 3 = blocks along N, bf16 out;
-// 4 = blocks along M, bf16 out (3, 4: no residual, no replicas); 5 = gated SiLU over interleaved gate / up column groups (EpiArgs::act 2).
+// 4 = blocks along M, bf16 out (3, 4: no residual, no replicas); 5 = gated SiLU over interleaved gate / up column groups (EpiArgs::act 2);
+// 6 = rotary position embedding + block quantiser (either direction), bf16 out (EpiArgs::rope_cos).
 // With CG == 2 a CTA pair computes a 256 x 256 tile: each CTA owns 128 rows of A and of the accumulator and HALF of the B tile,
 // which the pair's MMA reads from both shared memories — 2/3 of the smem fill traffic and operand reads per FLOP of CG == 1.
 template <int BN, int EPI = 0, int CG = 1> struct GemmCfg {
@@ -69,6 +70,13 @@ struct EpiArgs {
   // fused all-gather: the tile is also stored to the same position of n_rep peer-mapped copies of C (NVLink stores)
   int n_rep;
   void* rep[BQ_MAX_REPLICAS];
+  // rotary position embedding between the accumulator and the quantiser (EPI 6; Llama q_proj / k_proj -> matmul_0 operands):
+  // the N columns are heads of rope_d features, row m is the token at position rope_pos[m] (or m % rope_S)
+  const float* rope_cos;   // [rope_rows][rope_d] tables, already quantised by the host like the reference's; nullptr: no RoPE
+  const float* rope_sin;
+  const int64_t* rope_pos; // [M] or nullptr
+  int64_t rope_rows;
+  int rope_S, rope_d;
 };
 
 struct GemmArgs {
@@ -329,6 +337,98 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
   }
 }
 
+// Rotary position embedding + matmul_0 operand quantiser on TWO 32-column chunks of one accumulator row that are half a head apart
+// (features e0 .. e0+31 and e0 + d/2 .. e0 + d/2 + 31 of one head): replaces the fp32 store of q_proj / k_proj, the ~12 element-wise
+// torch kernels of the reference's apply_rotary_pos_emb (models/llama_quantized/modeling_llama.py:309-314 via
+// quantized_functions/rotary_positional_encoding.py:27-36) and the x / y quantizers of matmul_0 (quantized_functions/matmul.py:165-193).
+// Same arithmetic and order as rope_quant_q/k_kernel (quantize.cu), hence the same bits: rn(rn(x * cos) + rn(rot * sin)),
+// rot = -x[i + d/2] in the lower half and x[i - d/2] in the upper one.
+// 32 table rows (one per lane: row p_lane of a [rows][d] fp32 table) x 32 columns starting at col -> row-per-lane registers.  Loaded as
+// 8 instructions of 4 full 128-byte row segments (the row index of the segment's owner comes by shuffle) and transposed through the warp's
+// scratch — the inverse of chunk_to_coalesced.  (Lane-per-row 16-byte loads touched 32 lines per instruction: the epilogue then took
+// longer than its mainloop — 0.133 ms against 0.092 ms for the q_proj GEMM of a Llama-7B layer.)
+__device__ __forceinline__ void load_table_rows32(const float* table, int p_lane, int d, int col, float (&o)[32], uint32_t* scratch, int lane) {
+  float4* sc = reinterpret_cast<float4*>(scratch);
+  const int rsub = lane >> 3, c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const int pr = __shfl_sync(0xffffffffu, p_lane, r);
+    sc[r * 8 + (c ^ (r & 7))] = __ldg(reinterpret_cast<const float4*>(table + (int64_t)pr * d + col) + c);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = sc[lane * 8 + (j ^ (lane & 7))];
+    o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
+  }
+  __syncwarp();                                                  // scratch is reused by the next strip
+}
+
+__device__ __forceinline__ void epilogue_rope_pair(const GemmArgs& g, uint32_t (&lo)[32], uint32_t (&hi)[32], int row, int col_lo, int col_hi,
+                                                   bool row_ok, uint32_t* scratch, int lane, float* Cb) {
+  const EpiArgs& e = g.epi;
+  const int d = e.rope_d;
+  int p = 0;                                                   // table row of this lane's token (host: rope_rows < 2^31)
+  if (row_ok) p = e.rope_pos ? (int)min(max(e.rope_pos[row], (int64_t)0), e.rope_rows - 1) : (row % e.rope_S);
+  const int e0 = col_lo % d;                                   // position of the lower chunk inside its head (< d / 2)
+  float a[32], b[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { a[j] = __uint_as_float(lo[j]); b[j] = __uint_as_float(hi[j]); }
+  if (g.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b0 = *reinterpret_cast<const float4*>(g.bias + col_lo + j), b1 = *reinterpret_cast<const float4*>(g.bias + col_hi + j);
+      a[j] = __fadd_rn(a[j], b0.x); a[j + 1] = __fadd_rn(a[j + 1], b0.y); a[j + 2] = __fadd_rn(a[j + 2], b0.z); a[j + 3] = __fadd_rn(a[j + 3], b0.w);
+      b[j] = __fadd_rn(b[j], b1.x); b[j + 1] = __fadd_rn(b[j + 1], b1.y); b[j + 2] = __fadd_rn(b[j + 2], b1.z); b[j + 3] = __fadd_rn(b[j + 3], b1.w);
+    }
+  }
+  {
+    // products first (x * cos of both halves), then the sine terms: at most one table strip is live at a time
+    float t[32], xs[32];
+    load_table_rows32(e.rope_cos, p, d, e0, t, scratch, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { xs[j] = a[j]; a[j] = __fmul_rn(a[j], t[j]); }
+    load_table_rows32(e.rope_sin, p, d, e0, t, scratch, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = __fadd_rn(a[j], __fmul_rn(-b[j], t[j]));
+    load_table_rows32(e.rope_cos, p, d, e0 + (d >> 1), t, scratch, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = __fmul_rn(b[j], t[j]);
+    load_table_rows32(e.rope_sin, p, d, e0 + (d >> 1), t, scratch, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = __fadd_rn(b[j], __fmul_rn(xs[j], t[j]));
+  }
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = half ? b[j] : a[j];
+    if (e.qmode == 1) {
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        float t[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] = v[blk * 16 + i];
+        quantize_signed16_rt(t, e.q);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[blk * 16 + i] = t[i];
+      }
+    } else {
+      // blocks of 16 consecutive rows (k^T operand): every lane takes part; M % 16 == 0 keeps a block all-valid or all-invalid
+      if (e.q.kind == kBlockFP) quant_rowblocks32<kBlockFP>(v, e.q, scratch, lane);
+      else quant_rowblocks32<kBlockMinifloat>(v, e.q, scratch, lane);
+    }
+    if (row_ok) {
+      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(Cb) + (int64_t)row * g.ldc + (half ? col_hi : col_lo);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<uint4*>(c)[j] = make_uint4(pack_bf16_rn(v[8 * j], v[8 * j + 1]), pack_bf16_rn(v[8 * j + 2], v[8 * j + 3]),
+                                                    pack_bf16_rn(v[8 * j + 4], v[8 * j + 5]), pack_bf16_rn(v[8 * j + 6], v[8 * j + 7]));
+    }
+  }
+}
+
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GemmCfg<BN, EPI, CG>::kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
@@ -494,7 +594,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const int row = row0 + q * 32 + lane;
-      if (EPI) {
+      if (EPI == 6) {
+        // RoPE + quantiser: the unit of work is a PAIR of chunks half a head apart (host: rope_d % 64 == 0, BN % rope_d == 0, N % rope_d == 0)
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + Cfg::kEpiOff) + ew * kEpiWarpWords;
+        const int hc = g.epi.rope_d >> 6;             // chunks per half head
+#pragma unroll 1
+        for (int pi = c_first; pi < BN / 64; pi += c_step) {
+          const int c_lo = (pi / hc) * 2 * hc + (pi % hc), c_hi = c_lo + hc;
+          const int col_lo = nb * BN + c_lo * 32, col_hi = nb * BN + c_hi * 32;
+          if (col_lo >= g.N) continue;                // warp-uniform (chunk order is not monotonic in pi for hc > 1)
+          uint32_t rl[32], rh[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c_lo * 32), rl);
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c_hi * 32), rh);
+          ptx::tmem_ld_wait();
+          epilogue_rope_pair(g, rl, rh, row, col_lo, col_hi, row < g.M, scratch, lane, g.C);
+        }
+      } else if (EPI) {
         // fused epilogue (batch == 1, N % 32 == 0, all pointers 16-byte aligned: checked on the host)
         uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + Cfg::kEpiOff) + ew * kEpiWarpWords;
         const bool row_ok = row < g.M;
@@ -728,6 +843,12 @@ static void choose_tile(int64_t batch, int64_t M, int64_t N, int* BN, bool* pair
 template <bool EPI>
 static int launch_gemm_any(int BN, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st,
                            int kern_id) {
+  if (EPI && g.epi.rope_cos) {                                   // RoPE + quantiser (BN is a multiple of the head size: checked by the caller)
+    if (pair) return launch_gemm_cg<256, 6, 2>(tmA, tmB, g, st, kern_id);
+    if (BN == 128) return launch_gemm_cg<128, 6, 1>(tmA, tmB, g, st, kern_id);
+    if (BN == 256) return launch_gemm_cg<256, 6, 1>(tmA, tmB, g, st, kern_id);
+    return BQ_ERR_UNSUPPORTED;
+  }
   if (EPI && g.epi.act == 2) {                                   // gated SiLU: its own instances (N = 2 * features >= 128)
     if (pair) return launch_gemm_cg<256, 5, 2>(tmA, tmB, g, st, kern_id);
     if (BN == 128) return launch_gemm_cg<128, 5, 1>(tmA, tmB, g, st, kern_id);
@@ -839,6 +960,49 @@ int gemm_bf16_tn_epi_impl(const void* A, const void* B, void* C, const bq_gemm_e
   return launch_gemm_any<true>(BN, pair, tmA, tmB, g, st, kKernGemmEpi);
 }
 
+// q_proj / k_proj of a Llama layer with the rotary embedding and matmul_0's operand quantiser in the epilogue (see epilogue_rope_pair).
+int gemm_bf16_tn_rope_impl(const void* A, const void* B, void* C, const float* bias, const bq_format* qfmt, int qdir, const float* cos_t,
+                           const float* sin_t, const int64_t* pos, int64_t table_rows, int64_t S, int64_t d, int64_t M, int64_t N, int64_t K,
+                           int64_t lda, int64_t ldb, int64_t ldc, cudaStream_t st) {
+  if (!qfmt || M < 0 || N < 0 || K < 0 || S <= 0 || d <= 0) return BQ_ERR_BAD_ARG;
+  if (M == 0 || N == 0) return BQ_OK;
+  if (!A || !B || !C || !cos_t || !sin_t) return BQ_ERR_BAD_ARG;
+  if (K == 0) return BQ_ERR_UNSUPPORTED;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)C % 16) || ((uintptr_t)cos_t % 16) ||
+      ((uintptr_t)sin_t % 16) || (bias && ((uintptr_t)bias % 16)))
+    return BQ_ERR_BAD_ARG;
+  if (lda < K || ldb < K || ldc < N) return BQ_ERR_BAD_ARG;
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  if (table_rows < 1 || table_rows > 0x7fffffff || (!pos && table_rows < S)) return BQ_ERR_BAD_ARG;
+  if ((d != 64 && d != 128) || (N % d)) return BQ_ERR_UNSUPPORTED;      // a 128- or 256-column tile holds whole heads
+  if (qfmt->kind != BQ_KIND_BLOCK_FP && qfmt->kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
+  if (qfmt->block_rows != 1 || qfmt->block_cols != 16) return BQ_ERR_UNSUPPORTED;
+  if (qdir != 0 && qdir != 1) return BQ_ERR_BAD_ARG;
+  if (qdir == 1 && ((M % 16) || (S % 16))) return BQ_ERR_UNSUPPORTED;   // blocks of 16 tokens never straddle a sequence
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  int rc = make_params(qfmt, &g.epi.q);
+  if (rc) return rc;
+  g.epi.q.fold_zero = 0;
+  g.epi.qmode = qdir == 1 ? 2 : 1;
+  g.epi.out_bf16 = 1;
+  g.epi.scale = 1.0f;
+  g.epi.rope_cos = cos_t; g.epi.rope_sin = sin_t; g.epi.rope_pos = pos; g.epi.rope_rows = table_rows;
+  g.epi.rope_S = (int)S; g.epi.rope_d = (int)d;
+  int BN;
+  bool pair;
+  choose_tile(1, M, N, &BN, &pair);
+  if (BN < 128) { BN = 128; pair = false; }                              // N is a multiple of d >= 64; the 64-wide instance has no RoPE form
+  CUtensorMap tmA, tmB;
+  rc = make_tmap_bf16_kmajor(&tmA, A, K, M, 1, lda, 0, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, 1, ldb, 0, pair ? 128 : BN);
+  if (rc) return rc;
+  g.C = (float*)C; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = 1;
+  g.ldc = ldc; g.sc = 0; g.b_broadcast = 1; g.n_terms = 0;
+  return launch_gemm_any<true>(BN, pair, tmA, tmB, g, st, kKernGemmEpi);
+}
+
 // Split-precision GEMM: C = sum over terms (A_plane[ta] @ B_plane[tb]^T) (+ bias).  With x = x0 + x1 + x2 (three bf16
 // planes, see split3 in quantize.cu) and the six terms {(2,0),(0,2),(1,1),(1,0),(0,1),(0,0)} (smallest first) the
 // result carries ~2^-24 relative error per product, i.e. it stands in for an fp32 GEMM on the tensor cores.
@@ -923,6 +1087,14 @@ extern "C" int bq_bmm_split_tn(const void* A_planes, const void* B_planes, float
 extern "C" int bq_gemm_bf16_tn_ex(const void* A, const void* B, void* C, const bq_gemm_epilogue* ep, int64_t M, int64_t N,
                                   int64_t K, int64_t lda, int64_t ldb, int64_t ldc, void* stream) {
   return bq::gemm_bf16_tn_epi_impl(A, B, C, ep, M, N, K, lda, ldb, ldc, (cudaStream_t)stream);
+}
+
+extern "C" int bq_gemm_bf16_tn_rope(const void* A, const void* B, void* C_bf16, const float* bias, const bq_format* qfmt, int32_t qdir,
+                                    const float* cos_table, const float* sin_table, const int64_t* position_ids, int64_t table_rows,
+                                    int64_t S, int64_t head_dim, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                                    void* stream) {
+  return bq::gemm_bf16_tn_rope_impl(A, B, C_bf16, bias, qfmt, qdir, cos_table, sin_table, position_ids, table_rows, S, head_dim, M, N, K,
+                                    lda, ldb, ldc, (cudaStream_t)stream);
 }
 
 extern "C" int bq_gemm_split_tn(const void* A_planes, const void* B_planes, float* C, const float* bias, int64_t M, int64_t N,

@@ -43,11 +43,38 @@ def apply_token_major_quantized(q, k, cos, sin, position_ids, config, matmul0_co
     import ctypes
 
     from .... import _lib as L
-    from ..quantizers.utils import make_format, resolve_block_shape
 
     B, S, H = q.shape
     d = H // num_heads
-    if not (q.is_cuda and q.dtype == torch.float32 and k.dtype == torch.float32 and d % 32 == 0 and S % 16 == 0):
+    if not (q.is_cuda and q.dtype == torch.float32 and k.dtype == torch.float32):
+        return None
+    prep = rope_quantize_operands(cos, sin, position_ids, config, matmul0_config, B, S, d)
+    if prep is None:
+        return None
+    cos_t, sin_t, pos, fq, fk = prep
+    qc, kc = q, k
+    if qc.stride(-1) != 1 or qc.stride(0) != S * qc.stride(1):
+        qc = qc.contiguous()
+    if kc.stride(-1) != 1 or kc.stride(0) != S * kc.stride(1):
+        kc = kc.contiguous()
+    Qq = torch.empty((B, S, H), dtype=torch.bfloat16, device=q.device)
+    Kq = torch.empty((B, S, H), dtype=torch.bfloat16, device=q.device)
+    rc = L.load().bq_rope_quantize(qc.data_ptr(), kc.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(),
+                                   pos.data_ptr() if pos is not None else None, cos_t.shape[0], B, S, num_heads, d,
+                                   qc.stride(1), kc.stride(1), ctypes.byref(fq), ctypes.byref(fk), Qq.data_ptr(), Kq.data_ptr(),
+                                   L.stream_ptr(q.device))
+    L.check(rc, "bq_rope_quantize")
+    return Qq, Kq
+
+
+def rope_quantize_operands(cos, sin, position_ids, config, matmul0_config, B, S, d):
+    """What the fused RoPE kernels need besides q / k: the quantised [table_rows, d] cos / sin tables (quantised exactly as the
+    reference quantises them, :27-36), the validated int64 [B, S] positions (None for the default arange) and the formats of
+    matmul_0's x (q, blocks along d) and y (k^T, blocks along S) operands.  None when the configuration is not the [1,16]
+    block_fp / block_minifloat case those kernels serve."""
+    from ..quantizers.utils import make_format, resolve_block_shape
+
+    if d % 32 != 0 or S % 16 != 0:
         return None
     (qk_, qkw, qbs), (kk_, kkw, kbs) = operand_format(matmul0_config, "data_in"), operand_format(matmul0_config, "weight")
     if qk_ not in ("block_fp", "block_minifloat") or kk_ not in ("block_fp", "block_minifloat") or qbs is None or kbs is None:
@@ -57,13 +84,13 @@ def apply_token_major_quantized(q, k, cos, sin, position_ids, config, matmul0_co
     tq = _table_quantizer(config, config["name"])
     cos_t = tq(cos.squeeze(1).squeeze(0)).contiguous()          # [seq_len, d], quantised exactly as the reference does
     sin_t = tq(sin.squeeze(1).squeeze(0)).contiguous()
-    if cos_t.dtype != torch.float32 or cos_t.shape[-1] != d:
+    if cos_t.dtype != torch.float32 or cos_t.shape[-1] != d or not cos_t.is_cuda:
         return None
     pos = None
     if position_ids is not None:
         # explicit positions index the [table_rows, d] tables like the reference's cos[position_ids] (:44-45): out-of-range
         # raises IndexError, negative indices wrap.  One device-to-host look — the model classes pass None for the default
-        # arange, so the captured / steady-state forward never takes it.  (The kernel additionally clamps: no OOB read.)
+        # arange, so the captured / steady-state forward never takes it.  (The kernels additionally clamp: no OOB read.)
         rows = cos_t.shape[0]
         pos = position_ids.expand(B, S).to(torch.int64)
         lo, hi = (int(v) for v in torch.stack((pos.min(), pos.max())).tolist())
@@ -72,21 +99,7 @@ def apply_token_major_quantized(q, k, cos, sin, position_ids, config, matmul0_co
         if lo < 0:
             pos = torch.where(pos < 0, pos + rows, pos)
         pos = pos.contiguous()
-    qc, kc = q, k
-    if qc.stride(-1) != 1 or qc.stride(0) != S * qc.stride(1):
-        qc = qc.contiguous()
-    if kc.stride(-1) != 1 or kc.stride(0) != S * kc.stride(1):
-        kc = kc.contiguous()
-    fq = make_format(qk_, b0=1, b1=16, **qkw)
-    fk = make_format(kk_, b0=1, b1=16, **kkw)
-    Qq = torch.empty((B, S, H), dtype=torch.bfloat16, device=q.device)
-    Kq = torch.empty((B, S, H), dtype=torch.bfloat16, device=q.device)
-    rc = L.load().bq_rope_quantize(qc.data_ptr(), kc.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(),
-                                   pos.data_ptr() if pos is not None else None, cos_t.shape[0], B, S, num_heads, d,
-                                   qc.stride(1), kc.stride(1), ctypes.byref(fq), ctypes.byref(fk), Qq.data_ptr(), Kq.data_ptr(),
-                                   L.stream_ptr(q.device))
-    L.check(rc, "bq_rope_quantize")
-    return Qq, Kq
+    return cos_t, sin_t, pos, make_format(qk_, b0=1, b1=16, **qkw), make_format(kk_, b0=1, b1=16, **kkw)
 
 
 def _table_quantizer(config, name):

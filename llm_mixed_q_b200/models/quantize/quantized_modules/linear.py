@@ -370,6 +370,40 @@ class _LinearBase(nn.Linear):
             self.config.get("data_in_width", "NA"), self.config.get("weight_width", "NA"), self.config.get("bias_width", "NA"))
 
 
+ROPE_EPILOGUE = True      # False: q / k GEMMs with fp32 outputs + the RoPE+quantise kernels (A/B, tests)
+
+
+def rope_epilogue_fusable(lin: "_LinearBase", head_dim: int) -> bool:
+    return (ROPE_EPILOGUE and lin.accepts_prequantized() and head_dim in (64, 128) and lin.out_features % head_dim == 0
+            and (lin.bias is None or lin.bias.data_ptr() % 16 == 0))
+
+
+@torch.no_grad()
+def rope_prequantized(lin: "_LinearBase", xq: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, pos, fmt, seq_len: int, head_dim: int,
+                      along_rows: bool) -> torch.Tensor:
+    """Q_fmt(rope(lin(xq))) as bf16 [rows, N] in ONE GEMM launch (bq_gemm_bf16_tn_rope): q_proj / k_proj of a Llama layer with the
+    rotary embedding and matmul_0's operand quantizer in the epilogue (reference modeling_llama.py:274-276, :309-314).  `fmt`: the
+    bq_format of the operand (rope_quantize_operands), along_rows: blocks of 16 consecutive tokens (the k^T operand)."""
+    assert xq.dtype == torch.bfloat16 and xq.is_cuda and xq.shape[-1] == lin.in_features
+    lin._ensure_ptq()
+    lib = L.load()
+    K, N = lin.in_features, lin.out_features
+    x2 = xq.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0):
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=xq.device)
+    if M > 0:
+        wq = lin._weight_cache()
+        bias = lin.bias.detach() if lin.bias is not None else None
+        rc = lib.bq_gemm_bf16_tn_rope(x2.data_ptr(), wq.data_ptr(), y.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                      ctypes.byref(fmt), 1 if along_rows else 0, cos_t.data_ptr(), sin_t.data_ptr(),
+                                      pos.data_ptr() if pos is not None else None, cos_t.shape[0], seq_len, head_dim, M, N, K,
+                                      x2.stride(0) if M > 1 else K, K, N, L.stream_ptr(xq.device))
+        L.check(rc, "bq_gemm_bf16_tn_rope")
+    return y
+
+
 GATED_EPILOGUE = True     # False: gate / up GEMMs + the silu*mul quantizer kernel (A/B, tests)
 
 

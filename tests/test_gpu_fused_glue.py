@@ -484,6 +484,55 @@ def test_gated_silu_gemm_epilogue_is_bit_identical_to_two_gemms_and_the_silu_mul
     assert lib.bq_gemm_bf16_tn_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), ctypes.byref(ep), 32, 256, 64, 64, 64, 128, L.stream_ptr()) == 2
 
 
+@pytest.mark.parametrize("d", [128, 64])
+@pytest.mark.parametrize("kind", ["block_fp", "block_minifloat"])
+def test_rope_gemm_epilogue_is_bit_identical_to_gemm_then_rope_quantize(kind, d):
+    """bq_gemm_bf16_tn_rope (q_proj / k_proj with the rotary embedding and matmul_0's operand quantizer in the GEMM epilogue) against
+    the fp32 GEMM followed by bq_rope_quantize — which is itself bit-identical to the reference's torch ops + quantizers
+    (test above).  Pair tiles and single-CTA tiles, default and explicit positions, both block directions."""
+    import copy
+
+    from llm_mixed_q_b200.models.llama_quantized.modeling_llama import LlamaRotaryEmbedding
+    from llm_mixed_q_b200.models.quantize import get_quantized_cls
+    from llm_mixed_q_b200.models.quantize.quantized_functions.rotary_positional_encoding import (apply_token_major_quantized,
+                                                                                                 rope_quantize_operands)
+    from llm_mixed_q_b200.models.quantize.quantized_modules import linear as QL
+
+    if kind == "block_fp":
+        m0 = {"name": "block_fp", "bypass": False}
+        for p in ("data_in", "weight"):
+            m0.update({f"{p}_width": 6, f"{p}_exponent_width": 8, f"{p}_exponent_bias": 127, f"{p}_block_size": [1, 16]})
+    else:
+        m0 = {"name": "block_minifloat", "bypass": False}
+        for p in ("data_in", "weight"):
+            m0.update({f"{p}_width": 8, f"{p}_exponent_width": 4, f"{p}_exponent_bias_width": 8, f"{p}_block_size": [1, 16]})
+    rope_cfg = {"name": "integer", "bypass": False, "data_in_width": 8, "data_in_frac_width": 7}
+    cfg = bfp_cfg(6)
+    g = torch.Generator(device="cuda").manual_seed(13 + d)
+    for B, S, heads, K in [(2, 128, 4, 256), (1, 2048, 2, 128), (3, 48, 2, 64)]:
+        H = heads * d
+        lin_q = get_quantized_cls("linear", cfg)(K, H, bias=False, config=copy.deepcopy(cfg)).cuda()
+        lin_k = get_quantized_cls("linear", cfg)(K, H, bias=False, config=copy.deepcopy(cfg)).cuda()
+        with torch.no_grad():
+            lin_q.weight.mul_(8.0)
+            lin_k.weight.mul_(8.0)
+            lin_k.weight[5].zero_()                             # a feature whose k^T blocks are all zero
+        assert QL.rope_epilogue_fusable(lin_q, d) and QL.rope_epilogue_fusable(lin_k, d)
+        x = torch.randn(B * S, K, device="cuda", generator=g)
+        xq = QL.quantize_operand_bf16(x, "block_fp", dict(width=6, exponent_width=8, exponent_bias=127), [1, 16], True)
+        q32, k32 = lin_q.forward_prequantized(xq), lin_k.forward_prequantized(xq)
+        rot = LlamaRotaryEmbedding(d, max_position_embeddings=max(S, 256)).cuda()
+        cos, sin = rot(q32, seq_len=S)
+        for pos in (None, torch.randint(0, S, (B, S), device="cuda", generator=g)):
+            want = apply_token_major_quantized(q32.view(B, S, H), k32.view(B, S, H), cos, sin, pos, rope_cfg, m0, heads)
+            assert want is not None
+            cos_t, sin_t, p64, fq, fk = rope_quantize_operands(cos, sin, pos, rope_cfg, m0, B, S, d)
+            got_q = QL.rope_prequantized(lin_q, xq, cos_t, sin_t, p64, fq, S, d, False)
+            got_k = QL.rope_prequantized(lin_k, xq, cos_t, sin_t, p64, fk, S, d, True)
+            assert torch.equal(got_q.view(torch.int16), want[0].reshape(B * S, H).view(torch.int16)), (kind, d, B, S, pos is None)
+            assert torch.equal(got_k.view(torch.int16), want[1].reshape(B * S, H).view(torch.int16)), (kind, d, B, S, pos is None)
+
+
 def test_llama_layer_with_gated_epilogue_equals_three_launch_mlp():
     """The fused Llama layer with the gated GEMM epilogue is bit-identical to the same layer with gate GEMM + up GEMM + silu*mul
     quantizer (QL.GATED_EPILOGUE = False), block_minifloat W4A4-style config and block_log (split plan)."""
@@ -508,11 +557,11 @@ def test_llama_layer_with_gated_epilogue_equals_three_launch_mlp():
         outs = []
         try:
             for on in (True, False):
-                QL.GATED_EPILOGUE = on
+                QL.GATED_EPILOGUE = QL.ROPE_EPILOGUE = on        # (RoPE in the q / k GEMM epilogues: same A/B, same requirement)
                 with torch.no_grad():
                     outs.append(model(ids).logits)
         finally:
-            QL.GATED_EPILOGUE = True
+            QL.GATED_EPILOGUE = QL.ROPE_EPILOGUE = True
         assert torch.equal(outs[0], outs[1]), name
         assert getattr(model.model.layers[0].mlp.gate_proj, "_gu_cache", None) is not None
 
