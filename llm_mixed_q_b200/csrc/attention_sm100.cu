@@ -142,6 +142,16 @@ __device__ __forceinline__ uint32_t bf16x2_min(uint32_t a, uint32_t b) {
   asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
 }
+// {lo, hi} fp32 -> packed bf16x2, round to nearest even (one F2FP)
+__device__ __forceinline__ uint32_t cvt_bf16x2_rn(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+#ifndef BQ_PROBS_CVT_ROUND
+#define BQ_PROBS_CVT_ROUND 1
+#endif
+constexpr bool kProbsCvtRound = BQ_PROBS_CVT_ROUND != 0;
 // kMagicB = 1.5 * 2^23 + 0x4300: (t + kMagicB) - kMagicB == rintf(t) like kMagic, and the LOW 16 bits of the sum are
 // 0x4300 + q — the bf16 encoding of 128 + q (q <= 128).  Two such halves byte-permuted into one word are a bf16x2 pair on
 // which the clamp to qmax and the de-quantisation q * 2^(E-m) = fma(128 + q, step, -128 * step) run packed (every value
@@ -228,6 +238,20 @@ __device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, co
       const uint32_t base2 = pack_bf16_trunc(nb, nb);
       const float top = __fadd_rn(128.0f, p.qmax);
       const uint32_t top2 = pack_bf16_trunc(top, top);
+      if (SCALED && kProbsCvtRound) {
+        // FAST numerators only: 128 + (p + 1e-9f) * 2^(m-E) in ONE fused rounding, then cvt.rn.bf16x2.f32 — bf16 has an ulp of 1 in
+        // [128, 256), so the conversion IS the round-to-nearest-even to the mantissa grid and packs the pair: 2 FFMA + 1 F2FP instead
+        // of 2 FFMA + 2 FADD + 1 PRMT.  The sum is rounded at 2^-16 before the integer rounding (the reference rounds t at its own
+        // ulp): a probability moves by one step only when t sits within 2^-17 of a half-integer — the class of deviation the
+        // approximate exponential already has (|t| * 2^-22).
+        const float c128 = __fadd_rn(c0, 128.0f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t q2 = bf16x2_min(cvt_bf16x2_rn(__fmaf_rn(v[2 * i], g0, c128), __fmaf_rn(v[2 * i + 1], g0, c128)), top2);
+          w[i] = bf16x2_fma(q2, step2, base2);
+        }
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float t0 = __fadd_rn(__fmaf_rn(v[2 * i], g0, c0), kMagicB);            // kMagicB + rint((p + 1e-9f) * 2^(m-E))
@@ -268,16 +292,19 @@ __device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, co
   if (KIND == kBlockMinifloat) {
     // block_minifloat has no packed path above: this IS its hot path — keep it in registers (out of line it cost the Llama-7B W4A4
     // attention 0.37 -> 0.58 ms per layer: every block went through local memory and a call)
+    // The per-element log2 shortcut runs UNCHECKED here (NC = true): each element min-accumulates its distance from the log2 cliff and
+    // the block is tested once — the per-element zone test + branch of the checked variant kept the 16 element chains from
+    // interleaving.  A block with an element inside the zone (16 * 2^-14 of the blocks) is redone by the checked out-of-line path; v
+    // is left untouched for it.
     if (fs.ok) {
-      if (SCALED) {
+      uint32_t zacc = 0xffffffffu;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], inv_l);
+      for (int i = 0; i < 8; ++i) {
+        const float a = quant_elem_fast_impl<KIND, true>(SCALED ? __fmul_rn(v[2 * i], inv_l) : v[2 * i], fs, p, zacc);
+        const float b = quant_elem_fast_impl<KIND, true>(SCALED ? __fmul_rn(v[2 * i + 1], inv_l) : v[2 * i + 1], fs, p, zacc);
+        w[i] = pack_bf16_trunc(a, b);
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = quant_elem_fast<KIND>(v[i], fs, p);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = pack_bf16_trunc(v[2 * i], v[2 * i + 1]);
-      return;
+      if (!zone_hit<KIND>(zacc)) return;
     }
   }
   float vc[16];

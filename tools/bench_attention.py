@@ -26,6 +26,16 @@ out = {}
 shapes = [(8, 32, 2048, 64), (2, 32, 2048, 64), (8, 12, 2048, 64)]
 if len(sys.argv) > 1 and sys.argv[1] == "d128":
     shapes = [(2, 32, 2048, 128)]
+    # Llama-7B W4A4 block_minifloat (BASELINE configs[3]): P quantised per element (shared bias per block), score / sqrt(128) applied post-matmul
+    bmf = {"name": "block_minifloat", "bypass": False, "is_ptq": True}
+    for p in ("data_in", "weight", "bias"):
+        bmf.update({f"{p}_width": 4, f"{p}_exponent_width": 2, f"{p}_exponent_bias_width": 8, f"{p}_block_size": [16] if p == "bias" else [1, 16]})
+    B, heads, S, d = shapes[0]
+    g = torch.Generator(device=dev).manual_seed(0)
+    q = (torch.randn(B, S, heads * d, device=dev, generator=g)).to(torch.bfloat16)
+    k = (torch.randn(B, S, heads * d, device=dev, generator=g)).to(torch.bfloat16)
+    v = torch.randn(B, S, heads * d, device=dev, generator=g).to(torch.bfloat16)
+    out[f"B{B}h{heads}S{S}d{d}_block_minifloat_w4_ms"] = round(timeit(lambda: fused_causal_attention_q(q, k, v, bmf, heads, B, S, 128 ** 0.5, out_cfg=bmf), n=20), 4)
 if len(sys.argv) > 1 and sys.argv[1] == "peaked":
     # peaked softmax rows (trained checkpoints): score std 0.8 (random init) / 4 / 8 -> share of pass-through probabilities (<= 1e-8,
     # returned unquantised by the reference) ~0 / most / nearly all; default kernel only
@@ -38,6 +48,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "peaked":
         ms = timeit(lambda: fused_causal_attention_q(q, k, v, cfg, heads, B, S, 1.0, out_cfg=cfg), n=20)
         out[f"B{B}h{heads}S{S}d{d}_score_std_{q_std * 0.9 * 8:.1f}_ms"] = round(ms, 4)
     shapes = []
+    json.dump(out, open("gpurun_out/bench_attention_peaked.json", "w"), indent=1)
 for (B, heads, S, d) in shapes:
     Hh = heads * d
     g = torch.Generator(device=dev).manual_seed(0)
