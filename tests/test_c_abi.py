@@ -112,6 +112,32 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert lib.bq_bmm_split_tn(256, 256, 256, 0, 64, 64, 64, 1, 3, 3, t3a, t3b, 64, 4096, 0, None) == 0
     assert lib.bq_norm_quantize(256, 4, 64, 64, 256, None, 1e-5, 4, fm, outs, None) == 1
     assert lib.bq_norm_quantize(256, 0, 64, 64, 256, None, 1e-5, 1, fm, outs, None) == 0
+    # GEMM with the RoPE + quantizer epilogue (A, B, C, bias, fmt, qdir, cos, sin, pos, table_rows, S, head_dim, M, N, K, lda, ldb, ldc)
+    rope = lambda *a: lib.bq_gemm_bf16_tn_rope(*a, None)
+    assert rope(256, 256, 256, None, None, 0, 256, 256, None, 64, 64, 128, 64, 256, 64, 64, 64, 256) == 1                      # no format
+    assert rope(256, 256, 256, None, ctypes.byref(f6), 0, None, 256, None, 64, 64, 128, 64, 256, 64, 64, 64, 256) == 1         # no cos table
+    assert rope(256, 256, 256, None, ctypes.byref(f6), 0, 256, 256, None, 64, 64, 96, 64, 192, 64, 64, 64, 192) == 2           # head_dim 96
+    assert rope(256, 256, 256, None, ctypes.byref(f6), 0, 256, 256, None, 64, 64, 128, 64, 192, 64, 64, 64, 192) == 2          # N % head_dim
+    assert rope(256, 256, 256, None, ctypes.byref(fl), 0, 256, 256, None, 64, 64, 128, 64, 256, 64, 64, 64, 256) == 2          # block_log
+    assert rope(256, 256, 256, None, ctypes.byref(f6), 1, 256, 256, None, 64, 64, 128, 72, 256, 64, 64, 64, 256) == 2          # qdir 1: M % 16
+    assert rope(256, 256, 256, None, ctypes.byref(f6), 0, 256, 256, None, 32, 64, 128, 64, 256, 64, 64, 64, 256) == 1          # table shorter than S
+    assert rope(256, 256, 256, None, ctypes.byref(f6), 0, 256, 256, None, 64, 64, 128, 64, 256, 64, 64, 64, 128) == 1          # ldc < N
+    assert rope(None, None, None, None, ctypes.byref(f6), 0, None, None, None, 64, 64, 128, 0, 256, 64, 64, 64, 256) == 0      # empty problem
+    # gated-SiLU epilogue (act = 2): needs a format along N, bf16 output, no residual / replicas, ldc >= N / 2
+    ep = L.BqGemmEpilogue()
+    ep.scale, ep.act, ep.out_dtype = 1.0, 2, L.BQ_BF16
+    ex = lambda ldc=128: lib.bq_gemm_bf16_tn_ex(256, 256, 256, ctypes.byref(ep), 32, 256, 64, 64, 64, ldc, None)
+    assert ex() == 2                                                                              # no qfmt
+    ep.qfmt = ctypes.pointer(f6)
+    assert ex(64) == 1                                                                            # ldc < N / 2
+    ep.qdir = 1
+    assert ex() == 2                                                                              # blocks along M
+    ep.qdir, ep.out_dtype = 0, L.BQ_F32
+    assert ex() == 2                                                                              # fp32 output
+    ep.out_dtype, ep.scale = L.BQ_BF16, 0.5
+    assert ex() == 2                                                                              # scale
+    ep.scale, ep.act = 1.0, 3
+    assert ex(256) == 2                                                                           # unknown activation
     del q
 
 
