@@ -49,7 +49,11 @@ namespace bq {
 
 constexpr int kAtBM = 128;      // query rows per work item (UMMA M)
 constexpr int kAtBN = 128;      // keys per tile
-constexpr int kAtThreads = 640;
+constexpr int kAtThreads = 640;                    // 4 control warps + 16 softmax warps.  (Dropping the single-pipeline kernel's idle 20th warp
+                                                   // does not raise the 96-register cap: the file is 16 K registers per SM sub-partition and one
+                                                   // of them still hosts 5 warps — ptxas -v, 608 threads: 96 registers, same spills.)
+constexpr int kAt1Threads = kAtThreads;
+constexpr int kAt1FirstSoftmaxWarp = 4;
 constexpr int kSoftmaxWarps = 16;
 constexpr int kSubTile = 128 * 64 * 2;             // one 128-row x 128-byte swizzle-128B sub-tile = 16 KB
 constexpr uint32_t kAtTmemCols = 512;              // S: 2 x 128, O: up to 128  -> next power of two
@@ -148,8 +152,12 @@ __device__ __forceinline__ uint32_t cvt_bf16x2_rn(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// Build-time experiment, OFF: rounding to the mantissa grid by conversion (see quantize_probs16).  Measured 0.5705 -> 0.5575 ms at
+// B8 h32 S2048, but the sum is rounded at 2^-16 before the integer rounding: about one probability in 10^5 lands on the other side
+// of a half-integer, where the magic-constant path (one rounding at t's own ulp, like the reference) showed none — on a small W4
+// model the fused forward stopped being bit-identical to the op-by-op one (tests/test_gpu_fused_glue.py).  Parity first: not shipped.
 #ifndef BQ_PROBS_CVT_ROUND
-#define BQ_PROBS_CVT_ROUND 1
+#define BQ_PROBS_CVT_ROUND 0
 #endif
 constexpr bool kProbsCvtRound = BQ_PROBS_CVT_ROUND != 0;
 // kMagicB = 1.5 * 2^23 + 0x4300: (t + kMagicB) - kMagicB == rintf(t) like kMagic, and the LOW 16 bits of the sum are
@@ -239,11 +247,9 @@ __device__ __forceinline__ void quantize_probs16(float (&v)[16], float inv_l, co
       const float top = __fadd_rn(128.0f, p.qmax);
       const uint32_t top2 = pack_bf16_trunc(top, top);
       if (SCALED && kProbsCvtRound) {
-        // FAST numerators only: 128 + (p + 1e-9f) * 2^(m-E) in ONE fused rounding, then cvt.rn.bf16x2.f32 — bf16 has an ulp of 1 in
-        // [128, 256), so the conversion IS the round-to-nearest-even to the mantissa grid and packs the pair: 2 FFMA + 1 F2FP instead
-        // of 2 FFMA + 2 FADD + 1 PRMT.  The sum is rounded at 2^-16 before the integer rounding (the reference rounds t at its own
-        // ulp): a probability moves by one step only when t sits within 2^-17 of a half-integer — the class of deviation the
-        // approximate exponential already has (|t| * 2^-22).
+        // (experiment, compiled out by default — see BQ_PROBS_CVT_ROUND) 128 + (p + 1e-9f) * 2^(m-E) in ONE fused rounding, then
+        // cvt.rn.bf16x2.f32 — bf16 has an ulp of 1 in [128, 256), so the conversion is the round-to-nearest-even to the mantissa grid
+        // and packs the pair: 2 FFMA + 1 F2FP instead of 2 FFMA + 2 FADD + 1 PRMT.
         const float c128 = __fadd_rn(c0, 128.0f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -424,7 +430,7 @@ struct Ring {
 // MASKED = false: purely causal, no key-padding bitmap — the instance the benchmarked decoder path runs; the mask arithmetic of the
 // general instance (bidirectional mode, bitmap loads, per-bit selects) is compiled out of it
 template <int KIND, int D, bool FAST, bool MASKED>
-__global__ void __launch_bounds__(kAtThreads, 1)
+__global__ void __launch_bounds__(kAt1Threads, 1)
 attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, AttnArgs g) {
   using Cfg = AtCfg<D>;
@@ -596,10 +602,10 @@ attention_causal_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kAt1FirstSoftmaxWarp) {
     // ------------------------------------------------------------------ softmax / quantise / epilogue
-    const int quarter = warp & 3;                 // TMEM lane quarter
-    const int cq = (warp - 4) >> 2;               // which 32 key columns of every tile
+    const int quarter = warp & 3;                 // TMEM lane quarter (a warp may only touch lanes 32 * (warp % 4) ..)
+    const int cq = (warp - kAt1FirstSoftmaxWarp) >> 2;      // which 32 key columns of every tile
     const int r_in = quarter * 32 + lane;         // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int sw = r_in & 7;                      // SWIZZLE_128B: 16-byte chunk index ^= (row & 7)
@@ -1131,7 +1137,7 @@ static int launch_attention_fm(const CUtensorMap& tq, const CUtensorMap& tk, con
   const int grid = std::min(items, num_sms());
   {
     LaunchScope ls(kKernAttention, st);
-    BQ_CUDA_CHECK(launch_ex(attention_causal_kernel<KIND, D, FAST, MASKED>, grid, kAtThreads, Cfg::kSmemBytes, st, 1, tq, tk, tv, g));
+    BQ_CUDA_CHECK(launch_ex(attention_causal_kernel<KIND, D, FAST, MASKED>, grid, kAt1Threads, Cfg::kSmemBytes, st, 1, tq, tk, tv, g));
   }
   BQ_CUDA_CHECK(cudaGetLastError());
   return BQ_OK;
