@@ -268,6 +268,18 @@ BQ_API int bq_gemm_bf16_tn_rope(const void* A, const void* B, void* C_bf16, cons
                                 int64_t S, int64_t head_dim, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
                                 void* stream);
 
+/* q_proj | k_proj | v_proj of one Llama layer in ONE launch: B_qkv = the three quantised weights concatenated along N ([3 * H][K]; all
+ * three read the same x operand, i.e. their x-quantizers coincide), bias likewise ([3 * H] or NULL).  Segment 0 -> Cq: RoPE + fq in blocks
+ * of 16 features; segment 1 -> Ck: RoPE + fk in blocks of 16 consecutive tokens (the k^T operand of matmul_0); segment 2 -> Cv: fv in
+ * blocks of 16 features, no rotation (the y operand of matmul_1).  Each output bf16 [M][ldc].  H % 256 == 0 (a tile never straddles two
+ * projections), M % 16 == 0, S % 16 == 0.  Same bits as three bq_gemm_bf16_tn_rope / bq_gemm_bf16_tn_ex calls; 768 tiles in one
+ * persistent launch fill the last wave better than 3 x 256 at the Llama-7B shape and expose one epilogue tail instead of three. */
+BQ_API int bq_gemm_bf16_tn_qkv_rope(const void* A, const void* B_qkv, void* Cq_bf16, void* Ck_bf16, void* Cv_bf16, const float* bias,
+                                    const bq_format* fq, const bq_format* fk, const bq_format* fv, const float* cos_table,
+                                    const float* sin_table, const int64_t* position_ids, int64_t table_rows, int64_t S,
+                                    int64_t head_dim, int64_t M, int64_t H, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                                    void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * fp32-equivalent GEMM on the bf16 tensor cores, for the matmuls the reference leaves UNQUANTISED in fp32
  * (lm_head: models/opt_quantized/modeling_opt.py:942-944, models/llama_quantized/modeling_llama.py:772; bypass

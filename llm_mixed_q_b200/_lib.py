@@ -100,6 +100,8 @@ def load():
     lib.bq_gemm_bf16_tn_rope.restype = ctypes.c_int
     lib.bq_gemm_bf16_tn_rope.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BqFormat), c_int32, c_void_p, c_void_p, c_void_p] + \
         [c_int64] * 9 + [c_void_p]
+    lib.bq_gemm_bf16_tn_qkv_rope.restype = ctypes.c_int
+    lib.bq_gemm_bf16_tn_qkv_rope.argtypes = [c_void_p] * 6 + [POINTER(BqFormat)] * 3 + [c_void_p] * 3 + [c_int64] * 9 + [c_void_p]
     lib.bq_norm_quantize.restype = ctypes.c_int
     lib.bq_norm_quantize.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, ctypes.c_float, c_int32,
                                      POINTER(BqFormat), POINTER(c_void_p), c_void_p]

@@ -77,6 +77,14 @@ struct EpiArgs {
   const int64_t* rope_pos; // [M] or nullptr
   int64_t rope_rows;
   int rope_S, rope_d;
+  // EPI 6, q | k | v in ONE launch: the N columns are up to three segments of seg_cols columns (the projections' quantised weights
+  // concatenated along N, all reading the same x operand); segment s stores bf16 [M][ldc] to seg_C[s] with its own block direction,
+  // format and RoPE flag.  seg_cols == 0: one segment described by C / qmode / q above.
+  int seg_cols;
+  void* seg_C[3];
+  int seg_qmode[3];
+  int seg_rope[3];
+  FmtParams seg_q[3];
 };
 
 struct GemmArgs {
@@ -369,8 +377,23 @@ __device__ __forceinline__ void epilogue_rope_pair(const GemmArgs& g, uint32_t (
                                                    bool row_ok, uint32_t* scratch, int lane, float* Cb) {
   const EpiArgs& e = g.epi;
   const int d = e.rope_d;
+  // segment of this pair (warp-uniform): its destination, block direction, format and whether it is rotated at all (v_proj is not)
+  int qmode = e.qmode, rope = 1;
+  const FmtParams* qf = &e.q;
+  if (e.seg_cols > 0) {
+    const int seg = col_lo / e.seg_cols;
+    qmode = e.seg_qmode[seg];
+    rope = e.seg_rope[seg];
+    qf = &e.seg_q[seg];
+    Cb = reinterpret_cast<float*>(e.seg_C[seg]);
+  }
+  const int gcol_lo = col_lo, gcol_hi = col_hi;                // the bias keeps the global (concatenated) column index
+  if (e.seg_cols > 0) {                                        // column inside the segment's own output
+    col_lo %= e.seg_cols;
+    col_hi %= e.seg_cols;
+  }
   int p = 0;                                                   // table row of this lane's token (host: rope_rows < 2^31)
-  if (row_ok) p = e.rope_pos ? (int)min(max(e.rope_pos[row], (int64_t)0), e.rope_rows - 1) : (row % e.rope_S);
+  if (row_ok && rope) p = e.rope_pos ? (int)min(max(e.rope_pos[row], (int64_t)0), e.rope_rows - 1) : (row % e.rope_S);
   const int e0 = col_lo % d;                                   // position of the lower chunk inside its head (< d / 2)
   float a[32], b[32];
 #pragma unroll
@@ -378,12 +401,12 @@ __device__ __forceinline__ void epilogue_rope_pair(const GemmArgs& g, uint32_t (
   if (g.bias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 b0 = *reinterpret_cast<const float4*>(g.bias + col_lo + j), b1 = *reinterpret_cast<const float4*>(g.bias + col_hi + j);
+      const float4 b0 = *reinterpret_cast<const float4*>(g.bias + gcol_lo + j), b1 = *reinterpret_cast<const float4*>(g.bias + gcol_hi + j);
       a[j] = __fadd_rn(a[j], b0.x); a[j + 1] = __fadd_rn(a[j + 1], b0.y); a[j + 2] = __fadd_rn(a[j + 2], b0.z); a[j + 3] = __fadd_rn(a[j + 3], b0.w);
       b[j] = __fadd_rn(b[j], b1.x); b[j + 1] = __fadd_rn(b[j + 1], b1.y); b[j + 2] = __fadd_rn(b[j + 2], b1.z); b[j + 3] = __fadd_rn(b[j + 3], b1.w);
     }
   }
-  {
+  if (rope) {
     // products first (x * cos of both halves), then the sine terms: at most one table strip is live at a time
     float t[32], xs[32];
     load_table_rows32(e.rope_cos, p, d, e0, t, scratch, lane);
@@ -404,20 +427,20 @@ __device__ __forceinline__ void epilogue_rope_pair(const GemmArgs& g, uint32_t (
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = half ? b[j] : a[j];
-    if (e.qmode == 1) {
+    if (qmode == 1) {
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
         float t[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) t[i] = v[blk * 16 + i];
-        quantize_signed16_rt(t, e.q);
+        quantize_signed16_rt(t, *qf);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[blk * 16 + i] = t[i];
       }
     } else {
       // blocks of 16 consecutive rows (k^T operand): every lane takes part; M % 16 == 0 keeps a block all-valid or all-invalid
-      if (e.q.kind == kBlockFP) quant_rowblocks32<kBlockFP>(v, e.q, scratch, lane);
-      else quant_rowblocks32<kBlockMinifloat>(v, e.q, scratch, lane);
+      if (qf->kind == kBlockFP) quant_rowblocks32<kBlockFP>(v, *qf, scratch, lane);
+      else quant_rowblocks32<kBlockMinifloat>(v, *qf, scratch, lane);
     }
     if (row_ok) {
       __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(Cb) + (int64_t)row * g.ldc + (half ? col_hi : col_lo);
@@ -1003,6 +1026,61 @@ int gemm_bf16_tn_rope_impl(const void* A, const void* B, void* C, const float* b
   return launch_gemm_any<true>(BN, pair, tmA, tmB, g, st, kKernGemmEpi);
 }
 
+// q_proj | k_proj | v_proj of a Llama layer as ONE GEMM over the concatenated weights [3 * Hs][K] (same x operand): segment 0 = q (RoPE,
+// blocks along the features), 1 = k (RoPE, blocks of 16 tokens), 2 = v (no RoPE, blocks along the features) — three bf16 outputs.
+// 768 tiles in one persistent launch fill the last wave better than three launches of 256 (3 x 4 waves -> 11) and expose one
+// epilogue tail instead of three.
+int gemm_bf16_tn_qkv_rope_impl(const void* A, const void* B, void* Cq, void* Ck, void* Cv, const float* bias, const bq_format* fq,
+                               const bq_format* fk, const bq_format* fv, const float* cos_t, const float* sin_t, const int64_t* pos,
+                               int64_t table_rows, int64_t S, int64_t d, int64_t M, int64_t Hs, int64_t K, int64_t lda, int64_t ldb,
+                               int64_t ldc, cudaStream_t st) {
+  if (!fq || !fk || !fv || M < 0 || Hs < 0 || K < 0 || S <= 0 || d <= 0) return BQ_ERR_BAD_ARG;
+  if (M == 0 || Hs == 0) return BQ_OK;
+  if (!A || !B || !Cq || !Ck || !Cv || !cos_t || !sin_t) return BQ_ERR_BAD_ARG;
+  if (K == 0) return BQ_ERR_UNSUPPORTED;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16) || ((uintptr_t)Cq % 16) || ((uintptr_t)Ck % 16) ||
+      ((uintptr_t)Cv % 16) || ((uintptr_t)cos_t % 16) || ((uintptr_t)sin_t % 16) || (bias && ((uintptr_t)bias % 16)))
+    return BQ_ERR_BAD_ARG;
+  if (lda < K || ldb < K || ldc < Hs) return BQ_ERR_BAD_ARG;
+  const int64_t N = 3 * Hs;
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return BQ_ERR_UNSUPPORTED;
+  if (table_rows < 1 || table_rows > 0x7fffffff || (!pos && table_rows < S)) return BQ_ERR_BAD_ARG;
+  if ((d != 64 && d != 128) || (Hs % d) || (Hs % 256)) return BQ_ERR_UNSUPPORTED;      // a tile never straddles two segments
+  if ((M % 16) || (S % 16)) return BQ_ERR_UNSUPPORTED;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  const bq_format* fs[3] = {fq, fk, fv};
+  for (int i = 0; i < 3; ++i) {
+    if (fs[i]->kind != BQ_KIND_BLOCK_FP && fs[i]->kind != BQ_KIND_BLOCK_MINIFLOAT) return BQ_ERR_UNSUPPORTED;
+    if (fs[i]->block_rows != 1 || fs[i]->block_cols != 16) return BQ_ERR_UNSUPPORTED;
+    int rc = make_params(fs[i], &g.epi.seg_q[i]);
+    if (rc) return rc;
+    g.epi.seg_q[i].fold_zero = 0;
+  }
+  g.epi.seg_cols = (int)Hs;
+  g.epi.seg_C[0] = Cq; g.epi.seg_C[1] = Ck; g.epi.seg_C[2] = Cv;
+  g.epi.seg_qmode[0] = 1; g.epi.seg_qmode[1] = 2; g.epi.seg_qmode[2] = 1;
+  g.epi.seg_rope[0] = 1; g.epi.seg_rope[1] = 1; g.epi.seg_rope[2] = 0;
+  g.epi.q = g.epi.seg_q[0];
+  g.epi.qmode = 1;
+  g.epi.out_bf16 = 1;
+  g.epi.scale = 1.0f;
+  g.epi.rope_cos = cos_t; g.epi.rope_sin = sin_t; g.epi.rope_pos = pos; g.epi.rope_rows = table_rows;
+  g.epi.rope_S = (int)S; g.epi.rope_d = (int)d;
+  int BN;
+  bool pair;
+  choose_tile(1, M, N, &BN, &pair);
+  if (BN < 128) { BN = 128; pair = false; }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_kmajor(&tmA, A, K, M, 1, lda, 0, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_kmajor(&tmB, B, K, N, 1, ldb, 0, pair ? 128 : BN);
+  if (rc) return rc;
+  g.C = (float*)Cq; g.bias = bias; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.batch = 1;
+  g.ldc = ldc; g.sc = 0; g.b_broadcast = 1; g.n_terms = 0;
+  return launch_gemm_any<true>(BN, pair, tmA, tmB, g, st, kKernGemmEpi);
+}
+
 // Split-precision GEMM: C = sum over terms (A_plane[ta] @ B_plane[tb]^T) (+ bias).  With x = x0 + x1 + x2 (three bf16
 // planes, see split3 in quantize.cu) and the six terms {(2,0),(0,2),(1,1),(1,0),(0,1),(0,0)} (smallest first) the
 // result carries ~2^-24 relative error per product, i.e. it stands in for an fp32 GEMM on the tensor cores.
@@ -1095,6 +1173,15 @@ extern "C" int bq_gemm_bf16_tn_rope(const void* A, const void* B, void* C_bf16, 
                                     void* stream) {
   return bq::gemm_bf16_tn_rope_impl(A, B, C_bf16, bias, qfmt, qdir, cos_table, sin_table, position_ids, table_rows, S, head_dim, M, N, K,
                                     lda, ldb, ldc, (cudaStream_t)stream);
+}
+
+extern "C" int bq_gemm_bf16_tn_qkv_rope(const void* A, const void* B_qkv, void* Cq_bf16, void* Ck_bf16, void* Cv_bf16, const float* bias,
+                                        const bq_format* fq, const bq_format* fk, const bq_format* fv, const float* cos_table,
+                                        const float* sin_table, const int64_t* position_ids, int64_t table_rows, int64_t S,
+                                        int64_t head_dim, int64_t M, int64_t H, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                                        void* stream) {
+  return bq::gemm_bf16_tn_qkv_rope_impl(A, B_qkv, Cq_bf16, Ck_bf16, Cv_bf16, bias, fq, fk, fv, cos_table, sin_table, position_ids, table_rows,
+                                        S, head_dim, M, H, K, lda, ldb, ldc, (cudaStream_t)stream);
 }
 
 extern "C" int bq_gemm_split_tn(const void* A_planes, const void* B_planes, float* C, const float* bias, int64_t M, int64_t N,

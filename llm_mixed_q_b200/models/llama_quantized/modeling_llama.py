@@ -29,8 +29,8 @@ from ..quantize.quantized_functions.split_attention import rope_quantize_split, 
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major as _rope_token_major
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major_quantized as _rope_token_major_quantized
 from ..quantize.quantized_functions.rotary_positional_encoding import rope_quantize_operands
-from ..quantize.quantized_modules.linear import (gated_silu_fusable, gated_silu_prequantized, operand_format, quantize_operand_bf16,
-                                                 rope_epilogue_fusable, rope_prequantized)
+from ..quantize.quantized_modules.linear import (gated_silu_fusable, gated_silu_prequantized, operand_format, qkv_rope_fusable,
+                                                 qkv_rope_prequantized, quantize_operand_bf16, rope_epilogue_fusable, rope_prequantized)
 from .configuration_llama import LlamaQuantizedConfig
 
 
@@ -219,17 +219,24 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         n1, n2 = self.input_layernorm, self.post_attention_layernorm
         qc = at.quant_config
         xq, xk, xv = norm_quantize(h, n1.weight, None, n1.variance_epsilon, [plan["q_in"], plan["k_in"], plan["v_in"]])
-        Vq = at.v_proj.forward_prequantized(xv, out_format=plan["v_out"])        # bmm_1's y-quantizer in the GEMM epilogue
         cos, sin = at.rotary_emb(h, seq_len=S)
         pos_arg = None if default_positions else position_ids                    # default arange: the kernels derive it (graph-capturable)
-        fusedqk = None
+        fusedqk, Vq = None, None
         if self.fused_rope and rope_epilogue_fusable(at.q_proj, at.head_dim) and rope_epilogue_fusable(at.k_proj, at.head_dim):
             # RoPE + matmul_0's operand quantizers inside the q_proj / k_proj GEMM epilogues: no fp32 q / k in HBM at all
             prep = rope_quantize_operands(cos, sin, pos_arg, qc["rotary_positional_encoding"], qc["matmul_0"], B, S, at.head_dim)
             if prep is not None:
                 cos_t, sin_t, pos, fq, fk = prep
-                fusedqk = (rope_prequantized(at.q_proj, xq, cos_t, sin_t, pos, fq, S, at.head_dim, False).view(B, S, H),
-                           rope_prequantized(at.k_proj, xk, cos_t, sin_t, pos, fk, S, at.head_dim, True).view(B, S, H))
+                if (xq.data_ptr() == xk.data_ptr() == xv.data_ptr() and (B * S) % 16 == 0
+                        and qkv_rope_fusable(at.q_proj, at.k_proj, at.v_proj, at.head_dim)):
+                    # one x-quantizer for the three projections: ONE launch over the concatenated weights
+                    Qf, Kf, Vq = qkv_rope_prequantized(at.q_proj, at.k_proj, at.v_proj, xq, cos_t, sin_t, pos, fq, fk, plan["v_out"], S, at.head_dim)
+                    fusedqk = (Qf.view(B, S, H), Kf.view(B, S, H))
+                else:
+                    fusedqk = (rope_prequantized(at.q_proj, xq, cos_t, sin_t, pos, fq, S, at.head_dim, False).view(B, S, H),
+                               rope_prequantized(at.k_proj, xk, cos_t, sin_t, pos, fk, S, at.head_dim, True).view(B, S, H))
+        if Vq is None:
+            Vq = at.v_proj.forward_prequantized(xv, out_format=plan["v_out"])    # bmm_1's y-quantizer in the GEMM epilogue
         if fusedqk is None:
             q = at.q_proj.forward_prequantized(xq)                               # fp32: RoPE runs on unquantised projections
             k = at.k_proj.forward_prequantized(xk)

@@ -404,6 +404,50 @@ def rope_prequantized(lin: "_LinearBase", xq: torch.Tensor, cos_t: torch.Tensor,
     return y
 
 
+QKV_ONE_LAUNCH = True     # False: three GEMM launches for q / k / v (A/B, tests)
+
+
+def qkv_rope_fusable(q: "_LinearBase", k: "_LinearBase", v: "_LinearBase", head_dim: int) -> bool:
+    return (QKV_ONE_LAUNCH and all(rope_epilogue_fusable(m, head_dim) for m in (q, k)) and v.accepts_prequantized()
+            and q.in_features == k.in_features == v.in_features and q.out_features == k.out_features == v.out_features
+            and q.out_features % 256 == 0 and len({m.bias is None for m in (q, k, v)}) == 1)
+
+
+@torch.no_grad()
+def qkv_rope_prequantized(q: "_LinearBase", k: "_LinearBase", v: "_LinearBase", xq: torch.Tensor, cos_t, sin_t, pos, fq, fk, v_format,
+                          seq_len: int, head_dim: int):
+    """(Q_q(rope(q_proj(x))), Q_k(rope(k_proj(x))) along tokens, Q_v(v_proj(x))) as bf16 [rows, H] each, in ONE GEMM launch over the three
+    quantised weights concatenated along N (bq_gemm_bf16_tn_qkv_rope) — for a Llama layer whose q / k / v projections share their
+    x-quantizer (reference modeling_llama.py:274-276, :309-314, :341-344).  Same bits as three separate launches."""
+    assert xq.dtype == torch.bfloat16 and xq.is_cuda and xq.shape[-1] == q.in_features
+    for m in (q, k, v):
+        m._ensure_ptq()
+    lib = L.load()
+    K, H = q.in_features, q.out_features
+    key = tuple((m.weight.data_ptr(), m.weight._version) for m in (q, k, v)) + (q.weight.device,)
+    cache = getattr(q, "_qkv_cache", None)
+    if cache is None or cache[0] != key:
+        wcat = torch.cat([m._weight_cache() for m in (q, k, v)], dim=0).contiguous()
+        bcat = torch.cat([m.bias.detach() for m in (q, k, v)]).contiguous() if q.bias is not None else None
+        q._qkv_cache = cache = (key, wcat, bcat)
+        q._wq_bf16 = k._wq_bf16 = v._wq_bf16 = None
+    _, wcat, bcat = cache
+    x2 = xq.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0):
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    outs = [torch.empty((M, H), dtype=torch.bfloat16, device=xq.device) for _ in range(3)]
+    if M > 0:
+        vk, vkw = v_format
+        fv = make_format(vk, b0=1, b1=16, **vkw)
+        rc = lib.bq_gemm_bf16_tn_qkv_rope(x2.data_ptr(), wcat.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                                          bcat.data_ptr() if bcat is not None else None, ctypes.byref(fq), ctypes.byref(fk), ctypes.byref(fv),
+                                          cos_t.data_ptr(), sin_t.data_ptr(), pos.data_ptr() if pos is not None else None, cos_t.shape[0],
+                                          seq_len, head_dim, M, H, K, x2.stride(0) if M > 1 else K, K, H, L.stream_ptr(xq.device))
+        L.check(rc, "bq_gemm_bf16_tn_qkv_rope")
+    return outs
+
+
 GATED_EPILOGUE = True     # False: gate / up GEMMs + the silu*mul quantizer kernel (A/B, tests)
 
 

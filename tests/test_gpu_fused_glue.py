@@ -509,7 +509,7 @@ def test_rope_gemm_epilogue_is_bit_identical_to_gemm_then_rope_quantize(kind, d)
     rope_cfg = {"name": "integer", "bypass": False, "data_in_width": 8, "data_in_frac_width": 7}
     cfg = bfp_cfg(6)
     g = torch.Generator(device="cuda").manual_seed(13 + d)
-    for B, S, heads, K in [(2, 128, 4, 256), (1, 2048, 2, 128), (3, 48, 2, 64)]:
+    for B, S, heads, K in [(2, 128, 4, 256), (1, 2048, 2, 128), (3, 48, 2, 64), (2, 2048, 8, 512)]:
         H = heads * d
         lin_q = get_quantized_cls("linear", cfg)(K, H, bias=False, config=copy.deepcopy(cfg)).cuda()
         lin_k = get_quantized_cls("linear", cfg)(K, H, bias=False, config=copy.deepcopy(cfg)).cuda()
@@ -531,6 +531,18 @@ def test_rope_gemm_epilogue_is_bit_identical_to_gemm_then_rope_quantize(kind, d)
             got_k = QL.rope_prequantized(lin_k, xq, cos_t, sin_t, p64, fk, S, d, True)
             assert torch.equal(got_q.view(torch.int16), want[0].reshape(B * S, H).view(torch.int16)), (kind, d, B, S, pos is None)
             assert torch.equal(got_k.view(torch.int16), want[1].reshape(B * S, H).view(torch.int16)), (kind, d, B, S, pos is None)
+            # q | k | v in one launch over the concatenated weights (bq_gemm_bf16_tn_qkv_rope): same bits as the separate launches
+            if H % 256 == 0 and (B * S) % 16 == 0:
+                lin_v = get_quantized_cls("linear", cfg)(K, H, bias=False, config=copy.deepcopy(cfg)).cuda()
+                with torch.no_grad():
+                    lin_v.weight.mul_(8.0)
+                v_fmt = ("block_fp", dict(width=6, exponent_width=8, exponent_bias=127)) if kind == "block_fp" else \
+                        ("block_minifloat", dict(width=8, exponent_width=4, exponent_bias_width=8))
+                assert QL.qkv_rope_fusable(lin_q, lin_k, lin_v, d)
+                want_v = lin_v.forward_prequantized(xq, out_format=v_fmt)
+                q1, k1, v1 = QL.qkv_rope_prequantized(lin_q, lin_k, lin_v, xq, cos_t, sin_t, p64, fq, fk, v_fmt, S, d)
+                assert torch.equal(q1.view(torch.int16), got_q.view(torch.int16)) and torch.equal(k1.view(torch.int16), got_k.view(torch.int16))
+                assert torch.equal(v1.view(torch.int16), want_v.view(torch.int16))
 
 
 def test_llama_layer_with_gated_epilogue_equals_three_launch_mlp():
@@ -548,7 +560,7 @@ def test_llama_layer_with_gated_epilogue_equals_three_launch_mlp():
     for name in ("block_minifloat.toml", "block_log.toml", "bfp_6bit.toml"):
         if name not in raw:
             continue
-        cfg = LlamaQuantizedConfig(hidden_size=128, intermediate_size=352, num_hidden_layers=2, num_attention_heads=2, vocab_size=512,
+        cfg = LlamaQuantizedConfig(hidden_size=256, intermediate_size=352, num_hidden_layers=2, num_attention_heads=2, vocab_size=512,
                                    max_position_embeddings=128, quant_config=raw[name])
         torch.manual_seed(0)
         model = LlamaQuantizedForCausalLM(cfg).eval().cuda()
@@ -557,13 +569,16 @@ def test_llama_layer_with_gated_epilogue_equals_three_launch_mlp():
         outs = []
         try:
             for on in (True, False):
-                QL.GATED_EPILOGUE = QL.ROPE_EPILOGUE = on        # (RoPE in the q / k GEMM epilogues: same A/B, same requirement)
+                # (RoPE in the q / k GEMM epilogues and q | k | v as one launch: same A/B, same requirement)
+                QL.GATED_EPILOGUE = QL.ROPE_EPILOGUE = QL.QKV_ONE_LAUNCH = on
                 with torch.no_grad():
                     outs.append(model(ids).logits)
         finally:
-            QL.GATED_EPILOGUE = QL.ROPE_EPILOGUE = True
+            QL.GATED_EPILOGUE = QL.ROPE_EPILOGUE = QL.QKV_ONE_LAUNCH = True
         assert torch.equal(outs[0], outs[1]), name
         assert getattr(model.model.layers[0].mlp.gate_proj, "_gu_cache", None) is not None
+        if name != "block_log.toml":
+            assert getattr(model.model.layers[0].self_attn.q_proj, "_qkv_cache", None) is not None
 
 
 def test_fused_llama_block_log_takes_the_split_attention_plan():

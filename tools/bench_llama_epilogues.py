@@ -56,6 +56,24 @@ def qk_fused():
     return (QL.rope_prequantized(lq, xq, cos_t, sin_t, pos, fq, S, d, False), QL.rope_prequantized(lk, xq, cos_t, sin_t, pos, fk, S, d, True))
 
 
+lv = mk(H, H)
+with torch.no_grad():
+    lv.weight.mul_(64.0)
+
+
+def qkv_three():
+    return qk_fused() + (lv.forward_prequantized(xq, out_format=fmt),)
+
+
+def qkv_one():
+    return QL.qkv_rope_prequantized(lq, lk, lv, xq, cos_t, sin_t, pos, fq, fk, fmt, S, d)
+
+
+a3 = qkv_three()
+out["qkv_three_launches_ms"] = round(timeit(qkv_three), 4)
+b3 = qkv_one()
+out["qkv_one_launch_bit_identical"] = bool(all(torch.equal(x, y) for x, y in zip(a3, b3)))
+out["qkv_one_launch_ms"] = round(timeit(qkv_one), 4)
 a, b = qk_unfused(), qk_fused()
 out["qk_bit_identical"] = bool(torch.equal(a[0].view(M, H), b[0]) and torch.equal(a[1].view(M, H), b[1]))
 out["q_gemm_fp32_ms"] = round(timeit(lambda: lq.forward_prequantized(xq)), 4)
