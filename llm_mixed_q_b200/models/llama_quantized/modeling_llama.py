@@ -29,8 +29,8 @@ from ..quantize.quantized_functions.split_attention import rope_quantize_split, 
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major as _rope_token_major
 from ..quantize.quantized_functions.rotary_positional_encoding import apply_token_major_quantized as _rope_token_major_quantized
 from ..quantize.quantized_functions.rotary_positional_encoding import rope_quantize_operands
-from ..quantize.quantized_modules.linear import (gated_silu_fusable, gated_silu_prequantized, operand_format, qkv_rope_fusable,
-                                                 qkv_rope_prequantized, quantize_operand_bf16, rope_epilogue_fusable, rope_prequantized)
+from ..quantize.quantized_modules.linear import (gated_silu_fusable, gated_silu_prequantized, operand_format, qkv_plain_fusable,
+                                                 qkv_plain_prequantized, qkv_rope_fusable, qkv_rope_prequantized, quantize_operand_bf16, rope_epilogue_fusable, rope_prequantized)
 from .configuration_llama import LlamaQuantizedConfig
 
 
@@ -195,10 +195,13 @@ class LlamaQuantizedDecoderLayer(nn.Module):
         n1, n2 = self.input_layernorm, self.post_attention_layernorm
         qc = at.quant_config
         xq, xk, xv = norm_quantize(h, n1.weight, None, n1.variance_epsilon, [plan["q_in"], plan["k_in"], plan["v_in"]])
-        q = at.q_proj.forward_prequantized(xq)
-        k = at.k_proj.forward_prequantized(xk)
-        v = at.v_proj.forward_prequantized(xv)
-        cos, sin = at.rotary_emb(q, seq_len=S)
+        if xq.data_ptr() == xk.data_ptr() == xv.data_ptr() and qkv_plain_fusable(at.q_proj, at.k_proj, at.v_proj):
+            q, k, v = qkv_plain_prequantized(at.q_proj, at.k_proj, at.v_proj, xq.view(B * S, H))      # one launch, column views
+        else:
+            q = at.q_proj.forward_prequantized(xq)
+            k = at.k_proj.forward_prequantized(xk)
+            v = at.v_proj.forward_prequantized(xv)
+        cos, sin = at.rotary_emb(h, seq_len=S)
         Qq, Kp = rope_quantize_split(q.view(B, S, H), k.view(B, S, H), cos, sin, None if default_positions else position_ids,
                                      qc["rotary_positional_encoding"], qc["matmul_0"], at.num_heads)
         o = split_attention(Qq, Kp, v.view(B, S, H), qc["matmul_1"], at.num_heads, math.sqrt(at.head_dim), causal=True, key_mask=key_mask)

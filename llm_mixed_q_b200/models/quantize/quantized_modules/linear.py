@@ -424,14 +424,7 @@ def qkv_rope_prequantized(q: "_LinearBase", k: "_LinearBase", v: "_LinearBase", 
         m._ensure_ptq()
     lib = L.load()
     K, H = q.in_features, q.out_features
-    key = tuple((m.weight.data_ptr(), m.weight._version) for m in (q, k, v)) + (q.weight.device,)
-    cache = getattr(q, "_qkv_cache", None)
-    if cache is None or cache[0] != key:
-        wcat = torch.cat([m._weight_cache() for m in (q, k, v)], dim=0).contiguous()
-        bcat = torch.cat([m.bias.detach() for m in (q, k, v)]).contiguous() if q.bias is not None else None
-        q._qkv_cache = cache = (key, wcat, bcat)
-        q._wq_bf16 = k._wq_bf16 = v._wq_bf16 = None
-    _, wcat, bcat = cache
+    wcat, bcat = _qkv_concat_cache(q, k, v)
     x2 = xq.reshape(-1, K)
     if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0):
         x2 = x2.contiguous()
@@ -446,6 +439,46 @@ def qkv_rope_prequantized(q: "_LinearBase", k: "_LinearBase", v: "_LinearBase", 
                                           seq_len, head_dim, M, H, K, x2.stride(0) if M > 1 else K, K, H, L.stream_ptr(xq.device))
         L.check(rc, "bq_gemm_bf16_tn_qkv_rope")
     return outs
+
+
+def _qkv_concat_cache(q: "_LinearBase", k: "_LinearBase", v: "_LinearBase"):
+    """(weights [3H, K] bf16, bias [3H] fp32 or None) of three projections that read the same operand, built once per weight version."""
+    key = tuple((m.weight.data_ptr(), m.weight._version) for m in (q, k, v)) + (q.weight.device,)
+    cache = getattr(q, "_qkv_cache", None)
+    if cache is None or cache[0] != key:
+        wcat = torch.cat([m._weight_cache() for m in (q, k, v)], dim=0).contiguous()
+        bcat = torch.cat([m.bias.detach() for m in (q, k, v)]).contiguous() if q.bias is not None else None
+        q._qkv_cache = cache = (key, wcat, bcat)
+        q._wq_bf16 = k._wq_bf16 = v._wq_bf16 = None          # the separate bf16 copies are rebuilt on demand
+    return cache[1], cache[2]
+
+
+def qkv_plain_fusable(q: "_LinearBase", k: "_LinearBase", v: "_LinearBase") -> bool:
+    return (QKV_ONE_LAUNCH and all(m.accepts_prequantized() for m in (q, k, v)) and q.in_features == k.in_features == v.in_features
+            and q.out_features == k.out_features == v.out_features and len({m.bias is None for m in (q, k, v)}) == 1)
+
+
+@torch.no_grad()
+def qkv_plain_prequantized(q: "_LinearBase", k: "_LinearBase", v: "_LinearBase", xq: torch.Tensor):
+    """(q_proj(x), k_proj(x), v_proj(x)) as fp32 column views [rows, H] (row stride 3H) of ONE GEMM over the concatenated quantised
+    weights — for layers whose attention keeps fp32 operands (block_log split path) and whose three projections share an x-quantizer.
+    Same bits as three launches (an output column's K reduction does not depend on its neighbours)."""
+    assert xq.dtype == torch.bfloat16 and xq.is_cuda and xq.shape[-1] == q.in_features
+    for m in (q, k, v):
+        m._ensure_ptq()
+    lib = L.load()
+    K, H = q.in_features, q.out_features
+    wcat, bcat = _qkv_concat_cache(q, k, v)
+    x2 = xq.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0):
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    y = torch.empty((M, 3 * H), dtype=torch.float32, device=xq.device)
+    if M > 0:
+        rc = lib.bq_gemm_bf16_tn(x2.data_ptr(), wcat.data_ptr(), y.data_ptr(), bcat.data_ptr() if bcat is not None else None, 1, M, 3 * H, K,
+                                 x2.stride(0) if M > 1 else K, K, 3 * H, 0, 0, 0, L.stream_ptr(xq.device))
+        L.check(rc, "bq_gemm_bf16_tn(q|k|v)")
+    return y[:, :H], y[:, H:2 * H], y[:, 2 * H:]
 
 
 GATED_EPILOGUE = True     # False: gate / up GEMMs + the silu*mul quantizer kernel (A/B, tests)

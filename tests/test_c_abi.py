@@ -123,6 +123,15 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert rope(256, 256, 256, None, ctypes.byref(f6), 0, 256, 256, None, 32, 64, 128, 64, 256, 64, 64, 64, 256) == 1          # table shorter than S
     assert rope(256, 256, 256, None, ctypes.byref(f6), 0, 256, 256, None, 64, 64, 128, 64, 256, 64, 64, 64, 128) == 1          # ldc < N
     assert rope(None, None, None, None, ctypes.byref(f6), 0, None, None, None, 64, 64, 128, 0, 256, 64, 64, 64, 256) == 0      # empty problem
+    # q | k | v in one launch: H % 256, M % 16, missing output / format
+    qkv = lambda *a: lib.bq_gemm_bf16_tn_qkv_rope(*a, None)
+    F6 = ctypes.byref(f6)
+    assert qkv(256, 256, 256, 256, None, None, F6, F6, F6, 256, 256, None, 64, 64, 128, 64, 256, 64, 64, 64, 256) == 1          # no Cv
+    assert qkv(256, 256, 256, 256, 256, None, F6, None, F6, 256, 256, None, 64, 64, 128, 64, 256, 64, 64, 64, 256) == 1         # no fk
+    assert qkv(256, 256, 256, 256, 256, None, F6, F6, F6, 256, 256, None, 64, 64, 128, 64, 384, 64, 64, 64, 384) == 2           # H % 256
+    assert qkv(256, 256, 256, 256, 256, None, F6, F6, F6, 256, 256, None, 64, 64, 128, 72, 256, 64, 64, 64, 256) == 2           # M % 16
+    assert qkv(256, 256, 256, 256, 256, None, F6, F6, ctypes.byref(fl), 256, 256, None, 64, 64, 128, 64, 256, 64, 64, 64, 256) == 2   # block_log v
+    assert qkv(None, None, None, None, None, None, F6, F6, F6, None, None, None, 64, 64, 128, 0, 256, 64, 64, 64, 256) == 0     # empty
     # gated-SiLU epilogue (act = 2): needs a format along N, bf16 output, no residual / replicas, ldc >= N / 2
     ep = L.BqGemmEpilogue()
     ep.scale, ep.act, ep.out_dtype = 1.0, 2, L.BQ_BF16
