@@ -101,3 +101,36 @@ def test_ptq_linear_keeps_autograd_semantics_of_the_reference():
 
     src = inspect.getsource(lin_mod._LinearBase.forward)
     assert "wants_grad" in src and src.index("wants_grad =") < src.index("with torch.no_grad()")
+
+
+def test_llama_gemm_epilogue_eligibility_predicates():
+    """Host-side decisions of the Llama GEMM-epilogue fusions (quantized_modules/linear.py): the gated-SiLU epilogue needs two bias-free
+    PTQ projections of one shape with whole blocks of 16 features; the RoPE epilogue head sizes 64 / 128; q | k | v in one launch
+    additionally 256-column segments and either all or none of the three biases."""
+    from llm_mixed_q_b200.models.quantize import get_quantized_cls
+    from llm_mixed_q_b200.models.quantize.quantized_modules import linear as QL
+
+    cfg = {"name": "block_fp", "bypass": False, "is_ptq": True}
+    for p in ("data_in", "weight", "bias"):
+        cfg.update({f"{p}_width": 6, f"{p}_exponent_width": 8, f"{p}_exponent_bias": None, f"{p}_block_size": [1, 16]})
+    mk = lambda k, n, bias=False, c=cfg: get_quantized_cls("linear", c)(k, n, bias=bias, config=dict(c))
+    assert QL.gated_silu_fusable(mk(64, 352), mk(64, 352))
+    assert not QL.gated_silu_fusable(mk(64, 352), mk(64, 368))                  # different shapes
+    assert not QL.gated_silu_fusable(mk(64, 352, bias=True), mk(64, 352))       # a bias on one of them
+    assert not QL.gated_silu_fusable(mk(64, 40), mk(64, 40))                    # below one 64-column pair of chunks
+    qat = dict(cfg, is_ptq=False)
+    assert not QL.gated_silu_fusable(mk(64, 352, c=qat), mk(64, 352))           # QAT: weights are re-quantised every call
+    wide = dict(cfg, weight_width=12)
+    assert not QL.gated_silu_fusable(mk(64, 352, c=wide), mk(64, 352))          # > 8 significant bits: not bf16-exact
+    assert QL.rope_epilogue_fusable(mk(64, 256), 128) and QL.rope_epilogue_fusable(mk(64, 256), 64)
+    assert not QL.rope_epilogue_fusable(mk(64, 256), 32) and not QL.rope_epilogue_fusable(mk(64, 192), 128)
+    q, k, v = mk(64, 256), mk(64, 256), mk(64, 256)
+    assert QL.qkv_rope_fusable(q, k, v, 128) and QL.qkv_plain_fusable(q, k, v)
+    assert not QL.qkv_rope_fusable(mk(64, 384), mk(64, 384), mk(64, 384), 128)  # segments of 384 columns: a 256-wide tile would straddle two
+    assert QL.qkv_plain_fusable(mk(64, 384), mk(64, 384), mk(64, 384))
+    assert not QL.qkv_rope_fusable(q, k, mk(64, 256, bias=True), 128) and not QL.qkv_plain_fusable(q, k, mk(64, 256, bias=True))
+    try:
+        QL.QKV_ONE_LAUNCH = False
+        assert not QL.qkv_rope_fusable(q, k, v, 128) and not QL.qkv_plain_fusable(q, k, v)
+    finally:
+        QL.QKV_ONE_LAUNCH = True
