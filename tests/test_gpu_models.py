@@ -83,6 +83,52 @@ def test_llama_tiny_matches_reference_forward(tag, cfgkey):
     assert float(err.mean()) <= 0.03 * spread, (float(err.mean()), float(err.max()), spread)
 
 
+@pytest.mark.parametrize("tag,cfgkey", [("llama_small_bfp6", "bfp_6bit.toml"), ("llama_small_bmf8", "block_minifloat.toml")])
+def test_llama_fused_layers_match_reference_forward(tag, cfgkey):
+    """The FUSED Llama layer at head_dim 128 — RMSNorm + quantize, q | k | v as one GEMM with the RoPE / operand-quantizer epilogue,
+    one-kernel attention (key-padding bitmap for the right-padded row), o_proj / down_proj residual epilogues, gate | up as one GEMM
+    with the gated-SiLU epilogue — against the unmodified reference's forward (oracle/gen_golden_llama_fused.py; reference
+    models/llama_quantized/modeling_llama.py:246, :274-344).  The op-by-op path of this package is held to the same golden, and the
+    fused path may not be further from the reference than it (beyond the statistical noise of one-step rounding flips)."""
+    from llm_mixed_q_b200 import _lib as L
+    from llm_mixed_q_b200.models.llama_quantized import LlamaQuantizedConfig, LlamaQuantizedForCausalLM
+
+    g = raw_configs()
+    z = load(tag)
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    ids, am, labels = (torch.from_numpy(z[k]).cuda() for k in ("input_ids", "attention_mask", "labels"))
+    valid = am.bool().cpu()
+    res = {}
+    for fused in (True, False):
+        cfg = LlamaQuantizedConfig(hidden_size=256, intermediate_size=352, num_hidden_layers=2, num_attention_heads=2, vocab_size=512,
+                                   max_position_embeddings=128, initializer_range=float(z["initializer_range"]), pad_token_id=0,
+                                   quant_config=clone(g["raw"][cfgkey]))
+        model = LlamaQuantizedForCausalLM(cfg).eval()
+        missing, _ = model.load_state_dict(sd, strict=False)
+        assert not missing, missing
+        model = model.cuda()
+        model.model.fused_glue = fused
+        n_attn, n_epi = L.launch_counts()["attention_causal_kernel"], L.launch_counts()["gemm_bf16_tn_kernel<epilogue>"]
+        with torch.no_grad():
+            out = model(input_ids=ids, attention_mask=am, labels=labels)
+            out1 = model(input_ids=ids[:1], labels=ids[:1])
+        if fused:
+            layer = model.model.layers[0]
+            assert layer._fused_plan(ids.shape[1]) is not None and layer._fused_plan(ids.shape[1]).get("mode") != "split"
+            assert L.launch_counts()["attention_causal_kernel"] - n_attn == 4                 # 2 layers x 2 forwards, one kernel each
+            # per layer and forward: q | k | v (1), o_proj (1), gate | up (1), down_proj (1)
+            assert L.launch_counts()["gemm_bf16_tn_kernel<epilogue>"] - n_epi == 16
+            assert getattr(layer.self_attn.q_proj, "_qkv_cache", None) is not None and getattr(layer.mlp.gate_proj, "_gu_cache", None) is not None
+        for o, key, sel in ((out, "", valid), (out1, "_unpadded_row0", torch.ones(1, ids.shape[1], dtype=torch.bool))):
+            ref_logits, ref_loss = torch.from_numpy(z["logits" + key]), float(z["loss" + key])
+            assert abs(float(o.loss) - ref_loss) <= 5e-3 * abs(ref_loss), (fused, key, float(o.loss), ref_loss)
+            err = (o.logits.cpu() - ref_logits).abs()[sel]
+            spread = float(ref_logits[sel].std())
+            res[(fused, key)] = float(err.mean()) / spread
+            assert float(err.mean()) <= 0.03 * spread, (fused, key, float(err.mean()), float(err.max()), spread)
+    assert res[(True, "")] <= 1.5 * res[(False, "")] + 2e-3, res
+
+
 def _opt125m_from_seed():
     """BASELINE configs[0] model: OPT-125M shape (the config class defaults), random init under seed 0 on the CPU — bit-identical
     to the reference model the golden was generated from (oracle/gen_golden_opt125m.py), which the checksums re-verify."""
